@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- Gcell-steps/s of the fp32 Fenton-Karma Euler loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one checkpoint segment of SEG Euler steps (solve._forward_euler over [t, t+SEG)), the
+unit the reference's `forward` loop launches (cardiax/solve.py:198-217).
+
+Workloads (BASELINE.json configs):
+  fk4096   4096 x 4096 homogeneous D = 1e-3, PARAMSET_5, random rectangular excitations  (N = 1 default)
+  slab     row-slab decomposition of a (4096*N) x 4096 tissue over N GPUs, 4T-row halo exchange (N > 1 default)
+  ens256   ensemble of independent 256 x 256 tissues (128 per GPU), heterogeneous D, 3 stimuli each, no comms
+  fk512    512 x 512 scar map + S1-S2 (config 2)
+
+Rank 0 prints ONE JSON line.  `value` is device-timed (CUDA events, barrier + synchronize on both
+sides, max over ranks) with the state resident in HBM; `e2e` goes through the public
+cardiax.solve API from pinned HOST buffers with the H2D and D2H copies inside the timed region.
+`--impl reference` times the reference's CPU path (the C/OpenMP oracle port: the reference itself
+needs a 2021 JAX that is not installable here) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES = 28.0  # read u, v, w, D + write u, v, w (fp32) per cell-step
+SEG = 500         # Euler steps per checkpoint segment (experiments/generate_fd_data_256.py:11-12)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ workloads (host side, NumPy)
+def make_fk4096(H=4096, W=4096, seed=0):
+    rng = np.random.default_rng(seed)
+    u = np.zeros((H, W), np.float32)
+    for _ in range(max(4, H * W // 400000)):
+        r, c = rng.integers(0, H - 64), rng.integers(0, W - 64)
+        u[r:r + 48, c:c + 48] = 1.0
+    return dict(v=np.ones((H, W), np.float32), w=np.ones((H, W), np.float32), u=u,
+                D=np.full((H, W), 1e-3, np.float32), stimuli=[], params="5")
+
+
+def make_fk512(seed=0):
+    import oracle as O
+    from tests import common
+    shape = (512, 512)
+    _, D = common.smooth_case(shape, seed)
+    ang = float(np.random.default_rng(seed).uniform(0, 180))
+    s1 = O.triangular(shape, 0, ang, 0.2, 20.0, O.Protocol(0, 2, 1e9))
+    s2 = O.triangular(shape, 0, ang + 90, 0.5, 20.0, O.Protocol(40000, 2, 1e9))
+    return dict(v=np.ones(shape, np.float32), w=np.ones(shape, np.float32), u=np.zeros(shape, np.float32), D=D,
+                stimuli=[s1, s2], params="3")
+
+
+def make_ens256(nsims, seed=0):
+    import oracle as O
+    from tests import common
+    shape = (256, 256)
+    rng = np.random.default_rng(seed)
+    D = np.empty((nsims,) + shape, np.float32)
+    stim = []
+    for b in range(nsims):
+        _, D[b] = common.smooth_case(shape, seed * 100003 + b)
+        ss = []
+        for k in range(3):
+            kind = rng.integers(0, 3)
+            proto = O.Protocol(int(1 + k * 25000 + rng.integers(0, 2)), 2, int(rng.integers(400, 10 ** 9)))
+            if kind == 0:
+                size = rng.integers(10, 85, 2)
+                ss.append(O.rectangular(shape, rng.integers(int(size.min()), 256, 2), size, 20.0, proto))
+            elif kind == 1:
+                ss.append(O.triangular(shape, int(rng.integers(0, 3)), float(abs(rng.normal()) * 45),
+                                       float(abs(rng.normal()) * 0.2), 20.0, proto))
+            else:
+                ss.append(O.linear(shape, int(rng.integers(0, 3)), float(abs(rng.normal()) * 0.2), 20.0, proto))
+        stim.append(ss)
+    return dict(v=np.ones((nsims,) + shape, np.float32), w=np.ones((nsims,) + shape, np.float32),
+                u=np.zeros((nsims,) + shape, np.float32), D=D, stimuli=stim, params="3")
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_run(work, euler_steps, repeats=1):
+    """C/OpenMP port of the reference loop on all host cores; returns (cell_steps_per_s, cores, seconds)."""
+    import oracle as O
+    from oracle import c_oracle as C
+    cores = C.set_threads(os.cpu_count() or 1)
+    st = O.State(work["v"], work["w"], work["u"])
+    if st.u.ndim == 3:  # ensemble: one tissue is the sample
+        st = O.State(st.v[0], st.w[0], st.u[0])
+        D, stim = work["D"][0], work["stimuli"][0]
+    else:
+        D, stim = work["D"], work["stimuli"]
+    cells = st.u.size
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        C.forward_euler(st, 0, euler_steps, O.PARAMSETS[work["params"]], D, stim, 0.01, 0.01)
+    dt = time.perf_counter() - t0
+    return cells * euler_steps * repeats / dt, cores, dt
+
+
+def reference_arm(args, workload, work, config):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cells = work["u"].shape[-1] * work["u"].shape[-2]
+    n_euler = max(1, int(2.0e8 // cells))  # ~2e8 cell-steps (about a second of CPU work) per bench step
+    for _ in range(args.warmup):
+        cpu_run(work, 1)
+    t0 = time.perf_counter()
+    cores = 1
+    for _ in range(args.steps):
+        _, cores, _ = cpu_run(work, n_euler)
+    dt = time.perf_counter() - t0
+    val = cells * n_euler * args.steps / dt / 1e9
+    sample = "%s: one tissue, %d Euler steps per bench step" % (workload, n_euler)
+    print(json.dumps({
+        "impl": "reference", "metric": "Gcell-steps/s fp32 FK", "value": val, "unit": "Gcell-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {"value": val, "unit": "Gcell-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = C/OpenMP restatement of cardiax/solve.py (oracle/fk_oracle.c); the JAX reference is not installable here",
+    }))
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--seg", type=int, default=SEG)
+    ap.add_argument("--numerics", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--T", type=int, default=0)
+    ap.add_argument("--cta-threads", type=int, default=0)
+    ap.add_argument("--rows-per-cta", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = args.workload or ("fk4096" if args.gpus == 1 else "slab")
+
+    if workload == "fk4096":
+        work = make_fk4096()
+        config = {"workload": "fk4096: 4096x4096 homogeneous D=1e-3, PARAMSET_5, random rectangular excitations",
+                  "grid": [4096, 4096]}
+    elif workload == "slab":
+        work = make_fk4096(4096, 4096, seed=rank)
+        config = {"workload": "slab: (4096*N)x4096 tissue, row slabs of 4096 rows per GPU, 4T-row halo exchange",
+                  "grid": [4096 * world, 4096]}
+    elif workload == "fk512":
+        work = make_fk512()
+        config = {"workload": "fk512: 512x512 scar-map D, S1-S2 cross-field stimuli, PARAMSET_3", "grid": [512, 512]}
+    elif workload == "ens256":
+        work = make_ens256(128, seed=rank)
+        config = {"workload": "ens256: 128 independent 256x256 tissues per GPU, scar D, 3 random stimuli each",
+                  "grid": [128 * world, 256, 256]}
+    else:
+        raise SystemExit("unknown workload " + workload)
+    config.update({"euler_steps_per_step": args.seg, "dt": 0.01, "dx": 0.01, "numerics": args.numerics,
+                   "l2": "state (3 x 64 MiB per 4096^2 field) larger than the 126 MB L2" if workload in ("fk4096", "slab")
+                   else "working set is L2 resident by nature of the config; an L2 flush buffer is written between steps"})
+
+    if args.impl == "reference":
+        return reference_arm(args, workload, work, config)
+
+    import torch
+    import oracle as O
+    from cardiax_b200 import _lib, options, solve, stimulus
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    if _lib.needs_build():
+        _lib.build()
+    L = _lib.lib()
+    options.verbose = False
+    options.numerics = args.numerics
+    options.steps_per_launch = args.T
+    options.cta_threads, options.rows_per_cta, options.kernel = args.cta_threads, args.rows_per_cta, args.kernel
+    params = O.PARAMSETS[work["params"]]
+    seg = args.seg
+
+    def dev_stim(stimuli):
+        if len(stimuli) and isinstance(stimuli[0], list):
+            return [dev_stim(s) for s in stimuli]
+        return [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).to(dev)) for s in stimuli]
+
+    gstim = dev_stim(work["stimuli"])
+    D = torch.as_tensor(work["D"]).to(dev)
+    state0 = solve.State(*[torch.as_tensor(work[k]).to(dev) for k in "vwu"])
+    cells = state0.u.numel()
+    flush = None
+    if workload in ("fk512", "ens256"):
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    if workload == "slab" and world > 1:
+        from cardiax_b200 import slab
+        runner = slab.SlabRunner(state0, D, params, gstim, 0.01, 0.01, rank, world)
+        step_fn = lambda st, t: runner.advance(st, t, t + seg)  # noqa: E731
+        state0 = runner.scatter_local(state0)
+    else:
+        step_fn = lambda st, t: solve._forward_euler(st, t, t + seg, params, D, gstim, 0.01, 0.01)  # noqa: E731
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement
+    st, t = state0, 0
+    for _ in range(args.warmup):
+        st = step_fn(st, t); t += seg
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.fk_launch_count()
+    L.fk_profile_enable(1)
+    L.fk_profile_collect(None, None, None, None)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1.0)
+        st = step_fn(st, t); t += seg
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    import ctypes
+    sm_ms, sm_n, tl_ms, tl_n = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong()
+    L.fk_profile_collect(ctypes.byref(sm_ms), ctypes.byref(sm_n), ctypes.byref(tl_ms), ctypes.byref(tl_n))
+    L.fk_profile_enable(0)
+    launches = L.fk_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if flush is not None:  # take the flush writes out: time them alone
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); f0.record()
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+        f1.record(); torch.cuda.synchronize()
+        ms -= f0.elapsed_time(f1)
+    assert all(bool(torch.isfinite(x).all()) for x in st)
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    total_cells = cells * world
+    value = total_cells * seg * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API from pinned host buffers
+    host_in = [torch.as_tensor(work[k]).pin_memory() for k in "vwu"]
+    host_out = [torch.empty_like(x).pin_memory() for x in host_in]
+    h2d = sum(x.numel() * 4 for x in host_in)
+    d2h = sum(x.numel() * 4 for x in host_out)
+
+    def e2e_step(t):
+        s = solve.State(*[x.to(dev, non_blocking=True) for x in host_in])
+        if workload == "slab" and world > 1:
+            s = step_fn(runner.scatter_local(s), t)
+            s = runner.gather_local(s)
+        else:
+            s = step_fn(s, t)
+        for o, x in zip(host_out, s):
+            o.copy_(x, non_blocking=True)
+
+    e2e_step(0)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(args.steps):
+        e2e_step(i * seg)
+    g1.record()
+    barrier()
+    ems = g0.elapsed_time(g1)
+    if dist is not None:
+        tms = torch.tensor([ems], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ems = float(tms.item())
+    e2e = total_cells * seg * args.steps / (ems * 1e-3) / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    roof = None
+    if sm_n.value > 0:
+        # streaming kernel: T steps over the interior per launch
+        Tl = args.T or 2
+        Hh, Ww = state0.u.shape[-2:]
+        nb = state0.u.shape[0] if state0.u.dim() == 3 else 1
+        cs_per_launch = (Hh - 8 * Tl) * (Ww - 8 * Tl) * Tl * nb
+        achieved = ALG_BYTES * cs_per_launch / (sm_ms.value / sm_n.value * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind, "kernel": "fk_stream_kernel",
+                "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": sm_ms.value / sm_n.value,
+                "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms}
+    elif tl_n.value > 0:
+        achieved = ALG_BYTES * cells * seg * args.steps / (tl_ms.value * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind, "kernel": "fk_tile_kernel",
+                "kernel_share_of_step": tl_ms.value / ms}
+    cpu = None
+    if not args.no_cpu and world == 1:
+        n_e = max(1, int(1.5e9 // cells)) if workload in ("fk4096",) else max(1, int(1.5e9 // (work["u"].shape[-1] * work["u"].shape[-2])))
+        v, cores, secs = cpu_run(work, n_e)
+        cpu = {"value": v / 1e9, "unit": "Gcell-steps/s", "cores": cores, "kind": "port",
+               "sample": "%s: one tissue, %d Euler steps, %.1f s" % (workload, n_e, secs)}
+    out = {
+        "metric": "Gcell-steps/s fp32 FK", "value": value, "unit": "Gcell-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "Gcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "hbm_roofline_frac_whole_step": ALG_BYTES * value / world / peak,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

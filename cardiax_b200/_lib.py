@@ -1,0 +1,107 @@
+"""Loader and ctypes signatures of libfk.so (C ABI in include/fk.h).
+
+The library is built in-tree (``cardiax_b200/csrc/libfk.so``) by ``build()`` with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is no CPU fallback: every solver entry
+point raises if the library or a CUDA device is missing.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libfk.so")
+_SOURCES = ["fk_api.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+_lib = None
+
+
+class FkParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in (
+        "tau_v_plus", "tau_v1_minus", "tau_v2_minus", "tau_w_plus", "tau_w_minus", "tau_d", "tau_0", "tau_r", "tau_si",
+        "k", "V_csi", "V_c", "V_v", "Cm")]
+
+
+class FkStimulus(ctypes.Structure):
+    _fields_ = [("field", ctypes.c_void_p), ("start", ctypes.c_float), ("duration", ctypes.c_float),
+                ("period", ctypes.c_float)]
+
+
+class FkOptions(ctypes.Structure):
+    _fields_ = [("exact", ctypes.c_int), ("steps_per_launch", ctypes.c_int), ("kernel", ctypes.c_int),
+                ("phys_top", ctypes.c_int), ("phys_bottom", ctypes.c_int), ("cta_threads", ctypes.c_int),
+                ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("reserved", ctypes.c_int * 8)]
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(CSRC, s) for s in _SOURCES] + [os.path.join(_HERE, "..", "include", "fk.h")]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc-compile csrc/fk_api.cu into csrc/libfk.so (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, os.path.join(CSRC, "fk_api.cu")]
+    env = dict(os.environ)
+    env.pop("CC", None)   # the image's CC/CXX point at a gcc without its support files
+    env.pop("CXX", None)
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stderr)
+    return SO_PATH
+
+
+def lib():
+    """The loaded library; raises RuntimeError if it is not built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError("cardiax_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  There is no CPU fallback." % SO_PATH)
+    L = ctypes.CDLL(SO_PATH)
+    vp, ci, cf, cd, ll, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_longlong, ctypes.c_size_t
+    L.fk_abi_version.restype = ci
+    L.fk_last_error.restype = ctypes.c_char_p
+    L.fk_default_options.argtypes = [ctypes.POINTER(FkOptions)]
+    L.fk_default_options.restype = None
+    L.fk_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+    L.fk_workspace_bytes.restype = sz
+    L.fk_forward_euler.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci,
+                                              cd, cd, cf, cf, ctypes.POINTER(FkOptions), vp, sz, vp]
+    L.fk_forward_euler.restype = ci
+    L.fk_rhs.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd, cf,
+                                    ctypes.POINTER(FkOptions), vp, sz, vp]
+    L.fk_rhs.restype = ci
+    L.fk_gradient.argtypes = [vp, vp, ll, ll, ll, vp]
+    L.fk_gradient.restype = ci
+    L.fk_stimulate.argtypes = [cd, vp, vp, ci, ci, ctypes.POINTER(FkStimulus), ci, vp, sz, vp]
+    L.fk_stimulate.restype = ci
+    L.fk_diffusivity_gradients.argtypes = [vp, vp, vp, ci, ci, ci, cf, ci, ci, vp]
+    L.fk_diffusivity_gradients.restype = ci
+    L.fk_launch_count.restype = ll
+    L.fk_profile_enable.argtypes = [ci]
+    L.fk_profile_enable.restype = None
+    L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll)]
+    L.fk_profile_collect.restype = ci
+    if L.fk_abi_version() != 1:
+        raise RuntimeError("libfk.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().fk_last_error().decode()
+        if rc < 0:
+            raise ValueError("libfk: %s (code %d)" % (msg, rc))
+        raise RuntimeError("libfk: %s (cudaError %d)" % (msg, rc))

@@ -1,0 +1,363 @@
+// fk_api.cu -- kernels and the C ABI (include/fk.h) of libfk.so.  sm_100a only.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/fk.h"
+#include "fk_core.h"
+#include "fk_tile.h"
+#include "fk_stream.cuh"
+#include "fk_driver.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+#define FK_CUDA(call)                                     \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+long long g_launches = 0;
+int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// ------------------------------------------------------------------ kernels
+template <bool EXACT>
+__global__ void __launch_bounds__(256) fk_tile_kernel(const __grid_constant__ fk::TileArgs A) {
+    extern __shared__ __align__(16) float fk_smem[];
+    fk::TileCtx X;
+    fk::tile_setup(A, blockIdx.x, blockIdx.y, fk_smem, X);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ntx = 32, nty = blockDim.x >> 5;
+    fk::tile_load(A, X, tx, ty, ntx, nty);
+    __syncthreads();
+    float* Uc = X.U0;
+    float* Un = X.U1;
+    for (int s = 1; s <= A.T; ++s) {
+        fk::tile_grad<EXACT>(A, X, s, Uc, tx, ty, ntx, nty);
+        __syncthreads();
+        fk::tile_update<EXACT>(A, X, s, Uc, Un, tx, ty, ntx, nty);
+        __syncthreads();
+        float* t = Uc;
+        Uc = Un;
+        Un = t;
+    }
+}
+
+// solve.gradient on (outer, n, inner)
+__global__ void fk_gradient_kernel(const float* __restrict__ a, float* __restrict__ out, long long outer, long long n,
+                                   long long inner) {
+    const long long total = outer * n * inner;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx % inner, i = (idx / inner) % n, o = idx / (inner * n);
+        const float* base = a + o * n * inner + k;
+        const int kind = i < 2 ? fk::FWD : (i >= n - 2 ? fk::BWD : fk::CEN);
+        float k0, k1, k2, k3;
+        int o0, o1, o2, o3;
+        fk::kind_coeffs(kind, k0, k1, k2, k3, o0, o1, o2, o3);
+        out[idx] = fk::tap4<true>(k0, k1, k2, k3, base[(i + o0) * inner], base[(i + o1) * inner], base[(i + o2) * inner],
+                                  base[(i + o3) * inner]);
+    }
+}
+
+// D_x, D_y of solve.py:53-54
+__global__ void fk_dgrad_kernel(const float* __restrict__ D, float* __restrict__ DX, float* __restrict__ DY, int H, int W,
+                                float dx, int phys_top, int phys_bot) {
+    const long long plane = (long long)H * W;
+    const float* Ds = D + blockIdx.y * plane;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < plane;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / W), col = (int)(idx - (long long)row * W);
+        float gx, gy;
+        fk::dgrad_cell(Ds, H, W, dx, phys_top, phys_bot, row, col, gx, gy);
+        DX[blockIdx.y * plane + idx] = gx;
+        DY[blockIdx.y * plane + idx] = gy;
+    }
+}
+
+// solve.stimulate on one array
+__global__ void fk_stimulate_kernel(const float* __restrict__ x, float* __restrict__ out, long long n,
+                                    const fk::StimDev* __restrict__ stims, int n_stim, float t) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        float st = 0.0f;
+        for (int i = 0; i < n_stim; ++i) {
+            const fk::StimDev s = stims[i];
+            if (s.field && fk::stim_active(t, s.start, s.duration, s.period)) {
+                const float f = s.field[idx];
+                if (f != 0.0f) st = f;
+            }
+        }
+        out[idx] = st != 0.0f ? st : x[idx];
+    }
+}
+
+// ------------------------------------------------------------------ host helpers
+fk::Consts make_consts(const FkParams& p, float dt, float dx) {
+    static_assert(sizeof(FkParams) == 14 * sizeof(float), "FkParams layout");
+    return fk::make_consts(&p.tau_v_plus, dt, dx);
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+    float *DX, *DY, *pv, *pw, *pu;
+    fk::StimDev* stims;
+    size_t bytes;
+};
+
+Workspace carve(void* base, int H, int W, int batch, int n_stim, int d_batched) {
+    Workspace ws;
+    char* p = (char*)base;
+    const size_t plane = (size_t)H * W * sizeof(float);
+    const size_t dplanes = d_batched ? (size_t)batch : 1;
+    size_t off = 0;
+    ws.DX = (float*)(p + off); off = align_up(off + plane * dplanes, 256);
+    ws.DY = (float*)(p + off); off = align_up(off + plane * dplanes, 256);
+    ws.pv = (float*)(p + off); off = align_up(off + plane * batch, 256);
+    ws.pw = (float*)(p + off); off = align_up(off + plane * batch, 256);
+    ws.pu = (float*)(p + off); off = align_up(off + plane * batch, 256);
+    ws.stims = (fk::StimDev*)(p + off); off = align_up(off + sizeof(fk::StimDev) * (size_t)std::max(1, batch * n_stim), 256);
+    ws.bytes = off;
+    return ws;
+}
+
+int upload_stims(const FkStimulus* stimuli, int count, fk::StimDev* dev, cudaStream_t st) {
+    if (count <= 0) return 0;
+    static_assert(sizeof(fk::StimDev) == sizeof(FkStimulus), "layout");
+    // pageable source: the runtime stages it before returning, so the caller's array may die after the call
+    FK_CUDA(cudaMemcpyAsync(dev, stimuli, sizeof(FkStimulus) * (size_t)count, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int launch_dgrad(const float* D, float* DX, float* DY, int H, int W, int planes, float dx, int pt, int pb, cudaStream_t st) {
+    const long long plane = (long long)H * W;
+    int blocks = (int)std::min<long long>((plane + 255) / 256, 148LL * 16);
+    ++g_launches;
+    fk_dgrad_kernel<<<dim3(blocks, planes), 256, 0, st>>>(D, DX, DY, H, W, dx, pt, pb);
+    FK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- optional per-launch timing (bench.py): CUDA events around every launch, on the launch stream
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[2];   // [0] streaming kernel, [1] tile kernel : begin/end pairs
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
+        cudaEventCreate(&e);
+        return e;
+    }
+} g_prof;
+struct ProfScope {
+    int kind; cudaStream_t st; bool active;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), active(g_prof.on && g_prof.ev[k].size() < 8192) {
+        if (active) { cudaEvent_t e = g_prof.get(); cudaEventRecord(e, st); g_prof.ev[kind].push_back(e); }
+    }
+    ~ProfScope() {
+        if (active) { cudaEvent_t e = g_prof.get(); cudaEventRecord(e, st); g_prof.ev[kind].push_back(e); }
+    }
+};
+
+struct CudaBackend {
+    cudaStream_t st;
+    int num_sms() { return ::num_sms(); }
+    int max_stream_threads() { return 256; }
+    int tiles(fk::TileArgs& A, int exact, int batch) {
+        long long floats = 0;
+        const int total = fk::finish_regions(A, &floats);
+        if (total == 0) return 0;
+        const size_t smem = (size_t)floats * sizeof(float);
+        if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
+        ProfScope ps(1, st);
+        ++g_launches;
+        if (exact) {
+            FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fk_tile_kernel<true><<<dim3(total, batch), 256, smem, st>>>(A);
+        } else {
+            FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fk_tile_kernel<false><<<dim3(total, batch), 256, smem, st>>>(A);
+        }
+        FK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int stream(const fk::StreamPlan& P, const fk::TileArgs& A, int exact, int batch) {
+        ProfScope ps(0, st);
+        ++g_launches;
+        const int rc = fk::launch_stream(P, A, exact, batch, st);
+        if (rc > 0) return cuda_fail((cudaError_t)rc, "streaming kernel launch");
+        if (rc < 0) return fail(rc, "streaming kernel: unsupported steps_per_launch%s");
+        return 0;
+    }
+};
+
+int check_common(int H, int W, int batch, const FkParams* params, int n_stim, const FkStimulus* stimuli) {
+    if (H < 3 || W < 3) return fail(-1, "tissue must be at least 3 x 3 (the reference's gradient needs n + 2 >= 5)%s");
+    if (batch < 1) return fail(-1, "batch must be >= 1%s");
+    if (!params) return fail(-1, "params is NULL%s");
+    if (n_stim < 0 || n_stim > 32) return fail(-2, "n_stim must be in [0, 32]%s");
+    if (n_stim > 0 && !stimuli) return fail(-1, "stimuli is NULL%s");
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int fk_abi_version(void) { return FK_ABI_VERSION; }
+
+long long fk_launch_count(void) { return g_launches; }
+
+void fk_profile_enable(int on) { g_prof.on = on != 0; }
+
+int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches) {
+    double ms[2] = {0, 0};
+    long long n[2] = {0, 0};
+    for (int k = 0; k < 2; ++k) {
+        std::vector<cudaEvent_t>& v = g_prof.ev[k];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            FK_CUDA(cudaEventSynchronize(v[i + 1]));
+            float t = 0;
+            FK_CUDA(cudaEventElapsedTime(&t, v[i], v[i + 1]));
+            ms[k] += t;
+            ++n[k];
+        }
+        for (cudaEvent_t e : v) g_prof.pool.push_back(e);
+        v.clear();
+    }
+    if (stream_ms) *stream_ms = ms[0];
+    if (stream_launches) *stream_launches = n[0];
+    if (tile_ms) *tile_ms = ms[1];
+    if (tile_launches) *tile_launches = n[1];
+    return 0;
+}
+const char* fk_last_error(void) { return g_err; }
+
+void fk_default_options(FkOptions* opt) {
+    if (!opt) return;
+    memset(opt, 0, sizeof(*opt));
+    opt->phys_top = 1;
+    opt->phys_bottom = 1;
+}
+
+size_t fk_workspace_bytes(int H, int W, int batch, int n_stim, int d_batched) {
+    if (H <= 0 || W <= 0 || batch <= 0 || n_stim < 0) return 0;
+    return carve(nullptr, H, W, batch, n_stim, d_batched).bytes;
+}
+
+int fk_diffusivity_gradients(const float* D, float* DX, float* DY, int H, int W, int batch, float dx, int phys_top,
+                             int phys_bottom, void* stream) {
+    if (!D || !DX || !DY) return fail(-1, "NULL pointer%s");
+    if (H < 3 || W < 3 || batch < 1) return fail(-1, "bad shape%s");
+    return launch_dgrad(D, DX, DY, H, W, batch, dx, phys_top, phys_bottom, (cudaStream_t)stream);
+}
+
+int fk_gradient(const float* a, float* out, long long outer, long long n, long long inner, void* stream) {
+    if (!a || !out) return fail(-1, "NULL pointer%s");
+    if (n < 5) return fail(-1, "gradient needs at least 5 points along the axis%s");
+    if (outer < 0 || inner < 0) return fail(-1, "bad shape%s");
+    const long long total = outer * n * inner;
+    if (total == 0) return 0;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    fk_gradient_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out, outer, n, inner);
+    FK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fk_stimulate(double t, const float* x, float* out, int H, int W, const FkStimulus* stimuli, int n_stim, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    if (!x || !out) return fail(-1, "NULL pointer%s");
+    if (H < 1 || W < 1 || n_stim < 0) return fail(-1, "bad shape%s");
+    if (n_stim > 0 && (!workspace || workspace_bytes < sizeof(fk::StimDev) * (size_t)n_stim))
+        return fail(-4, "workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_stims(stimuli, n_stim, (fk::StimDev*)workspace, st);
+    if (rc) return rc;
+    const long long n = (long long)H * W;
+    int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 32);
+    fk_stimulate_kernel<<<blocks, 256, 0, st>>>(x, out, n, (const fk::StimDev*)workspace, n_stim, (float)t);
+    FK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int run_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                     const float* D, int d_batched, int H, int W, int batch, const FkParams* params,
+                     const FkStimulus* stimuli, int n_stim, double t0, long long nsteps, float dt, float dx,
+                     const FkOptions* opt_in, int rhs_mode, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(H, W, batch, params, n_stim, stimuli);
+    if (rc) return rc;
+    if (!v_in || !w_in || !u_in || !v_out || !w_out || !u_out || !D) return fail(-1, "NULL pointer%s");
+    FkOptions opt;
+    if (opt_in) opt = *opt_in; else fk_default_options(&opt);
+    if (opt.steps_per_launch < 0 || opt.steps_per_launch > 8) return fail(-1, "steps_per_launch must be in [0, 8]%s");
+    const size_t need = fk_workspace_bytes(H, W, batch, n_stim, d_batched);
+    if (!workspace || workspace_bytes < need) return fail(-4, "workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane_bytes = (size_t)H * W * sizeof(float) * batch;
+    if (nsteps <= 0 && !rhs_mode) {
+        FK_CUDA(cudaMemcpyAsync(v_out, v_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
+        FK_CUDA(cudaMemcpyAsync(w_out, w_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
+        FK_CUDA(cudaMemcpyAsync(u_out, u_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    Workspace ws = carve(workspace, H, W, batch, n_stim, d_batched);
+    rc = upload_stims(stimuli, batch * n_stim, ws.stims, st);
+    if (rc) return rc;
+    rc = launch_dgrad(D, ws.DX, ws.DY, H, W, d_batched ? batch : 1, dx, opt.phys_top, opt.phys_bottom, st);
+    if (rc) return rc;
+    fk::DriveBuffers B;
+    B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
+    B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu; B.D = D; B.DX = ws.DX; B.DY = ws.DY; B.stims = ws.stims;
+    fk::DriveOptions o;
+    o.exact = opt.exact; o.steps_per_launch = opt.steps_per_launch; o.kernel = opt.kernel;
+    o.phys_top = opt.phys_top; o.phys_bottom = opt.phys_bottom; o.cta_threads = opt.cta_threads;
+    o.rows_per_cta = opt.rows_per_cta; o.uniform_diffusivity = opt.uniform_diffusivity;
+    CudaBackend be;
+    be.st = st;
+    const char* why = "";
+    rc = fk::drive_euler(be, B, d_batched, H, W, batch, make_consts(*params, dt, dx), n_stim, t0, nsteps, o, rhs_mode, &why);
+    if (rc && why[0]) return fail(rc, "%s", why);
+    return rc;
+}
+
+int fk_forward_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                     const float* D, int d_batched, int H, int W, int batch, const FkParams* params,
+                     const FkStimulus* stimuli, int n_stim, double t0, double t1, float dt, float dx, const FkOptions* opt,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    const long long nsteps = fk::count_steps(t0, t1);
+    return run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, d_batched, H, W, batch, params, stimuli, n_stim, t0, nsteps,
+                     dt, dx, opt, 0, workspace, workspace_bytes, stream);
+}
+
+int fk_rhs(const float* v, const float* w, const float* u, float* dv, float* dw, float* du, const float* D, int d_batched,
+           int H, int W, int batch, const FkParams* params, const FkStimulus* stimuli, int n_stim, double t, float dx,
+           const FkOptions* opt, void* workspace, size_t workspace_bytes, void* stream) {
+    return run_euler(v, w, u, dv, dw, du, D, d_batched, H, W, batch, params, stimuli, n_stim, t, 1, 0.0f, dx, opt, 1,
+                     workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

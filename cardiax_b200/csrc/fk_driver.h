@@ -1,0 +1,156 @@
+// fk_driver.h -- the launch sequence of solve._forward_euler / solve.step, independent of where
+// the kernels run.  fk_api.cu instantiates it with the CUDA backend; tests/emu with the CPU
+// emulation, so the ping-pong / frame / tail logic is unit-tested without a GPU.
+#pragma once
+#include "fk_stream.h"
+#include "fk_tile.h"
+
+namespace fk {
+
+struct DriveOptions {
+    int exact;
+    int steps_per_launch;   // 0 = default
+    int kernel;             // 0 auto, 1 tiles only, 2 streaming required
+    int phys_top, phys_bottom;
+    int cta_threads, rows_per_cta;
+    int uniform_diffusivity;
+};
+
+struct DriveBuffers {
+    const float *v_in, *w_in, *u_in;
+    float *v_out, *w_out, *u_out;
+    float *pv, *pw, *pu;            // ping-pong scratch, (batch, H, W) each
+    const float *D, *DX, *DY;
+    const StimDev* stims;           // device/emulated copy of the stimulus table, or null
+};
+
+enum { FK_DEFAULT_T = 2 };
+
+// finalises the tile counts of A.reg[0..nreg)
+inline int finish_regions(TileArgs& A, long long* smem_floats) {
+    int total = 0;
+    long long maxfloats = 0;
+    for (int i = 0; i < A.nreg; ++i) {
+        TileRegion& R = A.reg[i];
+        R.ntr = (R.R1 - R.R0 + R.th - 1) / R.th;
+        R.ntc = (R.C1 - R.C0 + R.tw - 1) / R.tw;
+        R.first = total;
+        total += R.ntr * R.ntc;
+        const long long f = tile_smem_floats(R.th, R.tw, A.T);
+        if (f > maxfloats) maxfloats = f;
+    }
+    if (smem_floats) *smem_floats = maxfloats;
+    return total;
+}
+
+inline void add_region(TileArgs& A, int R0, int R1, int C0, int C1, int th, int tw) {
+    if (R1 <= R0 || C1 <= C0) return;
+    TileRegion& R = A.reg[A.nreg++];
+    R.R0 = R0; R.R1 = R1; R.C0 = C0; R.C1 = C1;
+    R.th = th < R1 - R0 ? th : R1 - R0;
+    R.tw = tw < C1 - C0 ? tw : C1 - C0;
+}
+
+// the frame of 4T cells the streaming kernel leaves out (only physical edges have a top/bottom band)
+inline void frame_regions(TileArgs& A, int T, int phys_top, int phys_bottom) {
+    const int F = 4 * T, H = A.H, W = A.W;
+    A.nreg = 0;
+    if (phys_top) add_region(A, 0, F, 0, W, F, 128);
+    if (phys_bottom) add_region(A, H - F, H, 0, W, F, 128);
+    add_region(A, F, H - F, 0, F, 64, F);
+    add_region(A, F, H - F, W - F, W, 64, F);
+}
+
+inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
+    // whole-tissue coverage by general tiles: 32 x 64 output cells (+ 4T apron) keeps two CTAs per SM at T <= 2
+    th = 32; tw = 64;
+    while (tile_smem_floats(th, tw, T) * 4 > 110 * 1024 && th > 8) th -= 8;
+    while (tile_smem_floats(th, tw, T) * 4 > 220 * 1024 && tw > 16) tw -= 16;
+    if (th > rows) th = rows;
+    if (tw > W) tw = W;
+}
+
+// Backend: int tiles(TileArgs&, int exact, int batch); int stream(const StreamPlan&, const TileArgs&, int exact, int batch);
+//          int num_sms(); int max_stream_threads();
+// Returns 0 or the backend's error code; *why gets a static message on argument errors.
+template <class Backend>
+int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, int batch, const Consts& K, int n_stim,
+                double t0, long long nsteps, const DriveOptions& opt, int rhs_mode, const char** why) {
+    *why = "";
+    int Tmax = rhs_mode ? 1 : (opt.steps_per_launch ? opt.steps_per_launch : FK_DEFAULT_T);
+    const bool slab = !opt.phys_top || !opt.phys_bottom;
+    if (slab) {
+        // slab decomposition: halo rows are inputs only and must be re-exchanged after every launch
+        if (nsteps > Tmax) { *why = "a slab call advances at most steps_per_launch steps (halos must be exchanged)"; return -1; }
+        Tmax = (int)nsteps;
+        if (H < 8 * Tmax + 1) { *why = "slab too thin for its halo"; return -1; }
+    }
+    StreamPlan plan;
+    bool use_stream = false;
+    if (!rhs_mode && opt.kernel != 1) {
+        use_stream = plan_stream(H, W, batch, Tmax, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
+                                 opt.uniform_diffusivity, plan) && plan.G.NT <= be.max_stream_threads();
+        if (!use_stream && opt.kernel == 2) { *why = "streaming kernel not applicable to this shape"; return -5; }
+    }
+
+    TileArgs A;
+    A = TileArgs();
+    A.D = B.D; A.DX = B.DX; A.DY = B.DY;
+    A.plane = (long long)H * W;
+    A.plane_D = d_batched ? A.plane : 0;
+    A.H = H; A.W = W;
+    A.phys_top = opt.phys_top; A.phys_bot = opt.phys_bottom; A.phys_left = 1; A.phys_right = 1;
+    A.rhs_mode = rhs_mode;
+    A.K = K;
+    A.stims = n_stim ? B.stims : nullptr;
+    A.n_stim = n_stim;
+
+    const long long nl = rhs_mode ? 1 : (nsteps + Tmax - 1) / Tmax;
+    const float *sv = B.v_in, *sw = B.w_in, *su = B.u_in;
+    long long remaining = rhs_mode ? 1 : nsteps;
+    double t = t0;
+    for (long long l = 0; l < nl; ++l) {
+        const int T = (int)(remaining < Tmax ? remaining : Tmax);
+        // the last launch lands in the caller's output; the ones before alternate with the scratch
+        const bool to_out = ((nl - 1 - l) % 2 == 0);
+        A.u_in = su; A.v_in = sv; A.w_in = sw;
+        A.u_out = to_out ? B.u_out : B.pu;
+        A.v_out = to_out ? B.v_out : B.pv;
+        A.w_out = to_out ? B.w_out : B.pw;
+        A.T = T; A.t0 = t;
+        int rc;
+        if (use_stream && T == plan.T) {
+            rc = be.stream(plan, A, opt.exact, batch);
+            if (rc) return rc;
+            frame_regions(A, T, opt.phys_top, opt.phys_bottom);
+            rc = be.tiles(A, opt.exact, batch);
+            if (rc) return rc;
+        } else {
+            // rows this rank owns: everything when both edges are physical, else minus the 4T halo rows
+            const int own_r0 = opt.phys_top ? 0 : 4 * T, own_r1 = opt.phys_bottom ? H : H - 4 * T;
+            int th, tw;
+            pick_tile(own_r1 - own_r0, W, T, th, tw);
+            A.nreg = 0;
+            add_region(A, own_r0, own_r1, 0, W, th, tw);
+            rc = be.tiles(A, opt.exact, batch);
+            if (rc) return rc;
+        }
+        su = A.u_out; sv = A.v_out; sw = A.w_out;
+        t += T;
+        remaining -= T;
+    }
+    return 0;
+}
+
+// lax.fori_loop(t0, t1, ...) with a float counter: iterations while t0 + k < t1
+inline long long count_steps(double t0, double t1) {
+    long long n = 0;
+    if (t1 > t0) {
+        n = (long long)ceil(t1 - t0);
+        while (n > 0 && t0 + (double)(n - 1) >= t1) --n;
+        while (t0 + (double)n < t1) ++n;
+    }
+    return n;
+}
+
+}  // namespace fk

@@ -1,0 +1,53 @@
+// fk_stream.cuh -- CUDA kernel + launcher around the streaming body in fk_stream.h
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fk_stream.h"
+
+namespace fk {
+
+template <bool EXACT, int T>
+__global__ void __launch_bounds__(256, 1)
+fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ StreamGeom G) {
+    extern __shared__ __align__(16) float fk_stream_smem[];
+    StreamSmem<T> S;
+    stream_carve<T>(fk_stream_smem, G, S);
+    const int strip = blockIdx.x % G.nstrips, chunk = blockIdx.x / G.nstrips;
+    StreamCta C;
+    stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, C);
+    StreamState<T> R;
+    {
+        float* f = reinterpret_cast<float*>(&R);
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(R) / sizeof(float)); ++q) f[q] = 0.0f;
+    }
+    const int tid = threadIdx.x;
+    stream_prefetch<T>(A, C, R, 0, C.cs + 4 * tid, C.cs + 4 * tid < C.c_end);
+    for (int i = 0; i < C.niter; ++i) {
+        stream_iter<EXACT, T>(A, G, C, S, R, i, tid);
+        __syncthreads();
+    }
+}
+
+template <bool EXACT, int T>
+inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)P.smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(P.G.nstrips * P.G.nchunks, batch);
+    fk_stream_kernel<EXACT, T><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
+    return (int)cudaGetLastError();
+}
+
+// returns 0, a cudaError_t (> 0), or < 0 when T is unsupported
+inline int launch_stream(const StreamPlan& P, const TileArgs& A, int exact, int batch, cudaStream_t st) {
+    switch (P.T) {
+#define FK_CASE(TT) \
+    case TT: return exact ? launch_stream_t<true, TT>(P, A, batch, st) : launch_stream_t<false, TT>(P, A, batch, st);
+        FK_CASE(1) FK_CASE(2) FK_CASE(3) FK_CASE(4)
+#undef FK_CASE
+    }
+    return -5;
+}
+
+}  // namespace fk

@@ -1,0 +1,220 @@
+// fk_tile.h -- the GENERAL multi-step tile: exact boundary semantics of the reference
+// (edge-pad by one, two passes of solve.gradient on the PADDED array, crop -- solve.py:29-32,
+// 49-55, 61-65) for any rectangle of the tissue, T Euler steps per launch with all
+// intermediate levels in shared memory.
+//
+// It is used (a) for the frame of 4T cells around the tissue that the streaming kernel
+// (fk_stream.h) leaves out, (b) for whole tissues that are too small or oddly shaped for the
+// streaming kernel, and (c) for solve.step (rhs_mode: T = 1, returns d_v, d_w, d_u).
+//
+// The body is written as PHASES separated by block barriers; each phase is a loop over items
+// strided by the thread grid (tx, ty, ntx, nty) and only talks to other items through shared
+// memory across a barrier.  The CUDA kernel calls the phases with __syncthreads() between them;
+// tests/emu calls the same phases with one emulated thread.
+#pragma once
+#include "fk_core.h"
+
+namespace fk {
+
+struct TileRegion {  // a rectangle of output cells cut into th x tw tiles
+    int R0, R1, C0, C1;
+    int th, tw;
+    int ntr, ntc;    // tile counts
+    int first;       // index of this region's first tile in the launch
+};
+
+struct TileArgs {
+    const float *u_in, *v_in, *w_in;   // (batch, H, W)
+    float *u_out, *v_out, *w_out;
+    const float *D, *DX, *DY;          // diffusivity and its two derivative maps (D_x, D_y of solve.py:53-54)
+    long long plane;                   // H*W   (stride between simulations)
+    long long plane_D;                 // H*W, or 0 when all simulations share one diffusivity map
+    int H, W;
+    int phys_top, phys_bot, phys_left, phys_right;  // which buffer edges are physical tissue edges
+    int T;                             // Euler steps in this launch (levels)
+    int rhs_mode;                      // 1: write (d_v, d_w, d_u) of a single step instead of the new state
+    Consts K;
+    const StimDev* stims;              // (batch, n_stim)
+    int n_stim;
+    double t0;                         // counter value of the first level
+    TileRegion reg[4];
+    int nreg;
+};
+
+struct TileCtx {  // per-tile geometry, identical for every thread of the block
+    int r0, r1, c0, c1;      // output rectangle
+    int ra, rb, ca, cb;      // level-0 (input) rectangle
+    int nr, nc, SG;
+    float *U0, *U1, *V, *Wd, *GX, *GY;  // shared memory
+    unsigned mask[8];        // active stimuli per level (bit i = stimulus i)
+    long long boff, boffD;   // batch offsets
+    const StimDev* stims;
+};
+
+FK_HD long long tile_smem_floats(int th, int tw, int T) {
+    long long nr = th + 8LL * T, nc = tw + 8LL * T;
+    return 4 * nr * nc + (nr + 3) * nc + nr * (nc + 3);
+}
+
+FK_HD void level_rect(const TileArgs& A, const TileCtx& X, int s, int& a, int& b, int& c, int& d) {
+    const int e = 4 * (A.T - s);
+    a = X.r0 - e < 0 ? 0 : X.r0 - e;
+    b = X.r1 + e > A.H ? A.H : X.r1 + e;
+    c = X.c0 - e < 0 ? 0 : X.c0 - e;
+    d = X.c1 + e > A.W ? A.W : X.c1 + e;
+}
+
+// locate tile `tile` of the launch and fill the context (smem carve-up included)
+FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx& X) {
+    int g = 0;
+    for (int i = 1; i < A.nreg; ++i)
+        if (tile >= A.reg[i].first) g = i;
+    const TileRegion& R = A.reg[g];
+    const int lt = tile - R.first;
+    const int tr = lt / R.ntc, tc = lt - tr * R.ntc;
+    X.r0 = R.R0 + tr * R.th;
+    X.r1 = X.r0 + R.th < R.R1 ? X.r0 + R.th : R.R1;
+    X.c0 = R.C0 + tc * R.tw;
+    X.c1 = X.c0 + R.tw < R.C1 ? X.c0 + R.tw : R.C1;
+    level_rect(A, X, 0, X.ra, X.rb, X.ca, X.cb);
+    X.nr = X.rb - X.ra;
+    X.nc = X.cb - X.ca;
+    X.SG = X.nc + 3;
+    const long long n = (long long)X.nr * X.nc;
+    X.U0 = smem;
+    X.U1 = X.U0 + n;
+    X.V = X.U1 + n;
+    X.Wd = X.V + n;
+    X.GX = X.Wd + n;
+    X.GY = X.GX + (long long)(X.nr + 3) * X.nc;
+    X.boff = (long long)sim * A.plane;
+    X.boffD = (long long)sim * A.plane_D;
+    X.stims = A.stims ? A.stims + (long long)sim * A.n_stim : nullptr;
+    for (int s = 0; s < 8; ++s) X.mask[s] = 0;
+    for (int s = 0; s < A.T; ++s) {
+        const float t = (float)(A.t0 + (double)s);
+        unsigned m = 0;
+        for (int i = 0; i < A.n_stim; ++i) {
+            const StimDev sd = X.stims[i];
+            if (sd.field && stim_active(t, sd.start, sd.duration, sd.period)) m |= 1u << i;
+        }
+        X.mask[s] = m;
+    }
+}
+
+// phase 0: level-0 state -> shared memory
+FK_HD void tile_load(const TileArgs& A, const TileCtx& X, int tx, int ty, int ntx, int nty) {
+    for (int r = X.ra + ty; r < X.rb; r += nty)
+        for (int c = X.ca + tx; c < X.cb; c += ntx) {
+            const long long g = X.boff + (long long)r * A.W + c;
+            const int i = (r - X.ra) * X.nc + (c - X.ca);
+            X.U0[i] = A.u_in[g];
+            X.V[i] = A.v_in[g];
+            X.Wd[i] = A.w_in[g];
+        }
+}
+
+// phase A of level s: u_x and u_y on the padded array (solve.py:49-50), from level s-1 in Uc
+template <bool EXACT>
+FK_HD void tile_grad(const TileArgs& A, const TileCtx& X, int s, const float* Uc, int tx, int ty, int ntx, int nty) {
+    int a, b, c, d;
+    level_rect(A, X, s, a, b, c, d);
+    // u_x at padded rows PA..PB, tissue columns c..d-1
+    const int PA = A.phys_top ? (a - 1 < 0 ? 0 : a - 1) : a - 1;
+    const int PB = A.phys_bot ? (b + 2 > A.H + 1 ? A.H + 1 : b + 2) : b + 2;
+    for (int P = PA + ty; P <= PB; P += nty) {
+        float k0, k1, k2, k3;
+        int o0, o1, o2, o3;
+        kind_coeffs(kind_of(P, A.H, A.phys_top, A.phys_bot), k0, k1, k2, k3, o0, o1, o2, o3);
+        const int i0 = (clampi(P + o0 - 1, 0, A.H - 1) - X.ra) * X.nc, i1 = (clampi(P + o1 - 1, 0, A.H - 1) - X.ra) * X.nc,
+                  i2 = (clampi(P + o2 - 1, 0, A.H - 1) - X.ra) * X.nc, i3 = (clampi(P + o3 - 1, 0, A.H - 1) - X.ra) * X.nc;
+        for (int col = c + tx; col < d; col += ntx) {
+            const int j = col - X.ca;
+            const float t = tap4<EXACT>(k0, k1, k2, k3, Uc[i0 + j], Uc[i1 + j], Uc[i2 + j], Uc[i3 + j]);
+            X.GX[(P - X.ra + 1) * X.nc + j] = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+        }
+    }
+    // u_y at tissue rows a..b-1, padded columns QA..QB
+    const int QA = A.phys_left ? (c - 1 < 0 ? 0 : c - 1) : c - 1;
+    const int QB = A.phys_right ? (d + 2 > A.W + 1 ? A.W + 1 : d + 2) : d + 2;
+    for (int row = a + ty; row < b; row += nty) {
+        const float* Ur = Uc + (row - X.ra) * X.nc - X.ca;
+        for (int Q = QA + tx; Q <= QB; Q += ntx) {
+            float k0, k1, k2, k3;
+            int o0, o1, o2, o3;
+            kind_coeffs(kind_of(Q, A.W, A.phys_left, A.phys_right), k0, k1, k2, k3, o0, o1, o2, o3);
+            const float t = tap4<EXACT>(k0, k1, k2, k3, Ur[clampi(Q + o0 - 1, 0, A.W - 1)], Ur[clampi(Q + o1 - 1, 0, A.W - 1)],
+                                        Ur[clampi(Q + o2 - 1, 0, A.W - 1)], Ur[clampi(Q + o3 - 1, 0, A.W - 1)]);
+            X.GY[(row - X.ra) * X.SG + (Q - X.ca + 1)] = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+        }
+    }
+}
+
+// phase B of level s: second derivatives, reaction, stimulus, Euler update (solve.py:35-59, 70)
+template <bool EXACT>
+FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* Uc, float* Un, int tx, int ty, int ntx,
+                       int nty) {
+    int a, b, c, d;
+    level_rect(A, X, s, a, b, c, d);
+    const bool last = (s == A.T);
+    const unsigned mask = X.mask[s - 1];
+    for (int row = a + ty; row < b; row += nty) {
+        float k0, k1, k2, k3;
+        int o0, o1, o2, o3;
+        const int P = row + 1;
+        kind_coeffs(kind_of(P, A.H, A.phys_top, A.phys_bot), k0, k1, k2, k3, o0, o1, o2, o3);
+        const float* G0 = X.GX + (P + o0 - X.ra + 1) * X.nc - X.ca;
+        const float* G1 = X.GX + (P + o1 - X.ra + 1) * X.nc - X.ca;
+        const float* G2 = X.GX + (P + o2 - X.ra + 1) * X.nc - X.ca;
+        const float* G3 = X.GX + (P + o3 - X.ra + 1) * X.nc - X.ca;
+        const float* GC = X.GX + (P - X.ra + 1) * X.nc - X.ca;
+        const float* GYr = X.GY + (row - X.ra) * X.SG - X.ca + 1;
+        for (int col = c + tx; col < d; col += ntx) {
+            const int Q = col + 1;
+            float t = tap4<EXACT>(k0, k1, k2, k3, G0[col], G1[col], G2[col], G3[col]);
+            const float u_xx = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+            float q0, q1, q2, q3;
+            int p0, p1, p2, p3;
+            kind_coeffs(kind_of(Q, A.W, A.phys_left, A.phys_right), q0, q1, q2, q3, p0, p1, p2, p3);
+            t = tap4<EXACT>(q0, q1, q2, q3, GYr[Q + p0], GYr[Q + p1], GYr[Q + p2], GYr[Q + p3]);
+            const float u_yy = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+            const float u_x = GC[col], u_y = GYr[Q];
+            const long long gd = X.boffD + (long long)row * A.W + col;
+            const float del_u = diffusion<EXACT>(A.D[gd], A.DX[gd], A.DY[gd], u_x, u_y, u_xx, u_yy);
+            const long long g = (long long)row * A.W + col;
+            float stim = 0.0f;
+            if (mask) {  // solve.py:260-269: later stimuli override earlier ones, zero cells never stimulate
+                for (int i = 0; i < A.n_stim; ++i)
+                    if (mask >> i & 1u) {
+                        const float f = X.stims[i].field[g];
+                        if (f != 0.0f) stim = f;
+                    }
+            }
+            const int i = (row - X.ra) * X.nc + (col - X.ca);
+            const float u = Uc[i], v = X.V[i], w = X.Wd[i];
+            float d_v, d_w, d_u;
+            cell_rhs<EXACT>(A.K, u, v, w, del_u, stim, d_v, d_w, d_u);
+            if (A.rhs_mode) {
+                A.v_out[X.boff + g] = d_v;
+                A.w_out[X.boff + g] = d_w;
+                A.u_out[X.boff + g] = d_u;
+                continue;
+            }
+            const float vn = euler<EXACT>(v, d_v, A.K.dt), wn = euler<EXACT>(w, d_w, A.K.dt),
+                        un = euler<EXACT>(u, d_u, A.K.dt);
+            if (last) {
+                if (row >= X.r0 && row < X.r1 && col >= X.c0 && col < X.c1) {
+                    A.v_out[X.boff + g] = vn;
+                    A.w_out[X.boff + g] = wn;
+                    A.u_out[X.boff + g] = un;
+                }
+            } else {
+                Un[i] = un;
+                X.V[i] = vn;
+                X.Wd[i] = wn;
+            }
+        }
+    }
+}
+
+}  // namespace fk

@@ -1,0 +1,15 @@
+"""Run-time knobs of the B200 solver (module-level, read at every call).
+
+numerics           "fast" (default): reciprocal multiplications + FMAs, a few ulp per step from the
+                   reference's operation order; "exact": the reference's order, op for op, bit-identical
+                   to the CPU oracle (about half the throughput).
+steps_per_launch   temporal blocking depth T (0 = library default).
+kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel.
+"""
+numerics = "fast"
+steps_per_launch = 0
+kernel = 0
+cta_threads = 0
+rows_per_cta = 0
+detect_uniform_diffusivity = True
+verbose = True

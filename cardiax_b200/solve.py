@@ -1,0 +1,286 @@
+"""The reference's solver API (cardiax/solve.py) on top of libfk.so.
+
+Same names, positional order and defaults as the reference; arrays are fp32 ``torch`` CUDA tensors
+instead of ``jax`` device arrays.  Inputs are never mutated, every call returns new tensors and is
+enqueued on the current torch CUDA stream without synchronising.
+
+Extension (not in the reference): every function that takes a ``State`` also accepts a batch of
+independent tissues, ``(batch, H, W)`` tensors, with ``diffusivity`` either ``(H, W)`` or
+``(batch, H, W)`` and ``stimuli`` either one list shared by all tissues or one list per tissue.
+"""
+import ctypes
+from enum import Enum
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+from . import _lib, convert, options
+
+
+class State(NamedTuple):
+    """cardiax/solve.py:12-15 -- (v, w, u): u is LAST."""
+    v: torch.Tensor
+    w: torch.Tensor
+    u: torch.Tensor
+
+
+# --------------------------------------------------------------------------- helpers
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("cardiax_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_f32(x, device=None):
+    device = device or _device()
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x))
+    return x.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _scalar(x):
+    """Python/NumPy/torch scalar or shape-(1,) array -> float (protocol entries, t, dt, dx)."""
+    if isinstance(x, torch.Tensor):
+        return float(x.detach().reshape(-1)[0].item())
+    return float(np.asarray(x).reshape(-1)[0])
+
+
+def _params_struct(params):
+    return _lib.FkParams(*[np.float32(_scalar(p)) for p in params])
+
+
+def _is_stimulus(s):
+    return hasattr(s, "protocol") and hasattr(s, "field")
+
+
+def _pack_stimuli(stimuli, batch, shape, device):
+    """-> (ctypes array of batch*n_stim FkStimulus, n_stim, keep-alive list)."""
+    stimuli = list(stimuli)
+    if len(stimuli) and not _is_stimulus(stimuli[0]):
+        per = [list(s) for s in stimuli]  # one list per tissue
+        if len(per) != batch:
+            raise ValueError("expected one stimulus list per tissue (%d), got %d" % (batch, len(per)))
+    else:
+        per = [stimuli] * batch
+    n_stim = max(len(p) for p in per) if per else 0
+    arr = (_lib.FkStimulus * max(1, batch * n_stim))()
+    keep = []
+    for b in range(batch):
+        for i in range(n_stim):
+            if i < len(per[b]):
+                s = per[b][i]
+                f = _as_f32(s.field, device)
+                if tuple(f.shape) != tuple(shape):
+                    raise ValueError("stimulus field shape %s != tissue shape %s" % (tuple(f.shape), tuple(shape)))
+                keep.append(f)
+                arr[b * n_stim + i] = _lib.FkStimulus(f.data_ptr(), _scalar(s.protocol.start),
+                                                      _scalar(s.protocol.duration), _scalar(s.protocol.period))
+            else:
+                arr[b * n_stim + i] = _lib.FkStimulus(None, 0.0, 0.0, 1.0)
+    return arr, n_stim, keep
+
+
+_uniform_cache = {}
+
+
+def _is_uniform(D):
+    """Is the diffusivity map one constant?  Checked once per tensor version (one host sync)."""
+    key = (D.data_ptr(), tuple(D.shape), D._version)
+    hit = _uniform_cache.get(key)
+    if hit is None:
+        if len(_uniform_cache) > 64:
+            _uniform_cache.clear()
+        hit = bool((D.min() == D.max()).item())
+        _uniform_cache[key] = hit
+    return hit
+
+
+def _options(D=None, **over):
+    o = _lib.FkOptions()
+    _lib.lib().fk_default_options(ctypes.byref(o))
+    o.exact = int(options.numerics == "exact")
+    o.steps_per_launch = int(options.steps_per_launch)
+    o.kernel = int(options.kernel)
+    o.cta_threads = int(options.cta_threads)
+    o.rows_per_cta = int(options.rows_per_cta)
+    if D is not None and options.detect_uniform_diffusivity:
+        o.uniform_diffusivity = int(_is_uniform(D))
+    for k, v in over.items():
+        setattr(o, k, int(v))
+    return o
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _prep(state, diffusivity):
+    dev = _device()
+    v, w, u = [_as_f32(x, dev) for x in state]
+    if not (v.shape == w.shape == u.shape) or u.dim() not in (2, 3):
+        raise ValueError("state arrays must share one (H, W) or (batch, H, W) shape")
+    batch = u.shape[0] if u.dim() == 3 else 1
+    H, W = u.shape[-2:]
+    D = _as_f32(diffusivity, dev)
+    if tuple(D.shape[-2:]) != (H, W) or D.dim() not in (2, 3) or (D.dim() == 3 and D.shape[0] != batch):
+        raise ValueError("diffusivity shape %s does not match the tissue %s" % (tuple(D.shape), tuple(u.shape)))
+    return dev, v, w, u, D, batch, H, W
+
+
+def _workspace(L, H, W, batch, n_stim, d_batched, dev):
+    nbytes = L.fk_workspace_bytes(H, W, batch, n_stim, d_batched)
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
+
+
+# --------------------------------------------------------------------------- reference API
+def init(shape):
+    """cardiax/solve.py:18-23 -- v = 1, w = 1, u = 0."""
+    dev = _device()
+    shape = tuple(int(s) for s in shape)
+    return State(torch.ones(shape, dtype=torch.float32, device=dev), torch.ones(shape, dtype=torch.float32, device=dev),
+                 torch.zeros(shape, dtype=torch.float32, device=dev))
+
+
+def step(state, t, params, diffusivity, stimuli, dx):
+    """cardiax/solve.py:26-65 -- time derivatives State(d_v, d_w, d_u) at counter ``t``."""
+    L = _lib.lib()
+    dev, v, w, u, D, batch, H, W = _prep(state, diffusivity)
+    arr, n_stim, keep = _pack_stimuli(stimuli, batch, (H, W), dev)
+    ws, nbytes = _workspace(L, H, W, batch, n_stim, int(D.dim() == 3), dev)
+    dv, dw, du = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
+    P = _params_struct(params)
+    o = _options()
+    _lib.check(L.fk_rhs(v.data_ptr(), w.data_ptr(), u.data_ptr(), dv.data_ptr(), dw.data_ptr(), du.data_ptr(),
+                        D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim, _scalar(t),
+                        np.float32(_scalar(dx)), ctypes.byref(o), ws.data_ptr(), nbytes, _stream()))
+    return State(dv, dw, du)
+
+
+def _forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx):
+    """cardiax/solve.py:92-100 -- ``lax.fori_loop(t, t_end, step_euler)``: Euler steps for counter in [t, t_end)."""
+    L = _lib.lib()
+    dev, v, w, u, D, batch, H, W = _prep(state, diffusivity)
+    arr, n_stim, keep = _pack_stimuli(stimuli, batch, (H, W), dev)
+    ws, nbytes = _workspace(L, H, W, batch, n_stim, int(D.dim() == 3), dev)
+    vo, wo, uo = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
+    P = _params_struct(params)
+    o = _options(D)
+    _lib.check(L.fk_forward_euler(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
+                                  D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
+                                  _scalar(t), _scalar(t_end), np.float32(_scalar(dt)), np.float32(_scalar(dx)),
+                                  ctypes.byref(o), ws.data_ptr(), nbytes, _stream()))
+    return State(vo, wo, uo)
+
+
+def step_euler(state, t, params, diffusivity, stimuli, dt, dx):
+    """cardiax/solve.py:68-70 -- one Euler step ``x + d_x * dt``."""
+    t = _scalar(t)
+    return _forward_euler(state, t, t + 1.0, params, diffusivity, stimuli, dt, dx)
+
+
+def step_heun(state, t, params, diffusivity, stimuli, dt, dx):
+    """cardiax/solve.py:73-85 -- Heun: both stages evaluated at the same counter ``t``."""
+    dt32 = float(np.float32(_scalar(dt)))
+    k1 = step(state, t, params, diffusivity, stimuli, dx)
+    pred = State(*[torch.add(x, d * dt32) for x, d in zip(state, k1)])
+    k2 = step(pred, t, params, diffusivity, stimuli, dx)
+    half = float(np.float32(dt32 * 0.5))
+    return State(*[torch.add(x, torch.add(a, b) * half) for x, a, b in zip(state, k1, k2)])
+
+
+def _forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx):
+    """cardiax/solve.py:103-111."""
+    i = _scalar(t)
+    t_end = _scalar(t_end)
+    state = State(*state)
+    while i < t_end:
+        state = step_heun(state, i, params, diffusivity, stimuli, dt, dx)
+        i += 1.0
+    return state
+
+
+def _forward_dormandprince(state, ts, params, diffusivity, stimuli, dt, dx):
+    """cardiax/solve.py:114-124 -- adaptive Dopri5 through jax.experimental.ode; not on the accelerated path."""
+    raise NotImplementedError("the adaptive Dormand-Prince integrator is outside the accelerated hot path")
+
+
+class TimeIntegrator(Enum):
+    """cardiax/solve.py:127-130 -- as in the reference the attributes ARE the forward functions."""
+    EULER = _forward_euler
+    HEUN = _forward_heun
+    DORMANDPRINCE = _forward_dormandprince
+
+
+def forward_dimensional(tissue_size, final_time, ms_step, params, diffusivity, stimuli, dt, dx,
+                        integrator=TimeIntegrator.EULER, plot_while=False):
+    """cardiax/solve.py:133-165 -- physical units (cm, ms) wrapper around ``forward``."""
+    shape = convert.realsize_to_shape(tissue_size, dx)
+    start = 0
+    stop = convert.ms_to_units(final_time, dt)
+    step_ = convert.ms_to_units(ms_step, dt)
+
+    assert shape == tuple(diffusivity.shape)
+    assert all([tuple(s.field.shape) == shape for s in stimuli])
+
+    state = init(shape)
+    checkpoints = np.arange(start, stop, step_)
+    return forward(state, checkpoints, params, diffusivity, stimuli, dt, dx, integrator, plot_while)
+
+
+def forward(state, checkpoints, params, diffusivity, stimuli, dt, dx, integrator=TimeIntegrator.EULER,
+            plot_while=False):
+    """cardiax/solve.py:168-222 -- checkpoint loop; returns the list of States at checkpoints[1:]."""
+    if plot_while:
+        from . import plot  # matplotlib is optional
+        plot.plot_stimuli(stimuli)
+        plot.plot_diffusivity(diffusivity)
+        plot.plot_state(state)
+
+    f = integrator
+    if f == TimeIntegrator.DORMANDPRINCE:
+        return f(state, checkpoints, params, diffusivity, stimuli, dt, dx)
+
+    cps = [_scalar(c) for c in checkpoints]
+    dtf = _scalar(dt)
+    states = []
+    for i in range(len(cps) - 1):
+        if options.verbose:
+            print("Solving at: %dms/%dms\t\t with %d passages" % (cps[i + 1] * dtf, cps[-1] * dtf, cps[i + 1] - cps[i]),
+                  end="\r")
+        state = f(state, float(cps[i]), float(cps[i + 1]), params, diffusivity, stimuli, dt, dx)
+        if plot_while:
+            from . import plot
+            plot.plot_state(state)
+        states.append(state)
+    return states
+
+
+def gradient(a, axis):
+    """cardiax/solve.py:225-254 -- first derivative times dx along ``axis`` of an N-D array (n >= 5)."""
+    L = _lib.lib()
+    a = _as_f32(a)
+    axis = int(axis)
+    if axis < 0:
+        axis += a.dim()
+    n = a.shape[axis]
+    outer = int(np.prod(a.shape[:axis], dtype=np.int64)) if axis > 0 else 1
+    inner = int(np.prod(a.shape[axis + 1:], dtype=np.int64)) if axis + 1 < a.dim() else 1
+    out = torch.empty_like(a)
+    _lib.check(L.fk_gradient(a.data_ptr(), out.data_ptr(), outer, n, inner, _stream()))
+    return out
+
+
+def stimulate(t, X, stimuli):
+    """cardiax/solve.py:257-271 -- X with the active stimuli written over it (later stimuli win)."""
+    L = _lib.lib()
+    X = _as_f32(X)
+    if X.dim() != 2:
+        raise ValueError("stimulate expects a 2-D array")
+    H, W = X.shape
+    arr, n_stim, keep = _pack_stimuli(stimuli, 1, (H, W), X.device)
+    ws = torch.empty(max(64, 32 * n_stim), dtype=torch.uint8, device=X.device)
+    out = torch.empty_like(X)
+    _lib.check(L.fk_stimulate(_scalar(t), X.data_ptr(), out.data_ptr(), H, W, arr, n_stim, ws.data_ptr(), ws.numel(),
+                              _stream()))
+    return out

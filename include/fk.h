@@ -1,0 +1,109 @@
+/* fk.h -- C ABI of libfk.so, the B200 (sm_100a) Fenton-Karma tissue stepper.
+ *
+ * The reference (epignatelli/cardiax) has no FFI: its boundary for this path is the Python
+ * module API of cardiax/solve.py.  Each entry point below replaces one reference function
+ * (cited as file:line relative to the reference tree) and is what a binding for that
+ * function would call -- see INTEGRATION.md for the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the
+ *     caller; the library never frees or retains it beyond the call
+ *   - arrays are row-major fp32, a state is three (batch, H, W) arrays in the reference's
+ *     State order v, w, u (solve.py:12-15)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises the device
+ *   - return value: 0 on success, < 0 argument error, > 0 a cudaError_t; fk_last_error()
+ *     gives the message (thread local).  Nothing throws.
+ */
+#ifndef FK_H_
+#define FK_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FK_ABI_VERSION 1
+
+/* cardiax/params.py:4-18 -- same 14 fields, same order, already converted to fp32. */
+typedef struct FkParams {
+    float tau_v_plus, tau_v1_minus, tau_v2_minus, tau_w_plus, tau_w_minus, tau_d, tau_0, tau_r, tau_si, k, V_csi, V_c,
+        V_v, Cm;
+} FkParams;
+
+/* cardiax/stimulus.py:13-21 -- Protocol (start, duration, period in STEP units, fp32 like the
+ * reference's loop counter) + field.  `field` is a device pointer to an (H, W) fp32 array (NULL =
+ * unused slot). */
+typedef struct FkStimulus {
+    const float* field;
+    float start, duration, period;
+} FkStimulus;
+
+typedef struct FkOptions {
+    int exact;            /* 1: reference operation order, bit-identical to the CPU oracle; 0: fast numerics */
+    int steps_per_launch; /* temporal blocking depth T (1..8); 0 = library default */
+    int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = streaming kernel + frame tiles */
+    int phys_top;         /* is buffer row 0 the physical tissue edge? (0 only for slab decomposition) */
+    int phys_bottom;      /* is buffer row H-1 the physical tissue edge? */
+    int cta_threads;      /* streaming kernel: threads per CTA (0 = auto) */
+    int rows_per_cta;     /* streaming kernel: rows per CTA chunk (0 = auto) */
+    int uniform_diffusivity; /* caller asserts the diffusivity map is one constant: the streaming kernel then keeps
+                                D, D_x, D_y as three scalars instead of reading three maps */
+    int reserved[8];
+} FkOptions;
+
+/* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */
+void fk_default_options(FkOptions* opt);
+
+int fk_abi_version(void);
+const char* fk_last_error(void);
+
+/* Bytes of device scratch fk_forward_euler / fk_rhs need for this problem. */
+size_t fk_workspace_bytes(int H, int W, int batch, int n_stim, int diffusivity_batched);
+
+/* solve._forward_euler (cardiax/solve.py:92-100) == lax.fori_loop(t0, t1, step_euler):
+ * advances `batch` independent tissues from counter t0 while counter < t1 (counter += 1).
+ *   diffusivity_dev      (H, W) shared by all tissues, or (batch, H, W) when diffusivity_batched
+ *   stimuli              HOST array of batch * n_stim entries (tissue-major); the schedule
+ *                        `t >= start && mod(start - t + 1, period) < duration` (solve.py:262-267)
+ *                        is evaluated on the device, per step, in fp32
+ * Outputs must not alias inputs. */
+int fk_forward_euler(const float* v_in_dev, const float* w_in_dev, const float* u_in_dev, float* v_out_dev,
+                     float* w_out_dev, float* u_out_dev, const float* diffusivity_dev, int diffusivity_batched, int H,
+                     int W, int batch, const FkParams* params, const FkStimulus* stimuli, int n_stim, double t0,
+                     double t1, float dt, float dx, const FkOptions* opt, void* workspace_dev, size_t workspace_bytes,
+                     void* stream);
+
+/* solve.step (cardiax/solve.py:26-65): the time derivatives (d_v, d_w, d_u) at counter t. */
+int fk_rhs(const float* v_dev, const float* w_dev, const float* u_dev, float* dv_dev, float* dw_dev, float* du_dev,
+           const float* diffusivity_dev, int diffusivity_batched, int H, int W, int batch, const FkParams* params,
+           const FkStimulus* stimuli, int n_stim, double t, float dx, const FkOptions* opt, void* workspace_dev,
+           size_t workspace_bytes, void* stream);
+
+/* solve.gradient (cardiax/solve.py:225-254) along one axis of an N-D array viewed as
+ * (outer, n, inner); n >= 5.  NOT divided by dx, exactly like the reference. */
+int fk_gradient(const float* a_dev, float* out_dev, long long outer, long long n, long long inner, void* stream);
+
+/* solve.stimulate (cardiax/solve.py:257-271) on one (H, W) array. */
+int fk_stimulate(double t, const float* x_dev, float* out_dev, int H, int W, const FkStimulus* stimuli, int n_stim,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* D_x, D_y of solve.py:53-54 (gradient of the edge-padded map / dx, cropped), the two static
+ * maps the step kernels read next to D. */
+int fk_diffusivity_gradients(const float* diffusivity_dev, float* dx_out_dev, float* dy_out_dev, int H, int W,
+                             int batch, float dx, int phys_top, int phys_bottom, void* stream);
+
+/* Instrumentation for bench.py (not part of the reference surface).
+ * fk_launch_count: kernels this library has launched since it was loaded.
+ * fk_profile_enable(1): record a CUDA event pair, on the launch stream, around every step-kernel launch;
+ * fk_profile_collect: wait for them, return summed device milliseconds and launch counts of the streaming kernel
+ * and of the general tile kernel since the last collect, and reset. */
+long long fk_launch_count(void);
+void fk_profile_enable(int on);
+int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FK_H_ */

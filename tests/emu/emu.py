@@ -1,0 +1,74 @@
+"""ctypes wrapper of tests/emu/fk_emu.cpp -- CPU emulation of the CUDA kernel bodies.  TESTS ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfk_emu.so")
+_CSRC = os.path.join(_HERE, "..", "..", "cardiax_b200", "csrc")
+_lib = None
+
+
+class _Stim(ctypes.Structure):
+    _fields_ = [("field", ctypes.c_void_p), ("start", ctypes.c_float), ("duration", ctypes.c_float),
+                ("period", ctypes.c_float)]
+
+
+def build(force=False):
+    deps = [os.path.join(_HERE, "fk_emu.cpp")] + [os.path.join(_CSRC, f) for f in
+                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h")]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return _SO
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                           "-Wno-unknown-pragmas", "-o", _SO, deps[0]])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.fk_emu_euler.restype = ctypes.c_int
+        _lib.fk_emu_stim_active.restype = ctypes.c_int
+        _lib.fk_emu_stim_active.argtypes = [ctypes.c_float] * 4
+    return _lib
+
+
+def stim_active(t, start, duration, period):
+    return bool(lib().fk_emu_stim_active(t, start, duration, period))
+
+
+def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, cta_threads=0, rows_per_cta=0,
+          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False):
+    """state: (v, w, u) arrays of shape (H, W) or (batch, H, W).  Returns (v, w, u) and launch counts."""
+    v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
+    batched = u.ndim == 3
+    batch = u.shape[0] if batched else 1
+    H, W = u.shape[-2:]
+    D = np.ascontiguousarray(D, dtype=np.float32)
+    d_batched = int(D.ndim == 3)
+    vo, wo, uo = np.full_like(v, np.nan), np.full_like(w, np.nan), np.full_like(u, np.nan)
+    par = np.array([float(np.asarray(x).reshape(-1)[0]) for x in params], dtype=np.float32)
+    # stimuli: list (shared by every tissue) or list of lists (per tissue)
+    per = stimuli if (len(stimuli) and isinstance(stimuli[0], (list, tuple)) and not hasattr(stimuli[0], "protocol")) \
+        else [stimuli] * batch
+    n_stim = len(per[0])
+    keep = []
+    arr = (_Stim * max(1, batch * n_stim))()
+    for b in range(batch):
+        for i, s in enumerate(per[b]):
+            f = np.ascontiguousarray(s.field, dtype=np.float32)
+            keep.append(f)
+            arr[b * n_stim + i] = _Stim(f.ctypes.data, *[float(np.asarray(x).reshape(-1)[0]) for x in s.protocol])
+    opts = (ctypes.c_int * 9)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse)
+    info = (ctypes.c_int * 2)()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib().fk_emu_euler(p(v), p(w), p(u), p(vo), p(wo), p(uo), p(D), d_batched, H, W, batch, p(par), arr, n_stim,
+                            ctypes.c_double(t0), ctypes.c_double(t1), ctypes.c_float(dt), ctypes.c_float(dx), opts,
+                            int(rhs), info)
+    if rc != 0:
+        raise RuntimeError("fk_emu_euler rc=%d" % rc)
+    return (vo, wo, uo), (info[0], info[1])

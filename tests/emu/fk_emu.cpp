@@ -1,0 +1,105 @@
+// TEST INFRASTRUCTURE ONLY -- CPU emulation of the kernel bodies in cardiax_b200/csrc.
+// The same FK_HD phase functions the CUDA kernels call are run here by ONE emulated thread per
+// tile (phases in order, barriers implicit) or, for the streaming kernel, by all threads of a
+// block one after the other inside each row iteration; the launch sequence is the product's own
+// fk::drive_euler.  g++ -ffp-contract=off keeps EXACT mode bit-identical to nvcc's
+// __fmul_rn/__fadd_rn/__fdiv_rn build.  Never loaded by the product.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../cardiax_b200/csrc/fk_core.h"
+#include "../../cardiax_b200/csrc/fk_tile.h"
+#include "../../cardiax_b200/csrc/fk_stream.h"
+#include "../../cardiax_b200/csrc/fk_driver.h"
+
+namespace {
+
+struct EmuBackend {
+    int reverse = 0;       // run the threads of a streaming block in reverse order (hazard check)
+    int launches_tile = 0, launches_stream = 0;
+    int num_sms() { return 148; }
+    int max_stream_threads() { return 256; }
+    int tiles(fk::TileArgs& A, int exact, int batch) {
+        long long floats = 0;
+        const int total = fk::finish_regions(A, &floats);
+        if (total == 0) return 0;
+        ++launches_tile;
+        std::vector<float> smem((size_t)floats);
+        for (int sim = 0; sim < batch; ++sim)
+            for (int tile = 0; tile < total; ++tile) {
+                // poison shared memory so a read of something never written shows up as NaN
+                for (auto& x : smem) x = __builtin_nanf("");
+                fk::TileCtx X;
+                fk::tile_setup(A, tile, sim, smem.data(), X);
+                fk::tile_load(A, X, 0, 0, 1, 1);
+                float *Uc = X.U0, *Un = X.U1;
+                for (int s = 1; s <= A.T; ++s) {
+                    if (exact) {
+                        fk::tile_grad<true>(A, X, s, Uc, 0, 0, 1, 1);
+                        fk::tile_update<true>(A, X, s, Uc, Un, 0, 0, 1, 1);
+                    } else {
+                        fk::tile_grad<false>(A, X, s, Uc, 0, 0, 1, 1);
+                        fk::tile_update<false>(A, X, s, Uc, Un, 0, 0, 1, 1);
+                    }
+                    float* t = Uc; Uc = Un; Un = t;
+                }
+            }
+        return 0;
+    }
+    int stream(const fk::StreamPlan& P, const fk::TileArgs& A, int exact, int batch) {
+        ++launches_stream;
+        return fk::emu_stream_launch(P, A, batch, exact, reverse);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+struct EmuStim {
+    const float* field;
+    float start, duration, period;
+};
+
+// options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse}
+// info (optional, 2 ints): tile launches, stream launches
+int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                 const float* D, int d_batched, int H, int W, int batch, const float* params14, const EmuStim* stims,
+                 int n_stim, double t0, double t1, float dt, float dx, const int* options, int rhs_mode, int* info) {
+    static_assert(sizeof(EmuStim) == sizeof(fk::StimDev), "layout");
+    const size_t plane = (size_t)H * W;
+    const size_t dplanes = d_batched ? batch : 1;
+    std::vector<float> DX(plane * dplanes), DY(plane * dplanes), pv(plane * batch), pw(plane * batch), pu(plane * batch);
+    for (size_t b = 0; b < dplanes; ++b)
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c)
+                fk::dgrad_cell(D + b * plane, H, W, dx, options[3], options[4], r, c, DX[b * plane + (size_t)r * W + c],
+                               DY[b * plane + (size_t)r * W + c]);
+    fk::DriveBuffers B;
+    B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
+    B.pv = pv.data(); B.pw = pw.data(); B.pu = pu.data(); B.D = D; B.DX = DX.data(); B.DY = DY.data();
+    B.stims = (const fk::StimDev*)stims;
+    fk::DriveOptions o;
+    o.exact = options[0]; o.steps_per_launch = options[1]; o.kernel = options[2]; o.phys_top = options[3];
+    o.phys_bottom = options[4]; o.cta_threads = options[5]; o.rows_per_cta = options[6]; o.uniform_diffusivity = options[7];
+    EmuBackend be;
+    be.reverse = options[8];
+    const long long nsteps = rhs_mode ? 1 : fk::count_steps(t0, t1);
+    if (nsteps <= 0 && !rhs_mode) {
+        memcpy(v_out, v_in, plane * batch * 4); memcpy(w_out, w_in, plane * batch * 4); memcpy(u_out, u_in, plane * batch * 4);
+        return 0;
+    }
+    const char* why = "";
+    const int rc = fk::drive_euler(be, B, d_batched, H, W, batch, fk::make_consts(params14, dt, dx), n_stim, t0, nsteps, o,
+                                   rhs_mode, &why);
+    if (info) { info[0] = be.launches_tile; info[1] = be.launches_stream; }
+    return rc;
+}
+
+int fk_emu_stim_active(float t, float start, float duration, float period) {
+    return fk::stim_active(t, start, duration, period) ? 1 : 0;
+}
+
+}  // extern "C"

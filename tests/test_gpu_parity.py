@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path, called through the reference-facing Python API (which goes
+through the C ABI of libfk.so), against the CPU oracle on the same seeded inputs.
+
+Bars
+  numerics="exact": BIT-EXACT against oracle.fk_oracle (np.array_equal; -0.0 == +0.0).
+  numerics="fast":  max-abs(u, v, w) <= 1e-5 over <= 1e3 steps (TOL_FAST), and no further from the
+                    fp64 twin than twice the fp32 oracle is (+ 1e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from oracle import c_oracle as C
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+TOL_FAST = 1e-5
+P3 = O.PARAMSETS["3"]
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    from cardiax_b200 import options
+    saved = {k: getattr(options, k) for k in ("numerics", "steps_per_launch", "kernel", "cta_threads", "rows_per_cta")}
+    options.verbose = False
+    yield
+    for k, v in saved.items():
+        setattr(options, k, v)
+
+
+def run_gpu(st, t0, t1, params, D, stim, dt=0.01, dx=0.01, **opts):
+    from cardiax_b200 import options, solve, stimulus
+    for k, v in opts.items():
+        setattr(options, k, v)
+    gstim = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in stim]
+    out = solve._forward_euler(solve.State(*[torch.as_tensor(x).cuda() for x in st]), t0, t1, params,
+                               torch.as_tensor(D).cuda(), gstim, dt, dx)
+    torch.cuda.synchronize()
+    return [x.cpu().numpy() for x in out]
+
+
+def assert_exact(got, ref, what=""):
+    for name, a, b in zip("vwu", got, ref):
+        assert not np.isnan(a).any(), "%s %s has NaN" % (what, name)
+        assert np.array_equal(a, b), "%s %s: max abs diff %g at %d cells" % (
+            what, name, np.abs(a - b).max(), int((a != b).sum()))
+
+
+@pytest.mark.parametrize("shape,T,kernel,extra", [
+    ((37, 53), 1, 1, {}), ((37, 53), 2, 1, {}), ((37, 53), 3, 1, {}), ((5, 7), 2, 1, {}), ((3, 3), 1, 1, {}),
+    ((128, 128), 2, 0, {}), ((72, 160), 1, 2, dict(cta_threads=32, rows_per_cta=16)),
+    ((72, 160), 2, 2, dict(cta_threads=32, rows_per_cta=16)), ((96, 288), 3, 2, dict(cta_threads=64, rows_per_cta=20)),
+    ((200, 1200), 2, 2, {}), ((256, 256), 2, 0, {}), ((130, 516), 4, 2, dict(cta_threads=128)),
+])
+def test_exact_bitwise_vs_oracle(shape, T, kernel, extra):
+    st, D, stim = common.random_case(shape, seed=3, n_stim=3)
+    ref = C.forward_euler(st, 0, 9, P3, D, stim, 0.01, 0.01)
+    got = run_gpu(st, 0, 9, P3, D, stim, numerics="exact", steps_per_launch=T, kernel=kernel, **extra)
+    assert_exact(got, ref, "shape %s T %d kernel %d" % (shape, T, kernel))
+
+
+@pytest.mark.parametrize("pset", sorted(O.PARAMSETS))
+def test_exact_all_paramsets(pset):
+    st, D, stim = common.random_case((64, 96), seed=5)
+    ref = C.forward_euler(st, 0, 6, O.PARAMSETS[pset], D, stim, 0.01, 0.01)
+    got = run_gpu(st, 0, 6, O.PARAMSETS[pset], D, stim, numerics="exact", kernel=2, cta_threads=32, rows_per_cta=24)
+    assert_exact(got, ref, "paramset " + pset)
+
+
+def test_exact_uniform_diffusivity_fast_path():
+    st, _, stim = common.random_case((96, 640), seed=7)
+    D = np.full((96, 640), 1e-3, np.float32)
+    ref = C.forward_euler(st, 0, 8, P3, D, stim, 0.01, 0.01)
+    got = run_gpu(st, 0, 8, P3, D, stim, numerics="exact", kernel=2)
+    assert_exact(got, ref, "uniform D")
+
+
+def test_exact_wave_1000_steps_128():
+    """BASELINE config 1: 128 x 128, PARAMSET_3, D = 1e-3, NORTH stripe, 1e3 steps -- bit-exact to the end."""
+    shape = (128, 128)
+    st = O.init(shape)
+    D = np.full(shape, 1e-3, np.float32)
+    stim = [O.linear(shape, 0, 0.2, 20.0, O.Protocol(0, 2, 1e9))]
+    ref = C.forward_euler(st, 0, 1000, P3, D, stim, 0.01, 0.01)
+    got = run_gpu(st, 0, 1000, P3, D, stim, numerics="exact")
+    assert_exact(got, ref, "config 1")
+    assert abs(float(got[2].max()) - 1.0080984) < 1e-6  # survey smoke value
+
+
+def test_fast_within_tolerance_and_f64_envelope():
+    shape = (128, 128)
+    st = O.init(shape)
+    D = np.full(shape, 1e-3, np.float32)
+    stim = [O.linear(shape, 0, 0.2, 20.0, O.Protocol(0, 2, 1e9))]
+    ref32 = C.forward_euler(st, 0, 1000, P3, D, stim, 0.01, 0.01)
+    ref64 = C.forward_euler(st, 0, 1000, P3, D, stim, 0.01, 0.01, dtype=np.float64)
+    got = run_gpu(st, 0, 1000, P3, D, stim, numerics="fast")
+    for name, g, a, b in zip("vwu", got, ref32, ref64):
+        err = np.abs(g - a).max()
+        assert err <= TOL_FAST, "%s: fast vs oracle_f32 %g" % (name, err)
+        assert np.abs(g - b).max() <= 2 * np.abs(a - b).max() + 1e-6, name
+
+
+@pytest.mark.parametrize("kernel,extra", [(1, {}), (2, dict(cta_threads=64, rows_per_cta=32))])
+def test_fast_hetero_scar_stimuli(kernel, extra):
+    (st, D) = common.smooth_case((160, 320), seed=2)
+    _, _, stim = common.random_case((160, 320), seed=2, n_stim=3)
+    ref = C.forward_euler(st, 0, 200, P3, D, stim, 0.01, 0.01)
+    got = run_gpu(st, 0, 200, P3, D, stim, numerics="fast", kernel=kernel, **extra)
+    for name, g, a in zip("vwu", got, ref):
+        assert np.abs(g - a).max() <= TOL_FAST, name
+
+
+def test_fast_is_tiling_independent():
+    """Every cell's arithmetic is the same whichever kernel/tiling/T produced it -> identical bits."""
+    (st, D) = common.smooth_case((136, 520), seed=4)
+    _, _, stim = common.random_case((136, 520), seed=4, n_stim=2)
+    a = run_gpu(st, 0, 12, P3, D, stim, numerics="fast", kernel=1, steps_per_launch=1)
+    for kw in (dict(kernel=1, steps_per_launch=3), dict(kernel=2, steps_per_launch=2, cta_threads=64, rows_per_cta=24),
+               dict(kernel=2, steps_per_launch=4, cta_threads=128), dict(kernel=2, steps_per_launch=1)):
+        b = run_gpu(st, 0, 12, P3, D, stim, numerics="fast", **kw)
+        assert_exact(b, a, str(kw))
+
+
+def test_segment_splitting_is_exact():
+    """forward()'s checkpoint semantics: [0, 37) in one call == [0, 10) + [10, 23) + [23, 37)."""
+    st, D, stim = common.random_case((96, 256), seed=9)
+    one = run_gpu(st, 0, 37, P3, D, stim, numerics="fast")
+    s = st
+    for a, b in ((0, 10), (10, 23), (23, 37)):
+        s = O.State(*run_gpu(s, a, b, P3, D, stim, numerics="fast"))
+    assert_exact(list(s), one, "segments")
+
+
+def test_batch_of_tissues_matches_single_runs():
+    from cardiax_b200 import options, solve, stimulus
+    options.numerics = "exact"
+    B, shape = 3, (64, 128)
+    cases = [common.random_case(shape, seed=20 + b, n_stim=2) for b in range(B)]
+    # different schedules per tissue
+    per = [[O.Stimulus(O.Protocol(b, 2, 5 + b), s.field) for s in cases[b][2]] for b in range(B)]
+    v = torch.as_tensor(np.stack([c[0].v for c in cases])).cuda()
+    w = torch.as_tensor(np.stack([c[0].w for c in cases])).cuda()
+    u = torch.as_tensor(np.stack([c[0].u for c in cases])).cuda()
+    D = torch.as_tensor(np.stack([c[1] for c in cases])).cuda()
+    gst = [[stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in p] for p in per]
+    out = solve._forward_euler(solve.State(v, w, u), 0, 11, P3, D, gst, 0.01, 0.01)
+    for b in range(B):
+        ref = C.forward_euler(cases[b][0], 0, 11, P3, cases[b][1], per[b], 0.01, 0.01)
+        assert_exact([x[b].cpu().numpy() for x in out], ref, "tissue %d" % b)
+
+
+def test_step_gradient_stimulate_api():
+    from cardiax_b200 import options, solve, stimulus
+    options.numerics = "exact"
+    st, D, stim = common.random_case((40, 56), seed=11, n_stim=3)
+    gstim = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in stim]
+    gs = solve.State(*[torch.as_tensor(x).cuda() for x in st])
+    for t in (0, 1, 3, 5):
+        d = solve.step(gs, t, P3, torch.as_tensor(D).cuda(), gstim, 0.01)
+        ref = O.step(st, t, P3, D, stim, 0.01)
+        assert_exact([x.cpu().numpy() for x in d], ref, "step t=%d" % t)
+        x = np.random.default_rng(t).random((40, 56), dtype=np.float32)
+        s = solve.stimulate(t, torch.as_tensor(x).cuda(), gstim).cpu().numpy()
+        assert np.array_equal(s, O.stimulate(t, x, stim))
+    a = np.random.default_rng(0).random((3, 7, 9, 11), dtype=np.float32)
+    for axis in (0, 1, 2, 3, -1, -2):
+        if a.shape[axis] >= 5:
+            g = solve.gradient(torch.as_tensor(a).cuda(), axis).cpu().numpy()
+            assert np.array_equal(g, O.gradient(a, axis)), axis
+    # step_euler == one Euler step of the oracle
+    e = solve.step_euler(gs, 3, P3, torch.as_tensor(D).cuda(), gstim, 0.01, 0.01)
+    assert_exact([x.cpu().numpy() for x in e], O.step_euler(st, 3, P3, D, stim, 0.01, 0.01), "step_euler")
+
+
+def test_stimulus_schedule_kat_on_device():
+    """tests/macro/stimulate_test.py:16-19 of the reference, through solve.stimulate on the GPU."""
+    from cardiax_b200 import solve, stimulus
+    shape = (80, 80)
+    A = stimulus.linear(shape, stimulus.Direction.NORTH, 0.05, 1.0, stimulus.Protocol(0, 2, 50))
+    B = stimulus.triangular(shape, stimulus.Direction.WEST, 30, 0.5, 1.0, stimulus.Protocol(10, 2, 50))
+    Cc = stimulus.rectangular(shape, (50, 50), (1, 1), 1.0, stimulus.Protocol(30, 2, 1000000))
+    active = {0, 1, 50, 51, 100, 101, 150, 151, 200, 201, 250, 251, 10, 11, 60, 61, 110, 111, 160, 161, 210, 211, 260,
+              261, 30, 31}
+    X = torch.zeros(shape, device="cuda")
+    for t in range(300):
+        nz = int((solve.stimulate(t, X, [A, B, Cc]) != 0).sum().item())
+        assert (nz != 0) == (t in active), t
+
+
+def test_forward_checkpoints_and_golden_fixture():
+    import os
+    from cardiax_b200 import options, solve, stimulus
+    options.numerics = "exact"
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_64x96_scar_s1s2.npz"))
+    stim = [stimulus.Stimulus(stimulus.Protocol(*g["proto%d" % i]), torch.as_tensor(g["field%d" % i]).cuda())
+            for i in range(2)]
+    params = O.Params(*g["params"])
+    states = solve.forward(solve.State(*[torch.as_tensor(g[k + "0"]).cuda() for k in "vwu"]), g["checkpoints"], params,
+                           torch.as_tensor(g["D"]).cuda(), stim, float(g["dt"]), float(g["dx"]))
+    assert len(states) == len(g["checkpoints"]) - 1
+    for i, s in enumerate(states):
+        assert_exact([x.cpu().numpy() for x in s], [g["%s%d" % (k, i + 1)] for k in "vwu"], "checkpoint %d" % i)
+
+
+def test_large_field_properties_4096():
+    """BASELINE config 3 size: no oracle run; size-independent properties instead."""
+    from cardiax_b200 import options, solve
+    options.numerics = "fast"
+    H = W = 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    u = torch.zeros(H, W, device="cuda")
+    idx = torch.randint(0, H - 64, (40, 2), generator=g, device="cuda").cpu().numpy()
+    for r, c in idx:
+        u[r:r + 48, c:c + 48] = 1.0
+    st = solve.State(torch.ones(H, W, device="cuda"), torch.ones(H, W, device="cuda"), u)
+    D = torch.full((H, W), 1e-3, device="cuda")
+    P5 = O.PARAMSETS["5"]
+    a = solve._forward_euler(st, 0, 24, P5, D, [], 0.01, 0.01)
+    # (1) segment splitting, (2) T and kernel independence
+    b = solve._forward_euler(solve._forward_euler(st, 0, 7, P5, D, [], 0.01, 0.01), 7, 24, P5, D, [], 0.01, 0.01)
+    options.kernel, options.steps_per_launch = 1, 1
+    c = solve._forward_euler(st, 0, 24, P5, D, [], 0.01, 0.01)
+    for x, y, z in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(x, z)
+        assert torch.isfinite(x).all()
+    # (3) a corner crop evolves exactly like the oracle's run of a tissue that contains its dependency cone
+    n = 8
+    sub = 96
+    crop = O.State(*[x[:sub + 4 * n, :sub + 4 * n].cpu().numpy() for x in st])
+    Dc = np.full(crop.u.shape, 1e-3, np.float32)
+    options.numerics, options.kernel, options.steps_per_launch = "exact", 0, 0
+    e = solve._forward_euler(st, 0, n, P5, D, [], 0.01, 0.01)
+    ref = C.forward_euler(crop, 0, n, P5, Dc, [], 0.01, 0.01)
+    for x, r in zip(e, ref):
+        assert np.array_equal(x[:sub, :sub].cpu().numpy(), r[:sub, :sub])
