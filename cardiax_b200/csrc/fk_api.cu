@@ -182,16 +182,55 @@ struct ProfScope {
     }
 };
 
+// side stream for the frame tiles (one per device, created on first use)
+struct Side {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, joined = nullptr;
+};
+Side g_side[64];
+
 struct CudaBackend {
     cudaStream_t st;
+    bool pending_join = false;
+    Side* side = nullptr;
     int num_sms() { return ::num_sms(); }
     int max_stream_threads() { return 256; }
-    int tiles(fk::TileArgs& A, int exact, int batch) {
+    int occupancy(int T, int exact, int NT, long long smem) { return fk::stream_occupancy(T, exact, NT, smem); }
+    int get_side() {
+        if (side) return 0;
+        int dev = 0;
+        FK_CUDA(cudaGetDevice(&dev));
+        Side& s = g_side[dev & 63];
+        if (!s.stream) {
+            FK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            FK_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+            FK_CUDA(cudaEventCreateWithFlags(&s.joined, cudaEventDisableTiming));
+        }
+        side = &s;
+        return 0;
+    }
+    int join() {
+        if (!pending_join) return 0;
+        pending_join = false;
+        FK_CUDA(cudaEventRecord(side->joined, side->stream));
+        FK_CUDA(cudaStreamWaitEvent(st, side->joined, 0));
+        return 0;
+    }
+    int tiles(fk::TileArgs& A, int exact, int batch, bool on_side) {
         long long floats = 0;
         const int total = fk::finish_regions(A, &floats);
         if (total == 0) return 0;
         const size_t smem = (size_t)floats * sizeof(float);
         if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
+        cudaStream_t st = this->st;
+        if (on_side) {
+            const int rc = get_side();
+            if (rc) return rc;
+            FK_CUDA(cudaEventRecord(side->fork, this->st));
+            FK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            st = side->stream;
+            pending_join = true;
+        }
         ProfScope ps(1, st);
         ++g_launches;
         if (exact) {

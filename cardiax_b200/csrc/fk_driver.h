@@ -70,8 +70,9 @@ inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
     if (tw > W) tw = W;
 }
 
-// Backend: int tiles(TileArgs&, int exact, int batch); int stream(const StreamPlan&, const TileArgs&, int exact, int batch);
-//          int num_sms(); int max_stream_threads();
+// Backend: int tiles(TileArgs&, int exact, int batch, bool side);  (side: may run concurrently until join())
+//          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);  int join();
+//          int num_sms(); int max_stream_threads(); int occupancy(int T, int exact, int NT, long long smem_bytes);
 // Returns 0 or the backend's error code; *why gets a static message on argument errors.
 template <class Backend>
 int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, int batch, const Consts& K, int n_stim,
@@ -89,7 +90,8 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     bool use_stream = false;
     if (!rhs_mode && opt.kernel != 1) {
         use_stream = plan_stream(H, W, batch, Tmax, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
-                                 opt.uniform_diffusivity, plan) && plan.G.NT <= be.max_stream_threads();
+                                 opt.uniform_diffusivity, be.max_stream_threads(),
+                                 [&](int NT, long long smem) { return be.occupancy(Tmax, opt.exact, NT, smem); }, plan);
         if (!use_stream && opt.kernel == 2) { *why = "streaming kernel not applicable to this shape"; return -5; }
     }
 
@@ -120,10 +122,15 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         A.T = T; A.t0 = t;
         int rc;
         if (use_stream && T == plan.T) {
+            // the frame tiles run beside the streaming kernel (side stream on the GPU): they read the same
+            // input and write a disjoint part of the output
+            TileArgs F = A;
+            frame_regions(F, T, opt.phys_top, opt.phys_bottom);
+            rc = be.tiles(F, opt.exact, batch, true);
+            if (rc) return rc;
             rc = be.stream(plan, A, opt.exact, batch);
             if (rc) return rc;
-            frame_regions(A, T, opt.phys_top, opt.phys_bottom);
-            rc = be.tiles(A, opt.exact, batch);
+            rc = be.join();
             if (rc) return rc;
         } else {
             // rows this rank owns: everything when both edges are physical, else minus the 4T halo rows
@@ -132,7 +139,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             pick_tile(own_r1 - own_r0, W, T, th, tw);
             A.nreg = 0;
             add_region(A, own_r0, own_r1, 0, W, th, tw);
-            rc = be.tiles(A, opt.exact, batch);
+            rc = be.tiles(A, opt.exact, batch, false);
             if (rc) return rc;
         }
         su = A.u_out; sv = A.v_out; sw = A.w_out;

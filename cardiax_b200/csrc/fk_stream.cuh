@@ -22,7 +22,8 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         for (int q = 0; q < (int)(sizeof(R) / sizeof(float)); ++q) f[q] = 0.0f;
     }
     const int tid = threadIdx.x;
-    stream_prefetch<T>(A, C, R, 0, C.cs + 4 * tid, C.cs + 4 * tid < C.c_end);
+#pragma unroll
+    for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, G, C, S, j, tid, C.cs + 4 * tid < C.c_end);
     for (int i = 0; i < C.niter; ++i) {
         stream_iter<EXACT, T>(A, G, C, S, R, i, tid);
         __syncthreads();
@@ -37,6 +38,32 @@ inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cu
     dim3 grid(P.G.nstrips * P.G.nchunks, batch);
     fk_stream_kernel<EXACT, T><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
     return (int)cudaGetLastError();
+}
+
+template <bool EXACT, int T>
+inline int stream_occupancy_t(int NT, long long smem) {
+    if (cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_stream_kernel<EXACT, T>, NT, (size_t)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// resident CTAs per SM of the streaming kernel for (T, numerics, threads, shared memory)
+inline int stream_occupancy(int T, int exact, int NT, long long smem) {
+    switch (T) {
+#define FK_CASE(TT) \
+    case TT: return exact ? stream_occupancy_t<true, TT>(NT, smem) : stream_occupancy_t<false, TT>(NT, smem);
+        FK_CASE(1) FK_CASE(2) FK_CASE(3) FK_CASE(4)
+#undef FK_CASE
+    }
+    return 0;
 }
 
 // returns 0, a cudaError_t (> 0), or < 0 when T is unsupported

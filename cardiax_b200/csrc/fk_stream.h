@@ -35,44 +35,72 @@ FK_HD void st4(float* p, const float* v) {
 }
 FK_HD void unpack4(const F4& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 
+// 16-byte asynchronous global -> shared copy (cp.async / LDGSTS on the device; the CPU emulation
+// copies immediately, which is the earliest legal completion).
+FK_HD void async_copy16(float* sdst, const float* gsrc) {
+#if defined(__CUDA_ARCH__)
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+#else
+    *reinterpret_cast<F4*>(sdst) = *reinterpret_cast<const F4*>(gsrc);
+#endif
+}
+FK_HD void async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+FK_HD void async_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+enum { FK_PF = 2 };      // level-0 rows are fetched this many iterations ahead
+enum { FK_U0DEP = 8 };   // stage-0 u ring: 5 window rows + FK_PF in flight, rounded to a power of two
+enum { FK_VWDEP = 4 };   // level-0 v, w staging ring (>= FK_PF + 1)
+
 struct StreamGeom {  // per launch
     int NT;          // threads per CTA
     int CW;          // 4 * NT, columns a CTA reads
     int RS;          // ring row stride in floats (CW + 8: 4 pad floats each side)
     int RH;          // output rows per CTA
     int nstrips, nchunks;
-    int cstride;     // CW - 8T: output columns per strip
+    int cstride;     // output columns per strip (<= CW - 8T)
     int uniformD;    // diffusivity (and so D_x, D_y) is one constant over the interior
 };
 
 template <int T>
 struct StreamSmem {
-    float* uring[T];  // [4][RS] last four input rows of stage s (level-s values)
+    float* uring[T];  // stage 0: [FK_U0DEP][RS] level-0 rows (cp.async target); stage s >= 1: [5][RS] level-s rows
     float* gyx[T];    // [2][RS] u_y rows of stage s, double buffered
-    float* vring[T];  // [5][CW] level-s v waiting for stage s (s >= 1)
+    float* vring[T];  // stage 0: [FK_VWDEP][CW] level-0 v (cp.async target); s >= 1: [5][CW] level-s v waiting 4 rows
     float* wring[T];
 };
 
 FK_HD long long stream_smem_floats(int T, int NT) {
     const long long CW = 4LL * NT, RS = CW + 8;
-    return (long long)T * 4 * RS + (long long)T * 2 * RS + (long long)(T - 1) * 2 * 5 * CW;
+    return (long long)(FK_U0DEP + 5 * (T - 1)) * RS + (long long)T * 2 * RS + 2LL * FK_VWDEP * CW +
+           (long long)(T - 1) * 2 * 5 * CW;
 }
 
 template <int T>
 FK_HD void stream_carve(float* smem, const StreamGeom& G, StreamSmem<T>& S) {
     float* p = smem;
-    for (int s = 0; s < T; ++s) { S.uring[s] = p; p += 4 * G.RS; }
+    for (int s = 0; s < T; ++s) { S.uring[s] = p; p += (s == 0 ? (int)FK_U0DEP : 5) * G.RS; }
     for (int s = 0; s < T; ++s) { S.gyx[s] = p; p += 2 * G.RS; }
-    S.vring[0] = S.wring[0] = nullptr;
-    for (int s = 1; s < T; ++s) { S.vring[s] = p; p += 5 * G.CW; S.wring[s] = p; p += 5 * G.CW; }
+    for (int s = 0; s < T; ++s) {
+        const int dep = s == 0 ? (int)FK_VWDEP : 5;
+        S.vring[s] = p; p += dep * G.CW;
+        S.wring[s] = p; p += dep * G.CW;
+    }
 }
 
 template <int T>
 struct StreamState {     // registers of one thread
-    float U[T][5][4];    // rows rho .. rho+4 of the stage's input level
-    float GX[T][4][4];   // u_x rows rho-2 .. rho+1
+    float GX[T][4][4];   // u_x rows rho-2 .. rho+1 of each stage
     float gy[T][4];      // u_y of row rho (made one iteration ahead)
-    float nu[4], nv[4], nw[4];  // level-0 rows prefetched for the next iteration
 };
 
 struct StreamCta {       // uniform per CTA
@@ -119,72 +147,95 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     }
 }
 
-// prefetch the level-0 rows iteration `i` will consume
+// start the asynchronous fetch of the level-0 rows iteration `i` will consume; always commits a group
 template <int T>
-FK_HD void stream_prefetch(const TileArgs& A, const StreamCta& C, StreamState<T>& R, int i, int c, bool act) {
+FK_HD void stream_prefetch(const TileArgs& A, const StreamGeom& G, const StreamCta& C, const StreamSmem<T>& S, int i,
+                           int tid, bool act) {
     const int n = C.rin0 + i;  // u row pushed at iteration i
-    if (act && n < C.rin_end) unpack4(ld4(A.u_in + C.boff + (long long)n * A.W + c), R.nu);
+    const int c = C.cs + 4 * tid;
+    if (act && n < C.rin_end)
+        async_copy16(S.uring[0] + (n & (FK_U0DEP - 1)) * G.RS + 4 + 4 * tid, A.u_in + C.boff + (long long)n * A.W + c);
     const int rho = n - 4;     // v, w row stage 0 emits at iteration i
     if (act && rho >= C.r0 - 4 * (T - 1) && rho < C.r1 + 4 * (T - 1)) {
-        unpack4(ld4(A.v_in + C.boff + (long long)rho * A.W + c), R.nv);
-        unpack4(ld4(A.w_in + C.boff + (long long)rho * A.W + c), R.nw);
+        const long long g = C.boff + (long long)rho * A.W + c;
+        async_copy16(S.vring[0] + (rho & (FK_VWDEP - 1)) * G.CW + 4 * tid, A.v_in + g);
+        async_copy16(S.wring[0] + (rho & (FK_VWDEP - 1)) * G.CW + 4 * tid, A.w_in + g);
+    }
+    async_commit();
+}
+
+FK_HD int mod5(int x) { return x >= 5 ? x - 5 : x; }  // for 0 <= x < 10
+
+// second derivatives, reaction, stimulus and Euler update of one row of one stage (4 cells)
+template <bool EXACT, bool HAS_STIM>
+FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const float* w, const float* gxm2,
+                       const float* gxm1, const float* gx0, const float* gxp1, const float* gxp2, const float* g,
+                       const float* gy0, const float* Dv, const float* DXv, const float* DYv, const float* stim,
+                       float* un, float* vn, float* wn) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
+        const float u_yy = dcen<EXACT>(K, g[k], g[k + 1], g[k + 3], g[k + 4]);    // solve.py:52
+        const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], gx0[k], gy0[k], u_xx, u_yy);
+        float d_v, d_w, d_u;
+        cell_rhs<EXACT, HAS_STIM>(K, u0[k], v[k], w[k], del_u, HAS_STIM ? stim[k] : 0.0f, d_v, d_w, d_u);
+        vn[k] = euler<EXACT>(v[k], d_v, K.dt);
+        wn[k] = euler<EXACT>(w[k], d_w, K.dt);
+        un[k] = euler<EXACT>(u0[k], d_u, K.dt);
     }
 }
 
-// one row iteration of one thread.  `tid` in [0, NT), c = first of its 4 columns.
+// one row iteration of one thread.  `tid` in [0, NT), its 4 columns start at C.cs + 4 tid.
 template <bool EXACT, int T>
 FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& C, const StreamSmem<T>& S,
                        StreamState<T>& R, int i, int tid) {
     const int c = C.cs + 4 * tid;
     const bool act = c < C.c_end;
-    const int own = 4 + 4 * tid;  // offset of the thread's columns inside a ring row
-    float in_u[4], in_v[4], in_w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { in_u[k] = R.nu[k]; in_v[k] = R.nv[k]; in_w[k] = R.nw[k]; }
-    stream_prefetch<T>(A, C, R, i + 1, c, act);
+    // rows fetched FK_PF iterations ago have landed (this thread's own columns; the neighbours'
+    // columns of a row are only read three barriers later)
+    stream_prefetch<T>(A, G, C, S, i + FK_PF, tid, act);
+    async_wait<FK_PF>();
     if (!act) return;
-    bool have_in = (C.rin0 + i) < C.rin_end;
+    const int own = 4 + 4 * tid;  // offset of the thread's columns inside a padded ring row
+    const int n0 = C.rin0 + i;
+    const int m8 = n0 & (FK_U0DEP - 1);
+    const int m5 = n0 % 5;
+    float in_u[4] = {0.f, 0.f, 0.f, 0.f};
+    bool have_in = n0 < C.rin_end;
 #pragma unroll
     for (int s = 0; s < T; ++s) {
-        const int rho = C.rin0 + i - 4 * (s + 1);  // row this stage emits (level s+1)
-        const int n = rho + 4;                     // newest input row (level s)
+        const int rho = n0 - 4 * (s + 1);  // row this stage emits (level s+1); its newest input row is rho+4
         const int lo = C.r0 - 4 * (T - 1 - s), hi = C.r1 + 4 * (T - 1 - s);
-        if (have_in) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) R.U[s][j][k] = R.U[s][j + 1][k];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) R.U[s][4][k] = in_u[k];
-            st4(S.uring[s] + (n & 3) * G.RS + own, in_u);
+        // ring slots of input rows rho+4 (new), rho+3, rho+1, rho
+        int sl_new, sl_r3, sl_r1, sl_r0;
+        if (s == 0) {
+            sl_new = m8; sl_r3 = (m8 + 7) & 7; sl_r1 = (m8 + 5) & 7; sl_r0 = (m8 + 4) & 7;
+        } else {
+            sl_new = mod5(m5 + (s % 5)); sl_r3 = mod5(sl_new + 4); sl_r1 = mod5(sl_new + 2); sl_r0 = mod5(sl_new + 1);
         }
+        float* ur = S.uring[s] + own;
+        if (s == 0) {
+            if (have_in) unpack4(ld4(ur + sl_new * G.RS), in_u);
+        } else if (have_in) {
+            st4(ur + sl_new * G.RS, in_u);
+        }
+        float u0[4], u1[4], u3[4];
+        unpack4(ld4(ur + sl_r0 * G.RS), u0);
+        unpack4(ld4(ur + sl_r1 * G.RS), u1);
+        unpack4(ld4(ur + sl_r3 * G.RS), u3);
         // u_x of row rho+2 (solve.py:49)
         float ngx[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, R.U[s][0][k], R.U[s][1][k], R.U[s][3][k], R.U[s][4][k]);
-        // u_y of row rho+1 (solve.py:50), published for the neighbours
-        float ngy[4] = {0.f, 0.f, 0.f, 0.f};
-        if (rho + 1 >= lo && rho + 1 < hi) {
-            const float* ur = S.uring[s] + ((rho + 1) & 3) * G.RS + own;
-            const F2 L = ld2(ur - 2), Rr = ld2(ur + 4);
-            const float e[8] = {L.x, L.y, R.U[s][1][0], R.U[s][1][1], R.U[s][1][2], R.U[s][1][3], Rr.x, Rr.y};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ngy[k] = dcen<EXACT>(A.K, e[k], e[k + 1], e[k + 3], e[k + 4]);
-            st4(S.gyx[s] + (i & 1) * G.RS + own, ngy);
-        }
+        for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, u0[k], u1[k], u3[k], in_u[k]);
         const bool emit = rho >= lo && rho < hi;
         if (emit) {
             const float* gr = S.gyx[s] + ((i + 1) & 1) * G.RS + own;
             const F2 L = ld2(gr - 2), Rr = ld2(gr + 4);
             const float g[8] = {L.x, L.y, R.gy[s][0], R.gy[s][1], R.gy[s][2], R.gy[s][3], Rr.x, Rr.y};
             float v[4], w[4];
-            if (s == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { v[k] = in_v[k]; w[k] = in_w[k]; }
-            } else {
-                unpack4(ld4(S.vring[s] + (rho % 5) * G.CW + 4 * tid), v);
-                unpack4(ld4(S.wring[s] + (rho % 5) * G.CW + 4 * tid), w);
-            }
+            const int vslot = s == 0 ? (rho & (FK_VWDEP - 1)) : sl_r0;
+            unpack4(ld4(S.vring[s] + vslot * G.CW + 4 * tid), v);
+            unpack4(ld4(S.wring[s] + vslot * G.CW + 4 * tid), w);
             float Dv[4], DXv[4], DYv[4];
             const long long grow = (long long)rho * A.W + c;
             if (G.uniformD) {
@@ -195,9 +246,10 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
                 unpack4(ld4(A.DX + C.boffD + grow), DXv);
                 unpack4(ld4(A.DY + C.boffD + grow), DYv);
             }
-            float stim[4] = {0.f, 0.f, 0.f, 0.f};
+            float un[4], vn[4], wn[4];
             const unsigned mask = C.mask[s];
-            if (mask) {  // solve.py:260-269
+            if (mask) {  // solve.py:260-269: later stimuli win, zero cells never stimulate
+                float stim[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int q = 0; q < A.n_stim; ++q)
                     if (mask >> q & 1u) {
                         float f[4];
@@ -206,18 +258,11 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
                         for (int k = 0; k < 4; ++k)
                             if (f[k] != 0.0f) stim[k] = f[k];
                     }
-            }
-            float un[4], vn[4], wn[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float u_xx = dcen<EXACT>(A.K, R.GX[s][0][k], R.GX[s][1][k], R.GX[s][3][k], ngx[k]);  // :51
-                const float u_yy = dcen<EXACT>(A.K, g[k], g[k + 1], g[k + 3], g[k + 4]);                   // :52
-                const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], R.GX[s][2][k], R.gy[s][k], u_xx, u_yy);
-                float d_v, d_w, d_u;
-                cell_rhs<EXACT>(A.K, R.U[s][0][k], v[k], w[k], del_u, stim[k], d_v, d_w, d_u);
-                vn[k] = euler<EXACT>(v[k], d_v, A.K.dt);
-                wn[k] = euler<EXACT>(w[k], d_w, A.K.dt);
-                un[k] = euler<EXACT>(R.U[s][0][k], d_u, A.K.dt);
+                stream_emit<EXACT, true>(A.K, u0, v, w, R.GX[s][0], R.GX[s][1], R.GX[s][2], R.GX[s][3], ngx, g, R.gy[s], Dv,
+                                         DXv, DYv, stim, un, vn, wn);
+            } else {
+                stream_emit<EXACT, false>(A.K, u0, v, w, R.GX[s][0], R.GX[s][1], R.GX[s][2], R.GX[s][3], ngx, g, R.gy[s],
+                                          Dv, DXv, DYv, nullptr, un, vn, wn);
             }
             if (s == T - 1) {
                 if (c >= C.out_c0 && c < C.out_c1) {
@@ -228,18 +273,27 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) in_u[k] = un[k];
-                st4(S.vring[s + 1] + (rho % 5) * G.CW + 4 * tid, vn);
-                st4(S.wring[s + 1] + (rho % 5) * G.CW + 4 * tid, wn);
+                // level s+1 row rho == newest input row of stage s+1: same mod-5 phase as its u ring
+                const int ns = mod5(m5 + ((s + 1) % 5));
+                st4(S.vring[s + 1] + ns * G.CW + 4 * tid, vn);
+                st4(S.wring[s + 1] + ns * G.CW + 4 * tid, wn);
             }
         }
-        // slide the u_x window, keep u_y of the next row
+        // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
+        if (rho + 1 >= lo && rho + 1 < hi) {
+            const F2 L = ld2(ur + sl_r1 * G.RS - 2), Rr = ld2(ur + sl_r1 * G.RS + 4);
+            const float e[8] = {L.x, L.y, u1[0], u1[1], u1[2], u1[3], Rr.x, Rr.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) R.gy[s][k] = dcen<EXACT>(A.K, e[k], e[k + 1], e[k + 3], e[k + 4]);
+            st4(S.gyx[s] + (i & 1) * G.RS + own, R.gy[s]);
+        }
+        // slide the u_x window
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             R.GX[s][0][k] = R.GX[s][1][k];
             R.GX[s][1][k] = R.GX[s][2][k];
             R.GX[s][2][k] = R.GX[s][3][k];
             R.GX[s][3][k] = ngx[k];
-            R.gy[s][k] = ngy[k];
         }
         have_in = emit;
     }
@@ -253,46 +307,63 @@ struct StreamPlan {
 };
 
 // Applicability + geometry.  cta_threads / rows_per_cta: 0 = choose.
+// occ(NT, smem_bytes) -> resident CTAs per SM for that configuration (0 = cannot launch).
+//
+// Strips are balanced (equal widths, multiple of 4 columns) and the row chunks are sized so that the
+// grid is a whole number of waves of num_sms * occ CTAs; candidates are ranked by a simple model:
+// rounds * iterations-per-CTA * resident warps / issue-efficiency(resident warps).
+template <class OccFn>
 inline bool plan_stream(int H, int W, int batch, int T, int cta_threads, int rows_per_cta, int num_sms, int uniformD,
-                        StreamPlan& P) {
+                        int max_threads, OccFn occ, StreamPlan& P) {
     if (T < 1 || T > 4) return false;
-    if (W % 4 != 0) return false;               // float4 rows
+    if (W % 4 != 0) return false;                       // float4 rows
     if (H < 8 * T + 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
     const int Wint = W - 8 * T, Hint = H - 8 * T;
-    int NT = cta_threads;
-    if (NT <= 0) {
-        // widest CTA that the interior can fill, 64..256 threads
-        NT = 256;
-        while (NT > 64 && (NT / 2) * 4 - 8 * T >= Wint) NT /= 2;
+    double best = -1.0;
+    const int ns_min = (Wint + (4 * max_threads - 8 * T) - 1) / (4 * max_threads - 8 * T);
+    for (int ns = ns_min; ns < ns_min + 24; ++ns) {
+        int stride = (Wint + ns - 1) / ns;
+        stride = (stride + 3) / 4 * 4;
+        const int need = stride + 8 * T;
+        int NT = (need + 127) / 128 * 32;
+        if (cta_threads > 0) {
+            if (NT > cta_threads) continue;
+            NT = cta_threads;
+        }
+        if (NT > max_threads || NT < 32) continue;
+        const int nstrips = (Wint + stride - 1) / stride;
+        const long long smem = stream_smem_floats(T, NT) * 4;
+        if (smem > 227 * 1024) continue;
+        const int o = occ(NT, smem);
+        if (o < 1) continue;
+        const long long slots = (long long)num_sms * o, units = (long long)nstrips * batch;
+        for (int waves = 1; waves <= 3; ++waves) {
+            int RH = rows_per_cta;
+            if (RH <= 0) {
+                long long nch = waves * slots / units;
+                if (nch < 1) nch = 1;
+                RH = (int)((Hint + nch - 1) / nch);
+                if (RH < 16) RH = 16;
+            }
+            if (RH > Hint) RH = Hint;
+            const int nchunks = (Hint + RH - 1) / RH;
+            const long long ncta = units * nchunks;
+            const double rounds = (double)((ncta + slots - 1) / slots);
+            const double warps = (double)((need + 127) / 128) * o;  // active warps resident on an SM
+            const double eff = warps / (warps + 8.0);
+            const double cost = rounds * (RH + 8.0 * T) * T * warps / eff;
+            if (best < 0 || cost < best) {
+                best = cost;
+                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RS = 4 * NT + 8; P.G.RH = RH;
+                P.G.nstrips = nstrips; P.G.nchunks = nchunks; P.G.cstride = stride; P.G.uniformD = uniformD;
+                P.T = T;
+                P.smem_bytes = smem;
+            }
+            if (rows_per_cta > 0) break;
+        }
+        if (cta_threads > 0) break;
     }
-    if (NT % 32 != 0 || NT < 32 || NT > 1024) return false;
-    StreamGeom& G = P.G;
-    G.NT = NT;
-    G.CW = 4 * NT;
-    G.RS = G.CW + 8;
-    if (G.CW - 8 * T < 4) return false;
-    // balanced strips: the fewest strips that cover the interior, equal widths (multiple of 4)
-    const int maxstride = G.CW - 8 * T;
-    G.nstrips = (Wint + maxstride - 1) / maxstride;
-    int stride = (Wint + G.nstrips - 1) / G.nstrips;
-    stride = (stride + 3) / 4 * 4;
-    G.cstride = stride;
-    int RH = rows_per_cta;
-    if (RH <= 0) {
-        // about one CTA per SM-slot; at least 32 rows so the 8T-row pipeline fill stays small
-        const long long slots = 2LL * num_sms;
-        long long per = (slots + (long long)G.nstrips * batch - 1) / ((long long)G.nstrips * batch);
-        if (per < 1) per = 1;
-        RH = (int)((Hint + per - 1) / per);
-        if (RH < 32) RH = 32;
-    }
-    if (RH > Hint) RH = Hint;
-    G.RH = RH;
-    G.nchunks = (Hint + RH - 1) / RH;
-    G.uniformD = uniformD;
-    P.T = T;
-    P.smem_bytes = stream_smem_floats(T, NT) * 4;
-    return P.smem_bytes <= 227 * 1024;
+    return best >= 0;
 }
 
 // ---------------------------------------------------------------- CPU emulation of one launch (tests only)
@@ -312,7 +383,8 @@ inline void emu_stream_cta(const TileArgs& A, const StreamGeom& G, int strip, in
         float* f = reinterpret_cast<float*>(&r);
         for (size_t q = 0; q < sizeof(r) / sizeof(float); ++q) f[q] = __builtin_nanf("");
     }
-    for (int tid = 0; tid < G.NT; ++tid) stream_prefetch<T>(A, C, R[tid], 0, C.cs + 4 * tid, C.cs + 4 * tid < C.c_end);
+    for (int tid = 0; tid < G.NT; ++tid)
+        for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, G, C, S, j, tid, C.cs + 4 * tid < C.c_end);
     for (int i = 0; i < C.niter; ++i) {
         if (!reverse)
             for (int tid = 0; tid < G.NT; ++tid) stream_iter<EXACT, T>(A, G, C, S, R[tid], i, tid);

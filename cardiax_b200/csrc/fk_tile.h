@@ -125,13 +125,14 @@ FK_HD void tile_grad(const TileArgs& A, const TileCtx& X, int s, const float* Uc
     for (int P = PA + ty; P <= PB; P += nty) {
         float k0, k1, k2, k3;
         int o0, o1, o2, o3;
-        kind_coeffs(kind_of(P, A.H, A.phys_top, A.phys_bot), k0, k1, k2, k3, o0, o1, o2, o3);
+        const int kind = kind_of(P, A.H, A.phys_top, A.phys_bot);
+        kind_coeffs(kind, k0, k1, k2, k3, o0, o1, o2, o3);
         const int i0 = (clampi(P + o0 - 1, 0, A.H - 1) - X.ra) * X.nc, i1 = (clampi(P + o1 - 1, 0, A.H - 1) - X.ra) * X.nc,
                   i2 = (clampi(P + o2 - 1, 0, A.H - 1) - X.ra) * X.nc, i3 = (clampi(P + o3 - 1, 0, A.H - 1) - X.ra) * X.nc;
         for (int col = c + tx; col < d; col += ntx) {
             const int j = col - X.ca;
-            const float t = tap4<EXACT>(k0, k1, k2, k3, Uc[i0 + j], Uc[i1 + j], Uc[i2 + j], Uc[i3 + j]);
-            X.GX[(P - X.ra + 1) * X.nc + j] = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+            X.GX[(P - X.ra + 1) * X.nc + j] =
+                deriv<EXACT>(A.K, kind, k0, k1, k2, k3, Uc[i0 + j], Uc[i1 + j], Uc[i2 + j], Uc[i3 + j]);
         }
     }
     // u_y at tissue rows a..b-1, padded columns QA..QB
@@ -142,10 +143,11 @@ FK_HD void tile_grad(const TileArgs& A, const TileCtx& X, int s, const float* Uc
         for (int Q = QA + tx; Q <= QB; Q += ntx) {
             float k0, k1, k2, k3;
             int o0, o1, o2, o3;
-            kind_coeffs(kind_of(Q, A.W, A.phys_left, A.phys_right), k0, k1, k2, k3, o0, o1, o2, o3);
-            const float t = tap4<EXACT>(k0, k1, k2, k3, Ur[clampi(Q + o0 - 1, 0, A.W - 1)], Ur[clampi(Q + o1 - 1, 0, A.W - 1)],
-                                        Ur[clampi(Q + o2 - 1, 0, A.W - 1)], Ur[clampi(Q + o3 - 1, 0, A.W - 1)]);
-            X.GY[(row - X.ra) * X.SG + (Q - X.ca + 1)] = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+            const int kind = kind_of(Q, A.W, A.phys_left, A.phys_right);
+            kind_coeffs(kind, k0, k1, k2, k3, o0, o1, o2, o3);
+            X.GY[(row - X.ra) * X.SG + (Q - X.ca + 1)] =
+                deriv<EXACT>(A.K, kind, k0, k1, k2, k3, Ur[clampi(Q + o0 - 1, 0, A.W - 1)], Ur[clampi(Q + o1 - 1, 0, A.W - 1)],
+                             Ur[clampi(Q + o2 - 1, 0, A.W - 1)], Ur[clampi(Q + o3 - 1, 0, A.W - 1)]);
         }
     }
 }
@@ -162,7 +164,8 @@ FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* 
         float k0, k1, k2, k3;
         int o0, o1, o2, o3;
         const int P = row + 1;
-        kind_coeffs(kind_of(P, A.H, A.phys_top, A.phys_bot), k0, k1, k2, k3, o0, o1, o2, o3);
+        const int kindr = kind_of(P, A.H, A.phys_top, A.phys_bot);
+        kind_coeffs(kindr, k0, k1, k2, k3, o0, o1, o2, o3);
         const float* G0 = X.GX + (P + o0 - X.ra + 1) * X.nc - X.ca;
         const float* G1 = X.GX + (P + o1 - X.ra + 1) * X.nc - X.ca;
         const float* G2 = X.GX + (P + o2 - X.ra + 1) * X.nc - X.ca;
@@ -171,13 +174,13 @@ FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* 
         const float* GYr = X.GY + (row - X.ra) * X.SG - X.ca + 1;
         for (int col = c + tx; col < d; col += ntx) {
             const int Q = col + 1;
-            float t = tap4<EXACT>(k0, k1, k2, k3, G0[col], G1[col], G2[col], G3[col]);
-            const float u_xx = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+            const float u_xx = deriv<EXACT>(A.K, kindr, k0, k1, k2, k3, G0[col], G1[col], G2[col], G3[col]);
             float q0, q1, q2, q3;
             int p0, p1, p2, p3;
-            kind_coeffs(kind_of(Q, A.W, A.phys_left, A.phys_right), q0, q1, q2, q3, p0, p1, p2, p3);
-            t = tap4<EXACT>(q0, q1, q2, q3, GYr[Q + p0], GYr[Q + p1], GYr[Q + p2], GYr[Q + p3]);
-            const float u_yy = EXACT ? Num<true>::div(t, A.K.dx) : t * A.K.r_dx;
+            const int kindc = kind_of(Q, A.W, A.phys_left, A.phys_right);
+            kind_coeffs(kindc, q0, q1, q2, q3, p0, p1, p2, p3);
+            const float u_yy =
+                deriv<EXACT>(A.K, kindc, q0, q1, q2, q3, GYr[Q + p0], GYr[Q + p1], GYr[Q + p2], GYr[Q + p3]);
             const float u_x = GC[col], u_y = GYr[Q];
             const long long gd = X.boffD + (long long)row * A.W + col;
             const float del_u = diffusion<EXACT>(A.D[gd], A.DX[gd], A.DY[gd], u_x, u_y, u_xx, u_yy);

@@ -21,7 +21,9 @@ struct EmuBackend {
     int launches_tile = 0, launches_stream = 0;
     int num_sms() { return 148; }
     int max_stream_threads() { return 256; }
-    int tiles(fk::TileArgs& A, int exact, int batch) {
+    int occupancy(int, int, int NT, long long) { return NT <= 128 ? 2 : 1; }
+    int join() { return 0; }
+    int tiles(fk::TileArgs& A, int exact, int batch, bool) {
         long long floats = 0;
         const int total = fk::finish_regions(A, &floats);
         if (total == 0) return 0;
@@ -103,3 +105,18 @@ int fk_emu_stim_active(float t, float start, float duration, float period) {
 }
 
 }  // extern "C"
+
+// planner probe (tests): occupancy modelled as min(65536 / (regs * NT), 227 KB / smem)
+extern "C" int fk_emu_plan(int H, int W, int batch, int T, int cta_threads, int rows_per_cta, int regs, int* out) {
+    fk::StreamPlan P;
+    const bool ok = fk::plan_stream(H, W, batch, T, cta_threads, rows_per_cta, 148, 0, 256,
+                                    [&](int NT, long long smem) {
+                                        const int a = 65536 / (((regs + 7) / 8 * 8) * NT);
+                                        const int b = (int)((228 * 1024) / (smem + 1024));
+                                        return a < b ? a : b;
+                                    }, P);
+    if (!ok) return 0;
+    out[0] = P.G.NT; out[1] = P.G.nstrips; out[2] = P.G.cstride; out[3] = P.G.RH; out[4] = P.G.nchunks;
+    out[5] = (int)P.smem_bytes;
+    return 1;
+}
