@@ -89,6 +89,8 @@ def lib():
     L.fk_diffusivity_gradients.argtypes = [vp, vp, vp, ci, ci, ci, cf, ci, ci, vp]
     L.fk_diffusivity_gradients.restype = ci
     L.fk_launch_count.restype = ll
+    L.fk_last_plan.argtypes = [ctypes.POINTER(ci * 8)]
+    L.fk_last_plan.restype = None
     L.fk_profile_enable.argtypes = [ci]
     L.fk_profile_enable.restype = None
     L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll)]
@@ -97,6 +99,13 @@ def lib():
         raise RuntimeError("libfk.so ABI version mismatch")
     _lib = L
     return L
+
+
+def last_plan():
+    out = (ctypes.c_int * 8)()
+    lib().fk_last_plan(ctypes.byref(out))
+    return dict(zip(("T", "cta_threads", "strips", "cols_per_strip", "rows_per_cta", "row_chunks", "ctas_per_sm",
+                     "smem_bytes"), list(out)))
 
 
 def check(rc):

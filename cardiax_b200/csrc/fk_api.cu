@@ -31,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* where) {
     } while (0)
 
 long long g_launches = 0;
+int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 int g_num_sms = 0;
 int num_sms() {
     if (!g_num_sms) {
@@ -244,6 +245,8 @@ struct CudaBackend {
         return 0;
     }
     int stream(const fk::StreamPlan& P, const fk::TileArgs& A, int exact, int batch) {
+        g_last_plan[0] = P.T; g_last_plan[1] = P.G.NT; g_last_plan[2] = P.G.nstrips; g_last_plan[3] = P.G.cstride;
+        g_last_plan[4] = P.G.RH; g_last_plan[5] = P.G.nchunks; g_last_plan[6] = P.occ; g_last_plan[7] = (int)P.smem_bytes;
         ProfScope ps(0, st);
         ++g_launches;
         const int rc = fk::launch_stream(P, A, exact, batch, st);
@@ -270,6 +273,10 @@ extern "C" {
 int fk_abi_version(void) { return FK_ABI_VERSION; }
 
 long long fk_launch_count(void) { return g_launches; }
+
+void fk_last_plan(int* out8) {
+    for (int i = 0; i < 8; ++i) out8[i] = g_last_plan[i];
+}
 
 void fk_profile_enable(int on) { g_prof.on = on != 0; }
 

@@ -32,11 +32,14 @@ inline int finish_regions(TileArgs& A, long long* smem_floats) {
     long long maxfloats = 0;
     for (int i = 0; i < A.nreg; ++i) {
         TileRegion& R = A.reg[i];
-        R.ntr = (R.R1 - R.R0 + R.th - 1) / R.th;
-        R.ntc = (R.C1 - R.C0 + R.tw - 1) / R.tw;
+        // The tissue's edge row/column reaches FIVE cells inwards (forward/backward formulas applied twice,
+        // solve.py:232-235 on top of itself), one more than a level's 4-cell apron: a tile must never be a
+        // single row or column, so a remainder of 1 is folded into the last tile (tile_setup).
+        R.ntr = tile_count(R.R1 - R.R0, R.th);
+        R.ntc = tile_count(R.C1 - R.C0, R.tw);
         R.first = total;
         total += R.ntr * R.ntc;
-        const long long f = tile_smem_floats(R.th, R.tw, A.T);
+        const long long f = tile_smem_floats(R.th + 1, R.tw + 1, A.T);
         if (f > maxfloats) maxfloats = f;
     }
     if (smem_floats) *smem_floats = maxfloats;
@@ -64,8 +67,8 @@ inline void frame_regions(TileArgs& A, int T, int phys_top, int phys_bottom) {
 inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
     // whole-tissue coverage by general tiles: 32 x 64 output cells (+ 4T apron) keeps two CTAs per SM at T <= 2
     th = 32; tw = 64;
-    while (tile_smem_floats(th, tw, T) * 4 > 110 * 1024 && th > 8) th -= 8;
-    while (tile_smem_floats(th, tw, T) * 4 > 220 * 1024 && tw > 16) tw -= 16;
+    while (tile_smem_floats(th + 1, tw + 1, T) * 4 > 110 * 1024 && th > 8) th -= 8;
+    while (tile_smem_floats(th + 1, tw + 1, T) * 4 > 220 * 1024 && tw > 16) tw -= 16;
     if (th > rows) th = rows;
     if (tw > W) tw = W;
 }

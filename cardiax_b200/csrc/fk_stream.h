@@ -304,6 +304,7 @@ struct StreamPlan {
     int T;
     StreamGeom G;
     long long smem_bytes;
+    int occ;  // resident CTAs per SM the plan assumed
 };
 
 // Applicability + geometry.  cta_threads / rows_per_cta: 0 = choose.
@@ -358,6 +359,7 @@ inline bool plan_stream(int H, int W, int batch, int T, int cta_threads, int row
                 P.G.nstrips = nstrips; P.G.nchunks = nchunks; P.G.cstride = stride; P.G.uniformD = uniformD;
                 P.T = T;
                 P.smem_bytes = smem;
+                P.occ = o;
             }
             if (rows_per_cta > 0) break;
         }

@@ -51,6 +51,12 @@ struct TileCtx {  // per-tile geometry, identical for every thread of the block
     const StimDev* stims;
 };
 
+// tiles along an axis of `len` cells: ceil(len / t), except that a last tile of ONE cell is folded into its neighbour
+FK_HD int tile_count(int len, int t) {
+    const int n = (len + t - 1) / t;
+    return (n > 1 && len % t == 1) ? n - 1 : n;
+}
+
 FK_HD long long tile_smem_floats(int th, int tw, int T) {
     long long nr = th + 8LL * T, nc = tw + 8LL * T;
     return 4 * nr * nc + (nr + 3) * nc + nr * (nc + 3);
@@ -73,9 +79,9 @@ FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx
     const int lt = tile - R.first;
     const int tr = lt / R.ntc, tc = lt - tr * R.ntc;
     X.r0 = R.R0 + tr * R.th;
-    X.r1 = X.r0 + R.th < R.R1 ? X.r0 + R.th : R.R1;
+    X.r1 = tr == R.ntr - 1 ? R.R1 : X.r0 + R.th;   // the last tile takes a remainder of one cell as well
     X.c0 = R.C0 + tc * R.tw;
-    X.c1 = X.c0 + R.tw < R.C1 ? X.c0 + R.tw : R.C1;
+    X.c1 = tc == R.ntc - 1 ? R.C1 : X.c0 + R.tw;
     level_rect(A, X, 0, X.ra, X.rb, X.ca, X.cb);
     X.nr = X.rb - X.ra;
     X.nc = X.cb - X.ca;

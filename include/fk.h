@@ -100,6 +100,9 @@ int fk_diffusivity_gradients(const float* diffusivity_dev, float* dx_out_dev, fl
  * fk_profile_collect: wait for them, return summed device milliseconds and launch counts of the streaming kernel
  * and of the general tile kernel since the last collect, and reset. */
 long long fk_launch_count(void);
+/* geometry of the most recent streaming-kernel launch: {T, cta_threads, strips, columns per strip, rows per CTA,
+ * row chunks, resident CTAs per SM, dynamic shared memory bytes} */
+void fk_last_plan(int* out8);
 void fk_profile_enable(int on);
 int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches);
 

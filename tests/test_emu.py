@@ -1,0 +1,121 @@
+"""CPU emulation of the CUDA kernel bodies (tests/emu) against the oracle: index, boundary, ring and launch logic of
+the product's kernels, checked without a GPU.  EXACT mode must be bit-identical; fast mode within tolerance."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import c_oracle as C
+from tests import common
+from tests.emu import emu
+
+P3 = O.PARAMSETS["3"]
+
+
+def _exact(shape, T, nsteps=7, n_stim=3, seed=0, **kw):
+    st, D, stim = common.random_case(shape, seed=seed, n_stim=n_stim)
+    ref = C.forward_euler(st, 0, nsteps, P3, D, stim, 0.01, 0.01)
+    got, info = emu.euler(st, 0, nsteps, P3, D, stim, 0.01, 0.01, exact=True, T=T, **kw)
+    for name, a, b in zip("vwu", got, ref):
+        assert not np.isnan(a).any(), name
+        assert np.array_equal(a, b), (name, float(np.abs(a - b).max()))
+    return info
+
+
+@pytest.mark.parametrize("shape,T", [((37, 53), 1), ((37, 53), 2), ((37, 53), 3), ((5, 7), 2), ((3, 3), 1), ((4, 9), 4),
+                                     ((70, 35), 2), ((33, 130), 8)])
+def test_tile_kernel_exact(shape, T):
+    info = _exact(shape, T, kernel=1)
+    assert info[1] == 0 and info[0] > 0
+
+
+@pytest.mark.parametrize("shape,T,nt,rh", [((72, 160), 1, 32, 16), ((72, 160), 2, 32, 16), ((96, 288), 3, 32, 20),
+                                           ((80, 300), 2, 64, 0), ((130, 516), 4, 64, 17), ((56, 1100), 2, 0, 0),
+                                           ((200, 64), 2, 0, 0)])
+def test_stream_plus_frame_exact(shape, T, nt, rh):
+    info = _exact(shape, T, nsteps=2 * T + 1, kernel=2, cta_threads=nt, rows_per_cta=rh)
+    assert info[1] > 0  # the streaming kernel really ran; the odd tail step goes through the tile kernel
+
+
+def test_stream_thread_order_independent():
+    """Threads of a block run in reverse order inside every iteration: any same-iteration hazard on the rings shows."""
+    _exact((72, 160), 2, kernel=2, cta_threads=32, rows_per_cta=16, reverse=1)
+    _exact((96, 288), 3, kernel=2, cta_threads=64, rows_per_cta=20, reverse=1)
+
+
+def test_stream_uniform_diffusivity_path():
+    st, _, stim = common.random_case((72, 288), seed=4)
+    D = np.full((72, 288), 1e-3, np.float32)
+    ref = C.forward_euler(st, 0, 6, P3, D, stim, 0.01, 0.01)
+    got, info = emu.euler(st, 0, 6, P3, D, stim, 0.01, 0.01, exact=True, T=2, kernel=2, cta_threads=32, uniform=1)
+    assert info[1] == 3
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("pset", sorted(O.PARAMSETS))
+def test_all_paramsets_exact(pset):
+    st, D, stim = common.random_case((48, 96), seed=5)
+    ref = C.forward_euler(st, 0, 5, O.PARAMSETS[pset], D, stim, 0.01, 0.01)
+    got, _ = emu.euler(st, 0, 5, O.PARAMSETS[pset], D, stim, 0.01, 0.01, exact=True, T=2, kernel=2, cta_threads=32)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+
+
+def test_fast_mode_tolerance_and_tiling_independence():
+    (st, D) = common.smooth_case((136, 520), seed=4)
+    _, _, stim = common.random_case((136, 520), seed=4, n_stim=2)
+    ref = C.forward_euler(st, 0, 12, P3, D, stim, 0.01, 0.01)
+    a, _ = emu.euler(st, 0, 12, P3, D, stim, 0.01, 0.01, exact=False, kernel=1, T=1)
+    for x, y in zip(a, ref):
+        assert float(np.abs(x - y).max()) <= 2e-5
+    for kw in (dict(kernel=1, T=3), dict(kernel=2, T=2, cta_threads=64, rows_per_cta=24), dict(kernel=2, T=4, cta_threads=128)):
+        b, _ = emu.euler(st, 0, 12, P3, D, stim, 0.01, 0.01, exact=False, **kw)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), kw
+
+
+def test_rhs_mode_is_solve_step():
+    st, D, stim = common.random_case((24, 40), seed=6, n_stim=3)
+    for t in (0, 1, 3, 4):
+        got, _ = emu.euler(st, t, t + 1, P3, D, stim, 0.0, 0.01, exact=True, rhs=True)
+        ref = O.step(st, t, P3, D, stim, 0.01)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+
+
+def test_batch_and_per_tissue_stimuli():
+    shape, B = (40, 160), 3
+    cases = [common.random_case(shape, seed=30 + b) for b in range(B)]
+    per = [[O.Stimulus(O.Protocol(b, 2, 4 + b), s.field) for s in cases[b][2]] for b in range(B)]
+    st = [np.stack([c[0][k] for c in cases]) for k in range(3)]
+    D = np.stack([c[1] for c in cases])
+    got, _ = emu.euler(st, 0, 9, P3, D, per, 0.01, 0.01, exact=True, T=2, kernel=2, cta_threads=32)
+    for b in range(B):
+        ref = C.forward_euler(cases[b][0], 0, 9, P3, cases[b][1], per[b], 0.01, 0.01)
+        for a, r in zip(got, ref):
+            assert np.array_equal(a[b], r)
+
+
+def test_slab_rows_with_halo_match_whole_tissue():
+    """Row-slab decomposition: a slab buffer with 4T halo rows and non-physical edges reproduces the whole tissue's rows."""
+    shape, T = (96, 160), 2
+    st, D, stim = common.random_case(shape, seed=8)
+    ref = C.forward_euler(st, 0, T, P3, D, stim, 0.01, 0.01)
+    F = 4 * T
+    for (r0, r1, top, bot) in ((0, 40, 1, 0), (40, 70, 0, 0), (70, 96, 0, 1)):
+        a, b = max(0, r0 - F), min(96, r1 + F)
+        sub = [x[a:b] for x in st]
+        sstim = [O.Stimulus(s.protocol, s.field[a:b]) for s in stim]
+        for kernel in (1, 2):
+            got, _ = emu.euler(sub, 0, T, P3, D[a:b], sstim, 0.01, 0.01, exact=True, T=T, kernel=kernel, cta_threads=32,
+                               phys_top=top, phys_bottom=bot)
+            for g, r in zip(got, ref):
+                assert np.array_equal(g[r0 - a:r1 - a], r[r0:r1]), (r0, r1, kernel)
+
+
+def test_device_schedule_function_equals_oracle():
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        start, dur, per = int(rng.integers(0, 50)), int(rng.integers(1, 6)), float(rng.choice([7, 50, 400, 1e6, 1e9]))
+        for t in range(0, 100):
+            assert emu.stim_active(t, start, dur, per) == O.stimulus_active(t, O.Protocol(start, dur, per))

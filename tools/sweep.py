@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import oracle as O  # noqa: E402
-from cardiax_b200 import options, solve  # noqa: E402
+from cardiax_b200 import _lib, options, solve  # noqa: E402
 
 
 def main():
@@ -52,7 +52,7 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     ms = e0.elapsed_time(e1) / (2 * n)
-                    print("T=%d nt=%3d rh=%4d  %.4f ms/step  %.1f Gcs/s" % (T, nt, rh, ms, args.batch * H * W / ms / 1e6), flush=True)
+                    print("T=%d nt=%3d rh=%4d  %.4f ms/step  %.1f Gcs/s  %s" % (T, nt, rh, ms, args.batch * H * W / ms / 1e6, _lib.last_plan()), flush=True)
                 except Exception as e:  # noqa: BLE001
                     print("T=%d nt=%3d rh=%4d  failed: %s" % (T, nt, rh, str(e)[:80]), flush=True)
 
