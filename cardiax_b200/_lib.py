@@ -79,6 +79,9 @@ def lib():
     L.fk_forward_euler.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci,
                                               cd, cd, cf, cf, ctypes.POINTER(FkOptions), vp, sz, vp]
     L.fk_forward_euler.restype = ci
+    L.fk_euler_rows.argtypes = [vp] * 6 + [vp, vp, vp, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd,
+                                           ci, cf, cf, ctypes.POINTER(FkOptions), ci, ci, vp, sz, vp]
+    L.fk_euler_rows.restype = ci
     L.fk_rhs.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd, cf,
                                     ctypes.POINTER(FkOptions), vp, sz, vp]
     L.fk_rhs.restype = ci

@@ -353,15 +353,19 @@ int fk_stimulate(double t, const float* x, float* out, int H, int W, const FkSti
 static int run_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
                      const float* D, int d_batched, int H, int W, int batch, const FkParams* params,
                      const FkStimulus* stimuli, int n_stim, double t0, long long nsteps, float dt, float dx,
-                     const FkOptions* opt_in, int rhs_mode, void* workspace, size_t workspace_bytes, void* stream) {
+                     const FkOptions* opt_in, int rhs_mode, void* workspace, size_t workspace_bytes, void* stream,
+                     const float* DXext = nullptr, const float* DYext = nullptr, int row0 = 0, int row1 = 0) {
     int rc = check_common(H, W, batch, params, n_stim, stimuli);
     if (rc) return rc;
     if (!v_in || !w_in || !u_in || !v_out || !w_out || !u_out || !D) return fail(-1, "NULL pointer%s");
     FkOptions opt;
     if (opt_in) opt = *opt_in; else fk_default_options(&opt);
     if (opt.steps_per_launch < 0 || opt.steps_per_launch > 8) return fail(-1, "steps_per_launch must be in [0, 8]%s");
-    const size_t need = fk_workspace_bytes(H, W, batch, n_stim, d_batched);
-    if (!workspace || workspace_bytes < need) return fail(-4, "workspace too small%s");
+    const bool rows_mode = row1 > 0;  // single launch into a row window: no ping-pong scratch, maps from the caller
+    const size_t need = rows_mode ? sizeof(fk::StimDev) * (size_t)std::max(1, batch * n_stim)
+                                  : fk_workspace_bytes(H, W, batch, n_stim, d_batched);
+    if (need && (!workspace || workspace_bytes < need)) return fail(-4, "workspace too small%s");
+    if (rows_mode && (!DXext || !DYext)) return fail(-1, "row-window calls need the D_x, D_y maps%s");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane_bytes = (size_t)H * W * sizeof(float) * batch;
     if (nsteps <= 0 && !rhs_mode) {
@@ -370,18 +374,29 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
         FK_CUDA(cudaMemcpyAsync(u_out, u_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
         return 0;
     }
-    Workspace ws = carve(workspace, H, W, batch, n_stim, d_batched);
+    Workspace ws;
+    if (rows_mode) {
+        memset(&ws, 0, sizeof(ws));
+        ws.stims = (fk::StimDev*)workspace;
+    } else {
+        ws = carve(workspace, H, W, batch, n_stim, d_batched);
+    }
     rc = upload_stims(stimuli, batch * n_stim, ws.stims, st);
     if (rc) return rc;
-    rc = launch_dgrad(D, ws.DX, ws.DY, H, W, d_batched ? batch : 1, dx, opt.phys_top, opt.phys_bottom, st);
-    if (rc) return rc;
+    if (!DXext || !DYext) {
+        rc = launch_dgrad(D, ws.DX, ws.DY, H, W, d_batched ? batch : 1, dx, opt.phys_top, opt.phys_bottom, st);
+        if (rc) return rc;
+    }
     fk::DriveBuffers B;
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
-    B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu; B.D = D; B.DX = ws.DX; B.DY = ws.DY; B.stims = ws.stims;
+    B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu; B.D = D; B.stims = ws.stims;
+    B.DX = DXext ? DXext : ws.DX;
+    B.DY = DYext ? DYext : ws.DY;
     fk::DriveOptions o;
     o.exact = opt.exact; o.steps_per_launch = opt.steps_per_launch; o.kernel = opt.kernel;
     o.phys_top = opt.phys_top; o.phys_bottom = opt.phys_bottom; o.cta_threads = opt.cta_threads;
     o.rows_per_cta = opt.rows_per_cta; o.uniform_diffusivity = opt.uniform_diffusivity;
+    o.row0 = row0; o.row1 = row1;
     CudaBackend be;
     be.st = st;
     const char* why = "";
@@ -397,6 +412,19 @@ int fk_forward_euler(const float* v_in, const float* w_in, const float* u_in, fl
     const long long nsteps = fk::count_steps(t0, t1);
     return run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, d_batched, H, W, batch, params, stimuli, n_stim, t0, nsteps,
                      dt, dx, opt, 0, workspace, workspace_bytes, stream);
+}
+
+int fk_euler_rows(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                  const float* D, const float* DX, const float* DY, int H, int W, const FkParams* params,
+                  const FkStimulus* stimuli, int n_stim, double t0, int nsteps, float dt, float dx, const FkOptions* opt,
+                  int row0, int row1, void* workspace, size_t workspace_bytes, void* stream) {
+    if (nsteps < 1 || nsteps > 4) return fail(-1, "fk_euler_rows advances 1..4 steps per call%s");
+    if (row1 <= row0 || row0 < 0 || row1 > H) return fail(-1, "bad row window%s");
+    FkOptions o;
+    if (opt) o = *opt; else fk_default_options(&o);
+    o.steps_per_launch = nsteps;
+    return run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, 0, H, W, 1, params, stimuli, n_stim, t0, nsteps, dt, dx, &o,
+                     0, workspace, workspace_bytes, stream, DX, DY, row0, row1);
 }
 
 int fk_rhs(const float* v, const float* w, const float* u, float* dv, float* dw, float* du, const float* D, int d_batched,

@@ -14,6 +14,7 @@ struct DriveOptions {
     int phys_top, phys_bottom;
     int cta_threads, rows_per_cta;
     int uniform_diffusivity;
+    int row0, row1;         // output rows of a single-launch call (slab building block); row1 <= 0: all the rows owned
 };
 
 struct DriveBuffers {
@@ -54,14 +55,14 @@ inline void add_region(TileArgs& A, int R0, int R1, int C0, int C1, int th, int 
     R.tw = tw < C1 - C0 ? tw : C1 - C0;
 }
 
-// the frame of 4T cells the streaming kernel leaves out (only physical edges have a top/bottom band)
-inline void frame_regions(TileArgs& A, int T, int phys_top, int phys_bottom) {
-    const int F = 4 * T, H = A.H, W = A.W;
+// the frame of 4T cells the streaming kernel leaves out: output rows [R0, R1), streaming rows [S0, S1)
+inline void frame_regions(TileArgs& A, int T, int R0, int R1, int S0, int S1) {
+    const int F = 4 * T, W = A.W;
     A.nreg = 0;
-    if (phys_top) add_region(A, 0, F, 0, W, F, 128);
-    if (phys_bottom) add_region(A, H - F, H, 0, W, F, 128);
-    add_region(A, F, H - F, 0, F, 64, F);
-    add_region(A, F, H - F, W - F, W, 64, F);
+    add_region(A, R0, S0, 0, W, F, 128);   // top band (only at the physical top edge)
+    add_region(A, S1, R1, 0, W, F, 128);   // bottom band
+    add_region(A, S0, S1, 0, F, 64, F);
+    add_region(A, S0, S1, W - F, W, 64, F);
 }
 
 inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
@@ -89,10 +90,31 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         Tmax = (int)nsteps;
         if (H < 8 * Tmax + 1) { *why = "slab too thin for its halo"; return -1; }
     }
+    // output rows [R0, R1) of a launch of T steps; the streaming kernel takes [S0, S1), everything that is at least
+    // 4T rows away from a physical edge
+    auto rows = [&](int T, int& R0, int& R1, int& S0, int& S1) {
+        if (opt.row1 > 0) { R0 = opt.row0; R1 = opt.row1; }
+        else { R0 = opt.phys_top ? 0 : 4 * T; R1 = opt.phys_bottom ? H : H - 4 * T; }
+        S0 = (opt.phys_top && R0 < 4 * T) ? 4 * T : R0;
+        S1 = (opt.phys_bottom && R1 > H - 4 * T) ? H - 4 * T : R1;
+    };
+    if (opt.row1 > 0) {
+        if (nsteps > Tmax) { *why = "a row-window call is a single launch: nsteps <= steps_per_launch"; return -1; }
+        Tmax = (int)nsteps;
+        const int lo = opt.row0 - 4 * Tmax, hi = opt.row1 + 4 * Tmax;
+        if (opt.row0 < 0 || opt.row1 > H || opt.row0 >= opt.row1 || (lo < 0 && !(opt.phys_top && opt.row0 == 0)) ||
+            (hi > H && !(opt.phys_bottom && opt.row1 == H))) {
+            *why = "row window needs 4*nsteps rows of input on each side (or a physical edge)";
+            return -1;
+        }
+    }
     StreamPlan plan;
     bool use_stream = false;
     if (!rhs_mode && opt.kernel != 1) {
-        use_stream = plan_stream(H, W, batch, Tmax, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
+        int R0, R1, S0, S1;
+        rows(Tmax, R0, R1, S0, S1);
+        use_stream = S1 > S0 &&
+                     plan_stream(S0, S1, W, batch, Tmax, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
                                  opt.uniform_diffusivity, be.max_stream_threads(),
                                  [&](int NT, long long smem) { return be.occupancy(Tmax, opt.exact, NT, smem); }, plan);
         if (!use_stream && opt.kernel == 2) { *why = "streaming kernel not applicable to this shape"; return -5; }
@@ -128,7 +150,9 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             // the frame tiles run beside the streaming kernel (side stream on the GPU): they read the same
             // input and write a disjoint part of the output
             TileArgs F = A;
-            frame_regions(F, T, opt.phys_top, opt.phys_bottom);
+            int R0, R1, S0, S1;
+            rows(T, R0, R1, S0, S1);
+            frame_regions(F, T, R0, R1, S0, S1);
             rc = be.tiles(F, opt.exact, batch, true);
             if (rc) return rc;
             rc = be.stream(plan, A, opt.exact, batch);
@@ -136,12 +160,12 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             rc = be.join();
             if (rc) return rc;
         } else {
-            // rows this rank owns: everything when both edges are physical, else minus the 4T halo rows
-            const int own_r0 = opt.phys_top ? 0 : 4 * T, own_r1 = opt.phys_bottom ? H : H - 4 * T;
+            int R0, R1, S0, S1;
+            rows(T, R0, R1, S0, S1);
             int th, tw;
-            pick_tile(own_r1 - own_r0, W, T, th, tw);
+            pick_tile(R1 - R0, W, T, th, tw);
             A.nreg = 0;
-            add_region(A, own_r0, own_r1, 0, W, th, tw);
+            add_region(A, R0, R1, 0, W, th, tw);
             rc = be.tiles(A, opt.exact, batch, false);
             if (rc) return rc;
         }

@@ -24,8 +24,14 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     const int tid = threadIdx.x;
 #pragma unroll
     for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, G, C, S, j, tid, C.cs + 4 * tid < C.c_end);
-    for (int i = 0; i < C.niter; ++i) {
-        stream_iter<EXACT, T>(A, G, C, S, R, i, tid);
+    const int nfill = (8 * T < C.niter && stream_steady_ok<T>(C)) ? 8 * T : C.niter;
+    int i = 0;
+    for (; i < nfill; ++i) {   // pipeline fill (and launches with an active stimulus): fully conditional body
+        stream_iter<EXACT, T, false>(A, G, C, S, R, i, tid);
+        __syncthreads();
+    }
+    for (; i < C.niter; ++i) {  // steady state: every stage consumes and emits one row
+        stream_iter<EXACT, T, true>(A, G, C, S, R, i, tid);
         __syncthreads();
     }
 }

@@ -69,6 +69,7 @@ struct StreamGeom {  // per launch
     int nstrips, nchunks;
     int cstride;     // output columns per strip (<= CW - 8T)
     int uniformD;    // diffusivity (and so D_x, D_y) is one constant over the interior
+    int row0, row1;  // output rows of this launch (every one needs 4T rows of input above and below)
 };
 
 template <int T>
@@ -119,8 +120,8 @@ struct StreamCta {       // uniform per CTA
 template <int T>
 FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, int chunk, int sim, StreamCta& C) {
     C.cs = strip * G.cstride;
-    C.r0 = 4 * T + chunk * G.RH;
-    C.r1 = C.r0 + G.RH < A.H - 4 * T ? C.r0 + G.RH : A.H - 4 * T;
+    C.r0 = G.row0 + chunk * G.RH;
+    C.r1 = C.r0 + G.RH < G.row1 ? C.r0 + G.RH : G.row1;
     C.rin0 = C.r0 - 4 * T;
     C.rin_end = C.r1 + 4 * T;
     C.out_c0 = C.cs + 4 * T;
@@ -142,7 +143,7 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     }
     C.Dc = C.DXc = C.DYc = 0.0f;
     if (G.uniformD) {
-        const long long g = C.boffD + (long long)(4 * T) * A.W + 4 * T;
+        const long long g = C.boffD + (long long)G.row0 * A.W + 4 * T;
         C.Dc = A.D[g]; C.DXc = A.DX[g]; C.DYc = A.DY[g];
     }
 }
@@ -166,6 +167,14 @@ FK_HD void stream_prefetch(const TileArgs& A, const StreamGeom& G, const StreamC
 
 FK_HD int mod5(int x) { return x >= 5 ? x - 5 : x; }  // for 0 <= x < 10
 
+// may iterations i >= 8T use the condition-free body?  (no stimulus active in any level of this launch)
+template <int T>
+FK_HD bool stream_steady_ok(const StreamCta& C) {
+    unsigned m = 0;
+    for (int s = 0; s < T; ++s) m |= C.mask[s];
+    return m == 0;
+}
+
 // second derivatives, reaction, stimulus and Euler update of one row of one stage (4 cells)
 template <bool EXACT, bool HAS_STIM>
 FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const float* w, const float* gxm2,
@@ -186,7 +195,9 @@ FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const f
 }
 
 // one row iteration of one thread.  `tid` in [0, NT), its 4 columns start at C.cs + 4 tid.
-template <bool EXACT, int T>
+// STEADY: the caller guarantees that every stage has input and emits in this iteration (i >= 8T) and that no
+// stimulus is active in this launch, so all the per-stage conditions fold away.
+template <bool EXACT, int T, bool STEADY>
 FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& C, const StreamSmem<T>& S,
                        StreamState<T>& R, int i, int tid) {
     const int c = C.cs + 4 * tid;
@@ -201,7 +212,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
     const int m8 = n0 & (FK_U0DEP - 1);
     const int m5 = n0 % 5;
     float in_u[4] = {0.f, 0.f, 0.f, 0.f};
-    bool have_in = n0 < C.rin_end;
+    bool have_in = STEADY || n0 < C.rin_end;
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         const int rho = n0 - 4 * (s + 1);  // row this stage emits (level s+1); its newest input row is rho+4
@@ -227,7 +238,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
         float ngx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, u0[k], u1[k], u3[k], in_u[k]);
-        const bool emit = rho >= lo && rho < hi;
+        const bool emit = STEADY || (rho >= lo && rho < hi);
         if (emit) {
             const float* gr = S.gyx[s] + ((i + 1) & 1) * G.RS + own;
             const F2 L = ld2(gr - 2), Rr = ld2(gr + 4);
@@ -247,7 +258,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
                 unpack4(ld4(A.DY + C.boffD + grow), DYv);
             }
             float un[4], vn[4], wn[4];
-            const unsigned mask = C.mask[s];
+            const unsigned mask = STEADY ? 0u : C.mask[s];
             if (mask) {  // solve.py:260-269: later stimuli win, zero cells never stimulate
                 float stim[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int q = 0; q < A.n_stim; ++q)
@@ -280,7 +291,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
             }
         }
         // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
-        if (rho + 1 >= lo && rho + 1 < hi) {
+        if (STEADY || (rho + 1 >= lo && rho + 1 < hi)) {
             const F2 L = ld2(ur + sl_r1 * G.RS - 2), Rr = ld2(ur + sl_r1 * G.RS + 4);
             const float e[8] = {L.x, L.y, u1[0], u1[1], u1[2], u1[3], Rr.x, Rr.y};
 #pragma unroll
@@ -314,12 +325,12 @@ struct StreamPlan {
 // grid is a whole number of waves of num_sms * occ CTAs; candidates are ranked by a simple model:
 // rounds * iterations-per-CTA * resident warps / issue-efficiency(resident warps).
 template <class OccFn>
-inline bool plan_stream(int H, int W, int batch, int T, int cta_threads, int rows_per_cta, int num_sms, int uniformD,
-                        int max_threads, OccFn occ, StreamPlan& P) {
+inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_threads, int rows_per_cta, int num_sms,
+                        int uniformD, int max_threads, OccFn occ, StreamPlan& P) {
     if (T < 1 || T > 4) return false;
     if (W % 4 != 0) return false;                       // float4 rows
-    if (H < 8 * T + 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
-    const int Wint = W - 8 * T, Hint = H - 8 * T;
+    if (row1 - row0 < 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
+    const int Wint = W - 8 * T, Hint = row1 - row0;
     double best = -1.0;
     const int ns_min = (Wint + (4 * max_threads - 8 * T) - 1) / (4 * max_threads - 8 * T);
     for (int ns = ns_min; ns < ns_min + 24; ++ns) {
@@ -357,6 +368,7 @@ inline bool plan_stream(int H, int W, int batch, int T, int cta_threads, int row
                 best = cost;
                 P.G.NT = NT; P.G.CW = 4 * NT; P.G.RS = 4 * NT + 8; P.G.RH = RH;
                 P.G.nstrips = nstrips; P.G.nchunks = nchunks; P.G.cstride = stride; P.G.uniformD = uniformD;
+                P.G.row0 = row0; P.G.row1 = row1;
                 P.T = T;
                 P.smem_bytes = smem;
                 P.occ = o;
@@ -387,11 +399,14 @@ inline void emu_stream_cta(const TileArgs& A, const StreamGeom& G, int strip, in
     }
     for (int tid = 0; tid < G.NT; ++tid)
         for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, G, C, S, j, tid, C.cs + 4 * tid < C.c_end);
+    const bool steady_ok = stream_steady_ok<T>(C);
     for (int i = 0; i < C.niter; ++i) {
-        if (!reverse)
-            for (int tid = 0; tid < G.NT; ++tid) stream_iter<EXACT, T>(A, G, C, S, R[tid], i, tid);
-        else
-            for (int tid = G.NT - 1; tid >= 0; --tid) stream_iter<EXACT, T>(A, G, C, S, R[tid], i, tid);
+        const bool steady = steady_ok && i >= 8 * T;
+        for (int q = 0; q < G.NT; ++q) {
+            const int tid = reverse ? G.NT - 1 - q : q;
+            if (steady) stream_iter<EXACT, T, true>(A, G, C, S, R[tid], i, tid);
+            else stream_iter<EXACT, T, false>(A, G, C, S, R[tid], i, tid);
+        }
     }
 }
 

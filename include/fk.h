@@ -75,6 +75,18 @@ int fk_forward_euler(const float* v_in_dev, const float* w_in_dev, const float* 
                      double t1, float dt, float dx, const FkOptions* opt, void* workspace_dev, size_t workspace_bytes,
                      void* stream);
 
+/* Building block of the row-slab decomposition of one large tissue over several GPUs (no reference counterpart: the
+ * reference runs a tissue on one device).  ONE launch of nsteps (1..4) Euler steps that writes output rows
+ * [row0, row1) of a local (H, W) buffer and nothing else; it reads input rows [row0 - 4 nsteps, row1 + 4 nsteps)
+ * -- the neighbour's halo rows -- except across an edge that opt->phys_top / phys_bottom declares physical.
+ * dx_map_dev / dy_map_dev come from fk_diffusivity_gradients (once per diffusivity map).
+ * workspace: at least 32 * n_stim bytes (stimulus table). */
+int fk_euler_rows(const float* v_in_dev, const float* w_in_dev, const float* u_in_dev, float* v_out_dev, float* w_out_dev,
+                  float* u_out_dev, const float* diffusivity_dev, const float* dx_map_dev, const float* dy_map_dev, int H,
+                  int W, const FkParams* params, const FkStimulus* stimuli, int n_stim, double t0, int nsteps, float dt,
+                  float dx, const FkOptions* opt, int row0, int row1, void* workspace_dev, size_t workspace_bytes,
+                  void* stream);
+
 /* solve.step (cardiax/solve.py:26-65): the time derivatives (d_v, d_w, d_u) at counter t. */
 int fk_rhs(const float* v_dev, const float* w_dev, const float* u_dev, float* dv_dev, float* dw_dev, float* du_dev,
            const float* diffusivity_dev, int diffusivity_batched, int H, int W, int batch, const FkParams* params,

@@ -65,7 +65,8 @@ struct EmuStim {
     float start, duration, period;
 };
 
-// options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse}
+// options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse,
+//           row0, row1}
 // info (optional, 2 ints): tile launches, stream launches
 int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
                  const float* D, int d_batched, int H, int W, int batch, const float* params14, const EmuStim* stims,
@@ -86,6 +87,7 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     fk::DriveOptions o;
     o.exact = options[0]; o.steps_per_launch = options[1]; o.kernel = options[2]; o.phys_top = options[3];
     o.phys_bottom = options[4]; o.cta_threads = options[5]; o.rows_per_cta = options[6]; o.uniform_diffusivity = options[7];
+    o.row0 = options[9]; o.row1 = options[10];
     EmuBackend be;
     be.reverse = options[8];
     const long long nsteps = rhs_mode ? 1 : fk::count_steps(t0, t1);
@@ -109,7 +111,7 @@ int fk_emu_stim_active(float t, float start, float duration, float period) {
 // planner probe (tests): occupancy modelled as min(65536 / (regs * NT), 227 KB / smem)
 extern "C" int fk_emu_plan(int H, int W, int batch, int T, int cta_threads, int rows_per_cta, int regs, int* out) {
     fk::StreamPlan P;
-    const bool ok = fk::plan_stream(H, W, batch, T, cta_threads, rows_per_cta, 148, 0, 256,
+    const bool ok = fk::plan_stream(4 * T, H - 4 * T, W, batch, T, cta_threads, rows_per_cta, 148, 0, 256,
                                     [&](int NT, long long smem) {
                                         const int a = 65536 / (((regs + 7) / 8 * 8) * NT);
                                         const int b = (int)((228 * 1024) / (smem + 1024));
@@ -119,4 +121,11 @@ extern "C" int fk_emu_plan(int H, int W, int batch, int T, int cta_threads, int 
     out[0] = P.G.NT; out[1] = P.G.nstrips; out[2] = P.G.cstride; out[3] = P.G.RH; out[4] = P.G.nchunks;
     out[5] = (int)P.smem_bytes;
     return 1;
+}
+
+extern "C" int fk_emu_dgrad(const float* D, float* DX, float* DY, int H, int W, float dx, int phys_top, int phys_bot) {
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c)
+            fk::dgrad_cell(D, H, W, dx, phys_top, phys_bot, r, c, DX[(long long)r * W + c], DY[(long long)r * W + c]);
+    return 0;
 }

@@ -113,6 +113,32 @@ def test_slab_rows_with_halo_match_whole_tissue():
                 assert np.array_equal(g[r0 - a:r1 - a], r[r0:r1]), (r0, r1, kernel)
 
 
+def test_row_windows_compose_to_the_whole_slab():
+    """fk_euler_rows building block: edge bands + interior, written into one output, equal a whole-tissue launch."""
+    shape, T = (120, 160), 2
+    st, D, stim = common.random_case(shape, seed=9)
+    ref = C.forward_euler(st, 0, T, P3, D, stim, 0.01, 0.01)
+    F = 4 * T
+    # middle rank of a 3-way split with a deeper (2F) halo: buffer rows 24..96, non-physical edges, owns 40..80
+    a, b = 24, 96
+    sub = [x[a:b] for x in st]
+    sstim = [O.Stimulus(s.protocol, s.field[a:b]) for s in stim]
+    out = [np.full((b - a,) + shape[1:], np.nan, np.float32) for _ in range(3)]
+    for (r0, r1) in ((16, 16 + F), (56 - F, 56), (16 + F, 56 - F)):   # top band, bottom band, interior (buffer coords)
+        got, _ = emu.euler(sub, 0, T, P3, D[a:b], sstim, 0.01, 0.01, exact=True, T=T, kernel=2, cta_threads=32,
+                           phys_top=0, phys_bottom=0, row0=r0, row1=r1)
+        for o, g in zip(out, got):
+            assert np.isnan(g[:r0]).all() and np.isnan(g[r1:]).all()      # nothing outside the window is written
+            o[r0:r1] = g[r0:r1]
+    for o, r in zip(out, ref):
+        assert np.array_equal(o[16:56], r[40:80])
+    # top rank: physical top edge, window starting at row 0
+    got, _ = emu.euler([x[:60] for x in st], 0, T, P3, D[:60], [O.Stimulus(s.protocol, s.field[:60]) for s in stim], 0.01,
+                       0.01, exact=True, T=T, kernel=2, cta_threads=32, phys_top=1, phys_bottom=0, row0=0, row1=44)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g[:44], r[:44])
+
+
 def test_device_schedule_function_equals_oracle():
     rng = np.random.default_rng(1)
     for _ in range(200):
