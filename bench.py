@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--rows-per-cta", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--halo-launches", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -261,7 +262,8 @@ def main():
 
     if workload == "slab" and world > 1:
         from cardiax_b200 import slab
-        runner = slab.SlabRunner(state0, D, params, gstim, 0.01, 0.01, rank, world)
+        runner = slab.SlabRunner(state0, D, params, gstim, 0.01, 0.01, rank, world, steps_per_launch=args.T or 0,
+                                 halo_launches=args.halo_launches)
         step_fn = lambda st, t: runner.advance(st, t, t + seg)  # noqa: E731
         state0 = runner.scatter_local(state0)
     else:
@@ -282,7 +284,7 @@ def main():
         sampler.start()
     launches0 = L.fk_launch_count()
     L.fk_profile_enable(1)
-    L.fk_profile_collect(None, None, None, None)
+    L.fk_profile_collect(None, None, None, None, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -294,8 +296,9 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     import ctypes
-    sm_ms, sm_n, tl_ms, tl_n = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong()
-    L.fk_profile_collect(ctypes.byref(sm_ms), ctypes.byref(sm_n), ctypes.byref(tl_ms), ctypes.byref(tl_n))
+    sm_ms, sm_n, tl_ms, tl_n, sm_cs = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+    L.fk_profile_collect(ctypes.byref(sm_ms), ctypes.byref(sm_n), ctypes.byref(tl_ms), ctypes.byref(tl_n), ctypes.byref(sm_cs))
+    plan = _lib.last_plan()
     L.fk_profile_enable(0)
     launches = L.fk_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -353,16 +356,15 @@ def main():
     peak, peak_kind = peaks()
     roof = None
     if sm_n.value > 0:
-        # streaming kernel: T steps over the interior per launch
-        Tl = args.T or 2
-        Hh, Ww = state0.u.shape[-2:]
-        nb = state0.u.shape[0] if state0.u.dim() == 3 else 1
-        cs_per_launch = (Hh - 8 * Tl) * (Ww - 8 * Tl) * Tl * nb
+        # streaming kernel: T steps over the rows/columns it owns per launch (counted by the library per launch)
+        cs_per_launch = sm_cs.value / sm_n.value
         achieved = ALG_BYTES * cs_per_launch / (sm_ms.value / sm_n.value * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_kind": peak_kind, "kernel": "fk_stream_kernel",
                 "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": sm_ms.value / sm_n.value,
-                "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms}
+                "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms,
+                "note": "the frame-tile kernel runs on a side stream concurrently with the streaming kernel, so the shares can add to more than 1",
+                "launch_geometry": plan}
     elif tl_n.value > 0:
         achieved = ALG_BYTES * cells * seg * args.steps / (tl_ms.value * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

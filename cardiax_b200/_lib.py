@@ -96,7 +96,8 @@ def lib():
     L.fk_last_plan.restype = None
     L.fk_profile_enable.argtypes = [ci]
     L.fk_profile_enable.restype = None
-    L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll)]
+    L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll),
+                                      ctypes.POINTER(cd)]
     L.fk_profile_collect.restype = ci
     if L.fk_abi_version() != 1:
         raise RuntimeError("libfk.so ABI version mismatch")

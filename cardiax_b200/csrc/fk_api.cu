@@ -166,6 +166,7 @@ struct Prof {
     bool on = false;
     std::vector<cudaEvent_t> ev[2];   // [0] streaming kernel, [1] tile kernel : begin/end pairs
     std::vector<cudaEvent_t> pool;
+    double stream_cs = 0;             // cell-steps the timed streaming launches produced
     cudaEvent_t get() {
         cudaEvent_t e;
         if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
@@ -248,6 +249,7 @@ struct CudaBackend {
         g_last_plan[0] = P.T; g_last_plan[1] = P.G.NT; g_last_plan[2] = P.G.nstrips; g_last_plan[3] = P.G.cstride;
         g_last_plan[4] = P.G.RH; g_last_plan[5] = P.G.nchunks; g_last_plan[6] = P.occ; g_last_plan[7] = (int)P.smem_bytes;
         ProfScope ps(0, st);
+        if (ps.active) g_prof.stream_cs += (double)(P.G.row1 - P.G.row0) * (A.W - 8 * P.T) * P.T * batch;
         ++g_launches;
         const int rc = fk::launch_stream(P, A, exact, batch, st);
         if (rc > 0) return cuda_fail((cudaError_t)rc, "streaming kernel launch");
@@ -280,7 +282,10 @@ void fk_last_plan(int* out8) {
 
 void fk_profile_enable(int on) { g_prof.on = on != 0; }
 
-int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches) {
+int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches,
+                       double* stream_cell_steps) {
+    if (stream_cell_steps) *stream_cell_steps = g_prof.stream_cs;
+    g_prof.stream_cs = 0;
     double ms[2] = {0, 0};
     long long n[2] = {0, 0};
     for (int k = 0; k < 2; ++k) {

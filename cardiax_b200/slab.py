@@ -1,7 +1,7 @@
 """Row-slab decomposition of ONE large tissue over the GPUs of a node (BASELINE config 5).
 
 Not in the reference (it runs a tissue on a single device); SURVEY 8e defines it.  Rank r owns a
-contiguous block of rows; every rank keeps ``halo_launches * 4T`` halo rows of u, v, w from each
+contiguous block of rows; every rank keeps ``halo_launches * 4T`` (default 8 * 8 = 64) halo rows of u, v, w from each
 neighbour, so halos are exchanged once per ``halo_launches`` kernel launches (T Euler steps each).
 Between exchanges a launch also recomputes the shrinking apron of halo rows it still needs.
 
@@ -73,7 +73,7 @@ class SlabRunner:
     the emulated kernels); ``group`` the torch.distributed process group used for the halo exchange.
     """
 
-    def __init__(self, state, diffusivity, params, stimuli, dt, dx, rank, world, steps_per_launch=0, halo_launches=2,
+    def __init__(self, state, diffusivity, params, stimuli, dt, dx, rank, world, steps_per_launch=0, halo_launches=8,
                  backend=None, group=None, overlap=True):
         import torch.distributed as dist
         self.dist = dist

@@ -110,13 +110,15 @@ int fk_diffusivity_gradients(const float* diffusivity_dev, float* dx_out_dev, fl
  * fk_launch_count: kernels this library has launched since it was loaded.
  * fk_profile_enable(1): record a CUDA event pair, on the launch stream, around every step-kernel launch;
  * fk_profile_collect: wait for them, return summed device milliseconds and launch counts of the streaming kernel
- * and of the general tile kernel since the last collect, and reset. */
+ * and of the general tile kernel since the last collect (plus the cell-steps those streaming launches produced), and
+ * reset. */
 long long fk_launch_count(void);
 /* geometry of the most recent streaming-kernel launch: {T, cta_threads, strips, columns per strip, rows per CTA,
  * row chunks, resident CTAs per SM, dynamic shared memory bytes} */
 void fk_last_plan(int* out8);
 void fk_profile_enable(int on);
-int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches);
+int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches,
+                       double* stream_cell_steps);
 
 #ifdef __cplusplus
 }
