@@ -32,7 +32,8 @@ class FkStimulus(ctypes.Structure):
 class FkOptions(ctypes.Structure):
     _fields_ = [("exact", ctypes.c_int), ("steps_per_launch", ctypes.c_int), ("kernel", ctypes.c_int),
                 ("phys_top", ctypes.c_int), ("phys_bottom", ctypes.c_int), ("cta_threads", ctypes.c_int),
-                ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("reserved", ctypes.c_int * 8)]
+                ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("safe_division", ctypes.c_int),
+                ("reserved", ctypes.c_int * 7)]
 
 
 def needs_build():
@@ -82,6 +83,8 @@ def lib():
     L.fk_euler_rows.argtypes = [vp] * 6 + [vp, vp, vp, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd,
                                            ci, cf, cf, ctypes.POINTER(FkOptions), ci, ci, vp, sz, vp]
     L.fk_euler_rows.restype = ci
+    L.fk_check_exact_division.argtypes = [ctypes.POINTER(FkParams), cf, ctypes.POINTER(ll), vp]
+    L.fk_check_exact_division.restype = ci
     L.fk_rhs.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd, cf,
                                     ctypes.POINTER(FkOptions), vp, sz, vp]
     L.fk_rhs.restype = ci

@@ -114,6 +114,24 @@ __global__ void fk_stimulate_kernel(const float* __restrict__ x, float* __restri
     }
 }
 
+// exhaustive check of Num<true>::divc against __fdiv_rn: every significand, three exponents, every divisor of a run
+__global__ void fk_divcheck_kernel(fk::Consts K, unsigned long long* bad) {
+    const float divisors[10] = {K.tau_d, K.tau_0, K.two_tau_si, K.Cm, K.tau_v_plus, K.tau_v1_minus, K.tau_v2_minus,
+                                K.tau_w_plus, K.tau_w_minus, K.dx};
+    const float recips[10] = {K.y_tau_d, K.y_tau_0, K.y_two_tau_si, K.y_Cm, K.y_tvp, K.y_tvm1, K.y_tvm2, K.y_twp, K.y_twm,
+                              K.y_dx};
+    unsigned long long local = 0;
+    for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < (1u << 23); m += gridDim.x * blockDim.x)
+        for (int e = 0; e < 3; ++e) {
+            const float a = __uint_as_float(((unsigned)(127 - 40 + 40 * e) << 23) | m);
+            for (int i = 0; i < 10; ++i) {
+                const float x = (i & 1) ? -a : a;
+                if (fk::Num<true>::divc(x, divisors[i], recips[i], K.div_lo, K.div_hi) != __fdiv_rn(x, divisors[i])) ++local;
+            }
+        }
+    if (local) atomicAdd(bad, local);
+}
+
 // ------------------------------------------------------------------ host helpers
 fk::Consts make_consts(const FkParams& p, float dt, float dx) {
     static_assert(sizeof(FkParams) == 14 * sizeof(float), "FkParams layout");
@@ -405,7 +423,9 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     CudaBackend be;
     be.st = st;
     const char* why = "";
-    rc = fk::drive_euler(be, B, d_batched, H, W, batch, make_consts(*params, dt, dx), n_stim, t0, nsteps, o, rhs_mode, &why);
+    fk::Consts K = make_consts(*params, dt, dx);
+    if (opt.safe_division) K.div_lo = INFINITY;   // every exact-mode division through __fdiv_rn
+    rc = fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t0, nsteps, o, rhs_mode, &why);
     if (rc && why[0]) return fail(rc, "%s", why);
     return rc;
 }
@@ -417,6 +437,22 @@ int fk_forward_euler(const float* v_in, const float* w_in, const float* u_in, fl
     const long long nsteps = fk::count_steps(t0, t1);
     return run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, d_batched, H, W, batch, params, stimuli, n_stim, t0, nsteps,
                      dt, dx, opt, 0, workspace, workspace_bytes, stream);
+}
+
+int fk_check_exact_division(const FkParams* params, float dx, long long* mismatches, void* stream) {
+    if (!params || !mismatches) return fail(-1, "NULL pointer%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* dev = nullptr;
+    FK_CUDA(cudaMalloc(&dev, sizeof(unsigned long long)));
+    FK_CUDA(cudaMemsetAsync(dev, 0, sizeof(unsigned long long), st));
+    fk_divcheck_kernel<<<148 * 8, 256, 0, st>>>(make_consts(*params, 0.01f, dx), dev);
+    unsigned long long host = 0;
+    cudaError_t e = cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "fk_check_exact_division");
+    *mismatches = (long long)host;
+    return 0;
 }
 
 int fk_euler_rows(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,

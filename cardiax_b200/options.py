@@ -12,4 +12,5 @@ kernel = 0
 cta_threads = 0
 rows_per_cta = 0
 detect_uniform_diffusivity = True
+safe_division = False   # exact numerics: force every division through __fdiv_rn
 verbose = True

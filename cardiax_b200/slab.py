@@ -58,6 +58,7 @@ class CudaBackend:
         o.cta_threads, o.rows_per_cta = int(options.cta_threads), int(options.rows_per_cta)
         o.phys_top, o.phys_bottom = int(phys_top), int(phys_bottom)
         o.uniform_diffusivity = int(uniform)
+        o.safe_division = int(options.safe_division)
         _lib.check(self.L.fk_euler_rows(src[0].data_ptr(), src[1].data_ptr(), src[2].data_ptr(), dst[0].data_ptr(),
                                         dst[1].data_ptr(), dst[2].data_ptr(), D.data_ptr(), DX.data_ptr(), DY.data_ptr(),
                                         H, W, ctypes.byref(P), arr, len(stimuli), float(t0), int(nsteps), np.float32(dt),

@@ -96,10 +96,27 @@ def _is_uniform(D):
     return hit
 
 
-def _options(D=None, **over):
+_division_checked = {}
+
+
+def _division_is_safe(P, dx):
+    """Exact numerics: verify the FMA division by this run's constants on the device, once per (params, dx)."""
+    key = (bytes(P), float(dx))
+    hit = _division_checked.get(key)
+    if hit is None:
+        bad = ctypes.c_longlong(-1)
+        _lib.check(_lib.lib().fk_check_exact_division(ctypes.byref(P), np.float32(dx), ctypes.byref(bad), _stream()))
+        hit = bad.value == 0
+        _division_checked[key] = hit
+    return hit
+
+
+def _options(D=None, P=None, dx=None, **over):
     o = _lib.FkOptions()
     _lib.lib().fk_default_options(ctypes.byref(o))
     o.exact = int(options.numerics == "exact")
+    if o.exact and P is not None:
+        o.safe_division = int(options.safe_division or not _division_is_safe(P, _scalar(dx)))
     o.steps_per_launch = int(options.steps_per_launch)
     o.kernel = int(options.kernel)
     o.cta_threads = int(options.cta_threads)
@@ -150,7 +167,7 @@ def step(state, t, params, diffusivity, stimuli, dx):
     ws, nbytes = _workspace(L, H, W, batch, n_stim, int(D.dim() == 3), dev)
     dv, dw, du = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
     P = _params_struct(params)
-    o = _options()
+    o = _options(None, P, dx)
     _lib.check(L.fk_rhs(v.data_ptr(), w.data_ptr(), u.data_ptr(), dv.data_ptr(), dw.data_ptr(), du.data_ptr(),
                         D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim, _scalar(t),
                         np.float32(_scalar(dx)), ctypes.byref(o), ws.data_ptr(), nbytes, _stream()))
@@ -165,7 +182,7 @@ def _forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx):
     ws, nbytes = _workspace(L, H, W, batch, n_stim, int(D.dim() == 3), dev)
     vo, wo, uo = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
     P = _params_struct(params)
-    o = _options(D)
+    o = _options(D, P, dx)
     _lib.check(L.fk_forward_euler(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
                                   D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
                                   _scalar(t), _scalar(t_end), np.float32(_scalar(dt)), np.float32(_scalar(dx)),

@@ -50,7 +50,9 @@ typedef struct FkOptions {
     int rows_per_cta;     /* streaming kernel: rows per CTA chunk (0 = auto) */
     int uniform_diffusivity; /* caller asserts the diffusivity map is one constant: the streaming kernel then keeps
                                 D, D_x, D_y as three scalars instead of reading three maps */
-    int reserved[8];
+    int safe_division;    /* exact numerics only: 1 = every division through the IEEE sequence (__fdiv_rn) instead of the
+                             3-instruction correctly rounded FMA division by constants (see fk_check_exact_division) */
+    int reserved[7];
 } FkOptions;
 
 /* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */
@@ -86,6 +88,12 @@ int fk_euler_rows(const float* v_in_dev, const float* w_in_dev, const float* u_i
                   int W, const FkParams* params, const FkStimulus* stimuli, int n_stim, double t0, int nsteps, float dt,
                   float dx, const FkOptions* opt, int row0, int row1, void* workspace_dev, size_t workspace_bytes,
                   void* stream);
+
+/* Exact numerics divide by the run's constants (time constants, dx) with q = RN(a * RN(1/b)); RN(q + (a - b q) RN(1/b)).
+ * This verifies that sequence against __fdiv_rn on the device for every significand x three exponents x both signs x
+ * every divisor of (params, dx) and returns the number of mismatches (0 expected; if not, set
+ * FkOptions.safe_division).  Synchronises `stream`. */
+int fk_check_exact_division(const FkParams* params, float dx, long long* mismatches, void* stream);
 
 /* solve.step (cardiax/solve.py:26-65): the time derivatives (d_v, d_w, d_u) at counter t. */
 int fk_rhs(const float* v_dev, const float* w_dev, const float* u_dev, float* dv_dev, float* dw_dev, float* du_dev,

@@ -72,6 +72,31 @@ def test_exact_all_paramsets(pset):
     assert_exact(got, ref, "paramset " + pset)
 
 
+def test_exact_division_selftest_all_paramsets():
+    """The 3-instruction correctly rounded division by constants equals __fdiv_rn for every significand (device)."""
+    import ctypes
+    from cardiax_b200 import _lib
+    L = _lib.lib()
+    for k, p in O.PARAMSETS.items():
+        for dx in (0.01, 0.03, 0.005, 0.1):
+            P = _lib.FkParams(*[np.float32(x) for x in p])
+            bad = ctypes.c_longlong(-1)
+            _lib.check(L.fk_check_exact_division(ctypes.byref(P), np.float32(dx), ctypes.byref(bad), None))
+            assert bad.value == 0, (k, dx, bad.value)
+
+
+def test_exact_safe_division_option_gives_the_same_bits():
+    from cardiax_b200 import options
+    st, D, stim = common.random_case((64, 160), seed=13)
+    a = run_gpu(st, 0, 9, P3, D, stim, numerics="exact", kernel=2, cta_threads=32)
+    options.safe_division = True
+    try:
+        b = run_gpu(st, 0, 9, P3, D, stim, numerics="exact", kernel=2, cta_threads=32)
+    finally:
+        options.safe_division = False
+    assert_exact(a, b, "safe division")
+
+
 def test_exact_uniform_diffusivity_fast_path():
     st, _, stim = common.random_case((96, 640), seed=7)
     D = np.full((96, 640), 1e-3, np.float32)
