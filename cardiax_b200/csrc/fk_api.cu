@@ -267,7 +267,7 @@ struct CudaBackend {
         g_last_plan[0] = P.T; g_last_plan[1] = P.G.NT; g_last_plan[2] = P.G.nstrips; g_last_plan[3] = P.G.cstride;
         g_last_plan[4] = P.G.RH; g_last_plan[5] = P.G.nchunks; g_last_plan[6] = P.occ; g_last_plan[7] = (int)P.smem_bytes;
         ProfScope ps(0, st);
-        if (ps.active) g_prof.stream_cs += (double)(P.G.row1 - P.G.row0) * (A.W - 8 * P.T) * P.T * batch;
+        if (ps.active) g_prof.stream_cs += (double)(P.G.row1 - P.G.row0) * A.W * P.T * batch;
         ++g_launches;
         const int rc = fk::launch_stream(P, A, exact, batch, st);
         if (rc > 0) return cuda_fail((cudaError_t)rc, "streaming kernel launch");

@@ -55,14 +55,13 @@ inline void add_region(TileArgs& A, int R0, int R1, int C0, int C1, int th, int 
     R.tw = tw < C1 - C0 ? tw : C1 - C0;
 }
 
-// the frame of 4T cells the streaming kernel leaves out: output rows [R0, R1), streaming rows [S0, S1)
+// what the streaming kernel leaves out: the bands of 4T rows at the physical top / bottom edge (it handles the
+// left / right edges itself).  Output rows [R0, R1), streaming rows [S0, S1).
 inline void frame_regions(TileArgs& A, int T, int R0, int R1, int S0, int S1) {
     const int F = 4 * T, W = A.W;
     A.nreg = 0;
-    add_region(A, R0, S0, 0, W, F, 64);    // top band (only at the physical top edge); 64 x F and F x 64 tiles need
-    add_region(A, S1, R1, 0, W, F, 64);    // the same shared memory, so four CTAs fit an SM
-    add_region(A, S0, S1, 0, F, 64, F);
-    add_region(A, S0, S1, W - F, W, 64, F);
+    add_region(A, R0, S0, 0, W, F, 64);
+    add_region(A, S1, R1, 0, W, F, 64);
 }
 
 inline void pick_tile(int rows, int W, int T, int& th, int& tw) {

@@ -102,6 +102,7 @@ template <int T>
 struct StreamState {     // registers of one thread
     float GX[T][4][4];   // u_x rows rho-2 .. rho+1 of each stage
     float gy[T][4];      // u_y of row rho (made one iteration ahead)
+    float gypad[T];      // edge threads only: u_y of the PAD column next to the tissue edge (padded index 0 / W+1)
 };
 
 struct StreamCta {       // uniform per CTA
@@ -110,8 +111,10 @@ struct StreamCta {       // uniform per CTA
     int rin0, rin_end;   // level-0 rows read
     int out_c0, out_c1;  // output columns
     int c_end;           // end of the columns this CTA needs
+    int edgeL, edgeR;    // thread that holds the tissue's first / last column (-1: not in this strip)
     long long boff, boffD;
     float Dc, DXc, DYc;  // uniform-diffusivity constants
+    float DYcL, DYcR;    // D_y of a constant map in the tissue's first / last column (one-sided formula: not DYc)
     unsigned mask[8];
     const StimDev* stims;
     int niter;
@@ -119,14 +122,18 @@ struct StreamCta {       // uniform per CTA
 
 template <int T>
 FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, int chunk, int sim, StreamCta& C) {
-    C.cs = strip * G.cstride;
+    // strip j owns output columns [j stride, (j+1) stride); it reads 4T more on each side unless that side is the
+    // tissue's physical left/right edge, which the edge thread handles with the reference's one-sided formulas
+    C.cs = strip * G.cstride - 4 * T < 0 ? 0 : strip * G.cstride - 4 * T;
     C.r0 = G.row0 + chunk * G.RH;
     C.r1 = C.r0 + G.RH < G.row1 ? C.r0 + G.RH : G.row1;
     C.rin0 = C.r0 - 4 * T;
     C.rin_end = C.r1 + 4 * T;
-    C.out_c0 = C.cs + 4 * T;
-    C.out_c1 = C.out_c0 + G.cstride < A.W - 4 * T ? C.out_c0 + G.cstride : A.W - 4 * T;
-    C.c_end = C.out_c1 + 4 * T;  // columns past this are nobody's input
+    C.out_c0 = strip * G.cstride;
+    C.out_c1 = C.out_c0 + G.cstride < A.W ? C.out_c0 + G.cstride : A.W;
+    C.c_end = C.out_c1 + 4 * T < A.W ? C.out_c1 + 4 * T : A.W;  // columns past this are nobody's input
+    C.edgeL = strip == 0 ? 0 : -1;
+    C.edgeR = C.out_c1 == A.W ? (A.W - 4 - C.cs) / 4 : -1;
     C.boff = (long long)sim * A.plane;
     C.boffD = (long long)sim * A.plane_D;
     C.stims = A.stims ? A.stims + (long long)sim * A.n_stim : nullptr;
@@ -141,10 +148,12 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
         }
         C.mask[s] = m;
     }
-    C.Dc = C.DXc = C.DYc = 0.0f;
+    C.Dc = C.DXc = C.DYc = C.DYcL = C.DYcR = 0.0f;
     if (G.uniformD) {
-        const long long g = C.boffD + (long long)G.row0 * A.W + 4 * T;
+        const long long g = C.boffD + (long long)G.row0 * A.W + 4 * T;  // any cell 2+ away from every edge
         C.Dc = A.D[g]; C.DXc = A.DX[g]; C.DYc = A.DY[g];
+        C.DYcL = A.DY[g - 4 * T];
+        C.DYcR = A.DY[g - 4 * T + A.W - 1];
     }
 }
 
@@ -167,6 +176,15 @@ FK_HD void stream_prefetch(const TileArgs& A, const StreamGeom& G, const StreamC
 
 FK_HD int mod5(int x) { return x >= 5 ? x - 5 : x; }  // for 0 <= x < 10
 
+// one-sided first derivative / dx (solve.py:232-235, 246-249) on four consecutive values
+template <bool EXACT>
+FK_HD float edge_deriv(const Consts& K, int kind, float a0, float a1, float a2, float a3) {
+    float k0, k1, k2, k3;
+    int o0, o1, o2, o3;
+    kind_coeffs(kind, k0, k1, k2, k3, o0, o1, o2, o3);
+    return deriv<EXACT>(K, kind, k0, k1, k2, k3, a0, a1, a2, a3);
+}
+
 // may iterations i >= 8T use the condition-free body?  (no stimulus active in any level of this launch)
 template <int T>
 FK_HD bool stream_steady_ok(const StreamCta& C) {
@@ -180,11 +198,14 @@ template <bool EXACT, bool HAS_STIM>
 FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const float* w, const float* gxm2,
                        const float* gxm1, const float* gx0, const float* gxp1, const float* gxp2, const float* g,
                        const float* gy0, const float* Dv, const float* DXv, const float* DYv, const float* stim,
-                       float* un, float* vn, float* wn) {
+                       bool edgeL, bool edgeR, float* un, float* vn, float* wn) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
-        const float u_yy = dcen<EXACT>(K, g[k], g[k + 1], g[k + 3], g[k + 4]);    // solve.py:52
+        float u_yy = dcen<EXACT>(K, g[k], g[k + 1], g[k + 3], g[k + 4]);          // solve.py:52
+        // the tissue's first / last column: forward / backward formula on u_y of padded columns 1..4 / W-3..W
+        if (k == 0 && edgeL) u_yy = edge_deriv<EXACT>(K, FWD, g[2], g[3], g[4], g[5]);
+        if (k == 3 && edgeR) u_yy = edge_deriv<EXACT>(K, BWD, g[2], g[3], g[4], g[5]);
         const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], gx0[k], gy0[k], u_xx, u_yy);
         float d_v, d_w, d_u;
         cell_rhs<EXACT, HAS_STIM>(K, u0[k], v[k], w[k], del_u, HAS_STIM ? stim[k] : 0.0f, d_v, d_w, d_u);
@@ -208,6 +229,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
     async_wait<FK_PF>();
     if (!act) return;
     const int own = 4 + 4 * tid;  // offset of the thread's columns inside a padded ring row
+    const bool edgeL = tid == C.edgeL, edgeR = tid == C.edgeR;
     const int n0 = C.rin0 + i;
     const int m8 = n0 & (FK_U0DEP - 1);
     const int m5 = n0 % 5;
@@ -242,7 +264,9 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
         if (emit) {
             const float* gr = S.gyx[s] + ((i + 1) & 1) * G.RS + own;
             const F2 L = ld2(gr - 2), Rr = ld2(gr + 4);
-            const float g[8] = {L.x, L.y, R.gy[s][0], R.gy[s][1], R.gy[s][2], R.gy[s][3], Rr.x, Rr.y};
+            // at a tissue edge the neighbour is the pad column, whose u_y this thread made itself
+            const float g[8] = {L.x, edgeL ? R.gypad[s] : L.y, R.gy[s][0], R.gy[s][1], R.gy[s][2], R.gy[s][3],
+                                edgeR ? R.gypad[s] : Rr.x, Rr.y};
             float v[4], w[4];
             const int vslot = s == 0 ? (rho & (FK_VWDEP - 1)) : sl_r0;
             unpack4(ld4(S.vring[s] + vslot * G.CW + 4 * tid), v);
@@ -252,6 +276,8 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
             if (G.uniformD) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { Dv[k] = C.Dc; DXv[k] = C.DXc; DYv[k] = C.DYc; }
+                if (edgeL) DYv[0] = C.DYcL;
+                if (edgeR) DYv[3] = C.DYcR;
             } else {
                 unpack4(ld4(A.D + C.boffD + grow), Dv);
                 unpack4(ld4(A.DX + C.boffD + grow), DXv);
@@ -270,10 +296,10 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
                             if (f[k] != 0.0f) stim[k] = f[k];
                     }
                 stream_emit<EXACT, true>(A.K, u0, v, w, R.GX[s][0], R.GX[s][1], R.GX[s][2], R.GX[s][3], ngx, g, R.gy[s], Dv,
-                                         DXv, DYv, stim, un, vn, wn);
+                                         DXv, DYv, stim, edgeL, edgeR, un, vn, wn);
             } else {
                 stream_emit<EXACT, false>(A.K, u0, v, w, R.GX[s][0], R.GX[s][1], R.GX[s][2], R.GX[s][3], ngx, g, R.gy[s],
-                                          Dv, DXv, DYv, nullptr, un, vn, wn);
+                                          Dv, DXv, DYv, nullptr, edgeL, edgeR, un, vn, wn);
             }
             if (s == T - 1) {
                 if (c >= C.out_c0 && c < C.out_c1) {
@@ -293,9 +319,18 @@ FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& 
         // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
         if (STEADY || (rho + 1 >= lo && rho + 1 < hi)) {
             const F2 L = ld2(ur + sl_r1 * G.RS - 2), Rr = ld2(ur + sl_r1 * G.RS + 4);
-            const float e[8] = {L.x, L.y, u1[0], u1[1], u1[2], u1[3], Rr.x, Rr.y};
+            // edge-pad (solve.py:31): the column outside the tissue repeats the edge column
+            const float e[8] = {L.x, edgeL ? u1[0] : L.y, u1[0], u1[1], u1[2], u1[3], edgeR ? u1[3] : Rr.x, Rr.y};
 #pragma unroll
             for (int k = 0; k < 4; ++k) R.gy[s][k] = dcen<EXACT>(A.K, e[k], e[k + 1], e[k + 3], e[k + 4]);
+            if (edgeL) {  // padded columns 0 (the pad) and 1 (tissue column 0) use the forward formula
+                R.gypad[s] = edge_deriv<EXACT>(A.K, FWD, e[1], e[2], e[3], e[4]);
+                R.gy[s][0] = edge_deriv<EXACT>(A.K, FWD, e[2], e[3], e[4], e[5]);
+            }
+            if (edgeR) {  // padded columns W (tissue column W-1) and W+1 (the pad) use the backward formula
+                R.gy[s][3] = edge_deriv<EXACT>(A.K, BWD, e[2], e[3], e[4], e[5]);
+                R.gypad[s] = edge_deriv<EXACT>(A.K, BWD, e[3], e[4], e[5], e[6]);
+            }
             st4(S.gyx[s] + (i & 1) * G.RS + own, R.gy[s]);
         }
         // slide the u_x window
@@ -330,7 +365,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
     if (T < 1 || T > 4) return false;
     if (W % 4 != 0) return false;                       // float4 rows
     if (row1 - row0 < 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
-    const int Wint = W - 8 * T, Hint = row1 - row0;
+    const int Wint = W, Hint = row1 - row0;
     double best = -1.0;
     const int ns_min = (Wint + (4 * max_threads - 8 * T) - 1) / (4 * max_threads - 8 * T);
     for (int ns = ns_min; ns < ns_min + 24; ++ns) {

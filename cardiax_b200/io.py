@@ -1,0 +1,342 @@
+"""Snapshot path of the reference (cardiax/io.py:13-124) with asynchronous device-to-host copies.
+
+Layout kept (io.py:18-22, 31-35, 43, 53-63): ``states (T, 3, H', W') f32`` in (v, w, u) order, ``stimuli``,
+``params/{D, dt, dx, <14 names>}``, ``diffusivity``, ``field/start/duration/period``.
+
+* ``init``/``add_params``/``add_diffusivity``/``add_stimuli``/``add_state``/``add_states``/``load*``/``imresize`` keep the
+  reference's names and arguments.  ``h5py`` is optional: without it the same calls go to an in-memory store that is
+  written as one ``.npz`` on ``close()`` (dataset names with ``/`` kept as keys).
+* ``imresize`` is ``jax.image.resize(a, shape, "bilinear")`` (anti-aliased triangle filter, half-pixel centres, edge
+  weights renormalised) evaluated on the GPU as two small dense products with host-built weight matrices.
+* ``AsyncSnapshotWriter`` is what the north star asks for: snapshots are (optionally resized and) copied into a ring of
+  PINNED host buffers on a SIDE stream, ordered after the producing kernels by an event, and written to the dataset by
+  a host thread -- the solver stream never waits for the disk or the PCIe copy.
+"""
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+from .params import Params
+from .stimulus import Protocol, Stimulus
+
+try:  # optional
+    import h5py  # noqa: F401
+    _HAVE_H5 = True
+except Exception:  # pragma: no cover - depends on the image
+    h5py = None
+    _HAVE_H5 = False
+
+
+# --------------------------------------------------------------------------- storage without h5py
+class _Dataset:
+    def __init__(self, array):
+        self.array = array
+
+    def __setitem__(self, key, value):
+        self.array[key] = _to_numpy(value)
+
+    def __getitem__(self, key):
+        return self.array[key]
+
+    def __len__(self):
+        return len(self.array)
+
+    @property
+    def shape(self):
+        return self.array.shape
+
+
+class NpzStore:
+    """Minimal stand-in for the part of ``h5py.File`` the reference uses; saved as ``<path>.npz`` on close."""
+
+    def __init__(self, path, mode="w"):
+        self.path = path if path.endswith(".npz") else path + ".npz"
+        self.data = {}
+        if mode == "r":
+            with np.load(self.path, allow_pickle=False) as f:
+                self.data = {k: _Dataset(f[k]) for k in f.files}
+
+    def create_dataset(self, name, shape=None, dtype=None, data=None):
+        if data is not None:
+            arr = np.array(_to_numpy(data), dtype=dtype)
+        else:
+            arr = np.zeros(shape, dtype=dtype or "float32")
+        self.data[name] = _Dataset(arr)
+        return self.data[name]
+
+    def __contains__(self, name):
+        return name in self.data
+
+    def __getitem__(self, name):
+        if name in self.data:
+            return self.data[name]
+        sub = {k[len(name) + 1:]: v for k, v in self.data.items() if k.startswith(name + "/")}
+        if not sub:
+            raise KeyError(name)
+        return sub
+
+    def __iter__(self):
+        return iter(self.data)
+
+    def close(self):
+        np.savez(self.path, **{k: v.array for k, v in self.data.items()})
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+
+def _to_numpy(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], torch.Tensor):
+        return np.stack([t.detach().cpu().numpy() for t in x])
+    return np.asarray(x)
+
+
+def _open(path, mode):
+    if _HAVE_H5:
+        return h5py.File(path, mode)
+    return NpzStore(path, mode)
+
+
+# --------------------------------------------------------------------------- reference API
+def init(path, shape, n_iter, n_stimuli, n_variables=3):
+    """io.py:13-23."""
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    hdf5 = _open(path, "w")
+    if "states" not in hdf5:
+        hdf5.create_dataset("states", shape=(n_iter, n_variables, *shape), dtype="float32")
+    if "stimuli" not in hdf5:
+        hdf5.create_dataset("stimuli", shape=(n_stimuli, *shape), dtype="float32")
+    return hdf5
+
+
+def add_params(hdf5, params, diffusivity, dt, dx, shape=None):
+    """io.py:26-36."""
+    if shape is not None:
+        diffusivity = imresize(diffusivity, shape)
+    hdf5.create_dataset("params/D", data=_to_numpy(diffusivity))
+    hdf5.create_dataset("params/dt", data=dt)
+    hdf5.create_dataset("params/dx", data=dx)
+    for i in range(len(params)):
+        hdf5.create_dataset("params/" + params._fields[i], data=params[i])
+    return True
+
+
+def add_diffusivity(hdf5, diffusivity, shape=None):
+    """io.py:39-44."""
+    if shape is not None:
+        diffusivity = imresize(diffusivity, shape)
+    hdf5.create_dataset("diffusivity", data=_to_numpy(diffusivity))
+    return True
+
+
+def add_stimuli(hdf5, stimuli, shape=None):
+    """io.py:47-64."""
+    if shape is not None:
+        fields = [_to_numpy(imresize(s.field, shape)) for s in stimuli]
+    else:
+        fields = [_to_numpy(s.field) for s in stimuli]
+    hdf5.create_dataset("field", data=np.array(fields, dtype=np.float32))
+    scal = lambda x: np.asarray(_to_numpy(x)).reshape(-1)[0]  # noqa: E731
+    hdf5.create_dataset("start", data=[scal(s.protocol.start) for s in stimuli])
+    hdf5.create_dataset("duration", data=[scal(s.protocol.duration) for s in stimuli])
+    hdf5.create_dataset("period", data=[scal(s.protocol.period) for s in stimuli])
+    return True
+
+
+def add_state(dset, state, t, shape=None):
+    """io.py:67-72 -- synchronous (resize +) store of one snapshot; see AsyncSnapshotWriter for the overlapped path."""
+    if shape is not None:
+        array = torch.stack(tuple(state))
+        state = imresize(array, tuple(shape[-2:]))
+    dset[t] = _to_numpy(state)
+    return True
+
+
+def add_states(dset, states, start, end):
+    """io.py:75-78."""
+    dset[start:end] = np.stack([_to_numpy(s) for s in states]) if isinstance(states, (list, tuple)) else _to_numpy(states)
+    return True
+
+
+def load(path, start=None, end=None, step=None):
+    """io.py:81-83."""
+    f = _open(path, "r")
+    try:
+        return [f[dset][start:end:step] for dset in f]
+    finally:
+        if _HAVE_H5:
+            f.close()
+
+
+def load_state(dset, start, end, step):
+    return dset[start:end:step]
+
+
+def load_stimuli(file):
+    """io.py:90-96."""
+    stimuli = []
+    for i in range(len(file["field"])):
+        protocol = Protocol(file["start"][i], file["duration"][i], file["period"][i])
+        stimuli.append(Stimulus(protocol, file["field"][i]))
+    return stimuli
+
+
+def load_params(filepath):
+    """io.py:99-110."""
+    params = {}
+    D = None
+    f = _open(filepath, "r")
+    stored = f["params"]
+    for key in stored:
+        if key == "D":
+            D = stored[key][...]
+        else:
+            params[key] = stored[key][...]
+    if _HAVE_H5:
+        f.close()
+    return Params(*[params[k] for k in Params._fields]), D
+
+
+def load_diffusivity(filepath):
+    f = _open(filepath, "r")
+    try:
+        return f["diffusivity"][:]
+    finally:
+        if _HAVE_H5:
+            f.close()
+
+
+# --------------------------------------------------------------------------- jax.image.resize(..., "bilinear")
+_weights_cache = {}
+
+
+def _weight_matrix(n_in, n_out, device):
+    """(n_in, n_out) weights of jax.image.resize's separable triangle filter with anti-aliasing."""
+    key = (n_in, n_out, str(device))
+    w = _weights_cache.get(key)
+    if w is None:
+        scale = n_out / n_in
+        inv_scale = 1.0 / scale
+        kernel_scale = max(inv_scale, 1.0)
+        sample_f = (np.arange(n_out, dtype=np.float64) + 0.5) * inv_scale - 0.5
+        x = np.abs(sample_f[None, :] - np.arange(n_in, dtype=np.float64)[:, None]) / kernel_scale
+        wt = np.maximum(0.0, 1.0 - x)
+        total = wt.sum(axis=0, keepdims=True)
+        wt = np.where(np.abs(total) > 1000.0 * np.finfo(np.float32).eps, wt / np.where(total == 0, 1, total), 0.0)
+        inside = (sample_f >= -0.5) & (sample_f <= n_in - 0.5)
+        wt = np.where(inside[None, :], wt, 0.0).astype(np.float32)
+        w = torch.from_numpy(wt).to(device)
+        _weights_cache[key] = w
+    return w
+
+
+def imresize(a, size, method="bilinear"):
+    """io.py:118-124 -- resize the last two axes of a 2-D or 3-D array to ``size``."""
+    if method != "bilinear":
+        raise NotImplementedError("only the reference's default 'bilinear' is provided")
+    if not isinstance(a, torch.Tensor):
+        a = torch.as_tensor(np.asarray(a))
+    a = a.to(torch.float32)
+    H, W = a.shape[-2:]
+    if (H, W) == tuple(size):
+        return a.clone()
+    wh = _weight_matrix(H, int(size[0]), a.device)  # (H, H')
+    ww = _weight_matrix(W, int(size[1]), a.device)  # (W, W')
+    return torch.matmul(wh.t(), torch.matmul(a, ww))
+
+
+# --------------------------------------------------------------------------- asynchronous snapshots
+class AsyncSnapshotWriter:
+    """Overlapped snapshotting: ``submit(state, t)`` returns at once; the copy runs on a side stream into pinned memory
+    and a host thread stores it into ``dset[t]``.
+
+    dset        any object with ``__setitem__`` (the ``states`` dataset of ``init``)
+    shape       snapshot shape (3, H', W'); if (H', W') differs from the state's grid it is resized on the GPU first
+    slots       pinned ring depth; ``submit`` blocks only when all slots are still waiting for the writer thread
+    """
+
+    def __init__(self, dset, shape, slots=4, device=None):
+        self.dset = dset
+        self.shape = tuple(shape)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.pinned = [torch.empty(self.shape, dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.free = queue.Queue()
+        for i in range(slots):
+            self.free.put(i)
+        self.work = queue.Queue()
+        self.error = None
+        self.bytes_copied = 0
+        self.thread = threading.Thread(target=self._drain, daemon=True)
+        self.thread.start()
+
+    def submit(self, state, t):
+        slot = self.free.get()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))      # after the kernels that produced `state`
+        keep = tuple(state)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            arr = torch.stack(keep)
+            if tuple(arr.shape[-2:]) != self.shape[-2:]:
+                arr = imresize(arr, self.shape[-2:])
+            self.pinned[slot].copy_(arr, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        for x in keep:                                              # the side stream still reads them
+            x.record_stream(self.stream)
+        self.bytes_copied += self.pinned[slot].numel() * 4
+        self.work.put((slot, t, done))
+
+    def _drain(self):
+        while True:
+            item = self.work.get()
+            if item is None:
+                return
+            slot, t, done = item
+            try:
+                done.synchronize()
+                self.dset[t] = self.pinned[slot].numpy()
+            except Exception as e:  # noqa: BLE001 - reported by close()
+                self.error = e
+            self.free.put(slot)
+
+    def close(self):
+        self.work.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
+def sequence(start, stop, step, dt, dx, params, diffusivity, stimuli, filename, reshape=None, use_memory=False,
+             plot_while=False):
+    """deepx/generate.py:135-210 -- checkpointed run with snapshots; D2H and file writes overlap the solver."""
+    from . import solve
+    shape = tuple(diffusivity.shape)
+    out_shape = tuple(reshape) if reshape is not None else shape
+    checkpoints = np.arange(int(start), int(stop), int(step))
+    hdf5 = init(filename, out_shape, n_iter=len(checkpoints), n_stimuli=len(stimuli))
+    add_params(hdf5, params, diffusivity, dt, dx, shape=out_shape)
+    add_stimuli(hdf5, stimuli, shape=out_shape)
+    add_diffusivity(hdf5, diffusivity, shape=out_shape)
+    states_dset = hdf5["states"]
+    state = solve.init(shape)
+    writer = AsyncSnapshotWriter(states_dset, (3,) + out_shape)
+    try:
+        for i in range(len(checkpoints) - 1):
+            state = solve._forward_euler(state, checkpoints[i], checkpoints[i + 1], params, diffusivity, stimuli, dt, dx)
+            writer.submit(state, i)
+    finally:
+        writer.close()
+    hdf5.close()
+    return state
