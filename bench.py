@@ -11,6 +11,7 @@ Workloads (BASELINE.json configs):
   slab     row-slab decomposition of a (4096*N) x 4096 tissue over N GPUs, 4T-row halo exchange (N > 1 default)
   ens256   ensemble of independent 256 x 256 tissues (128 per GPU), heterogeneous D, 3 stimuli each, no comms
   fk512    512 x 512 scar map + S1-S2 (config 2)
+  fk128    128 x 128 plane wave (config 1, the README benchmark shape)
 
 Rank 0 prints ONE JSON line.  `value` is device-timed (CUDA events, barrier + synchronize on both
 sides, max over ranks) with the state resident in HBM; `e2e` goes through the public
@@ -92,6 +93,15 @@ def make_fk4096(H=4096, W=4096, seed=0):
         u[r:r + 48, c:c + 48] = 1.0
     return dict(v=np.ones((H, W), np.float32), w=np.ones((H, W), np.float32), u=u,
                 D=np.full((H, W), 1e-3, np.float32), stimuli=[], params="5")
+
+
+def make_fk128():
+    """BASELINE config 1 (the README benchmark): 128 x 128, PARAMSET_3, D = 1e-3, NORTH stripe, one stimulus."""
+    import oracle as O
+    shape = (128, 128)
+    return dict(v=np.ones(shape, np.float32), w=np.ones(shape, np.float32), u=np.zeros(shape, np.float32),
+                D=np.full(shape, 1e-3, np.float32), stimuli=[O.linear(shape, 0, 0.2, 20.0, O.Protocol(0, 2, 1e9))],
+                params="3")
 
 
 def make_fk512(seed=0):
@@ -213,6 +223,9 @@ def main():
     elif workload == "fk512":
         work = make_fk512()
         config = {"workload": "fk512: 512x512 scar-map D, S1-S2 cross-field stimuli, PARAMSET_3", "grid": [512, 512]}
+    elif workload == "fk128":
+        work = make_fk128()
+        config = {"workload": "fk128: 128x128 plane wave, PARAMSET_3, D=1e-3 (README benchmark shape)", "grid": [128, 128]}
     elif workload == "ens256":
         work = make_ens256(128, seed=rank)
         config = {"workload": "ens256: 128 independent 256x256 tissues per GPU, scar D, 3 random stimuli each",
@@ -257,7 +270,7 @@ def main():
     state0 = solve.State(*[torch.as_tensor(work[k]).to(dev) for k in "vwu"])
     cells = state0.u.numel()
     flush = None
-    if workload in ("fk512", "ens256"):
+    if workload in ("fk512", "ens256", "fk128"):
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     if workload == "slab" and world > 1:

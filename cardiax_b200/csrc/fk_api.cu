@@ -122,8 +122,10 @@ __global__ void fk_divcheck_kernel(fk::Consts K, unsigned long long* bad) {
                               K.y_dx};
     unsigned long long local = 0;
     for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < (1u << 23); m += gridDim.x * blockDim.x)
-        for (int e = 0; e < 3; ++e) {
-            const float a = __uint_as_float(((unsigned)(127 - 40 + 40 * e) << 23) | m);
+        for (int e = 0; e < 7; ++e) {
+            // exponents 2^-40, 2^0, 2^40 (direct path), 2^-104, 2^-120 (scaled path), 2^-126 and denormals (fp64 path)
+            const unsigned ex[7] = {87u, 127u, 167u, 23u, 7u, 1u, 0u};
+            const float a = __uint_as_float((ex[e] << 23) | m);
             for (int i = 0; i < 10; ++i) {
                 const float x = (i & 1) ? -a : a;
                 if (fk::Num<true>::divc(x, divisors[i], recips[i], K.div_lo, K.div_hi) != __fdiv_rn(x, divisors[i])) ++local;

@@ -110,12 +110,24 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     StreamPlan plan;
     bool use_stream = false;
     if (!rhs_mode && opt.kernel != 1) {
-        int R0, R1, S0, S1;
-        rows(Tmax, R0, R1, S0, S1);
-        use_stream = S1 > S0 &&
-                     plan_stream(S0, S1, W, batch, Tmax, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
-                                 opt.uniform_diffusivity, be.max_stream_threads(),
-                                 [&](int NT, long long smem) { return be.occupancy(Tmax, opt.exact, NT, smem); }, plan);
+        auto try_plan = [&](int T, StreamPlan& P) {
+            int R0, R1, S0, S1;
+            rows(T, R0, R1, S0, S1);
+            return S1 > S0 && plan_stream(S0, S1, W, batch, T, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
+                                          opt.uniform_diffusivity, be.max_stream_threads(),
+                                          [&](int NT, long long smem) { return be.occupancy(T, opt.exact, NT, smem); }, P);
+        };
+        use_stream = try_plan(Tmax, plan);
+        if (opt.steps_per_launch == 0 && !slab && opt.row1 <= 0 && nsteps > 1) {
+            // no depth requested: a tissue too small to fill the machine is latency-bound, and there one step per
+            // launch (8 rows of pipeline fill instead of 16) beats two.  ~12 units of launch overhead per launch.
+            StreamPlan p1;
+            if (try_plan(1, p1) && (!use_stream || p1.cost + 12.0 < (plan.cost + 12.0) / Tmax)) {
+                plan = p1;
+                Tmax = 1;
+                use_stream = true;
+            }
+        }
         if (!use_stream && opt.kernel == 2) { *why = "streaming kernel not applicable to this shape"; return -5; }
     }
 

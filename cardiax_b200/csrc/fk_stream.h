@@ -350,7 +350,8 @@ struct StreamPlan {
     int T;
     StreamGeom G;
     long long smem_bytes;
-    int occ;  // resident CTAs per SM the plan assumed
+    int occ;      // resident CTAs per SM the plan assumed
+    double cost;  // modelled time of one launch (arbitrary units; compare plans of the same problem only)
 };
 
 // Applicability + geometry.  cta_threads / rows_per_cta: 0 = choose.
@@ -390,15 +391,19 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
                 long long nch = waves * slots / units;
                 if (nch < 1) nch = 1;
                 RH = (int)((Hint + nch - 1) / nch);
-                if (RH < 16) RH = 16;
+                if (RH < 8) RH = 8;
             }
             if (RH > Hint) RH = Hint;
             const int nchunks = (Hint + RH - 1) / RH;
             const long long ncta = units * nchunks;
             const double rounds = (double)((ncta + slots - 1) / slots);
-            const double warps = (double)((need + 127) / 128) * o;  // active warps resident on an SM
-            const double eff = warps / (warps + 8.0);
-            const double cost = rounds * (RH + 8.0 * T) * T * warps / eff;
+            // CTAs actually resident on an SM (a small tissue does not fill the machine), their active warps, and
+            // the time of one row iteration: T stages, each at least a lone warp's dependent chain (~2 units) and
+            // growing with the warps that share the four schedulers
+            long long res = (ncta + num_sms - 1) / num_sms;
+            if (res > o) res = o;
+            const double warps = (double)((need + 127) / 128) * (double)res;
+            const double cost = rounds * (RH + 8.0 * T) * T * (warps + 8.0) / 4.0;
             if (best < 0 || cost < best) {
                 best = cost;
                 P.G.NT = NT; P.G.CW = 4 * NT; P.G.RS = 4 * NT + 8; P.G.RH = RH;
@@ -407,6 +412,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
                 P.T = T;
                 P.smem_bytes = smem;
                 P.occ = o;
+                P.cost = cost;
             }
             if (rows_per_cta > 0) break;
         }
