@@ -214,6 +214,7 @@ Side g_side[64];
 struct CudaBackend {
     cudaStream_t st;
     bool pending_join = false;
+    bool small_problem = false;   // launch-bound tissue: keep everything on one stream
     Side* side = nullptr;
     int num_sms() { return ::num_sms(); }
     int max_stream_threads() { return 256; }
@@ -245,7 +246,7 @@ struct CudaBackend {
         const size_t smem = (size_t)floats * sizeof(float);
         if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
         cudaStream_t st = this->st;
-        if (on_side) {
+        if (on_side && !small_problem) {
             const int rc = get_side();
             if (rc) return rc;
             FK_CUDA(cudaEventRecord(side->fork, this->st));
@@ -255,13 +256,14 @@ struct CudaBackend {
         }
         ProfScope ps(1, st);
         ++g_launches;
-        if (exact) {
-            FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            fk_tile_kernel<true><<<dim3(total, batch), 256, smem, st>>>(A);
-        } else {
-            FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            fk_tile_kernel<false><<<dim3(total, batch), 256, smem, st>>>(A);
+        static size_t attr_set[2] = {0, 0};   // largest dynamic shared memory already allowed, per instantiation
+        if (smem > attr_set[exact ? 1 : 0]) {
+            if (exact) FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[exact ? 1 : 0] = smem;
         }
+        if (exact) fk_tile_kernel<true><<<dim3(total, batch), 256, smem, st>>>(A);
+        else fk_tile_kernel<false><<<dim3(total, batch), 256, smem, st>>>(A);
         FK_CUDA(cudaGetLastError());
         return 0;
     }
@@ -424,6 +426,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.row0 = row0; o.row1 = row1;
     CudaBackend be;
     be.st = st;
+    be.small_problem = (long long)H * W * batch < (1LL << 21);
     const char* why = "";
     fk::Consts K = make_consts(*params, dt, dx);
     if (opt.safe_division) K.div_lo = INFINITY;   // every exact-mode division through __fdiv_rn

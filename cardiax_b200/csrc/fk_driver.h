@@ -118,7 +118,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
                                           [&](int NT, long long smem) { return be.occupancy(T, opt.exact, NT, smem); }, P);
         };
         use_stream = try_plan(Tmax, plan);
-        if (opt.steps_per_launch == 0 && !slab && opt.row1 <= 0 && nsteps > 1) {
+        if (opt.steps_per_launch == 0 && !slab && opt.row1 <= 0 && nsteps > 1 && (long long)H * W * batch < (1LL << 21)) {
             // no depth requested: a tissue too small to fill the machine is latency-bound, and there one step per
             // launch (8 rows of pipeline fill instead of 16) beats two.  ~12 units of launch overhead per launch.
             StreamPlan p1;

@@ -38,9 +38,13 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
 
 template <bool EXACT, int T>
 inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)P.smem_bytes);
-    if (e != cudaSuccess) return (int)e;
+    static long long attr_set = 0;   // largest dynamic shared memory already allowed for this instantiation
+    if (P.smem_bytes > attr_set && attr_set < 227 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)P.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = P.smem_bytes;
+    }
     dim3 grid(P.G.nstrips * P.G.nchunks, batch);
     fk_stream_kernel<EXACT, T><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
     return (int)cudaGetLastError();
@@ -48,7 +52,12 @@ inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cu
 
 template <bool EXACT, int T>
 inline int stream_occupancy_t(int NT, long long smem) {
-    if (cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+    // memoised: the planner asks for the same few configurations at every call
+    static int memo_nt[64], memo_n[64], memo_cnt = 0;
+    static long long memo_smem[64];
+    for (int i = 0; i < memo_cnt; ++i)
+        if (memo_nt[i] == NT && memo_smem[i] == smem) return memo_n[i];
+    if (cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -58,6 +67,7 @@ inline int stream_occupancy_t(int NT, long long smem) {
         cudaGetLastError();
         return 0;
     }
+    if (memo_cnt < 64) { memo_nt[memo_cnt] = NT; memo_smem[memo_cnt] = smem; memo_n[memo_cnt] = n; ++memo_cnt; }
     return n;
 }
 
