@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libfk.so")
-_SOURCES = ["fk_api.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h"]
+_SOURCES = ["fk_api.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h", "fk_wide.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -65,6 +65,16 @@ __global__ void __launch_bounds__(256) fk_tile_kernel(const __grid_constant__ fk
     }
 }
 
+// low-latency single-step kernel for small tissues (fk_wide.h): one thread per 4 cells of a row, no barrier
+template <bool EXACT>
+__global__ void __launch_bounds__(128) fk_wide_kernel(const __grid_constant__ fk::TileArgs A) {
+    const int wq = A.W >> 2;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)A.H * wq) return;
+    const int row = (int)(t / wq), c = 4 * (int)(t - (long long)row * wq);
+    fk::wide_thread<EXACT>(A, blockIdx.y, row, c, fk::wide_mask(A, blockIdx.y));
+}
+
 // solve.gradient on (outer, n, inner)
 __global__ void fk_gradient_kernel(const float* __restrict__ a, float* __restrict__ out, long long outer, long long n,
                                    long long inner) {
@@ -246,7 +256,7 @@ struct CudaBackend {
         const size_t smem = (size_t)floats * sizeof(float);
         if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
         cudaStream_t st = this->st;
-        if (on_side && !small_problem) {
+        if (on_side) {
             const int rc = get_side();
             if (rc) return rc;
             FK_CUDA(cudaEventRecord(side->fork, this->st));
@@ -264,6 +274,19 @@ struct CudaBackend {
         }
         if (exact) fk_tile_kernel<true><<<dim3(total, batch), 256, smem, st>>>(A);
         else fk_tile_kernel<false><<<dim3(total, batch), 256, smem, st>>>(A);
+        FK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    int wide(const fk::TileArgs& A, int exact, int batch) {
+        const long long threads = (long long)A.H * (A.W >> 2);
+        const unsigned blocks = (unsigned)((threads + 127) / 128);
+        g_last_plan[0] = 1; g_last_plan[1] = 128; g_last_plan[2] = 0; g_last_plan[3] = A.W; g_last_plan[4] = 1;
+        g_last_plan[5] = (int)blocks; g_last_plan[6] = 0; g_last_plan[7] = 0;
+        ProfScope ps(0, st);
+        if (ps.active) g_prof.stream_cs += (double)A.H * A.W * batch;
+        ++g_launches;
+        if (exact) fk_wide_kernel<true><<<dim3(blocks, batch), 128, 0, st>>>(A);
+        else fk_wide_kernel<false><<<dim3(blocks, batch), 128, 0, st>>>(A);
         FK_CUDA(cudaGetLastError());
         return 0;
     }

@@ -4,13 +4,14 @@
 #pragma once
 #include "fk_stream.h"
 #include "fk_tile.h"
+#include "fk_wide.h"
 
 namespace fk {
 
 struct DriveOptions {
     int exact;
     int steps_per_launch;   // 0 = default
-    int kernel;             // 0 auto, 1 tiles only, 2 streaming required
+    int kernel;             // 0 auto, 1 tiles only, 2 streaming required, 3 low-latency wide kernel required
     int phys_top, phys_bottom;
     int cta_threads, rows_per_cta;
     int uniform_diffusivity;
@@ -75,6 +76,7 @@ inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
 
 // Backend: int tiles(TileArgs&, int exact, int batch, bool side);  (side: may run concurrently until join())
 //          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);  int join();
+//          int wide(const TileArgs&, int exact, int batch);
 //          int num_sms(); int max_stream_threads(); int occupancy(int T, int exact, int NT, long long smem_bytes);
 // Returns 0 or the backend's error code; *why gets a static message on argument errors.
 template <class Backend>
@@ -107,9 +109,14 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             return -1;
         }
     }
+    // tissues too small to fill the machine: one launch of the barrier-free wide kernel per step
+    const bool wide_ok = !rhs_mode && !slab && opt.row1 <= 0 && W % 4 == 0 && H >= 3 && W >= 4;
+    const bool use_wide = wide_ok && (opt.kernel == 3 || (opt.kernel == 0 && opt.steps_per_launch == 0 &&
+                                                          (long long)H * W * batch < (1LL << 20)));
+    if (opt.kernel == 3 && !use_wide) { *why = "wide kernel not applicable (needs W % 4 == 0, whole tissue)"; return -5; }
     StreamPlan plan;
     bool use_stream = false;
-    if (!rhs_mode && opt.kernel != 1) {
+    if (!rhs_mode && opt.kernel != 1 && !use_wide) {
         auto try_plan = [&](int T, StreamPlan& P) {
             int R0, R1, S0, S1;
             rows(T, R0, R1, S0, S1);
@@ -143,6 +150,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     A.stims = n_stim ? B.stims : nullptr;
     A.n_stim = n_stim;
 
+    if (use_wide) Tmax = 1;
     const long long nl = rhs_mode ? 1 : (nsteps + Tmax - 1) / Tmax;
     const float *sv = B.v_in, *sw = B.w_in, *su = B.u_in;
     long long remaining = rhs_mode ? 1 : nsteps;
@@ -157,7 +165,10 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         A.w_out = to_out ? B.w_out : B.pw;
         A.T = T; A.t0 = t;
         int rc;
-        if (use_stream && T == plan.T) {
+        if (use_wide) {
+            rc = be.wide(A, opt.exact, batch);
+            if (rc) return rc;
+        } else if (use_stream && T == plan.T) {
             // the frame tiles run beside the streaming kernel (side stream on the GPU): they read the same
             // input and write a disjoint part of the output
             TileArgs F = A;

@@ -43,7 +43,8 @@ typedef struct FkStimulus {
 typedef struct FkOptions {
     int exact;            /* 1: reference operation order, bit-identical to the CPU oracle; 0: fast numerics */
     int steps_per_launch; /* temporal blocking depth T (1..8); 0 = library default */
-    int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = streaming kernel + frame tiles */
+    int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = streaming kernel + frame tiles,
+                             3 = low-latency one-step kernel for small tissues */
     int phys_top;         /* is buffer row 0 the physical tissue edge? (0 only for slab decomposition) */
     int phys_bottom;      /* is buffer row H-1 the physical tissue edge? */
     int cta_threads;      /* streaming kernel: threads per CTA (0 = auto) */

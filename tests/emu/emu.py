@@ -18,7 +18,7 @@ class _Stim(ctypes.Structure):
 
 def build(force=False):
     deps = [os.path.join(_HERE, "fk_emu.cpp")] + [os.path.join(_CSRC, f) for f in
-                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h")]
+                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h", "fk_wide.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",

@@ -50,6 +50,19 @@ struct EmuBackend {
             }
         return 0;
     }
+    int launches_wide = 0;
+    int wide(const fk::TileArgs& A, int exact, int batch) {
+        ++launches_wide;
+        for (int sim = 0; sim < batch; ++sim) {
+            const unsigned mask = fk::wide_mask(A, sim);
+            for (int row = 0; row < A.H; ++row)
+                for (int c = 0; c < A.W; c += 4) {
+                    if (exact) fk::wide_thread<true>(A, sim, row, c, mask);
+                    else fk::wide_thread<false>(A, sim, row, c, mask);
+                }
+        }
+        return 0;
+    }
     int stream(const fk::StreamPlan& P, const fk::TileArgs& A, int exact, int batch) {
         ++launches_stream;
         return fk::emu_stream_launch(P, A, batch, exact, reverse);
@@ -98,7 +111,7 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     const char* why = "";
     const int rc = fk::drive_euler(be, B, d_batched, H, W, batch, fk::make_consts(params14, dt, dx), n_stim, t0, nsteps, o,
                                    rhs_mode, &why);
-    if (info) { info[0] = be.launches_tile; info[1] = be.launches_stream; }
+    if (info) { info[0] = be.launches_tile; info[1] = be.launches_stream + 1000 * be.launches_wide; }
     return rc;
 }
 

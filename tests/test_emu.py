@@ -36,6 +36,23 @@ def test_stream_plus_frame_exact(shape, T, nt, rh):
     assert info[1] > 0  # the streaming kernel really ran; the odd tail step goes through the tile kernel
 
 
+@pytest.mark.parametrize("shape", [(12, 16), (3, 4), (5, 8), (40, 64), (9, 132), (130, 20)])
+def test_wide_kernel_exact(shape):
+    info = _exact(shape, 1, nsteps=6, kernel=3)
+    assert info == (0, 6000)   # six launches of the wide kernel, nothing else
+
+
+def test_small_tissue_defaults_to_the_wide_kernel_and_fast_matches_other_kernels():
+    (st, D) = common.smooth_case((64, 96), seed=6)
+    _, _, stim = common.random_case((64, 96), seed=6, n_stim=2)
+    a, info = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False)
+    assert info == (0, 7000)
+    b, _ = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False, kernel=1, T=2)
+    c, _ = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False, kernel=2, T=2, cta_threads=32)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
 def test_stream_thread_order_independent():
     """Threads of a block run in reverse order inside every iteration: any same-iteration hazard on the rings shows."""
     _exact((72, 160), 2, kernel=2, cta_threads=32, rows_per_cta=16, reverse=1)

@@ -56,6 +56,7 @@ def assert_exact(got, ref, what=""):
     ((128, 128), 2, 0, {}), ((72, 160), 1, 2, dict(cta_threads=32, rows_per_cta=16)),
     ((72, 160), 2, 2, dict(cta_threads=32, rows_per_cta=16)), ((96, 288), 3, 2, dict(cta_threads=64, rows_per_cta=20)),
     ((200, 1200), 2, 2, {}), ((256, 256), 2, 0, {}), ((130, 516), 4, 2, dict(cta_threads=128)),
+    ((128, 128), 0, 3, {}), ((12, 16), 0, 3, {}), ((3, 4), 0, 3, {}), ((512, 512), 0, 0, {}), ((9, 132), 0, 3, {}),
 ])
 def test_exact_bitwise_vs_oracle(shape, T, kernel, extra):
     st, D, stim = common.random_case(shape, seed=3, n_stim=3)
@@ -149,7 +150,8 @@ def test_fast_is_tiling_independent():
     _, _, stim = common.random_case((136, 520), seed=4, n_stim=2)
     a = run_gpu(st, 0, 12, P3, D, stim, numerics="fast", kernel=1, steps_per_launch=1)
     for kw in (dict(kernel=1, steps_per_launch=3), dict(kernel=2, steps_per_launch=2, cta_threads=64, rows_per_cta=24),
-               dict(kernel=2, steps_per_launch=4, cta_threads=128), dict(kernel=2, steps_per_launch=1)):
+               dict(kernel=2, steps_per_launch=4, cta_threads=128), dict(kernel=2, steps_per_launch=1),
+               dict(kernel=3, steps_per_launch=0, cta_threads=0, rows_per_cta=0)):
         b = run_gpu(st, 0, 12, P3, D, stim, numerics="fast", **kw)
         assert_exact(b, a, str(kw))
 
