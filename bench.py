@@ -8,7 +8,8 @@ unit the reference's `forward` loop launches (cardiax/solve.py:198-217).
 
 Workloads (BASELINE.json configs):
   fk4096   4096 x 4096 homogeneous D = 1e-3, PARAMSET_5, random rectangular excitations  (N = 1 default)
-  slab     row-slab decomposition of a (4096*N) x 4096 tissue over N GPUs, 4T-row halo exchange (N > 1 default)
+  slab     row-slab decomposition of a (2048*N) x 16384 tissue over N GPUs (N = 8: BASELINE config 5, 16384^2),
+           NCCL halo exchange over NVLink overlapped with the interior (N > 1 default)
   ens256   ensemble of independent 256 x 256 tissues (128 per GPU), heterogeneous D, 3 stimuli each, no comms
   fk512    512 x 512 scar map + S1-S2 (config 2)
   fk128    128 x 128 plane wave (config 1, the README benchmark shape)
@@ -217,9 +218,10 @@ def main():
         config = {"workload": "fk4096: 4096x4096 homogeneous D=1e-3, PARAMSET_5, random rectangular excitations",
                   "grid": [4096, 4096]}
     elif workload == "slab":
-        work = make_fk4096(4096, 4096, seed=rank)
-        config = {"workload": "slab: (4096*N)x4096 tissue, row slabs of 4096 rows per GPU, 4T-row halo exchange",
-                  "grid": [4096 * world, 4096]}
+        work = make_fk4096(2048, 16384, seed=rank)
+        config = {"workload": "slab: (2048*N)x16384 tissue (16384^2 at N=8), row slabs of 2048 rows per GPU, "
+                              "halo rows exchanged over NCCL/NVLink and overlapped with the interior",
+                  "grid": [2048 * world, 16384]}
     elif workload == "fk512":
         work = make_fk512()
         config = {"workload": "fk512: 512x512 scar-map D, S1-S2 cross-field stimuli, PARAMSET_3", "grid": [512, 512]}
@@ -233,7 +235,7 @@ def main():
     else:
         raise SystemExit("unknown workload " + workload)
     config.update({"euler_steps_per_step": args.seg, "dt": 0.01, "dx": 0.01, "numerics": args.numerics,
-                   "l2": "state (3 x 64 MiB per 4096^2 field) larger than the 126 MB L2" if workload in ("fk4096", "slab")
+                   "l2": "state (3 arrays of >= 64 MiB per GPU) larger than the 126 MB L2" if workload in ("fk4096", "slab")
                    else "working set is L2 resident by nature of the config; an L2 flush buffer is written between steps"})
 
     if args.impl == "reference":
@@ -296,7 +298,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = L.fk_launch_count()
-    L.fk_profile_enable(1)
+    L.fk_profile_enable(0 if os.environ.get("FK_BENCH_NOPROF") else 1)
     L.fk_profile_collect(None, None, None, None, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
