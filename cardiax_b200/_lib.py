@@ -11,9 +11,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libfk.so")
-_SOURCES = ["fk_api.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h", "fk_wide.h"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+_SOURCES = ["fk_api.cu", "fk_stream_tu.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h",
+            "fk_wide.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+STREAM_DEPTHS = (1, 2, 3, 4)   # one translation unit per (temporal-blocking depth, numerics), compiled in parallel
 
 _lib = None
 
@@ -45,19 +46,43 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """nvcc-compile csrc/fk_api.cu into csrc/libfk.so (cross-compiles without a GPU)."""
+    """nvcc-compile csrc/*.cu into csrc/libfk.so (cross-compiles without a GPU): fk_api.cu and one object of
+    fk_stream_tu.cu per (temporal-blocking depth, numerics), in parallel, then one link."""
     if not force and not needs_build():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, os.path.join(CSRC, "fk_api.cu")]
     env = dict(os.environ)
     env.pop("CC", None)   # the image's CC/CXX point at a gcc without its support files
     env.pop("CXX", None)
-    out = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    depths = STREAM_DEPTHS
+    if os.environ.get("FK_DEPTHS"):   # development: e.g. FK_DEPTHS=2 links only the T = 2 kernels (others: "unsupported")
+        depths = tuple(int(x) for x in os.environ["FK_DEPTHS"].split(","))
+    mask = sum(1 << t for t in depths)
+    jobs = [(os.path.join(objdir, "fk_api.o"), ["-DFK_DEPTH_MASK=%d" % mask, "-c", os.path.join(CSRC, "fk_api.cu")])]
+    for t in reversed(depths):   # the deepest (slowest to compile) first
+        for e in (1, 0):
+            jobs.append((os.path.join(objdir, "fk_stream_T%d_E%d.o" % (t, e)),
+                         ["-DFK_TU_T=%d" % t, "-DFK_TU_EXACT=%d" % e, "-c", os.path.join(CSRC, "fk_stream_tu.cu")]))
+    ptxas = ["-Xptxas", "-v"] if verbose else []
+
+    def run(job):
+        obj, args = job
+        out = subprocess.run([nvcc] + NVCC_FLAGS + ptxas + args + ["-o", obj], capture_output=True, text=True, env=env)
+        if out.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
+        return out.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+        logs = list(pool.map(run, jobs))
+    out = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + [j[0] for j in jobs],
+                         capture_output=True, text=True, env=env)
     if out.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
+        raise RuntimeError("nvcc link failed:\n" + out.stdout + out.stderr)
     if verbose:
-        print(out.stderr)
+        print("\n".join(logs))
     return SO_PATH
 
 

@@ -227,8 +227,7 @@ struct CudaBackend {
     bool small_problem = false;   // launch-bound tissue: keep everything on one stream
     Side* side = nullptr;
     int num_sms() { return ::num_sms(); }
-    int max_stream_threads() { return 256; }
-    int occupancy(int T, int exact, int NT, long long smem) { return fk::stream_occupancy(T, exact, NT, smem); }
+    int occupancy(int T, int exact, int uni, int NT, long long smem) { return fk::stream_occupancy(T, exact, uni, NT, smem); }
     int get_side() {
         if (side) return 0;
         int dev = 0;

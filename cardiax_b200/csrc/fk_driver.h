@@ -77,7 +77,7 @@ inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
 // Backend: int tiles(TileArgs&, int exact, int batch, bool side);  (side: may run concurrently until join())
 //          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);  int join();
 //          int wide(const TileArgs&, int exact, int batch);
-//          int num_sms(); int max_stream_threads(); int occupancy(int T, int exact, int NT, long long smem_bytes);
+//          int num_sms(); int occupancy(int T, int exact, int uniform, int NT, long long smem_bytes);
 // Returns 0 or the backend's error code; *why gets a static message on argument errors.
 template <class Backend>
 int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, int batch, const Consts& K, int n_stim,
@@ -121,8 +121,8 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             int R0, R1, S0, S1;
             rows(T, R0, R1, S0, S1);
             return S1 > S0 && plan_stream(S0, S1, W, batch, T, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
-                                          opt.uniform_diffusivity, be.max_stream_threads(),
-                                          [&](int NT, long long smem) { return be.occupancy(T, opt.exact, NT, smem); }, P);
+                                          opt.uniform_diffusivity, stream_max_threads(T),
+                                          [&](int NT, long long smem) { return be.occupancy(T, opt.exact, opt.uniform_diffusivity, NT, smem); }, P);
         };
         use_stream = try_plan(Tmax, plan);
         if (opt.steps_per_launch == 0 && !slab && opt.row1 <= 0 && nsteps > 1 && (long long)H * W * batch < (1LL << 21)) {

@@ -6,64 +6,89 @@
 
 namespace fk {
 
-template <bool EXACT, int T>
-__global__ void __launch_bounds__(256, 1)
+template <bool EXACT, int T, bool UNI>
+__global__ void __launch_bounds__(T == 2 ? 192 : 256, T <= 2 ? 2 : 1)
 fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ StreamGeom G) {
     extern __shared__ __align__(16) float fk_stream_smem[];
-    StreamSmem<T> S;
-    stream_carve<T>(fk_stream_smem, G, S);
     const int strip = blockIdx.x % G.nstrips, chunk = blockIdx.x / G.nstrips;
     StreamCta C;
     stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, C);
-    StreamState<T> R;
-    {
-        float* f = reinterpret_cast<float*>(&R);
-#pragma unroll
-        for (int q = 0; q < (int)(sizeof(R) / sizeof(float)); ++q) f[q] = 0.0f;
-    }
     const int tid = threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, G, C, S, j, tid, C.cs + 4 * tid < C.c_end);
-    const int nfill = (8 * T < C.niter && stream_steady_ok<T>(C)) ? 8 * T : C.niter;
-    int i = 0;
+    float* tb = stream_chunk<T>(fk_stream_smem, tid);
+    StreamState<T> R;
+    stream_state_init<T>(A, C, tid, R);
+    stream_warm_load<T>(A, C, tb, tid);
+    const int nfill = stream_nfill<T>(C);
+    // the split barrier of the steady-state loop lives in the pad granule of the CTA's first (pad) chunk
+    float* bar = fk_stream_smem + StreamLay<T>::CHUNK - 4;
+    if (tid == 0) sb_init(bar, (int)blockDim.x);
+    async_wait<0>();
+    __syncthreads();
+    stream_warm_start<EXACT, T>(A, C, R, tb, tid);   // stands for iterations 0 .. 7
+    __syncthreads();
+    int i = FK_WARM;
     for (; i < nfill; ++i) {   // pipeline fill (and launches with an active stimulus): fully conditional body
-        stream_iter<EXACT, T, false>(A, G, C, S, R, i, tid);
+        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
         __syncthreads();
     }
-    for (; i < C.niter; ++i) {  // steady state: every stage consumes and emits one row
-        stream_iter<EXACT, T, true>(A, G, C, S, R, i, tid);
+    // steady state: every stage consumes and emits one row per iteration; unrolled U-fold so that every ring slot is a
+    // per-body base register plus a compile-time offset.  Iterations are separated by the split barrier: phase k of it
+    // completes when every thread has finished iteration k - 1 of this loop.
+    constexpr int U = stream_unroll(T);
+    if (i + U <= C.niter) {
+        sb_arrive(bar);   // phase 0: the fill loop's last block barrier stands for "iteration -1"
+        const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
+#define FK_STEADY_LOOP(EDGE)                                                                                           \
+    for (; i + U <= C.niter; i += U) {                                                                                 \
+        const StreamBody<T> Y = stream_body_at<T>(tb, i);                                                              \
+        stream_iter<EXACT, T, 0, UNI, EDGE, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
+        stream_iter<EXACT, T, 1, UNI, EDGE, U>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
+        if (U == 4) {                                                                                                  \
+            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U>(A, C, R, tb, i + 2, tid,                               \
+                                                                stream_ptrs_phase<T, U, U == 4 ? 2 : 0>(Y), bar);      \
+            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U>(A, C, R, tb, i + 3, tid,                               \
+                                                                stream_ptrs_phase<T, U, U == 4 ? 3 : 1>(Y), bar);      \
+        }                                                                                                              \
+    }
+        if (edge) { FK_STEADY_LOOP(true) } else { FK_STEADY_LOOP(false) }
+#undef FK_STEADY_LOOP
+        sb_wait(bar, 0);   // an even number of iterations later: everybody is through the last one
+    }
+    for (; i < C.niter; ++i) {  // tail (fewer than U rows left)
+        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
         __syncthreads();
     }
 }
 
-template <bool EXACT, int T>
+template <bool EXACT, int T, bool UNI>
 inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
     static long long attr_set = 0;   // largest dynamic shared memory already allowed for this instantiation
     if (P.smem_bytes > attr_set && attr_set < 227 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)P.smem_bytes);
         if (e != cudaSuccess) return (int)e;
         attr_set = P.smem_bytes;
     }
     dim3 grid(P.G.nstrips * P.G.nchunks, batch);
-    fk_stream_kernel<EXACT, T><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
+    fk_stream_kernel<EXACT, T, UNI><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
     return (int)cudaGetLastError();
 }
 
-template <bool EXACT, int T>
+template <bool EXACT, int T, bool UNI>
 inline int stream_occupancy_t(int NT, long long smem) {
     // memoised: the planner asks for the same few configurations at every call
     static int memo_nt[64], memo_n[64], memo_cnt = 0;
     static long long memo_smem[64];
     for (int i = 0; i < memo_cnt; ++i)
         if (memo_nt[i] == NT && memo_smem[i] == smem) return memo_n[i];
-    if (cudaFuncSetAttribute(fk_stream_kernel<EXACT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+    if (cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_stream_kernel<EXACT, T>, NT, (size_t)smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_stream_kernel<EXACT, T, UNI>, NT, (size_t)smem) !=
+        cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -71,11 +96,27 @@ inline int stream_occupancy_t(int NT, long long smem) {
     return n;
 }
 
-// resident CTAs per SM of the streaming kernel for (T, numerics, threads, shared memory)
-inline int stream_occupancy(int T, int exact, int NT, long long smem) {
+// One translation unit per (T, numerics) -- fk_stream_tu.cu compiled with -DFK_TU_T=<T> -DFK_TU_EXACT=<0|1> --
+// instantiates the kernels of that depth and defines these two entry points, so that they compile in parallel.
+#define FK_STREAM_TU_DECL(TT)                                                                                      \
+    int launch_stream_T##TT##_E0(const StreamPlan& P, const TileArgs& A, int batch, cudaStream_t st);              \
+    int launch_stream_T##TT##_E1(const StreamPlan& P, const TileArgs& A, int batch, cudaStream_t st);              \
+    int stream_occupancy_T##TT##_E0(int uni, int NT, long long smem);                                              \
+    int stream_occupancy_T##TT##_E1(int uni, int NT, long long smem);
+FK_STREAM_TU_DECL(1) FK_STREAM_TU_DECL(2) FK_STREAM_TU_DECL(3) FK_STREAM_TU_DECL(4)
+#undef FK_STREAM_TU_DECL
+#ifndef FK_DEPTH_MASK        // development builds may link a subset of the depths (bit T set = depth T present)
+#define FK_DEPTH_MASK 0x1e
+#endif
+
+// resident CTAs per SM of the streaming kernel for (T, numerics, diffusivity kind, threads, shared memory)
+inline int stream_occupancy(int T, int exact, int uni, int NT, long long smem) {
     switch (T) {
-#define FK_CASE(TT) \
-    case TT: return exact ? stream_occupancy_t<true, TT>(NT, smem) : stream_occupancy_t<false, TT>(NT, smem);
+#define FK_CASE(TT)                                                                                     \
+    case TT:                                                                                            \
+        if constexpr ((FK_DEPTH_MASK >> TT) & 1)                                                        \
+            return exact ? stream_occupancy_T##TT##_E1(uni, NT, smem) : stream_occupancy_T##TT##_E0(uni, NT, smem); \
+        break;
         FK_CASE(1) FK_CASE(2) FK_CASE(3) FK_CASE(4)
 #undef FK_CASE
     }
@@ -85,8 +126,11 @@ inline int stream_occupancy(int T, int exact, int NT, long long smem) {
 // returns 0, a cudaError_t (> 0), or < 0 when T is unsupported
 inline int launch_stream(const StreamPlan& P, const TileArgs& A, int exact, int batch, cudaStream_t st) {
     switch (P.T) {
-#define FK_CASE(TT) \
-    case TT: return exact ? launch_stream_t<true, TT>(P, A, batch, st) : launch_stream_t<false, TT>(P, A, batch, st);
+#define FK_CASE(TT)                                                                                     \
+    case TT:                                                                                            \
+        if constexpr ((FK_DEPTH_MASK >> TT) & 1)                                                        \
+            return exact ? launch_stream_T##TT##_E1(P, A, batch, st) : launch_stream_T##TT##_E0(P, A, batch, st); \
+        break;
         FK_CASE(1) FK_CASE(2) FK_CASE(3) FK_CASE(4)
 #undef FK_CASE
     }

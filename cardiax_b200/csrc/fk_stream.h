@@ -29,6 +29,16 @@ struct alignas(8) F2 { float x, y; };
 struct alignas(16) F4 { float x, y, z, w; };
 FK_HD F2 ld2(const float* p) { return *reinterpret_cast<const F2*>(p); }
 FK_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+// read-only global data (diffusivity maps, stimulus fields): non-coherent path on the device
+FK_HD F4 ldg4(const float* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    F4 r; r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
+    return r;
+#else
+    return *reinterpret_cast<const F4*>(p);
+#endif
+}
 FK_HD void st4(float* p, const float* v) {
     F4 t; t.x = v[0]; t.y = v[1]; t.z = v[2]; t.w = v[3];
     *reinterpret_cast<F4*>(p) = t;
@@ -45,6 +55,14 @@ FK_HD void async_copy16(float* sdst, const float* gsrc) {
     *reinterpret_cast<F4*>(sdst) = *reinterpret_cast<const F4*>(gsrc);
 #endif
 }
+// keeps a loop-carried offset in its register (the compiler would otherwise rebuild it from the loop counter with a
+// 64-bit multiply at every use)
+FK_HD long long opaque(long long x) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(x));
+#endif
+    return x;
+}
 FK_HD void async_commit() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -57,14 +75,71 @@ FK_HD void async_wait() {
 #endif
 }
 
-enum { FK_PF = 2 };      // level-0 rows are fetched this many iterations ahead
-enum { FK_U0DEP = 8 };   // stage-0 u ring: 5 window rows + FK_PF in flight, rounded to a power of two
-enum { FK_VWDEP = 4 };   // level-0 v, w staging ring (>= FK_PF + 1)
+// Split block barrier on an mbarrier in shared memory (steady-state loop): a thread ARRIVES when its shared-memory
+// writes of an iteration are done and WAITS, in the next iteration, only just before it reads what the others wrote --
+// its own columns are loaded and the halo-free arithmetic issued in between.  (The CPU emulation runs the threads of an
+// iteration one after the other, so these are no-ops there.)
+FK_HD void sb_init(float* bar, int count) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+#endif
+}
+FK_HD void sb_arrive(float* bar) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+FK_HD void sb_wait(float* bar, int parity) {
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "FK_SB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FK_SB_DONE_%=;\n\t"
+        "bra FK_SB_WAIT_%=;\n"
+        "FK_SB_DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+#endif
+}
+
+enum { FK_PF = 3 };      // level-0 rows are fetched this many iterations ahead
+
+// Shared memory is THREAD-major: every thread owns one chunk of StreamLay<T>::CHUNK floats that holds its 4 columns
+// (one 16-byte granule) of every ring row, so that each access is `chunk base + compile-time offset` -- the
+// neighbours' halo values sit at +-CHUNK.  CHUNK is an odd number of granules, which keeps the 16-byte accesses of
+// consecutive threads on distinct banks.  One pad chunk on each side of the CTA absorbs the halo reads of its first and
+// last thread (garbage that only reaches columns which are never stored).
+//
+// Ring slots are functions of the CTA-local iteration index i alone, so that the steady-state loop, unrolled by 4
+// with the phase i & 3 as a template parameter, addresses every slot with a compile-time offset:
+//   U(0)     8 slots: level-0 row rin0 + i (the newest input of stage 0 at iteration i) sits in slot i & 7; it is
+//            fetched at iteration i - FK_PF.  The two halves of this ring are passed as tA (holding slot i & 7) and tB.
+//   U(s>=1)  4 slots: the level-s row stage s receives at iteration i goes to slot i & 3 -- the slot of the row it read
+//            as its window's oldest row (rho) a moment before; only row rho + 1 is ever read by the neighbours.
+//   V/W(0)   4 slots: level-0 v, w of the row stage 0 emits at iteration i: slot i & 3, fetched at iteration i - FK_PF.
+//   V/W(s)   4 slots: level-s v, w emitted by stage s-1 at iteration i: slot i & 3, consumed by stage s at iteration
+//            i + 4 from the same slot BEFORE stage s-1 overwrites it (the loads of every stage are hoisted).
+//   GY(s)    2 slots: u_y of row rho + 1, written at iteration i into slot i & 1 and read at iteration i + 1.
+template <int T>
+struct StreamLay {
+    enum {
+        U0 = 0,
+        U1 = 32,                     // U(s) = U1 + 16 (s - 1) for s >= 1
+        GY = U1 + 16 * (T - 1),      // GY(s) = GY + 8 s
+        V = GY + 8 * T,              // V(s) = V + 16 s
+        W = V + 16 * T,              // W(s) = W + 16 s
+        CHUNK = W + 16 * T + 4       // + one pad granule: (5 + 14 T) granules, odd
+    };
+    static FK_HD int U(int s) { return s == 0 ? (int)U0 : (int)U1 + 16 * (s - 1); }
+};
+
+// Largest CTA of the streaming kernel and the resident CTAs per SM its register budget is compiled for: 2 x 192
+// threads at T = 2 (168 registers; shared memory allows no more than 13 warps anyway), 2 x 256 at T = 1.
+FK_HD int stream_max_threads(int T) { return T == 2 ? 192 : 256; }
+FK_HD int stream_min_ctas(int T) { return T <= 2 ? 2 : 1; }
 
 struct StreamGeom {  // per launch
     int NT;          // threads per CTA
     int CW;          // 4 * NT, columns a CTA reads
-    int RS;          // ring row stride in floats (CW + 8: 4 pad floats each side)
     int RH;          // output rows per CTA
     int nstrips, nchunks;
     int cstride;     // output columns per strip (<= CW - 8T)
@@ -72,37 +147,16 @@ struct StreamGeom {  // per launch
     int row0, row1;  // output rows of this launch (every one needs 4T rows of input above and below)
 };
 
-template <int T>
-struct StreamSmem {
-    float* uring[T];  // stage 0: [FK_U0DEP][RS] level-0 rows (cp.async target); stage s >= 1: [5][RS] level-s rows
-    float* gyx[T];    // [2][RS] u_y rows of stage s, double buffered
-    float* vring[T];  // stage 0: [FK_VWDEP][CW] level-0 v (cp.async target); s >= 1: [5][CW] level-s v waiting 4 rows
-    float* wring[T];
-};
-
-FK_HD long long stream_smem_floats(int T, int NT) {
-    const long long CW = 4LL * NT, RS = CW + 8;
-    return (long long)(FK_U0DEP + 5 * (T - 1)) * RS + (long long)T * 2 * RS + 2LL * FK_VWDEP * CW +
-           (long long)(T - 1) * 2 * 5 * CW;
-}
-
-template <int T>
-FK_HD void stream_carve(float* smem, const StreamGeom& G, StreamSmem<T>& S) {
-    float* p = smem;
-    for (int s = 0; s < T; ++s) { S.uring[s] = p; p += (s == 0 ? (int)FK_U0DEP : 5) * G.RS; }
-    for (int s = 0; s < T; ++s) { S.gyx[s] = p; p += 2 * G.RS; }
-    for (int s = 0; s < T; ++s) {
-        const int dep = s == 0 ? (int)FK_VWDEP : 5;
-        S.vring[s] = p; p += dep * G.CW;
-        S.wring[s] = p; p += dep * G.CW;
-    }
-}
+FK_HD long long stream_smem_floats(int T, int NT) { return (long long)(NT + 2) * (20 + 56 * T); }
 
 template <int T>
 struct StreamState {     // registers of one thread
-    float GX[T][4][4];   // u_x rows rho-2 .. rho+1 of each stage
+    float GX[T][4][4];   // u_x rows rho-2 .. rho+1 of each stage (a rotating window inside the unrolled steady loop)
     float gy[T][4];      // u_y of row rho (made one iteration ahead)
     float gypad[T];      // edge threads only: u_y of the PAD column next to the tissue edge (padded index 0 / W+1)
+    float prev[T][4];    // the row each stage received one iteration ago (row rho + 3 of its window)
+    long long g0;        // offset of (tissue `sim`, row rin0 + i, this thread's first column) in the state arrays
+    long long gd;        // the same in the diffusivity maps (one shared map, or one per tissue)
 };
 
 struct StreamCta {       // uniform per CTA
@@ -157,24 +211,46 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     }
 }
 
-// start the asynchronous fetch of the level-0 rows iteration `i` will consume; always commits a group
+// this thread's chunk of the CTA's shared memory, and its registers at the start of a CTA
 template <int T>
-FK_HD void stream_prefetch(const TileArgs& A, const StreamGeom& G, const StreamCta& C, const StreamSmem<T>& S, int i,
-                           int tid, bool act) {
+FK_HD float* stream_chunk(float* smem, int tid) { return smem + (long long)(tid + 1) * StreamLay<T>::CHUNK; }
+
+template <int T>
+FK_HD void stream_state_init(const TileArgs& A, const StreamCta& C, int tid, StreamState<T>& R) {
+    for (int s = 0; s < T; ++s) {
+        for (int k = 0; k < 4; ++k) {
+            R.GX[s][0][k] = R.GX[s][1][k] = R.GX[s][2][k] = R.GX[s][3][k] = 0.0f;
+            R.gy[s][k] = R.prev[s][k] = 0.0f;
+        }
+        R.gypad[s] = 0.0f;
+    }
+    R.g0 = opaque(C.boff + (long long)C.rin0 * A.W + C.cs + 4 * tid);
+    R.gd = opaque(C.boffD + (long long)C.rin0 * A.W + C.cs + 4 * tid);
+}
+
+// start the asynchronous fetch of the level-0 rows iteration `i` will consume (gi: offset of row rin0 + i of this
+// tissue at this thread's columns) into the given granules; always commits a group
+template <int T>
+FK_HD void stream_prefetch_to(const TileArgs& A, const StreamCta& C, float* udst, float* vdst, float* wdst, int i,
+                              long long gi, bool act) {
     const int n = C.rin0 + i;  // u row pushed at iteration i
-    const int c = C.cs + 4 * tid;
-    if (act && n < C.rin_end)
-        async_copy16(S.uring[0] + (n & (FK_U0DEP - 1)) * G.RS + 4 + 4 * tid, A.u_in + C.boff + (long long)n * A.W + c);
+    if (act && n < C.rin_end) async_copy16(udst, A.u_in + gi);
     const int rho = n - 4;     // v, w row stage 0 emits at iteration i
     if (act && rho >= C.r0 - 4 * (T - 1) && rho < C.r1 + 4 * (T - 1)) {
-        const long long g = C.boff + (long long)rho * A.W + c;
-        async_copy16(S.vring[0] + (rho & (FK_VWDEP - 1)) * G.CW + 4 * tid, A.v_in + g);
-        async_copy16(S.wring[0] + (rho & (FK_VWDEP - 1)) * G.CW + 4 * tid, A.w_in + g);
+        const long long g = gi - 4LL * A.W;
+        async_copy16(vdst, A.v_in + g);
+        async_copy16(wdst, A.w_in + g);
     }
     async_commit();
 }
 
-FK_HD int mod5(int x) { return x >= 5 ? x - 5 : x; }  // for 0 <= x < 10
+// the same with the slots computed from i (pipeline prologue); tb: the thread's chunk
+template <int T>
+FK_HD void stream_prefetch(const TileArgs& A, const StreamCta& C, float* tb, int i, int tid, bool act) {
+    typedef StreamLay<T> L;
+    stream_prefetch_to<T>(A, C, tb + L::U0 + 4 * (i & 7), tb + L::V + 4 * (i & 3), tb + L::W + 4 * (i & 3), i,
+                          C.boff + (long long)(C.rin0 + i) * A.W + C.cs + 4 * tid, act);
+}
 
 // one-sided first derivative / dx (solve.py:232-235, 246-249) on four consecutive values
 template <bool EXACT>
@@ -185,6 +261,10 @@ FK_HD float edge_deriv(const Consts& K, int kind, float a0, float a1, float a2, 
     return deriv<EXACT>(K, kind, k0, k1, k2, k3, a0, a1, a2, a3);
 }
 
+// steady-state unroll factor: 4 (a phase knows i & 3, only the halves of the 8-slot ring alternate) while the loop body
+// fits the instruction cache, 2 from T = 2 on (32 KB of code per loop otherwise: every instruction line would miss)
+FK_HD constexpr int stream_unroll(int T) { return T >= 2 ? 2 : 4; }
+
 // may iterations i >= 8T use the condition-free body?  (no stimulus active in any level of this launch)
 template <int T>
 FK_HD bool stream_steady_ok(const StreamCta& C) {
@@ -193,8 +273,80 @@ FK_HD bool stream_steady_ok(const StreamCta& C) {
     return m == 0;
 }
 
+// iterations [stream_nfill, stream_nfill + U * stream_nbody) run the unrolled steady-state body, phase (i - nfill) % U
+template <int T>
+FK_HD int stream_nfill(const StreamCta& C) {
+    return (8 * T + 4 <= C.niter && stream_steady_ok<T>(C)) ? 8 * T : C.niter;
+}
+template <int T>
+FK_HD int stream_nbody(const StreamCta& C) { return (C.niter - stream_nfill<T>(C)) / stream_unroll(T); }
+
+// u_y (solve.py:50) of one row at the thread's 4 columns: u1 = the row's own values, r1p = its granule in the thread's
+// chunk (the neighbours' values sit one chunk to the left / right); gypad: u_y of the pad column at a tissue edge
+template <bool EXACT, int T>
+FK_HD void stream_make_gy(const Consts& K, const float* r1p, const float* u1, bool edgeL, bool edgeR, float* gy,
+                          float& gypad) {
+    constexpr int CH = StreamLay<T>::CHUNK;
+    const F2 Lh = ld2(r1p - CH + 2), Rh = ld2(r1p + CH);
+    // edge-pad (solve.py:31): the column outside the tissue repeats the edge column
+    const float e[8] = {Lh.x, edgeL ? u1[0] : Lh.y, u1[0], u1[1], u1[2], u1[3], edgeR ? u1[3] : Rh.x, Rh.y};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gy[k] = dcen<EXACT>(K, e[k], e[k + 1], e[k + 3], e[k + 4]);
+    if (edgeL) {  // padded columns 0 (the pad) and 1 (tissue column 0) use the forward formula
+        gypad = edge_deriv<EXACT>(K, FWD, e[1], e[2], e[3], e[4]);
+        gy[0] = edge_deriv<EXACT>(K, FWD, e[2], e[3], e[4], e[5]);
+    }
+    if (edgeR) {  // padded columns W (tissue column W-1) and W+1 (the pad) use the backward formula
+        gy[3] = edge_deriv<EXACT>(K, BWD, e[2], e[3], e[4], e[5]);
+        gypad = edge_deriv<EXACT>(K, BWD, e[3], e[4], e[5], e[6]);
+    }
+}
+
+// ---- warm start: iterations 0..7 of a CTA only stream level-0 rows in (stage 0 first emits at iteration 8), so the
+// kernel fetches those 8 rows at once (stream_warm_load), and after one block barrier builds stage 0's registers from
+// them directly (stream_warm_start): the u_x window, the previous row, u_y of the first row it will emit (published in
+// slot 1 of GY(0), as iteration 7 would have) -- and starts the fetches of iterations 8 .. 8 + FK_PF - 1.  A second
+// block barrier later the general body continues at iteration 8.
+enum { FK_WARM = 8 };
+
+template <int T>
+FK_HD void stream_warm_load(const TileArgs& A, const StreamCta& C, float* tb, int tid) {
+    const int c = C.cs + 4 * tid;
+    if (c < C.c_end) {
+        const long long g = C.boff + (long long)C.rin0 * A.W + c;
+#pragma unroll
+        for (int m = 0; m < FK_WARM; ++m) async_copy16(tb + StreamLay<T>::U0 + 4 * m, A.u_in + g + (long long)m * A.W);
+    }
+    async_commit();
+}
+
+template <bool EXACT, int T>
+FK_HD void stream_warm_start(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int tid) {
+    typedef StreamLay<T> L;
+    const int c = C.cs + 4 * tid;
+    const bool act = c < C.c_end;
+    if (act) {
+        float u[FK_WARM][4];
+#pragma unroll
+        for (int m = 0; m < FK_WARM; ++m) unpack4(ld4(tb + L::U0 + 4 * m), u[m]);
+        // u_x of rows rin0 + 2 .. rin0 + 5: the window (rho-2 .. rho+1) of iteration 8, rho = rin0 + 4
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) R.GX[0][m][k] = dcen<EXACT>(A.K, u[m][k], u[m + 1][k], u[m + 3][k], u[m + 4][k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) R.prev[0][k] = u[7][k];
+        stream_make_gy<EXACT, T>(A.K, tb + L::U0 + 4 * 4, u[4], tid == C.edgeL, tid == C.edgeR, R.gy[0], R.gypad[0]);
+        st4(tb + L::GY + 4 * 1, R.gy[0]);
+    }
+    // rows 0 .. FK_PF-1 of the ring are free again: fetch what iterations 8 .. 8 + FK_PF - 1 consume
+    for (int m = 0; m < FK_PF; ++m) stream_prefetch<T>(A, C, tb, FK_WARM + m, tid, act);
+    R.g0 = opaque(R.g0 + (long long)FK_WARM * A.W);
+    R.gd = opaque(R.gd + (long long)FK_WARM * A.W);
+}
+
 // second derivatives, reaction, stimulus and Euler update of one row of one stage (4 cells)
-template <bool EXACT, bool HAS_STIM>
+template <bool EXACT, bool HAS_STIM, bool EDGE>
 FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const float* w, const float* gxm2,
                        const float* gxm1, const float* gx0, const float* gxp1, const float* gxp2, const float* g,
                        const float* gy0, const float* Dv, const float* DXv, const float* DYv, const float* stim,
@@ -204,8 +356,8 @@ FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const f
         const float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
         float u_yy = dcen<EXACT>(K, g[k], g[k + 1], g[k + 3], g[k + 4]);          // solve.py:52
         // the tissue's first / last column: forward / backward formula on u_y of padded columns 1..4 / W-3..W
-        if (k == 0 && edgeL) u_yy = edge_deriv<EXACT>(K, FWD, g[2], g[3], g[4], g[5]);
-        if (k == 3 && edgeR) u_yy = edge_deriv<EXACT>(K, BWD, g[2], g[3], g[4], g[5]);
+        if (EDGE && k == 0 && edgeL) u_yy = edge_deriv<EXACT>(K, FWD, g[2], g[3], g[4], g[5]);
+        if (EDGE && k == 3 && edgeR) u_yy = edge_deriv<EXACT>(K, BWD, g[2], g[3], g[4], g[5]);
         const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], gx0[k], gy0[k], u_xx, u_yy);
         float d_v, d_w, d_u;
         cell_rhs<EXACT, HAS_STIM>(K, u0[k], v[k], w[k], del_u, HAS_STIM ? stim[k] : 0.0f, d_v, d_w, d_u);
@@ -215,134 +367,256 @@ FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const f
     }
 }
 
-// one row iteration of one thread.  `tid` in [0, NT), its 4 columns start at C.cs + 4 tid.
-// STEADY: the caller guarantees that every stage has input and emits in this iteration (i >= 8T) and that no
-// stimulus is active in this launch, so all the per-stage conditions fold away.
-template <bool EXACT, int T, bool STEADY>
-FK_HD void stream_iter(const TileArgs& A, const StreamGeom& G, const StreamCta& C, const StreamSmem<T>& S,
-                       StreamState<T>& R, int i, int tid) {
+// Where one iteration finds its ring slots.  Ring offsets inside the chunk are added by the user (bj + L::V + 16 s is
+// slot j of V(s), and so on), so that they fold into the instructions' immediate fields.
+struct StreamPtrs {
+    float* bj;     // chunk base shifted to slot j = i & 3 of the 4-slot rings
+    float* bj1;    // ... to slot (j + 1) & 3
+    float* bpf;    // ... to slot (j + FK_PF) & 3
+    float *u0new, *u0r1, *u0r0, *u0pf;   // stage-0 ring granules of iterations i, i-3, i-4, i+FK_PF
+};
+
+// general body: everything computed from i
+template <int T>
+FK_HD StreamPtrs stream_ptrs_any(float* tb, int i) {
+    typedef StreamLay<T> L;
+    StreamPtrs P;
+    P.bj = tb + 4 * (i & 3);
+    P.bj1 = tb + 4 * ((i + 1) & 3);
+    P.bpf = tb + 4 * ((i + FK_PF) & 3);
+    P.u0new = tb + L::U0 + 4 * (i & 7);
+    P.u0r1 = tb + L::U0 + 4 * ((i + 5) & 7);
+    P.u0r0 = tb + L::U0 + 4 * ((i + 4) & 7);
+    P.u0pf = tb + L::U0 + 4 * ((i + FK_PF) & 7);
+    return P;
+}
+
+// the per-body bases of the unrolled loop (body = U consecutive iterations starting at a multiple of U)
+template <int T>
+struct StreamBody {
+    float* tb;
+    float *tA, *tB;         // U = 4: halves of the stage-0 ring, slot i & 7 in tA
+    float *tH, *tO;         // U = 2: chunk base shifted to the pair of 4-ring slots holding slot i & 3 / the other pair
+    float *Q0, *Q1, *Q2, *Q3;   // U = 2: stage-0 ring shifted to slot pairs q, q+1, q+2, q+3 (q = (i >> 1) & 3)
+};
+
+template <int T>
+FK_HD StreamBody<T> stream_body_at(float* tb, int i) {   // i: first iteration of the body
+    typedef StreamLay<T> L;
+    StreamBody<T> Y;
+    Y.tb = tb;
+    Y.tA = tb + L::U0 + ((i & 4) ? 16 : 0);
+    Y.tB = tb + L::U0 + ((i & 4) ? 0 : 16);
+    const int qo = (i & 6) * 4;   // floats: 8 per slot pair
+    Y.tH = tb + (qo & 8);
+    Y.tO = tb + (8 - (qo & 8));
+    Y.Q0 = tb + L::U0 + qo;
+    Y.Q1 = tb + L::U0 + ((qo + 8) & 24);
+    Y.Q2 = tb + L::U0 + ((qo + 16) & 24);
+    Y.Q3 = tb + L::U0 + ((qo + 24) & 24);
+    return Y;
+}
+
+// slots of phase PH of a body, every offset a compile-time constant
+template <int T, int U, int PH>
+FK_HD StreamPtrs stream_ptrs_phase(const StreamBody<T>& Y) {
+    StreamPtrs P;
+    if (U == 4) {
+        P.bj = Y.tb + 4 * PH;
+        P.bj1 = Y.tb + 4 * ((PH + 1) & 3);
+        P.bpf = Y.tb + 4 * ((PH + FK_PF) & 3);
+        P.u0new = Y.tA + 4 * PH;
+        P.u0r0 = Y.tB + 4 * PH;
+        P.u0r1 = PH == 3 ? Y.tA : Y.tB + 4 * (PH + 1);
+        P.u0pf = PH + FK_PF < 4 ? Y.tA + 4 * (PH + FK_PF) : Y.tB + 4 * (PH + FK_PF - 4);
+    } else {   // U == 2, FK_PF == 3: slot j = 2 h + PH, stage-0 slot = 2 q + PH
+        P.bj = Y.tH + 4 * PH;
+        P.bj1 = PH == 0 ? Y.tH + 4 : Y.tO;
+        P.bpf = PH == 0 ? Y.tO + 4 : Y.tH;
+        P.u0new = Y.Q0 + 4 * PH;
+        P.u0r0 = Y.Q2 + 4 * PH;                    // i + 4
+        P.u0r1 = PH == 0 ? Y.Q2 + 4 : Y.Q3;        // i + 5
+        P.u0pf = PH == 0 ? Y.Q1 + 4 : Y.Q2;        // i + 3
+    }
+    return P;
+}
+static_assert(FK_PF == 3, "stream_ptrs_phase<U = 2> spells the prefetch slots out for FK_PF == 3");
+
+// one row iteration of one thread.  `tid` in [0, NT), its 4 columns start at C.cs + 4 tid, its chunk is tb.
+//   PH < 0   general body: every per-stage condition evaluated, ring slots computed from i, u_x window slid by moves;
+//            the caller separates iterations with a block barrier.
+//   PH >= 0  steady state, phase PH == (i - nfill) % U of the U-way unrolled loop: the caller guarantees that every
+//            stage has input and emits in this iteration and that no stimulus is active in this launch; every slot in P
+//            is a base register plus a compile-time offset and the u_x window is renamed, not moved.  Iterations are
+//            separated by the split barrier `bar`: wait for the others' previous iteration just before the first halo
+//            read, arrive after the last shared-memory write.
+//   UNI      one constant diffusivity (C.Dc, C.DXc, C.DYc) instead of three maps
+//   EDGE     this CTA's strip may contain the tissue's first / last column
+template <bool EXACT, int T, int PH, bool UNI, bool EDGE, int U = 4>
+FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid,
+                       const StreamPtrs& P, float* bar) {
+    typedef StreamLay<T> L;
+    constexpr bool ST = PH >= 0;
+    // positions of the u_x window rows (rho-2, rho-1, rho, rho+1) in R.GX[s]: U = 4 rotates by one per phase; U = 2
+    // keeps the rows of each parity in a pair of register sets and moves one set per phase
+    constexpr int W0 = !ST ? 0 : PH;
+    constexpr int W1 = !ST ? 1 : (U == 4 ? (PH + 1) & 3 : 1 - PH);
+    constexpr int W2 = !ST ? 2 : (U == 4 ? (PH + 2) & 3 : 2 + PH);
+    constexpr int W3 = !ST ? 3 : (U == 4 ? (PH + 3) & 3 : 3 - PH);
+    constexpr int CH = L::CHUNK;
     const int c = C.cs + 4 * tid;
     const bool act = c < C.c_end;
+    const long long g0 = R.g0;         // row n0 = rin0 + i at this thread's columns
+    R.g0 = opaque(g0 + A.W);           // carried, not recomputed from i
+    const long long gd = R.gd;
+    if (!UNI) R.gd = opaque(gd + A.W);
     // rows fetched FK_PF iterations ago have landed (this thread's own columns; the neighbours'
     // columns of a row are only read three barriers later)
-    stream_prefetch<T>(A, G, C, S, i + FK_PF, tid, act);
+    stream_prefetch_to<T>(A, C, P.u0pf, P.bpf + L::V, P.bpf + L::W, i + FK_PF, g0 + (long long)FK_PF * A.W, act);
     async_wait<FK_PF>();
-    if (!act) return;
-    const int own = 4 + 4 * tid;  // offset of the thread's columns inside a padded ring row
-    const bool edgeL = tid == C.edgeL, edgeR = tid == C.edgeR;
+    // Threads beyond the strip's last needed column: the general body skips them.  The steady-state body lets them
+    // compute on whatever their chunk holds (nothing of theirs is stored, nobody reads their columns): an early exit
+    // would cost every thread a block of register moves at the join, and the planner never leaves a whole warp idle.
+    if (!ST && !act) return;
+    const bool edgeL = EDGE && tid == C.edgeL, edgeR = EDGE && tid == C.edgeR;
     const int n0 = C.rin0 + i;
-    const int m8 = n0 & (FK_U0DEP - 1);
-    const int m5 = n0 % 5;
+    // ---- this thread's own columns: nothing here was written by another thread, so it is read before the barrier wait
+    // v, w of the rows the stages emit now: slot j of every stage, read before stage s-1 refills slot j of stage s
+    float vv[T][4], ww[T][4], u0[T][4], u1[T][4];
+    float* r0p[T];
+    float* r1p[T];
     float in_u[4] = {0.f, 0.f, 0.f, 0.f};
-    bool have_in = STEADY || n0 < C.rin_end;
+    bool have_in = ST || n0 < C.rin_end;
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+        unpack4(ld4(P.bj + L::V + 16 * s), vv[s]);
+        unpack4(ld4(P.bj + L::W + 16 * s), ww[s]);
+        // input rows rho, rho+1 of the stage (row rho+3 is still in registers, row rho+4 arrives below)
+        if (s == 0) {
+            r0p[s] = P.u0r0; r1p[s] = P.u0r1;
+            if (have_in) unpack4(ld4(P.u0new), in_u);
+        } else {
+            r0p[s] = P.bj + L::U(s); r1p[s] = P.bj1 + L::U(s);
+        }
+        unpack4(ld4(r0p[s]), u0[s]);
+        unpack4(ld4(r1p[s]), u1[s]);
+    }
+    if (ST) sb_wait(bar, PH & 1);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         const int rho = n0 - 4 * (s + 1);  // row this stage emits (level s+1); its newest input row is rho+4
         const int lo = C.r0 - 4 * (T - 1 - s), hi = C.r1 + 4 * (T - 1 - s);
-        // ring slots of input rows rho+4 (new), rho+3, rho+1, rho
-        int sl_new, sl_r3, sl_r1, sl_r0;
-        if (s == 0) {
-            sl_new = m8; sl_r3 = (m8 + 7) & 7; sl_r1 = (m8 + 5) & 7; sl_r0 = (m8 + 4) & 7;
-        } else {
-            sl_new = mod5(m5 + (s % 5)); sl_r3 = mod5(sl_new + 4); sl_r1 = mod5(sl_new + 2); sl_r0 = mod5(sl_new + 1);
-        }
-        float* ur = S.uring[s] + own;
-        if (s == 0) {
-            if (have_in) unpack4(ld4(ur + sl_new * G.RS), in_u);
-        } else if (have_in) {
-            st4(ur + sl_new * G.RS, in_u);
-        }
-        float u0[4], u1[4], u3[4];
-        unpack4(ld4(ur + sl_r0 * G.RS), u0);
-        unpack4(ld4(ur + sl_r1 * G.RS), u1);
-        unpack4(ld4(ur + sl_r3 * G.RS), u3);
+        if (s > 0 && have_in) st4(r0p[s], in_u);  // row rho+4 takes the slot of row rho
         // u_x of row rho+2 (solve.py:49)
         float ngx[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, u0[k], u1[k], u3[k], in_u[k]);
-        const bool emit = STEADY || (rho >= lo && rho < hi);
+        for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, u0[s][k], u1[s][k], R.prev[s][k], in_u[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) R.prev[s][k] = in_u[k];
+        const bool emit = ST || (rho >= lo && rho < hi);
         if (emit) {
-            const float* gr = S.gyx[s] + ((i + 1) & 1) * G.RS + own;
-            const F2 L = ld2(gr - 2), Rr = ld2(gr + 4);
+            const float* gr = tb + L::GY + 8 * s + 4 * (ST ? (PH + 1) & 1 : (i + 1) & 1);
+            const F2 Lh = ld2(gr - CH + 2), Rh = ld2(gr + CH);
             // at a tissue edge the neighbour is the pad column, whose u_y this thread made itself
-            const float g[8] = {L.x, edgeL ? R.gypad[s] : L.y, R.gy[s][0], R.gy[s][1], R.gy[s][2], R.gy[s][3],
-                                edgeR ? R.gypad[s] : Rr.x, Rr.y};
-            float v[4], w[4];
-            const int vslot = s == 0 ? (rho & (FK_VWDEP - 1)) : sl_r0;
-            unpack4(ld4(S.vring[s] + vslot * G.CW + 4 * tid), v);
-            unpack4(ld4(S.wring[s] + vslot * G.CW + 4 * tid), w);
+            const float g[8] = {Lh.x, edgeL ? R.gypad[s] : Lh.y, R.gy[s][0], R.gy[s][1], R.gy[s][2], R.gy[s][3],
+                                edgeR ? R.gypad[s] : Rh.x, Rh.y};
             float Dv[4], DXv[4], DYv[4];
-            const long long grow = (long long)rho * A.W + c;
-            if (G.uniformD) {
+            const long long back = 4LL * (s + 1) * A.W;
+            const long long grow = g0 - back;   // (sim, rho, c)
+            if (UNI) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { Dv[k] = C.Dc; DXv[k] = C.DXc; DYv[k] = C.DYc; }
                 if (edgeL) DYv[0] = C.DYcL;
                 if (edgeR) DYv[3] = C.DYcR;
             } else {
-                unpack4(ld4(A.D + C.boffD + grow), Dv);
-                unpack4(ld4(A.DX + C.boffD + grow), DXv);
-                unpack4(ld4(A.DY + C.boffD + grow), DYv);
+                unpack4(ldg4(A.D + gd - back), Dv);
+                unpack4(ldg4(A.DX + gd - back), DXv);
+                unpack4(ldg4(A.DY + gd - back), DYv);
             }
             float un[4], vn[4], wn[4];
-            const unsigned mask = STEADY ? 0u : C.mask[s];
+            const unsigned mask = ST ? 0u : C.mask[s];
             if (mask) {  // solve.py:260-269: later stimuli win, zero cells never stimulate
                 float stim[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int q = 0; q < A.n_stim; ++q)
                     if (mask >> q & 1u) {
                         float f[4];
-                        unpack4(ld4(C.stims[q].field + grow), f);
+                        unpack4(ldg4(C.stims[q].field + (grow - C.boff)), f);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (f[k] != 0.0f) stim[k] = f[k];
                     }
-                stream_emit<EXACT, true>(A.K, u0, v, w, R.GX[s][0], R.GX[s][1], R.GX[s][2], R.GX[s][3], ngx, g, R.gy[s], Dv,
-                                         DXv, DYv, stim, edgeL, edgeR, un, vn, wn);
+                stream_emit<EXACT, true, EDGE>(A.K, u0[s], vv[s], ww[s], R.GX[s][W0], R.GX[s][W1], R.GX[s][W2],
+                                               R.GX[s][W3], ngx, g, R.gy[s], Dv, DXv, DYv,
+                                               stim, edgeL, edgeR, un, vn, wn);
             } else {
-                stream_emit<EXACT, false>(A.K, u0, v, w, R.GX[s][0], R.GX[s][1], R.GX[s][2], R.GX[s][3], ngx, g, R.gy[s],
-                                          Dv, DXv, DYv, nullptr, edgeL, edgeR, un, vn, wn);
+                stream_emit<EXACT, false, EDGE>(A.K, u0[s], vv[s], ww[s], R.GX[s][W0], R.GX[s][W1], R.GX[s][W2],
+                                                R.GX[s][W3], ngx, g, R.gy[s], Dv, DXv, DYv,
+                                                nullptr, edgeL, edgeR, un, vn, wn);
             }
             if (s == T - 1) {
                 if (c >= C.out_c0 && c < C.out_c1) {
-                    st4(A.u_out + C.boff + grow, un);
-                    st4(A.v_out + C.boff + grow, vn);
-                    st4(A.w_out + C.boff + grow, wn);
+                    st4(A.u_out + grow, un);
+                    st4(A.v_out + grow, vn);
+                    st4(A.w_out + grow, wn);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) in_u[k] = un[k];
-                // level s+1 row rho == newest input row of stage s+1: same mod-5 phase as its u ring
-                const int ns = mod5(m5 + ((s + 1) % 5));
-                st4(S.vring[s + 1] + ns * G.CW + 4 * tid, vn);
-                st4(S.wring[s + 1] + ns * G.CW + 4 * tid, wn);
+                st4(P.bj + L::V + 16 * (s + 1), vn);
+                st4(P.bj + L::W + 16 * (s + 1), wn);
             }
         }
         // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
-        if (STEADY || (rho + 1 >= lo && rho + 1 < hi)) {
-            const F2 L = ld2(ur + sl_r1 * G.RS - 2), Rr = ld2(ur + sl_r1 * G.RS + 4);
-            // edge-pad (solve.py:31): the column outside the tissue repeats the edge column
-            const float e[8] = {L.x, edgeL ? u1[0] : L.y, u1[0], u1[1], u1[2], u1[3], edgeR ? u1[3] : Rr.x, Rr.y};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) R.gy[s][k] = dcen<EXACT>(A.K, e[k], e[k + 1], e[k + 3], e[k + 4]);
-            if (edgeL) {  // padded columns 0 (the pad) and 1 (tissue column 0) use the forward formula
-                R.gypad[s] = edge_deriv<EXACT>(A.K, FWD, e[1], e[2], e[3], e[4]);
-                R.gy[s][0] = edge_deriv<EXACT>(A.K, FWD, e[2], e[3], e[4], e[5]);
-            }
-            if (edgeR) {  // padded columns W (tissue column W-1) and W+1 (the pad) use the backward formula
-                R.gy[s][3] = edge_deriv<EXACT>(A.K, BWD, e[2], e[3], e[4], e[5]);
-                R.gypad[s] = edge_deriv<EXACT>(A.K, BWD, e[3], e[4], e[5], e[6]);
-            }
-            st4(S.gyx[s] + (i & 1) * G.RS + own, R.gy[s]);
+        if (ST || (rho + 1 >= lo && rho + 1 < hi)) {
+            stream_make_gy<EXACT, T>(A.K, r1p[s], u1[s], edgeL, edgeR, R.gy[s], R.gypad[s]);
+            st4(tb + L::GY + 8 * s + 4 * (ST ? PH & 1 : i & 1), R.gy[s]);
         }
-        // slide the u_x window
+        // the u_x window takes the new row
+        if (ST && U == 4) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            R.GX[s][0][k] = R.GX[s][1][k];
-            R.GX[s][1][k] = R.GX[s][2][k];
-            R.GX[s][2][k] = R.GX[s][3][k];
-            R.GX[s][3][k] = ngx[k];
+            for (int k = 0; k < 4; ++k) R.GX[s][W0][k] = ngx[k];
+        } else if (ST) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { R.GX[s][W0][k] = R.GX[s][W2][k]; R.GX[s][W2][k] = ngx[k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                R.GX[s][0][k] = R.GX[s][1][k];
+                R.GX[s][1][k] = R.GX[s][2][k];
+                R.GX[s][2][k] = R.GX[s][3][k];
+                R.GX[s][3][k] = ngx[k];
+            }
         }
         have_in = emit;
     }
+    if (ST) sb_arrive(bar);
+}
+
+// iteration i of a CTA in whichever form the kernel runs it: general body during the pipeline fill, the tail and any
+// launch with an active stimulus; phase (i - nfill) & 3 of the unrolled body in between.  (The CUDA kernel spells the
+// same schedule out as three loops; the CPU emulation calls this.)
+template <bool EXACT, int T, bool UNI, int U, int PH>
+FK_HD void stream_iter_phase(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid,
+                             const StreamBody<T>& Y, bool edge, float* bar) {
+    if (edge) stream_iter<EXACT, T, PH, UNI, true, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, PH>(Y), bar);
+    else stream_iter<EXACT, T, PH, UNI, false, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, PH>(Y), bar);
+}
+
+template <bool EXACT, int T, bool UNI>
+FK_HD void stream_iter_any(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid) {
+    constexpr int U = stream_unroll(T);
+    const int nfill = stream_nfill<T>(C), nbody = stream_nbody<T>(C);
+    if (i < nfill || i >= nfill + U * nbody) {
+        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+        return;
+    }
+    const int ph = (i - nfill) % U;   // nfill is a multiple of 8
+    const StreamBody<T> Y = stream_body_at<T>(tb, i - ph);
+    const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
+    if (ph == 0) stream_iter_phase<EXACT, T, UNI, U, 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
+    else if (ph == 1) stream_iter_phase<EXACT, T, UNI, U, 1>(A, C, R, tb, i, tid, Y, edge, nullptr);
+    else if (ph == 2) stream_iter_phase<EXACT, T, UNI, U == 4 ? 4 : 4, U == 4 ? 2 : 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
+    else stream_iter_phase<EXACT, T, UNI, U == 4 ? 4 : 4, U == 4 ? 3 : 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
 }
 
 // ---------------------------------------------------------------- host-side planning (no CUDA calls)
@@ -391,6 +665,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
                 long long nch = waves * slots / units;
                 if (nch < 1) nch = 1;
                 RH = (int)((Hint + nch - 1) / nch);
+                RH = (RH + 3) / 4 * 4;   // whole bodies of the 4-way unrolled steady-state loop
                 if (RH < 8) RH = 8;
             }
             if (RH > Hint) RH = Hint;
@@ -406,7 +681,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             const double cost = rounds * (RH + 8.0 * T) * T * (warps + 8.0) / 4.0;
             if (best < 0 || cost < best) {
                 best = cost;
-                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RS = 4 * NT + 8; P.G.RH = RH;
+                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RH = RH;
                 P.G.nstrips = nstrips; P.G.nchunks = nchunks; P.G.cstride = stride; P.G.uniformD = uniformD;
                 P.G.row0 = row0; P.G.row1 = row1;
                 P.T = T;
@@ -429,26 +704,24 @@ namespace fk {
 template <bool EXACT, int T>
 inline void emu_stream_cta(const TileArgs& A, const StreamGeom& G, int strip, int chunk, int sim, bool reverse) {
     std::vector<float> smem((size_t)stream_smem_floats(T, G.NT), __builtin_nanf(""));
-    StreamSmem<T> S;
-    stream_carve<T>(smem.data(), G, S);
     StreamCta C;
     stream_cta_setup<T>(A, G, strip, chunk, sim, C);
     std::vector<StreamState<T>> R((size_t)G.NT);
-    for (auto& r : R) {
-        float* f = reinterpret_cast<float*>(&r);
-        for (size_t q = 0; q < sizeof(r) / sizeof(float); ++q) f[q] = __builtin_nanf("");
+    for (int tid = 0; tid < G.NT; ++tid) {
+        stream_state_init<T>(A, C, tid, R[tid]);
+        stream_warm_load<T>(A, C, stream_chunk<T>(smem.data(), tid), tid);
     }
-    for (int tid = 0; tid < G.NT; ++tid)
-        for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, G, C, S, j, tid, C.cs + 4 * tid < C.c_end);
-    const bool steady_ok = stream_steady_ok<T>(C);
-    for (int i = 0; i < C.niter; ++i) {
-        const bool steady = steady_ok && i >= 8 * T;
+    for (int q = 0; q < G.NT; ++q) {   // after the first block barrier
+        const int tid = reverse ? G.NT - 1 - q : q;
+        stream_warm_start<EXACT, T>(A, C, R[tid], stream_chunk<T>(smem.data(), tid), tid);
+    }
+    for (int i = FK_WARM; i < C.niter; ++i)
         for (int q = 0; q < G.NT; ++q) {
             const int tid = reverse ? G.NT - 1 - q : q;
-            if (steady) stream_iter<EXACT, T, true>(A, G, C, S, R[tid], i, tid);
-            else stream_iter<EXACT, T, false>(A, G, C, S, R[tid], i, tid);
+            float* tb = stream_chunk<T>(smem.data(), tid);
+            if (G.uniformD) stream_iter_any<EXACT, T, true>(A, C, R[tid], tb, i, tid);
+            else stream_iter_any<EXACT, T, false>(A, C, R[tid], tb, i, tid);
         }
-    }
 }
 
 inline int emu_stream_launch(const StreamPlan& P, const TileArgs& A, int batch, int exact, int reverse) {

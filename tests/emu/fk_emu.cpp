@@ -20,8 +20,7 @@ struct EmuBackend {
     int reverse = 0;       // run the threads of a streaming block in reverse order (hazard check)
     int launches_tile = 0, launches_stream = 0;
     int num_sms() { return 148; }
-    int max_stream_threads() { return 256; }
-    int occupancy(int, int, int NT, long long) { return NT <= 128 ? 2 : 1; }
+    int occupancy(int, int, int, int NT, long long) { return NT <= 128 ? 2 : 1; }
     int join() { return 0; }
     int tiles(fk::TileArgs& A, int exact, int batch, bool) {
         long long floats = 0;

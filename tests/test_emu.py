@@ -59,6 +59,27 @@ def test_stream_thread_order_independent():
     _exact((96, 288), 3, kernel=2, cta_threads=64, rows_per_cta=20, reverse=1)
 
 
+@pytest.mark.parametrize("shape,T,nt,rh,reverse", [((96, 400), 2, 32, 40, 0), ((96, 400), 2, 32, 40, 1),
+                                                   ((70, 264), 1, 32, 27, 0), ((120, 520), 3, 64, 50, 1),
+                                                   ((150, 64), 2, 0, 0, 0)])
+def test_stream_steady_state_body_exact(shape, T, nt, rh, reverse):
+    """No stimulus: after the pipeline fill the kernel runs its unrolled steady-state body (static ring slots, rotating
+    u_x window, swapped ring halves), several bodies per CTA, in edge strips and interior strips."""
+    info = _exact(shape, T, nsteps=2 * T, n_stim=0, kernel=2, cta_threads=nt, rows_per_cta=rh, reverse=reverse)
+    assert info[1] == 2
+
+
+def test_stream_steady_state_uniform_fast_matches_tiles():
+    st, _ = common.smooth_case((96, 400), seed=3)
+    D = np.full((96, 400), 1e-3, np.float32)
+    a, _ = emu.euler(st, 0, 4, P3, D, [], 0.01, 0.01, exact=False, T=2, kernel=2, cta_threads=32, rows_per_cta=40, uniform=1)
+    b, _ = emu.euler(st, 0, 4, P3, D, [], 0.01, 0.01, exact=False, T=2, kernel=1)
+    e, _ = emu.euler(st, 0, 4, P3, D, [], 0.01, 0.01, exact=True, T=2, kernel=2, cta_threads=32, rows_per_cta=40, uniform=1)
+    ref = C.forward_euler(st, 0, 4, P3, D, [], 0.01, 0.01)
+    for x, y, z, r in zip(a, b, e, ref):
+        assert np.array_equal(x, y) and np.array_equal(z, r)
+
+
 def test_stream_uniform_diffusivity_path():
     st, _, stim = common.random_case((72, 288), seed=4)
     D = np.full((72, 288), 1e-3, np.float32)
