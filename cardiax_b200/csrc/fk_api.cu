@@ -1,6 +1,7 @@
 // fk_api.cu -- kernels and the C ABI (include/fk.h) of libfk.so.  sm_100a only.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -255,6 +256,9 @@ struct CudaBackend {
         const size_t smem = (size_t)floats * sizeof(float);
         if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
         cudaStream_t st = this->st;
+        static const int dbg_frame = getenv("FK_DEBUG_FRAME") ? atoi(getenv("FK_DEBUG_FRAME")) : 0;
+        if (on_side && dbg_frame == 1) return 0;   // timing experiment only: skip the frame tiles (wrong results)
+        if (on_side && dbg_frame == 2) on_side = false;   // timing experiment: frame tiles on the main stream, serial
         if (on_side) {
             const int rc = get_side();
             if (rc) return rc;

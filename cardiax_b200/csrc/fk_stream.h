@@ -101,6 +101,21 @@ FK_HD void sb_wait(float* bar, int parity) {
 #endif
 }
 
+// non-blocking look at the barrier, issued at the top of an iteration so that its latency overlaps the loads of the
+// thread's own columns; sb_wait is only entered when the phase was not complete yet
+FK_HD int sb_test(float* bar, int parity) {
+#if defined(__CUDA_ARCH__)
+    int done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.s32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return done;
+#else
+    return 1;
+#endif
+}
+
 enum { FK_PF = 3 };      // level-0 rows are fetched this many iterations ahead
 
 // Shared memory is THREAD-major: every thread owns one chunk of StreamLay<T>::CHUNK floats that holds its 4 columns
@@ -478,6 +493,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
     // compute on whatever their chunk holds (nothing of theirs is stored, nobody reads their columns): an early exit
     // would cost every thread a block of register moves at the join, and the planner never leaves a whole warp idle.
     if (!ST && !act) return;
+    const int bar_done = ST ? sb_test(bar, PH & 1) : 1;
     const bool edgeL = EDGE && tid == C.edgeL, edgeR = EDGE && tid == C.edgeR;
     const int n0 = C.rin0 + i;
     // ---- this thread's own columns: nothing here was written by another thread, so it is read before the barrier wait
@@ -501,7 +517,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         unpack4(ld4(r0p[s]), u0[s]);
         unpack4(ld4(r1p[s]), u1[s]);
     }
-    if (ST) sb_wait(bar, PH & 1);
+    if (ST && !bar_done) sb_wait(bar, PH & 1);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         const int rho = n0 - 4 * (s + 1);  // row this stage emits (level s+1); its newest input row is rho+4
@@ -678,7 +694,10 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             long long res = (ncta + num_sms - 1) / num_sms;
             if (res > o) res = o;
             const double warps = (double)((need + 127) / 128) * (double)res;
-            const double cost = rounds * (RH + 8.0 * T) * T * (warps + 8.0) / 4.0;
+            // (CTAs of more than 4 warps pay a little for the coarser split barrier: measured 242 vs 255 Gcell-steps/s
+            // for 6- vs 4-warp CTAs at equal residency)
+            const int wpc = (need + 127) / 128;
+            const double cost = rounds * (RH + 8.0 * T) * T * (warps + 8.0) / 4.0 * (1.0 + 0.02 * (wpc > 4 ? wpc - 4 : 0));
             if (best < 0 || cost < best) {
                 best = cost;
                 P.G.NT = NT; P.G.CW = 4 * NT; P.G.RH = RH;
