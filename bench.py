@@ -37,6 +37,15 @@ ALG_BYTES = 28.0  # read u, v, w, D + write u, v, w (fp32) per cell-s
 SEG = 500         # Euler steps per checkpoint segment (experiments/generate_fd_data_256.py:11-12)
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            return float(json.load(f)[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -375,7 +384,7 @@ def main():
         cs_per_launch = sm_cs.value / sm_n.value
         achieved = ALG_BYTES * cs_per_launch / (sm_ms.value / sm_n.value * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind, "kernel": "fk_stream_kernel",
+                "traffic": ncu_traffic(workload), "peak_kind": peak_kind, "kernel": "fk_stream_kernel",
                 "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": sm_ms.value / sm_n.value,
                 "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms,
                 "note": "the frame-tile kernel runs on a side stream concurrently with the streaming kernel, so the shares can add to more than 1",

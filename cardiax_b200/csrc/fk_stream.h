@@ -517,6 +517,24 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         unpack4(ld4(r0p[s]), u0[s]);
         unpack4(ld4(r1p[s]), u1[s]);
     }
+    // heterogeneous diffusivity: the three maps at the rows the stages emit, requested before the wait as well
+    float Dm[UNI ? 1 : T][4], DXm[UNI ? 1 : T][4], DYm[UNI ? 1 : T][4];
+    if (!UNI) {
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const int rho = n0 - 4 * (s + 1);
+            // only rows this stage emits (all of them in the steady state), only threads inside the tissue
+            const bool need = act && (ST || (rho >= C.r0 - 4 * (T - 1 - s) && rho < C.r1 + 4 * (T - 1 - s)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Dm[s][k] = DXm[s][k] = DYm[s][k] = 0.0f;
+            if (need) {
+                const long long back = 4LL * (s + 1) * A.W;
+                unpack4(ldg4(A.D + gd - back), Dm[s]);
+                unpack4(ldg4(A.DX + gd - back), DXm[s]);
+                unpack4(ldg4(A.DY + gd - back), DYm[s]);
+            }
+        }
+    }
     if (ST && !bar_done) sb_wait(bar, PH & 1);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
@@ -545,9 +563,8 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                 if (edgeL) DYv[0] = C.DYcL;
                 if (edgeR) DYv[3] = C.DYcR;
             } else {
-                unpack4(ldg4(A.D + gd - back), Dv);
-                unpack4(ldg4(A.DX + gd - back), DXv);
-                unpack4(ldg4(A.DY + gd - back), DYv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { Dv[k] = Dm[UNI ? 0 : s][k]; DXv[k] = DXm[UNI ? 0 : s][k]; DYv[k] = DYm[UNI ? 0 : s][k]; }
             }
             float un[4], vn[4], wn[4];
             const unsigned mask = ST ? 0u : C.mask[s];

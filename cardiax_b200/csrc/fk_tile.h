@@ -111,12 +111,24 @@ FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx
 // phase 0: level-0 state -> shared memory
 FK_HD void tile_load(const TileArgs& A, const TileCtx& X, int tx, int ty, int ntx, int nty) {
     for (int r = X.ra + ty; r < X.rb; r += nty)
-        for (int c = X.ca + tx; c < X.cb; c += ntx) {
-            const long long g = X.boff + (long long)r * A.W + c;
-            const int i = (r - X.ra) * X.nc + (c - X.ca);
-            X.U0[i] = A.u_in[g];
-            X.V[i] = A.v_in[g];
-            X.Wd[i] = A.w_in[g];
+        for (int c0 = X.ca + tx; c0 < X.cb; c0 += 4 * ntx) {   // batches of 4 cells: 12 loads in flight per thread
+            float uu[4], vv[4], ww[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = c0 + q * ntx;
+                if (c < X.cb) {
+                    const long long g = X.boff + (long long)r * A.W + c;
+                    uu[q] = ldg1(A.u_in + g); vv[q] = ldg1(A.v_in + g); ww[q] = ldg1(A.w_in + g);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = c0 + q * ntx;
+                if (c < X.cb) {
+                    const int i = (r - X.ra) * X.nc + (c - X.ca);
+                    X.U0[i] = uu[q]; X.V[i] = vv[q]; X.Wd[i] = ww[q];
+                }
+            }
         }
 }
 
@@ -178,49 +190,64 @@ FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* 
         const float* G3 = X.GX + (P + o3 - X.ra + 1) * X.nc - X.ca;
         const float* GC = X.GX + (P - X.ra + 1) * X.nc - X.ca;
         const float* GYr = X.GY + (row - X.ra) * X.SG - X.ca + 1;
-        for (int col = c + tx; col < d; col += ntx) {
-            const int Q = col + 1;
-            const float u_xx = deriv<EXACT>(A.K, kindr, k0, k1, k2, k3, G0[col], G1[col], G2[col], G3[col]);
-            float q0, q1, q2, q3;
-            int p0, p1, p2, p3;
-            const int kindc = kind_of(Q, A.W, A.phys_left, A.phys_right);
-            kind_coeffs(kindc, q0, q1, q2, q3, p0, p1, p2, p3);
-            const float u_yy =
-                deriv<EXACT>(A.K, kindc, q0, q1, q2, q3, GYr[Q + p0], GYr[Q + p1], GYr[Q + p2], GYr[Q + p3]);
-            const float u_x = GC[col], u_y = GYr[Q];
-            const long long gd = X.boffD + (long long)row * A.W + col;
-            const float del_u = diffusion<EXACT>(A.D[gd], A.DX[gd], A.DY[gd], u_x, u_y, u_xx, u_yy);
-            const long long g = (long long)row * A.W + col;
-            float stim = 0.0f;
-            if (mask) {  // solve.py:260-269: later stimuli override earlier ones, zero cells never stimulate
-                for (int i = 0; i < A.n_stim; ++i)
-                    if (mask >> i & 1u) {
-                        const float f = X.stims[i].field[g];
-                        if (f != 0.0f) stim = f;
+        for (int col0 = c + tx; col0 < d; col0 += 4 * ntx) {
+            // batches of 4 cells: the diffusivity maps (and stimulus fields) of all four are requested before any is used
+            float Dq[4], DXq[4], DYq[4], stq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int col = col0 + q * ntx;
+                Dq[q] = DXq[q] = DYq[q] = stq[q] = 0.0f;
+                if (col < d) {
+                    const long long gd = X.boffD + (long long)row * A.W + col;
+                    Dq[q] = ldg1(A.D + gd); DXq[q] = ldg1(A.DX + gd); DYq[q] = ldg1(A.DY + gd);
+                    if (mask) {  // solve.py:260-269: later stimuli override earlier ones, zero cells never stimulate
+                        const long long g = (long long)row * A.W + col;
+                        for (int i = 0; i < A.n_stim; ++i)
+                            if (mask >> i & 1u) {
+                                const float f = ldg1(X.stims[i].field + g);
+                                if (f != 0.0f) stq[q] = f;
+                            }
                     }
-            }
-            const int i = (row - X.ra) * X.nc + (col - X.ca);
-            const float u = Uc[i], v = X.V[i], w = X.Wd[i];
-            float d_v, d_w, d_u;
-            cell_rhs<EXACT>(A.K, u, v, w, del_u, stim, d_v, d_w, d_u);
-            if (A.rhs_mode) {
-                A.v_out[X.boff + g] = d_v;
-                A.w_out[X.boff + g] = d_w;
-                A.u_out[X.boff + g] = d_u;
-                continue;
-            }
-            const float vn = euler<EXACT>(v, d_v, A.K.dt), wn = euler<EXACT>(w, d_w, A.K.dt),
-                        un = euler<EXACT>(u, d_u, A.K.dt);
-            if (last) {
-                if (row >= X.r0 && row < X.r1 && col >= X.c0 && col < X.c1) {
-                    A.v_out[X.boff + g] = vn;
-                    A.w_out[X.boff + g] = wn;
-                    A.u_out[X.boff + g] = un;
                 }
-            } else {
-                Un[i] = un;
-                X.V[i] = vn;
-                X.Wd[i] = wn;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int col = col0 + q * ntx;
+                if (col >= d) continue;
+                const int Q = col + 1;
+                const float u_xx = deriv<EXACT>(A.K, kindr, k0, k1, k2, k3, G0[col], G1[col], G2[col], G3[col]);
+                float q0, q1, q2, q3;
+                int p0, p1, p2, p3;
+                const int kindc = kind_of(Q, A.W, A.phys_left, A.phys_right);
+                kind_coeffs(kindc, q0, q1, q2, q3, p0, p1, p2, p3);
+                const float u_yy =
+                    deriv<EXACT>(A.K, kindc, q0, q1, q2, q3, GYr[Q + p0], GYr[Q + p1], GYr[Q + p2], GYr[Q + p3]);
+                const float u_x = GC[col], u_y = GYr[Q];
+                const float del_u = diffusion<EXACT>(Dq[q], DXq[q], DYq[q], u_x, u_y, u_xx, u_yy);
+                const long long g = (long long)row * A.W + col;
+                const int i = (row - X.ra) * X.nc + (col - X.ca);
+                const float u = Uc[i], v = X.V[i], w = X.Wd[i];
+                float d_v, d_w, d_u;
+                cell_rhs<EXACT>(A.K, u, v, w, del_u, stq[q], d_v, d_w, d_u);
+                if (A.rhs_mode) {
+                    A.v_out[X.boff + g] = d_v;
+                    A.w_out[X.boff + g] = d_w;
+                    A.u_out[X.boff + g] = d_u;
+                    continue;
+                }
+                const float vn = euler<EXACT>(v, d_v, A.K.dt), wn = euler<EXACT>(w, d_w, A.K.dt),
+                            un = euler<EXACT>(u, d_u, A.K.dt);
+                if (last) {
+                    if (row >= X.r0 && row < X.r1 && col >= X.c0 && col < X.c1) {
+                        A.v_out[X.boff + g] = vn;
+                        A.w_out[X.boff + g] = wn;
+                        A.u_out[X.boff + g] = un;
+                    }
+                } else {
+                    Un[i] = un;
+                    X.V[i] = vn;
+                    X.Wd[i] = wn;
+                }
             }
         }
     }
