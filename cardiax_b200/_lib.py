@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libfk.so")
+SO_PATH = os.environ.get("FK_SO") or os.path.join(CSRC, "libfk.so")   # FK_SO: development A/B of two builds
 _SOURCES = ["fk_api.cu", "fk_stream_tu.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h",
             "fk_wide.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

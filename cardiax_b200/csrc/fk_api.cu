@@ -1,7 +1,6 @@
 // fk_api.cu -- kernels and the C ABI (include/fk.h) of libfk.so.  sm_100a only.
 #include <cuda_runtime.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -215,58 +214,16 @@ struct ProfScope {
     }
 };
 
-// side stream for the frame tiles (one per device, created on first use)
-struct Side {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, joined = nullptr;
-};
-Side g_side[64];
-
 struct CudaBackend {
     cudaStream_t st;
-    bool pending_join = false;
-    bool small_problem = false;   // launch-bound tissue: keep everything on one stream
-    Side* side = nullptr;
     int num_sms() { return ::num_sms(); }
     int occupancy(int T, int exact, int uni, int NT, long long smem) { return fk::stream_occupancy(T, exact, uni, NT, smem); }
-    int get_side() {
-        if (side) return 0;
-        int dev = 0;
-        FK_CUDA(cudaGetDevice(&dev));
-        Side& s = g_side[dev & 63];
-        if (!s.stream) {
-            FK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            FK_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-            FK_CUDA(cudaEventCreateWithFlags(&s.joined, cudaEventDisableTiming));
-        }
-        side = &s;
-        return 0;
-    }
-    int join() {
-        if (!pending_join) return 0;
-        pending_join = false;
-        FK_CUDA(cudaEventRecord(side->joined, side->stream));
-        FK_CUDA(cudaStreamWaitEvent(st, side->joined, 0));
-        return 0;
-    }
-    int tiles(fk::TileArgs& A, int exact, int batch, bool on_side) {
+    int tiles(fk::TileArgs& A, int exact, int batch, bool) {
         long long floats = 0;
         const int total = fk::finish_regions(A, &floats);
         if (total == 0) return 0;
         const size_t smem = (size_t)floats * sizeof(float);
         if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
-        cudaStream_t st = this->st;
-        static const int dbg_frame = getenv("FK_DEBUG_FRAME") ? atoi(getenv("FK_DEBUG_FRAME")) : 0;
-        if (on_side && dbg_frame == 1) return 0;   // timing experiment only: skip the frame tiles (wrong results)
-        if (on_side && dbg_frame == 2) on_side = false;   // timing experiment: frame tiles on the main stream, serial
-        if (on_side) {
-            const int rc = get_side();
-            if (rc) return rc;
-            FK_CUDA(cudaEventRecord(side->fork, this->st));
-            FK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-            st = side->stream;
-            pending_join = true;
-        }
         ProfScope ps(1, st);
         ++g_launches;
         static size_t attr_set[2] = {0, 0};   // largest dynamic shared memory already allowed, per instantiation
@@ -452,7 +409,6 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.row0 = row0; o.row1 = row1;
     CudaBackend be;
     be.st = st;
-    be.small_problem = (long long)H * W * batch < (1LL << 21);
     const char* why = "";
     fk::Consts K = make_consts(*params, dt, dx);
     if (opt.safe_division) K.div_lo = INFINITY;   // every exact-mode division through __fdiv_rn

@@ -56,15 +56,6 @@ inline void add_region(TileArgs& A, int R0, int R1, int C0, int C1, int th, int 
     R.tw = tw < C1 - C0 ? tw : C1 - C0;
 }
 
-// what the streaming kernel leaves out: the bands of 4T rows at the physical top / bottom edge (it handles the
-// left / right edges itself).  Output rows [R0, R1), streaming rows [S0, S1).
-inline void frame_regions(TileArgs& A, int T, int R0, int R1, int S0, int S1) {
-    const int F = 4 * T, W = A.W;
-    A.nreg = 0;
-    add_region(A, R0, S0, 0, W, F, 64);
-    add_region(A, S1, R1, 0, W, F, 64);
-}
-
 inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
     // whole-tissue coverage by general tiles: 32 x 64 output cells (+ 4T apron) keeps two CTAs per SM at T <= 2
     th = 32; tw = 64;
@@ -74,8 +65,8 @@ inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
     if (tw > W) tw = W;
 }
 
-// Backend: int tiles(TileArgs&, int exact, int batch, bool side);  (side: may run concurrently until join())
-//          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);  int join();
+// Backend: int tiles(TileArgs&, int exact, int batch, bool side);
+//          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);
 //          int wide(const TileArgs&, int exact, int batch);
 //          int num_sms(); int occupancy(int T, int exact, int uniform, int NT, long long smem_bytes);
 // Returns 0 or the backend's error code; *why gets a static message on argument errors.
@@ -91,13 +82,13 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         Tmax = (int)nsteps;
         if (H < 8 * Tmax + 1) { *why = "slab too thin for its halo"; return -1; }
     }
-    // output rows [R0, R1) of a launch of T steps; the streaming kernel takes [S0, S1), everything that is at least
-    // 4T rows away from a physical edge
-    auto rows = [&](int T, int& R0, int& R1, int& S0, int& S1) {
+    // output rows [R0, R1) of a launch of T steps.  The streaming kernel takes all of them, physical top / bottom edge
+    // included (its first / last row chunk uses the reference's one-sided formulas there) -- unless a row window starts
+    // or ends INSIDE the 4T rows next to a physical edge, where neither a halo nor the edge itself is available to it.
+    auto rows = [&](int T, int& R0, int& R1, bool& streamable) {
         if (opt.row1 > 0) { R0 = opt.row0; R1 = opt.row1; }
         else { R0 = opt.phys_top ? 0 : 4 * T; R1 = opt.phys_bottom ? H : H - 4 * T; }
-        S0 = (opt.phys_top && R0 < 4 * T) ? 4 * T : R0;
-        S1 = (opt.phys_bottom && R1 > H - 4 * T) ? H - 4 * T : R1;
+        streamable = !(opt.phys_top && R0 > 0 && R0 < 4 * T) && !(opt.phys_bottom && R1 < H && R1 > H - 4 * T);
     };
     if (opt.row1 > 0) {
         if (nsteps > Tmax) { *why = "a row-window call is a single launch: nsteps <= steps_per_launch"; return -1; }
@@ -118,9 +109,10 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     bool use_stream = false;
     if (!rhs_mode && opt.kernel != 1 && !use_wide) {
         auto try_plan = [&](int T, StreamPlan& P) {
-            int R0, R1, S0, S1;
-            rows(T, R0, R1, S0, S1);
-            return S1 > S0 && plan_stream(S0, S1, W, batch, T, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
+            int R0, R1;
+            bool ok;
+            rows(T, R0, R1, ok);
+            return ok && R1 > R0 && plan_stream(R0, R1, W, batch, T, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
                                           opt.uniform_diffusivity, stream_max_threads(T),
                                           [&](int NT, long long smem) { return be.occupancy(T, opt.exact, opt.uniform_diffusivity, NT, smem); }, P);
         };
@@ -169,21 +161,12 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             rc = be.wide(A, opt.exact, batch);
             if (rc) return rc;
         } else if (use_stream && T == plan.T) {
-            // the frame tiles run beside the streaming kernel (side stream on the GPU): they read the same
-            // input and write a disjoint part of the output
-            TileArgs F = A;
-            int R0, R1, S0, S1;
-            rows(T, R0, R1, S0, S1);
-            frame_regions(F, T, R0, R1, S0, S1);
-            rc = be.tiles(F, opt.exact, batch, true);
-            if (rc) return rc;
             rc = be.stream(plan, A, opt.exact, batch);
             if (rc) return rc;
-            rc = be.join();
-            if (rc) return rc;
         } else {
-            int R0, R1, S0, S1;
-            rows(T, R0, R1, S0, S1);
+            int R0, R1;
+            bool ok;
+            rows(T, R0, R1, ok);
             int th, tw;
             pick_tile(R1 - R0, W, T, th, tw);
             A.nreg = 0;

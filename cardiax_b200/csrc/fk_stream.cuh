@@ -17,16 +17,24 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     float* tb = stream_chunk<T>(fk_stream_smem, tid);
     StreamState<T> R;
     stream_state_init<T>(A, C, tid, R);
-    stream_warm_load<T>(A, C, tb, tid);
     const int nfill = stream_nfill<T>(C);
     // the split barrier of the steady-state loop lives in the pad granule of the CTA's first (pad) chunk
     float* bar = fk_stream_smem + StreamLay<T>::CHUNK - 4;
     if (tid == 0) sb_init(bar, (int)blockDim.x);
-    async_wait<0>();
-    __syncthreads();
-    stream_warm_start<EXACT, T>(A, C, R, tb, tid);   // stands for iterations 0 .. 7
-    __syncthreads();
-    int i = FK_WARM;
+    int i = 0;
+    if (!stream_use_warm<T>(C)) {
+        // (a chunk at the physical top edge emits from iteration 4 on): plain prologue, general body from iteration 0
+#pragma unroll
+        for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, C, tb, j, tid, C.cs + 4 * tid < C.c_end);
+        __syncthreads();
+    } else {
+        stream_warm_load<T>(A, C, tb, tid);
+        async_wait<0>();
+        __syncthreads();
+        stream_warm_start<EXACT, T>(A, C, R, tb, tid);   // stands for iterations 0 .. 7
+        __syncthreads();
+        i = FK_WARM;
+    }
     for (; i < nfill; ++i) {   // pipeline fill (and launches with an active stimulus): fully conditional body
         stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
         __syncthreads();
@@ -35,11 +43,12 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     // per-body base register plus a compile-time offset.  Iterations are separated by the split barrier: phase k of it
     // completes when every thread has finished iteration k - 1 of this loop.
     constexpr int U = stream_unroll(T);
-    if (i + U <= C.niter) {
+    const int i_end = nfill + U * stream_nbody<T>(C);   // (a chunk at the bottom edge ends its steady state early)
+    if (i < i_end) {
         sb_arrive(bar);   // phase 0: the fill loop's last block barrier stands for "iteration -1"
         const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
 #define FK_STEADY_LOOP(EDGE)                                                                                           \
-    for (; i + U <= C.niter; i += U) {                                                                                 \
+    for (; i < i_end; i += U) {                                                                                        \
         const StreamBody<T> Y = stream_body_at<T>(tb, i);                                                              \
         stream_iter<EXACT, T, 0, UNI, EDGE, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
         stream_iter<EXACT, T, 1, UNI, EDGE, U>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
@@ -54,9 +63,16 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
 #undef FK_STEADY_LOOP
         sb_wait(bar, 0);   // an even number of iterations later: everybody is through the last one
     }
-    for (; i < C.niter; ++i) {  // tail (fewer than U rows left)
-        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
-        __syncthreads();
+    if (i < C.niter) {
+        // tail: fewer than U rows left, or the stages of a chunk at the physical bottom edge running dry.  The CTA's
+        // constants are rebuilt here rather than kept alive across the unrolled loop, where every uniform register
+        // counts (with them live, ptxas moved the loop's constants from uniform to ordinary registers: -12 %)
+        StreamCta Ct;
+        stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, Ct);
+        for (; i < Ct.niter; ++i) {
+            stream_iter<EXACT, T, -1, UNI, true>(A, Ct, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+            __syncthreads();
+        }
     }
 }
 

@@ -156,6 +156,8 @@ struct StreamGeom {  // per launch
     int NT;          // threads per CTA
     int CW;          // 4 * NT, columns a CTA reads
     int RH;          // output rows per CTA
+    int RH0;         // ... of the first row chunk (shorter when it starts at the physical top edge); the last chunk
+                     // takes what is left
     int nstrips, nchunks;
     int cstride;     // output columns per strip (<= CW - 8T)
     int uniformD;    // diffusivity (and so D_x, D_y) is one constant over the interior
@@ -170,6 +172,8 @@ struct StreamState {     // registers of one thread
     float gy[T][4];      // u_y of row rho (made one iteration ahead)
     float gypad[T];      // edge threads only: u_y of the PAD column next to the tissue edge (padded index 0 / W+1)
     float prev[T][4];    // the row each stage received one iteration ago (row rho + 3 of its window)
+    float sv[T][4][4];   // general body only, CTAs at the physical top / bottom edge: values a stage carries from one
+                         // special iteration to the next (see "physical top / bottom edge" below)
     long long g0;        // offset of (tissue `sim`, row rin0 + i, this thread's first column) in the state arrays
     long long gd;        // the same in the diffusivity maps (one shared map, or one per tissue)
 };
@@ -178,6 +182,9 @@ struct StreamCta {       // uniform per CTA
     int cs;              // first column of the strip
     int r0, r1;          // output rows
     int rin0, rin_end;   // level-0 rows read
+    int top, bot;        // this chunk starts at the physical top edge / ends at the physical bottom edge
+    int vw_lo, vw_hi;    // level-0 v, w rows read
+    float DXcT, DXcB;    // uniform diffusivity: D_x in the tissue's first / last row (one-sided formula)
     int out_c0, out_c1;  // output columns
     int c_end;           // end of the columns this CTA needs
     int edgeL, edgeR;    // thread that holds the tissue's first / last column (-1: not in this strip)
@@ -194,10 +201,16 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     // strip j owns output columns [j stride, (j+1) stride); it reads 4T more on each side unless that side is the
     // tissue's physical left/right edge, which the edge thread handles with the reference's one-sided formulas
     C.cs = strip * G.cstride - 4 * T < 0 ? 0 : strip * G.cstride - 4 * T;
-    C.r0 = G.row0 + chunk * G.RH;
-    C.r1 = C.r0 + G.RH < G.row1 ? C.r0 + G.RH : G.row1;
-    C.rin0 = C.r0 - 4 * T;
-    C.rin_end = C.r1 + 4 * T;
+    C.r0 = G.row0 + (chunk == 0 ? 0 : G.RH0 + (chunk - 1) * G.RH);
+    C.r1 = chunk == G.nchunks - 1 ? G.row1 : C.r0 + (chunk == 0 ? G.RH0 : G.RH);   // the last chunk takes the remainder (>= 4T rows)
+    // A chunk at a physical edge has no rows beyond it: its stages start at row 0 / run dry after row H-1 and use the
+    // reference's one-sided formulas there.  Every other chunk reads 4T apron rows on that side.
+    C.top = A.phys_top && C.r0 == 0;
+    C.bot = A.phys_bot && C.r1 == A.H;
+    C.rin0 = C.top ? 0 : C.r0 - 4 * T;
+    C.rin_end = C.bot ? A.H : C.r1 + 4 * T;
+    C.vw_lo = C.top ? 0 : C.r0 - 4 * (T - 1);
+    C.vw_hi = C.bot ? A.H : C.r1 + 4 * (T - 1);
     C.out_c0 = strip * G.cstride;
     C.out_c1 = C.out_c0 + G.cstride < A.W ? C.out_c0 + G.cstride : A.W;
     C.c_end = C.out_c1 + 4 * T < A.W ? C.out_c1 + 4 * T : A.W;  // columns past this are nobody's input
@@ -206,7 +219,7 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     C.boff = (long long)sim * A.plane;
     C.boffD = (long long)sim * A.plane_D;
     C.stims = A.stims ? A.stims + (long long)sim * A.n_stim : nullptr;
-    C.niter = (C.r1 - C.r0) + 8 * T;
+    C.niter = C.r1 + 4 * T - C.rin0;   // the last stage emits row r1 - 1 when (virtual) row r1 - 1 + 4T is the newest
     for (int s = 0; s < 8; ++s) C.mask[s] = 0;
     for (int s = 0; s < T; ++s) {
         const float t = (float)(A.t0 + (double)s);
@@ -217,12 +230,15 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
         }
         C.mask[s] = m;
     }
-    C.Dc = C.DXc = C.DYc = C.DYcL = C.DYcR = 0.0f;
+    C.Dc = C.DXc = C.DYc = C.DYcL = C.DYcR = C.DXcT = C.DXcB = 0.0f;
     if (G.uniformD) {
-        const long long g = C.boffD + (long long)G.row0 * A.W + 4 * T;  // any cell 2+ away from every edge
+        const int rmid = (G.row0 + G.row1) / 2;   // a row 2+ away from the top and bottom edges
+        const long long g = C.boffD + (long long)rmid * A.W + 4 * T;  // ... and a column 2+ away from left and right
         C.Dc = A.D[g]; C.DXc = A.DX[g]; C.DYc = A.DY[g];
         C.DYcL = A.DY[g - 4 * T];
         C.DYcR = A.DY[g - 4 * T + A.W - 1];
+        C.DXcT = C.top ? A.DX[C.boffD + 4 * T] : C.DXc;
+        C.DXcB = C.bot ? A.DX[C.boffD + (long long)(A.H - 1) * A.W + 4 * T] : C.DXc;
     }
 }
 
@@ -236,6 +252,7 @@ FK_HD void stream_state_init(const TileArgs& A, const StreamCta& C, int tid, Str
         for (int k = 0; k < 4; ++k) {
             R.GX[s][0][k] = R.GX[s][1][k] = R.GX[s][2][k] = R.GX[s][3][k] = 0.0f;
             R.gy[s][k] = R.prev[s][k] = 0.0f;
+            R.sv[s][0][k] = R.sv[s][1][k] = R.sv[s][2][k] = R.sv[s][3][k] = 0.0f;
         }
         R.gypad[s] = 0.0f;
     }
@@ -251,7 +268,7 @@ FK_HD void stream_prefetch_to(const TileArgs& A, const StreamCta& C, float* udst
     const int n = C.rin0 + i;  // u row pushed at iteration i
     if (act && n < C.rin_end) async_copy16(udst, A.u_in + gi);
     const int rho = n - 4;     // v, w row stage 0 emits at iteration i
-    if (act && rho >= C.r0 - 4 * (T - 1) && rho < C.r1 + 4 * (T - 1)) {
+    if (act && rho >= C.vw_lo && rho < C.vw_hi) {
         const long long g = gi - 4LL * A.W;
         async_copy16(vdst, A.v_in + g);
         async_copy16(wdst, A.w_in + g);
@@ -276,6 +293,8 @@ FK_HD float edge_deriv(const Consts& K, int kind, float a0, float a1, float a2, 
     return deriv<EXACT>(K, kind, k0, k1, k2, k3, a0, a1, a2, a3);
 }
 
+enum { FK_WARM = 8 };   // iterations the warm start stands for
+
 // steady-state unroll factor: 4 (a phase knows i & 3, only the halves of the 8-slot ring alternate) while the loop body
 // fits the instruction cache, 2 from T = 2 on (32 KB of code per loop otherwise: every instruction line would miss)
 FK_HD constexpr int stream_unroll(int T) { return T >= 2 ? 2 : 4; }
@@ -289,12 +308,29 @@ FK_HD bool stream_steady_ok(const StreamCta& C) {
 }
 
 // iterations [stream_nfill, stream_nfill + U * stream_nbody) run the unrolled steady-state body, phase (i - nfill) % U
+// (a chunk at the bottom edge leaves the steady state before its stage 0 receives the tissue's last row)
 template <int T>
-FK_HD int stream_nfill(const StreamCta& C) {
-    return (8 * T + 4 <= C.niter && stream_steady_ok<T>(C)) ? 8 * T : C.niter;
+FK_HD int stream_steady_end(const StreamCta& C) { return C.bot ? C.niter - 4 * T - 1 : C.niter; }
+// First iteration of the unrolled body.  Right after the warm start (iteration 8) in an ordinary chunk: stage 0 is in
+// its steady state from there, and the later stages, which are still filling, simply run on whatever their rings hold
+// -- nothing of it reaches a valid row (a stage's first valid emission only uses rows the stage before emitted validly)
+// and the last stage's stores are masked until its first row (iteration 8T).  In a chunk that starts at the physical
+// top edge, where stage s receives row m at iteration m + 4s and needs the general body up to m = 5: 4T + 2, rounded
+// up to whole bodies.
+template <int T>
+FK_HD int stream_fill_len(const StreamCta& C) {
+    return C.top ? (4 * T + 2 + stream_unroll(T) - 1) / stream_unroll(T) * stream_unroll(T) : (int)FK_WARM;
 }
 template <int T>
-FK_HD int stream_nbody(const StreamCta& C) { return (C.niter - stream_nfill<T>(C)) / stream_unroll(T); }
+FK_HD int stream_nfill(const StreamCta& C) {
+    const int f = stream_fill_len<T>(C);
+    return (f + 4 <= stream_steady_end<T>(C) && stream_steady_ok<T>(C)) ? f : C.niter;
+}
+template <int T>
+FK_HD int stream_nbody(const StreamCta& C) {
+    const int n = stream_steady_end<T>(C) - stream_nfill<T>(C);
+    return n > 0 ? n / stream_unroll(T) : 0;
+}
 
 // u_y (solve.py:50) of one row at the thread's 4 columns: u1 = the row's own values, r1p = its granule in the thread's
 // chunk (the neighbours' values sit one chunk to the left / right); gypad: u_y of the pad column at a tissue edge
@@ -322,7 +358,10 @@ FK_HD void stream_make_gy(const Consts& K, const float* r1p, const float* u1, bo
 // them directly (stream_warm_start): the u_x window, the previous row, u_y of the first row it will emit (published in
 // slot 1 of GY(0), as iteration 7 would have) -- and starts the fetches of iterations 8 .. 8 + FK_PF - 1.  A second
 // block barrier later the general body continues at iteration 8.
-enum { FK_WARM = 8 };
+// not for a chunk at the physical top edge (it emits from iteration 4 on), nor for a bottom chunk so short that its
+// stage 0 receives the tissue's last row -- a special iteration -- before iteration 8
+template <int T>
+FK_HD bool stream_use_warm(const StreamCta& C) { return !C.top && !(C.bot && C.niter - 4 * T - 1 < FK_WARM); }
 
 template <int T>
 FK_HD void stream_warm_load(const TileArgs& A, const StreamCta& C, float* tb, int tid) {
@@ -365,20 +404,25 @@ template <bool EXACT, bool HAS_STIM, bool EDGE>
 FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const float* w, const float* gxm2,
                        const float* gxm1, const float* gx0, const float* gxp1, const float* gxp2, const float* g,
                        const float* gy0, const float* Dv, const float* DXv, const float* DYv, const float* stim,
-                       bool edgeL, bool edgeR, float* un, float* vn, float* wn) {
+                       bool edgeL, bool edgeR, float* un, float* vn, float* wn, int mode = 0,
+                       float (*sv)[4] = nullptr) {
+    // mode 0: the ordinary row.  mode 2: u_xx supplied in sv[3] (the tissue's last row).  mode 1: the caller finishes u
+    // itself one iteration later (the tissue's first row): u_yy and j_ion go to sv[2], sv[3], un is not meaningful.
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
+        float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
+        if (mode == 2) u_xx = sv[3][k];
         float u_yy = dcen<EXACT>(K, g[k], g[k + 1], g[k + 3], g[k + 4]);          // solve.py:52
         // the tissue's first / last column: forward / backward formula on u_y of padded columns 1..4 / W-3..W
         if (EDGE && k == 0 && edgeL) u_yy = edge_deriv<EXACT>(K, FWD, g[2], g[3], g[4], g[5]);
         if (EDGE && k == 3 && edgeR) u_yy = edge_deriv<EXACT>(K, BWD, g[2], g[3], g[4], g[5]);
         const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], gx0[k], gy0[k], u_xx, u_yy);
-        float d_v, d_w, d_u;
-        cell_rhs<EXACT, HAS_STIM>(K, u0[k], v[k], w[k], del_u, HAS_STIM ? stim[k] : 0.0f, d_v, d_w, d_u);
+        float d_v, d_w, j_ion;
+        cell_rhs_parts<EXACT, HAS_STIM>(K, u0[k], v[k], w[k], HAS_STIM ? stim[k] : 0.0f, d_v, d_w, j_ion);
+        if (mode == 1) { sv[2][k] = u_yy; sv[3][k] = j_ion; }
         vn[k] = euler<EXACT>(v[k], d_v, K.dt);
         wn[k] = euler<EXACT>(w[k], d_w, K.dt);
-        un[k] = euler<EXACT>(u0[k], d_u, K.dt);
+        un[k] = euler<EXACT>(u0[k], Num<EXACT>::add(del_u, j_ion), K.dt);   // solve.py:59, 70
     }
 }
 
@@ -524,7 +568,8 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         for (int s = 0; s < T; ++s) {
             const int rho = n0 - 4 * (s + 1);
             // only rows this stage emits (all of them in the steady state), only threads inside the tissue
-            const bool need = act && (ST || (rho >= C.r0 - 4 * (T - 1 - s) && rho < C.r1 + 4 * (T - 1 - s)));
+            const bool need = act && (ST || (rho >= (C.top ? 0 : C.r0 - 4 * (T - 1 - s)) &&
+                                             rho < (C.bot ? A.H : C.r1 + 4 * (T - 1 - s))));
 #pragma unroll
             for (int k = 0; k < 4; ++k) Dm[s][k] = DXm[s][k] = DYm[s][k] = 0.0f;
             if (need) {
@@ -539,12 +584,60 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         const int rho = n0 - 4 * (s + 1);  // row this stage emits (level s+1); its newest input row is rho+4
-        const int lo = C.r0 - 4 * (T - 1 - s), hi = C.r1 + 4 * (T - 1 - s);
+        const int lo = C.top ? 0 : C.r0 - 4 * (T - 1 - s), hi = C.bot ? A.H : C.r1 + 4 * (T - 1 - s);
         if (s > 0 && have_in) st4(r0p[s], in_u);  // row rho+4 takes the slot of row rho
         // u_x of row rho+2 (solve.py:49)
         float ngx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, u0[s][k], u1[s][k], R.prev[s][k], in_u[k]);
+        // ---- physical top / bottom edge (general body, chunks that touch it).  m = the newest input row of this stage.
+        // Along the rows the reference differentiates the edge-PADDED array twice (solve.py:29-32, 49, 51) with one-sided
+        // formulas in padded rows 0, 1 and H, H+1.  In terms of tissue rows, with gx[r] = u_x of row r:
+        //   top     gxpad = FWD(u0,u0,u1,u2), gx[0] = FWD(u0..u3), gx[1] = CEN(u0,u0,u2,u3): made when row 3 arrives;
+        //           u_xx[0] = FWD(gx[0..3]) needs row 5, ONE ROW MORE than the pipeline's lag: row 0's v, w are emitted
+        //           on time (m = 4), its u one iteration later (m = 5) and handed to the next stage retroactively;
+        //           u_xx[1] = CEN(gxpad, gx[0], gx[2], gx[3]) is the ordinary formula on that window.
+        //   bottom  gx[H-2] = CEN(u[H-4],u[H-3],u[H-1],u[H-1]), gx[H-1] = BWD(u[H-4..H-1]), gxpad = BWD(u[H-3],u[H-2],
+        //           u[H-1],u[H-1]) are made when the last row arrives (m = H-1) and fed to the window while the stage runs
+        //           dry (m = H .. H+2); u_xx[H-1] = BWD(gx[H-4..H-1]) is taken from the window one iteration early.
+        const int m = rho + 4;
+        bool defer_u = false, give_uxx = false, top_init = false;
+        float tgx[3][4];
+        if (!ST && (C.top || C.bot)) {
+            float rm2[4] = {0.f, 0.f, 0.f, 0.f};   // row m-2: the only window row the ordinary formulas never read
+            if ((C.top && m == 3) || (C.bot && m == A.H - 1))
+                unpack4(ld4(s == 0 ? tb + L::U0 + 4 * ((i + 6) & 7) : tb + L::U(s) + 4 * ((i + 2) & 3)), rm2);
+            if (C.top && m == 3) {
+                top_init = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a0 = u1[s][k], a1 = rm2[k], a2 = R.prev[s][k], a3 = in_u[k];   // rows 0, 1, 2, 3
+                    tgx[0][k] = edge_deriv<EXACT>(A.K, FWD, a0, a0, a1, a2);
+                    tgx[1][k] = edge_deriv<EXACT>(A.K, FWD, a0, a1, a2, a3);
+                    tgx[2][k] = dcen<EXACT>(A.K, a0, a0, a2, a3);
+                }
+            }
+            if (C.top && m == 4) defer_u = true;
+            if (C.bot && m == A.H - 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a0 = u1[s][k], a1 = rm2[k], a2 = R.prev[s][k], a3 = in_u[k];   // rows H-4 .. H-1
+                    R.sv[s][0][k] = dcen<EXACT>(A.K, a0, a1, a3, a3);
+                    R.sv[s][1][k] = edge_deriv<EXACT>(A.K, BWD, a0, a1, a2, a3);
+                    R.sv[s][2][k] = edge_deriv<EXACT>(A.K, BWD, a1, a2, a3, a3);
+                }
+            }
+            if (C.bot && m >= A.H && m <= A.H + 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ngx[k] = m == A.H ? R.sv[s][0][k] : (m == A.H + 1 ? R.sv[s][1][k] : R.sv[s][2][k]);
+            }
+            if (C.bot && m == A.H + 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    R.sv[s][3][k] = edge_deriv<EXACT>(A.K, BWD, R.GX[s][0][k], R.GX[s][1][k], R.GX[s][2][k], R.GX[s][3][k]);
+            }
+            if (C.bot && m == A.H + 3) give_uxx = true;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) R.prev[s][k] = in_u[k];
         const bool emit = ST || (rho >= lo && rho < hi);
@@ -562,9 +655,22 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                 for (int k = 0; k < 4; ++k) { Dv[k] = C.Dc; DXv[k] = C.DXc; DYv[k] = C.DYc; }
                 if (edgeL) DYv[0] = C.DYcL;
                 if (edgeR) DYv[3] = C.DYcR;
+                if (!ST && C.top && rho == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) DXv[k] = C.DXcT;
+                }
+                if (!ST && C.bot && rho == A.H - 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) DXv[k] = C.DXcB;
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { Dv[k] = Dm[UNI ? 0 : s][k]; DXv[k] = DXm[UNI ? 0 : s][k]; DYv[k] = DYm[UNI ? 0 : s][k]; }
+            }
+            const int emode = ST ? 0 : (defer_u ? 1 : (give_uxx ? 2 : 0));
+            if (!ST && defer_u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { R.sv[s][0][k] = u0[s][k]; R.sv[s][1][k] = R.gy[s][k]; }
             }
             float un[4], vn[4], wn[4];
             const unsigned mask = ST ? 0u : C.mask[s];
@@ -580,15 +686,15 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                     }
                 stream_emit<EXACT, true, EDGE>(A.K, u0[s], vv[s], ww[s], R.GX[s][W0], R.GX[s][W1], R.GX[s][W2],
                                                R.GX[s][W3], ngx, g, R.gy[s], Dv, DXv, DYv,
-                                               stim, edgeL, edgeR, un, vn, wn);
+                                               stim, edgeL, edgeR, un, vn, wn, emode, R.sv[s]);
             } else {
                 stream_emit<EXACT, false, EDGE>(A.K, u0[s], vv[s], ww[s], R.GX[s][W0], R.GX[s][W1], R.GX[s][W2],
                                                 R.GX[s][W3], ngx, g, R.gy[s], Dv, DXv, DYv,
-                                                nullptr, edgeL, edgeR, un, vn, wn);
+                                                nullptr, edgeL, edgeR, un, vn, wn, emode, R.sv[s]);
             }
             if (s == T - 1) {
-                if (c >= C.out_c0 && c < C.out_c1) {
-                    st4(A.u_out + grow, un);
+                if (c >= C.out_c0 && c < C.out_c1 && rho >= C.r0) {   // (rho < r0: the unrolled body while it fills)
+                    if (ST || !defer_u) st4(A.u_out + grow, un);   // (a deferred first row's u follows below)
                     st4(A.v_out + grow, vn);
                     st4(A.w_out + grow, wn);
                 }
@@ -597,6 +703,37 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                 for (int k = 0; k < 4; ++k) in_u[k] = un[k];
                 st4(P.bj + L::V + 16 * (s + 1), vn);
                 st4(P.bj + L::W + 16 * (s + 1), wn);
+            }
+        }
+        if (!ST && C.top && m == 5) {
+            // the tissue's first row, one iteration late: u_xx[0] = FWD(gx[0], gx[1], gx[2], gx[3]) with gx[3] the new row
+            // of the window, u_x[0] = gx[0]; u_y, u_yy, j_ion and u itself were saved when its v, w were emitted
+            const long long grow0 = g0 - 4LL * (s + 1) * A.W - A.W;   // (sim, 0, c)
+            float Dv[4], DXv[4], DYv[4], un0[4];
+            if (UNI) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { Dv[k] = C.Dc; DXv[k] = C.DXcT; DYv[k] = C.DYc; }
+                if (edgeL) DYv[0] = C.DYcL;
+                if (edgeR) DYv[3] = C.DYcR;
+            } else {
+                const long long gd0 = gd - 4LL * (s + 1) * A.W - A.W;
+                unpack4(ldg4(A.D + gd0), Dv);
+                unpack4(ldg4(A.DX + gd0), DXv);
+                unpack4(ldg4(A.DY + gd0), DYv);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float u_xx = edge_deriv<EXACT>(A.K, FWD, R.GX[s][1][k], R.GX[s][2][k], R.GX[s][3][k], ngx[k]);
+                const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], R.GX[s][1][k], R.sv[s][1][k], u_xx, R.sv[s][2][k]);
+                un0[k] = euler<EXACT>(R.sv[s][0][k], Num<EXACT>::add(del_u, R.sv[s][3][k]), A.K.dt);
+            }
+            if (s == T - 1) {
+                if (c >= C.out_c0 && c < C.out_c1) st4(A.u_out + grow0, un0);
+            } else {
+                // the next stage should have received this row one iteration ago: its ring slot and its "previous row"
+                st4(tb + L::U(s + 1 < T ? s + 1 : s) + 4 * ((i + 3) & 3), un0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) R.prev[s + 1 < T ? s + 1 : s][k] = un0[k];
             }
         }
         // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
@@ -618,6 +755,10 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                 R.GX[s][1][k] = R.GX[s][2][k];
                 R.GX[s][2][k] = R.GX[s][3][k];
                 R.GX[s][3][k] = ngx[k];
+            }
+            if (top_init) {   // the window the first emissions need: (-, gxpad, gx[0], gx[1])
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { R.GX[s][1][k] = tgx[0][k]; R.GX[s][2][k] = tgx[1][k]; R.GX[s][3][k] = tgx[2][k]; }
             }
         }
         have_in = emit;
@@ -643,7 +784,7 @@ FK_HD void stream_iter_any(const TileArgs& A, const StreamCta& C, StreamState<T>
         stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
         return;
     }
-    const int ph = (i - nfill) % U;   // nfill is a multiple of 8
+    const int ph = (i - nfill) % U;   // nfill is a multiple of U
     const StreamBody<T> Y = stream_body_at<T>(tb, i - ph);
     const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
     if (ph == 0) stream_iter_phase<EXACT, T, UNI, U, 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
@@ -669,7 +810,8 @@ struct StreamPlan {
 // rounds * iterations-per-CTA * resident warps / issue-efficiency(resident warps).
 template <class OccFn>
 inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_threads, int rows_per_cta, int num_sms,
-                        int uniformD, int max_threads, OccFn occ, StreamPlan& P) {
+                        int uniformD, int max_threads, OccFn occ, StreamPlan& P, int first_chunk_discount = 0,
+                        int last_chunk_discount = 0) {
     if (T < 1 || T > 4) return false;
     if (W % 4 != 0) return false;                       // float4 rows
     if (row1 - row0 < 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
@@ -697,12 +839,23 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             if (RH <= 0) {
                 long long nch = waves * slots / units;
                 if (nch < 1) nch = 1;
-                RH = (int)((Hint + nch - 1) / nch);
+                // (discounts: rows a first / last chunk could be made shorter by.  Measured on 4096^2: the chunks at the
+                // physical top / bottom edge, which run 4T + 2 / 4T + 1 iterations in the general body, are NOT the
+                // last to finish, and any discount only lengthens the others -- so the driver passes 0)
+                RH = (int)((Hint + first_chunk_discount + last_chunk_discount + nch - 1) / nch);
                 RH = (RH + 3) / 4 * 4;   // whole bodies of the 4-way unrolled steady-state loop
-                if (RH < 8) RH = 8;
             }
+            // every chunk but the first / last must stay clear of the one-sided rows at a physical edge at every level:
+            // at least 4T rows per chunk, and a remainder of fewer than 4T rows is left to the last chunk
+            if (RH < 8) RH = 8;
+            if (RH < 4 * T) RH = 4 * T;
             if (RH > Hint) RH = Hint;
-            const int nchunks = (Hint + RH - 1) / RH;
+            int RH0 = RH - first_chunk_discount;
+            if (RH0 < 8) RH0 = 8;
+            if (RH0 < 4 * T) RH0 = 4 * T;
+            if (RH0 > Hint) RH0 = Hint;
+            int nchunks = 1 + (Hint - RH0 + RH - 1) / RH;
+            if (nchunks > 1 && Hint - RH0 - (nchunks - 2) * RH < 4 * T) --nchunks;
             const long long ncta = units * nchunks;
             const double rounds = (double)((ncta + slots - 1) / slots);
             // CTAs actually resident on an SM (a small tissue does not fill the machine), their active warps, and
@@ -717,7 +870,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             const double cost = rounds * (RH + 8.0 * T) * T * (warps + 8.0) / 4.0 * (1.0 + 0.02 * (wpc > 4 ? wpc - 4 : 0));
             if (best < 0 || cost < best) {
                 best = cost;
-                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RH = RH;
+                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RH = RH; P.G.RH0 = RH0;
                 P.G.nstrips = nstrips; P.G.nchunks = nchunks; P.G.cstride = stride; P.G.uniformD = uniformD;
                 P.G.row0 = row0; P.G.row1 = row1;
                 P.T = T;
@@ -745,13 +898,16 @@ inline void emu_stream_cta(const TileArgs& A, const StreamGeom& G, int strip, in
     std::vector<StreamState<T>> R((size_t)G.NT);
     for (int tid = 0; tid < G.NT; ++tid) {
         stream_state_init<T>(A, C, tid, R[tid]);
-        stream_warm_load<T>(A, C, stream_chunk<T>(smem.data(), tid), tid);
+        float* tb = stream_chunk<T>(smem.data(), tid);
+        if (!stream_use_warm<T>(C)) for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, C, tb, j, tid, C.cs + 4 * tid < C.c_end);
+        else stream_warm_load<T>(A, C, tb, tid);
     }
-    for (int q = 0; q < G.NT; ++q) {   // after the first block barrier
-        const int tid = reverse ? G.NT - 1 - q : q;
-        stream_warm_start<EXACT, T>(A, C, R[tid], stream_chunk<T>(smem.data(), tid), tid);
-    }
-    for (int i = FK_WARM; i < C.niter; ++i)
+    if (stream_use_warm<T>(C))
+        for (int q = 0; q < G.NT; ++q) {   // after the first block barrier
+            const int tid = reverse ? G.NT - 1 - q : q;
+            stream_warm_start<EXACT, T>(A, C, R[tid], stream_chunk<T>(smem.data(), tid), tid);
+        }
+    for (int i = stream_use_warm<T>(C) ? (int)FK_WARM : 0; i < C.niter; ++i)
         for (int q = 0; q < G.NT; ++q) {
             const int tid = reverse ? G.NT - 1 - q : q;
             float* tb = stream_chunk<T>(smem.data(), tid);

@@ -21,7 +21,6 @@ struct EmuBackend {
     int launches_tile = 0, launches_stream = 0;
     int num_sms() { return 148; }
     int occupancy(int, int, int, int NT, long long) { return NT <= 128 ? 2 : 1; }
-    int join() { return 0; }
     int tiles(fk::TileArgs& A, int exact, int batch, bool) {
         long long floats = 0;
         const int total = fk::finish_regions(A, &floats);

@@ -69,6 +69,42 @@ def test_stream_steady_state_body_exact(shape, T, nt, rh, reverse):
     assert info[1] == 2
 
 
+@pytest.mark.parametrize("shape,T,nt,rh,n_stim,uniform", [
+    ((8, 64), 1, 0, 0, 0, 0), ((9, 64), 1, 0, 0, 2, 0), ((16, 48), 2, 32, 0, 0, 1), ((24, 64), 3, 32, 24, 0, 0),
+    ((33, 64), 2, 32, 8, 0, 0), ((41, 64), 2, 32, 16, 2, 0), ((40, 64), 1, 32, 40, 0, 1), ((72, 160), 2, 32, 16, 0, 1),
+    ((44, 96), 1, 32, 40, 0, 0), ((130, 516), 4, 64, 17, 0, 0), ((57, 132), 2, 32, 20, 3, 0), ((200, 64), 2, 0, 0, 0, 1)])
+def test_stream_owns_the_physical_top_and_bottom_edges(shape, T, nt, rh, n_stim, uniform):
+    """No frame tiles any more: the first / last row chunk of the streaming kernel evaluates the reference's one-sided
+    formulas at the tissue's top / bottom edge (first row deferred by one iteration, last rows from saved u_x), for
+    single-chunk tissues, short last chunks, every T, with and without stimuli -- bit for bit, zero tile launches."""
+    st, D, stim = common.random_case(shape, seed=7, n_stim=n_stim)
+    if uniform:
+        D = np.full(shape, 1e-3, np.float32)
+    n = 2 * T
+    ref = C.forward_euler(st, 0, n, P3, D, stim, 0.01, 0.01)
+    got, info = emu.euler(st, 0, n, P3, D, stim, 0.01, 0.01, exact=True, T=T, kernel=2, cta_threads=nt, rows_per_cta=rh,
+                          uniform=uniform)
+    assert info == (0, 2)
+    for name, a, b in zip("vwu", got, ref):
+        assert np.array_equal(a, b), (name, np.argwhere(a != b)[:4].tolist())
+
+
+@pytest.mark.parametrize("lo,hi,pt,pb,row0,row1", [(0, 48, 1, 0, 0, 44), (0, 48, 1, 0, 32, 40), (32, 80, 0, 1, 4, 48),
+                                                   (32, 80, 0, 1, 8, 16), (32, 80, 0, 1, 16, 48), (16, 64, 0, 0, 4, 44)])
+def test_stream_row_windows_of_a_slab(lo, hi, pt, pb, row0, row1):
+    """fk_euler_rows building block: a window of output rows of a slab buffer, physical edge on one side or none."""
+    H, W = 80, 160
+    st, D, stim = common.random_case((H, W), seed=12, n_stim=2)
+    ref = C.forward_euler(st, 0, 1, P3, D, stim, 0.01, 0.01)
+    sub = [x[lo:hi] for x in st]
+    ss = [O.Stimulus(s.protocol, s.field[lo:hi]) for s in stim]
+    got, info = emu.euler(sub, 0, 1, P3, D[lo:hi], ss, 0.01, 0.01, exact=True, T=1, kernel=2, cta_threads=32, phys_top=pt,
+                          phys_bottom=pb, row0=row0, row1=row1)
+    assert info == (0, 1)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g[row0:row1], r[lo + row0:lo + row1])
+
+
 def test_stream_steady_state_uniform_fast_matches_tiles():
     st, _ = common.smooth_case((96, 400), seed=3)
     D = np.full((96, 400), 1e-3, np.float32)
