@@ -817,11 +817,13 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
     if (row1 - row0 < 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
     const int Wint = W, Hint = row1 - row0;
     double best = -1.0;
-    const int ns_min = (Wint + (4 * max_threads - 8 * T) - 1) / (4 * max_threads - 8 * T);
+    const int ns_min = Wint <= 4 * max_threads ? 1 : (Wint + (4 * max_threads - 8 * T) - 1) / (4 * max_threads - 8 * T);
     for (int ns = ns_min; ns < ns_min + 24; ++ns) {
         int stride = (Wint + ns - 1) / ns;
         stride = (stride + 3) / 4 * 4;
-        const int need = stride + 8 * T;
+        // columns a CTA must hold: its strip plus a 4T apron towards every neighbouring strip (none towards a physical
+        // left / right edge: a single strip spans the tissue with no apron at all)
+        const int need = stride + (ns == 1 ? 0 : (ns == 2 ? 4 * T : 8 * T));
         int NT = (need + 127) / 128 * 32;
         if (cta_threads > 0) {
             if (NT > cta_threads) continue;
