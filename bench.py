@@ -416,7 +416,8 @@ def main():
                 "traffic": ncu_traffic(workload), "peak_kind": peak_kind, "kernel": "fk_stream_kernel",
                 "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": sm_ms.value / sm_n.value,
                 "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms,
-                "note": "the frame-tile kernel runs on a side stream concurrently with the streaming kernel, so the shares can add to more than 1",
+                "note": "the streaming kernel covers the whole tissue, physical edges included; the rest of the step is "
+                        "fk_dgrad_kernel (once per call) and launch gaps",
                 "launch_geometry": plan}
     elif tl_n.value > 0:
         achieved = ALG_BYTES * cells * seg * args.steps / (tl_ms.value * 1e-3) / 1e9
