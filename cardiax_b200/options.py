@@ -4,7 +4,7 @@ numerics           "fast" (default): reciprocal multiplications + FMAs, a few ul
                    reference's operation order; "exact": the reference's order, op for op, bit-identical
                    to the CPU oracle (about half the throughput).
 steps_per_launch   temporal blocking depth T (0 = library default).
-kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel.
+kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel, 3 require the one-step wide kernel.
 """
 numerics = "fast"
 steps_per_launch = 0
