@@ -568,8 +568,9 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         for (int s = 0; s < T; ++s) {
             const int rho = n0 - 4 * (s + 1);
             // only rows this stage emits (all of them in the steady state), only threads inside the tissue
-            const bool need = act && (ST || (rho >= (C.top ? 0 : C.r0 - 4 * (T - 1 - s)) &&
-                                             rho < (C.bot ? A.H : C.r1 + 4 * (T - 1 - s))));
+            // (the unrolled body also runs while the later stages are still filling: their rows may lie above the tissue)
+            const bool need = act && (ST ? rho >= 0 : (rho >= (C.top ? 0 : C.r0 - 4 * (T - 1 - s)) &&
+                                                       rho < (C.bot ? A.H : C.r1 + 4 * (T - 1 - s))));
 #pragma unroll
             for (int k = 0; k < 4; ++k) Dm[s][k] = DXm[s][k] = DYm[s][k] = 0.0f;
             if (need) {
