@@ -11,8 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("FK_SO") or os.path.join(CSRC, "libfk.so")   # FK_SO: development A/B of two builds
-_SOURCES = ["fk_api.cu", "fk_stream_tu.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh", "fk_driver.h",
-            "fk_wide.h"]
+_SOURCES = ["fk_api.cu", "fk_stream_tu.cu", "fk_resident.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh",
+            "fk_driver.h", "fk_wide.h", "fk_resident.h", "fk_resident.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 STREAM_DEPTHS = (1, 2, 3, 4)   # one translation unit per (temporal-blocking depth, numerics), compiled in parallel
 
@@ -34,7 +34,7 @@ class FkOptions(ctypes.Structure):
     _fields_ = [("exact", ctypes.c_int), ("steps_per_launch", ctypes.c_int), ("kernel", ctypes.c_int),
                 ("phys_top", ctypes.c_int), ("phys_bottom", ctypes.c_int), ("cta_threads", ctypes.c_int),
                 ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("safe_division", ctypes.c_int),
-                ("reserved", ctypes.c_int * 7)]
+                ("tiles_r", ctypes.c_int), ("tiles_c", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
 
 
 def needs_build():
@@ -62,14 +62,25 @@ def build(force=False, verbose=False):
         depths = tuple(int(x) for x in os.environ["FK_DEPTHS"].split(","))
     mask = sum(1 << t for t in depths)
     jobs = [(os.path.join(objdir, "fk_api.o"), ["-DFK_DEPTH_MASK=%d" % mask, "-c", os.path.join(CSRC, "fk_api.cu")])]
+    jobs.append((os.path.join(objdir, "fk_resident.o"), ["-c", os.path.join(CSRC, "fk_resident.cu")]))
     for t in reversed(depths):   # the deepest (slowest to compile) first
         for e in (1, 0):
             jobs.append((os.path.join(objdir, "fk_stream_T%d_E%d.o" % (t, e)),
                          ["-DFK_TU_T=%d" % t, "-DFK_TU_EXACT=%d" % e, "-c", os.path.join(CSRC, "fk_stream_tu.cu")]))
     ptxas = ["-Xptxas", "-v"] if verbose else []
+    stream_deps = ["fk_stream_tu.cu", "fk_stream.cuh", "fk_stream.h", "fk_tile.h", "fk_core.h"]
+
+    def fresh(job):   # an object newer than everything its translation unit includes is kept (FK_DEPTHS changes: force)
+        obj, args = job
+        if force or not os.path.exists(obj) or "fk_api.cu" in args[-1]:
+            return False
+        deps = stream_deps if "fk_stream_tu.cu" in args[-1] else _SOURCES
+        return all(os.path.getmtime(obj) >= os.path.getmtime(os.path.join(CSRC, d)) for d in deps)
 
     def run(job):
         obj, args = job
+        if fresh(job):
+            return ""
         out = subprocess.run([nvcc] + NVCC_FLAGS + ptxas + args + ["-o", obj], capture_output=True, text=True, env=env)
         if out.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
@@ -122,6 +133,7 @@ def lib():
     L.fk_launch_count.restype = ll
     L.fk_last_plan.argtypes = [ctypes.POINTER(ci * 8)]
     L.fk_last_plan.restype = None
+    L.fk_last_kernel.restype = ctypes.c_char_p
     L.fk_profile_enable.argtypes = [ci]
     L.fk_profile_enable.restype = None
     L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll),
@@ -133,9 +145,16 @@ def lib():
     return L
 
 
+def last_kernel():
+    return lib().fk_last_kernel().decode()
+
+
 def last_plan():
     out = (ctypes.c_int * 8)()
     lib().fk_last_plan(ctypes.byref(out))
+    if last_kernel() == "fk_resident_kernel":
+        return dict(zip(("steps", "cta_threads", "tile_cols", "tile_w", "tile_h", "tile_rows", "ctas_per_sm", "smem_bytes"),
+                        list(out)))
     return dict(zip(("T", "cta_threads", "strips", "cols_per_strip", "rows_per_cta", "row_chunks", "ctas_per_sm",
                      "smem_bytes"), list(out)))
 

@@ -10,6 +10,7 @@
 #include "fk_core.h"
 #include "fk_tile.h"
 #include "fk_stream.cuh"
+#include "fk_resident.cuh"
 #include "fk_driver.h"
 
 namespace {
@@ -32,6 +33,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 long long g_launches = 0;
 int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+const char* g_last_kernel = "";
 int g_num_sms = 0;
 int num_sms() {
     if (!g_num_sms) {
@@ -155,6 +157,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     float *DX, *DY, *pv, *pw, *pu;
     fk::StimDev* stims;
+    unsigned* flags;
     size_t bytes;
 };
 
@@ -170,6 +173,7 @@ Workspace carve(void* base, int H, int W, int batch, int n_stim, int d_batched) 
     ws.pw = (float*)(p + off); off = align_up(off + plane * batch, 256);
     ws.pu = (float*)(p + off); off = align_up(off + plane * batch, 256);
     ws.stims = (fk::StimDev*)(p + off); off = align_up(off + sizeof(fk::StimDev) * (size_t)std::max(1, batch * n_stim), 256);
+    ws.flags = (unsigned*)(p + off); off = align_up(off + sizeof(unsigned) * fk::FK_RES_MAX_CTAS, 256);
     ws.bytes = off;
     return ws;
 }
@@ -225,6 +229,7 @@ struct CudaBackend {
         const size_t smem = (size_t)floats * sizeof(float);
         if (smem > 227 * 1024) return fail(-3, "tile does not fit shared memory%s");
         ProfScope ps(1, st);
+        g_last_kernel = "fk_tile_kernel";
         ++g_launches;
         static size_t attr_set[2] = {0, 0};   // largest dynamic shared memory already allowed, per instantiation
         if (smem > attr_set[exact ? 1 : 0]) {
@@ -243,6 +248,7 @@ struct CudaBackend {
         g_last_plan[0] = 1; g_last_plan[1] = 128; g_last_plan[2] = 0; g_last_plan[3] = A.W; g_last_plan[4] = 1;
         g_last_plan[5] = (int)blocks; g_last_plan[6] = 0; g_last_plan[7] = 0;
         ProfScope ps(0, st);
+        g_last_kernel = "fk_wide_kernel";
         if (ps.active) g_prof.stream_cs += (double)A.H * A.W * batch;
         ++g_launches;
         if (exact) fk_wide_kernel<true><<<dim3(blocks, batch), 128, 0, st>>>(A);
@@ -250,10 +256,25 @@ struct CudaBackend {
         FK_CUDA(cudaGetLastError());
         return 0;
     }
+    long long resident_smem_limit() { return 227 * 1024 - 64; }
+    int resident(const fk::ResPlan& P, const fk::TileArgs& A, int exact, int batch) {
+        g_last_plan[0] = P.G.nsteps; g_last_plan[1] = P.threads; g_last_plan[2] = P.G.ntc; g_last_plan[3] = P.G.tw_max;
+        g_last_plan[4] = P.G.th_max; g_last_plan[5] = P.G.ntr; g_last_plan[6] = 1; g_last_plan[7] = (int)P.smem_bytes;
+        const int cap = fk::resident_capacity(exact, P.threads, P.smem_bytes, num_sms());
+        if ((long long)P.G.ntr * P.G.ntc * batch > cap) return fail(-3, "resident kernel: the tiles are not co-resident on this device%s");
+        ProfScope ps(0, st);
+        g_last_kernel = "fk_resident_kernel";
+        if (ps.active) g_prof.stream_cs += (double)A.H * A.W * batch * P.G.nsteps;
+        ++g_launches;
+        const int rc = fk::launch_resident(P, A, exact, batch, st);
+        if (rc) return cuda_fail((cudaError_t)rc, "resident kernel launch");
+        return 0;
+    }
     int stream(const fk::StreamPlan& P, const fk::TileArgs& A, int exact, int batch) {
         g_last_plan[0] = P.T; g_last_plan[1] = P.G.NT; g_last_plan[2] = P.G.nstrips; g_last_plan[3] = P.G.cstride;
         g_last_plan[4] = P.G.RH; g_last_plan[5] = P.G.nchunks; g_last_plan[6] = P.occ; g_last_plan[7] = (int)P.smem_bytes;
         ProfScope ps(0, st);
+        g_last_kernel = "fk_stream_kernel";
         if (ps.active) g_prof.stream_cs += (double)(P.G.row1 - P.G.row0) * A.W * P.T * batch;
         ++g_launches;
         const int rc = fk::launch_stream(P, A, exact, batch, st);
@@ -284,6 +305,8 @@ long long fk_launch_count(void) { return g_launches; }
 void fk_last_plan(int* out8) {
     for (int i = 0; i < 8; ++i) out8[i] = g_last_plan[i];
 }
+
+const char* fk_last_kernel(void) { return g_last_kernel; }
 
 void fk_profile_enable(int on) { g_prof.on = on != 0; }
 
@@ -400,6 +423,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     fk::DriveBuffers B;
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu; B.D = D; B.stims = ws.stims;
+    B.flags = rows_mode ? nullptr : ws.flags;
     B.DX = DXext ? DXext : ws.DX;
     B.DY = DYext ? DYext : ws.DY;
     fk::DriveOptions o;
@@ -407,6 +431,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.phys_top = opt.phys_top; o.phys_bottom = opt.phys_bottom; o.cta_threads = opt.cta_threads;
     o.rows_per_cta = opt.rows_per_cta; o.uniform_diffusivity = opt.uniform_diffusivity;
     o.row0 = row0; o.row1 = row1;
+    o.tiles_r = opt.tiles_r; o.tiles_c = opt.tiles_c;
     CudaBackend be;
     be.st = st;
     const char* why = "";

@@ -5,17 +5,20 @@
 #include "fk_stream.h"
 #include "fk_tile.h"
 #include "fk_wide.h"
+#include "fk_resident.h"
 
 namespace fk {
 
 struct DriveOptions {
     int exact;
     int steps_per_launch;   // 0 = default
-    int kernel;             // 0 auto, 1 tiles only, 2 streaming required, 3 low-latency wide kernel required
+    int kernel;             // 0 auto, 1 tiles only, 2 streaming required, 3 low-latency wide kernel required,
+                            // 4 resident kernel required
     int phys_top, phys_bottom;
     int cta_threads, rows_per_cta;
     int uniform_diffusivity;
     int row0, row1;         // output rows of a single-launch call (slab building block); row1 <= 0: all the rows owned
+    int tiles_r, tiles_c;   // resident kernel: tile grid (0 = planner's choice)
 };
 
 struct DriveBuffers {
@@ -24,9 +27,14 @@ struct DriveBuffers {
     float *pv, *pw, *pu;            // ping-pong scratch, (batch, H, W) each
     const float *D, *DX, *DY;
     const StimDev* stims;           // device/emulated copy of the stimulus table, or null
+    unsigned* flags;                // resident kernel: FK_RES_MAX_CTAS progress flags (zeroed by the backend), or null
 };
 
-enum { FK_DEFAULT_T = 2 };
+enum { FK_DEFAULT_T = 2, FK_RES_MAX_CTAS = 1024 };
+// Tissues (x batch) up to this many cells that fit the SMs' shared memory run whole calls in ONE resident launch.
+#ifndef FK_RES_MAX_CELLS
+#define FK_RES_MAX_CELLS (1LL << 20)
+#endif
 
 // finalises the tile counts of A.reg[0..nreg)
 inline int finish_regions(TileArgs& A, long long* smem_floats) {
@@ -68,6 +76,7 @@ inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
 // Backend: int tiles(TileArgs&, int exact, int batch, bool side);
 //          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);
 //          int wide(const TileArgs&, int exact, int batch);
+//          int resident(const ResPlan&, const TileArgs&, int exact, int batch);  long long resident_smem_limit();
 //          int num_sms(); int occupancy(int T, int exact, int uniform, int NT, long long smem_bytes);
 // Returns 0 or the backend's error code; *why gets a static message on argument errors.
 template <class Backend>
@@ -100,14 +109,24 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             return -1;
         }
     }
+    // tissues that fit the machine's shared memory: the whole call in one resident launch (fk_resident.h)
+    ResPlan rplan;
+    bool use_res = false;
+    if (!rhs_mode && !slab && opt.row1 <= 0 && B.flags && nsteps < (1LL << 30) &&
+        (opt.kernel == 4 || (opt.kernel == 0 && opt.steps_per_launch == 0 && nsteps >= 4 &&
+                             (long long)H * W * batch <= FK_RES_MAX_CELLS))) {
+        const int cap = be.num_sms() < FK_RES_MAX_CTAS ? be.num_sms() : FK_RES_MAX_CTAS;
+        use_res = plan_resident(H, W, batch, cap, be.resident_smem_limit(), opt.tiles_r, opt.tiles_c, opt.cta_threads, rplan);
+    }
+    if (opt.kernel == 4 && !use_res) { *why = "resident kernel not applicable (needs W % 4 == 0, a whole tissue that fits shared memory)"; return -5; }
     // tissues too small to fill the machine: one launch of the barrier-free wide kernel per step
     const bool wide_ok = !rhs_mode && !slab && opt.row1 <= 0 && W % 4 == 0 && H >= 3 && W >= 4;
-    const bool use_wide = wide_ok && (opt.kernel == 3 || (opt.kernel == 0 && opt.steps_per_launch == 0 &&
+    const bool use_wide = !use_res && wide_ok && (opt.kernel == 3 || (opt.kernel == 0 && opt.steps_per_launch == 0 &&
                                                           (long long)H * W * batch < (1LL << 20)));
     if (opt.kernel == 3 && !use_wide) { *why = "wide kernel not applicable (needs W % 4 == 0, whole tissue)"; return -5; }
     StreamPlan plan;
     bool use_stream = false;
-    if (!rhs_mode && opt.kernel != 1 && !use_wide) {
+    if (!rhs_mode && opt.kernel != 1 && !use_wide && !use_res) {
         auto try_plan = [&](int T, StreamPlan& P) {
             int R0, R1;
             bool ok;
@@ -142,6 +161,16 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     A.stims = n_stim ? B.stims : nullptr;
     A.n_stim = n_stim;
 
+    if (use_res) {
+        A.u_in = B.u_in; A.v_in = B.v_in; A.w_in = B.w_in;
+        A.u_out = B.u_out; A.v_out = B.v_out; A.w_out = B.w_out;
+        A.T = 1; A.t0 = t0;
+        rplan.G.nsteps = (int)nsteps;
+        rplan.G.xb[0] = B.pu; rplan.G.xb[1] = B.pv;
+        rplan.G.flags = B.flags;
+        rplan.G.spin_limit = 1u << 24;
+        return be.resident(rplan, A, opt.exact, batch);
+    }
     if (use_wide) Tmax = 1;
     const long long nl = rhs_mode ? 1 : (nsteps + Tmax - 1) / Tmax;
     const float *sv = B.v_in, *sw = B.w_in, *su = B.u_in;

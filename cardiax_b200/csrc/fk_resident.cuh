@@ -1,0 +1,14 @@
+// fk_resident.cuh -- entry points of the resident-kernel translation unit (fk_resident.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fk_resident.h"
+
+namespace fk {
+
+// returns 0 or a cudaError_t; zeroes the flags, then one cooperative launch of P.G.nsteps Euler steps
+int launch_resident(const ResPlan& P, const TileArgs& A, int exact, int batch, cudaStream_t st);
+// CTAs of this shape the device holds at once (0: does not fit)
+int resident_capacity(int exact, int threads, long long smem_bytes, int num_sms);
+
+}  // namespace fk

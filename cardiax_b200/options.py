@@ -4,13 +4,16 @@ numerics           "fast" (default): reciprocal multiplications + FMAs, a few ul
                    reference's operation order; "exact": the reference's order, op for op, bit-identical
                    to the CPU oracle (about half the throughput).
 steps_per_launch   temporal blocking depth T (0 = library default).
-kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel, 3 require the one-step wide kernel.
+kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel, 3 require the one-step wide kernel,
+                   4 require the resident kernel (whole call in one cooperative launch, state in shared memory).
+tiles              resident kernel: (rows, columns) of the tile grid, one CTA per tile ((0, 0) = planner's choice).
 """
 numerics = "fast"
 steps_per_launch = 0
 kernel = 0
 cta_threads = 0
 rows_per_cta = 0
+tiles = (0, 0)
 detect_uniform_diffusivity = True
 safe_division = False   # exact numerics: force every division through __fdiv_rn
 verbose = True

@@ -44,7 +44,8 @@ typedef struct FkOptions {
     int exact;            /* 1: reference operation order, bit-identical to the CPU oracle; 0: fast numerics */
     int steps_per_launch; /* temporal blocking depth T (1..8); 0 = library default */
     int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = streaming kernel + frame tiles,
-                             3 = low-latency one-step kernel for small tissues */
+                             3 = low-latency one-step kernel for small tissues, 4 = resident kernel (whole call in one
+                             cooperative launch, state in shared memory) */
     int phys_top;         /* is buffer row 0 the physical tissue edge? (0 only for slab decomposition) */
     int phys_bottom;      /* is buffer row H-1 the physical tissue edge? */
     int cta_threads;      /* streaming kernel: threads per CTA (0 = auto) */
@@ -53,7 +54,8 @@ typedef struct FkOptions {
                                 D, D_x, D_y as three scalars instead of reading three maps */
     int safe_division;    /* exact numerics only: 1 = every division through the IEEE sequence (__fdiv_rn) instead of the
                              3-instruction correctly rounded FMA division by constants (see fk_check_exact_division) */
-    int reserved[7];
+    int tiles_r, tiles_c; /* resident kernel: tile grid rows x columns, one CTA per tile (0 = auto) */
+    int reserved[5];
 } FkOptions;
 
 /* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */
@@ -125,6 +127,10 @@ long long fk_launch_count(void);
 /* geometry of the most recent streaming-kernel launch: {T, cta_threads, strips, columns per strip, rows per CTA,
  * row chunks, resident CTAs per SM, dynamic shared memory bytes} */
 void fk_last_plan(int* out8);
+/* name of the step kernel launched most recently: "fk_stream_kernel", "fk_resident_kernel", "fk_wide_kernel",
+ * "fk_tile_kernel" (resident launches report {steps, cta_threads, tile columns, tile width, tile height, tile rows, 1,
+ * shared memory bytes} through fk_last_plan) */
+const char* fk_last_kernel(void);
 void fk_profile_enable(int on);
 int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches,
                        double* stream_cell_steps);

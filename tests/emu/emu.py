@@ -18,7 +18,7 @@ class _Stim(ctypes.Structure):
 
 def build(force=False):
     deps = [os.path.join(_HERE, "fk_emu.cpp")] + [os.path.join(_CSRC, f) for f in
-                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h", "fk_wide.h")]
+                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h", "fk_wide.h", "fk_resident.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
@@ -42,7 +42,7 @@ def stim_active(t, start, duration, period):
 
 
 def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, cta_threads=0, rows_per_cta=0,
-          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0):
+          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0, tiles=(0, 0)):
     """state: (v, w, u) arrays of shape (H, W) or (batch, H, W).  Returns (v, w, u) and launch counts."""
     v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
     batched = u.ndim == 3
@@ -63,8 +63,8 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
             f = np.ascontiguousarray(s.field, dtype=np.float32)
             keep.append(f)
             arr[b * n_stim + i] = _Stim(f.ctypes.data, *[float(np.asarray(x).reshape(-1)[0]) for x in s.protocol])
-    opts = (ctypes.c_int * 11)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse,
-                               row0, row1)
+    opts = (ctypes.c_int * 13)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse,
+                               row0, row1, int(tiles[0]), int(tiles[1]))
     info = (ctypes.c_int * 2)()
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib().fk_emu_euler(p(v), p(w), p(u), p(vo), p(wo), p(uo), p(D), d_batched, H, W, batch, p(par), arr, n_stim,
@@ -73,3 +73,11 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
     if rc != 0:
         raise RuntimeError("fk_emu_euler rc=%d" % rc)
     return (vo, wo, uo), (info[0], info[1])
+
+
+def plan_resident(H, W, batch=1):
+    """The resident kernel's geometry for a problem: dict or None."""
+    out = (ctypes.c_int * 6)()
+    if not lib().fk_emu_plan_resident(H, W, batch, out):
+        return None
+    return dict(zip(("ntr", "ntc", "th_max", "tw_max", "threads", "smem_bytes"), list(out)))

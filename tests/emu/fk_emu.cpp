@@ -61,6 +61,14 @@ struct EmuBackend {
         }
         return 0;
     }
+    int launches_res = 0;
+    long long resident_smem_limit() { return 227 * 1024 - 64; }
+    int resident(const fk::ResPlan& P, const fk::TileArgs& A, int exact, int batch) {
+        ++launches_res;
+        last_res = P;
+        return fk::emu_resident_launch(P, A, batch, exact);
+    }
+    fk::ResPlan last_res;
     int stream(const fk::StreamPlan& P, const fk::TileArgs& A, int exact, int batch) {
         ++launches_stream;
         return fk::emu_stream_launch(P, A, batch, exact, reverse);
@@ -77,8 +85,8 @@ struct EmuStim {
 };
 
 // options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse,
-//           row0, row1}
-// info (optional, 2 ints): tile launches, stream launches
+//           row0, row1, tiles_r, tiles_c}
+// info (optional, 2 ints): tile launches, stream launches + 1000 * wide launches + 1000000 * resident launches
 int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
                  const float* D, int d_batched, int H, int W, int batch, const float* params14, const EmuStim* stims,
                  int n_stim, double t0, double t1, float dt, float dx, const int* options, int rhs_mode, int* info) {
@@ -95,10 +103,12 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = pv.data(); B.pw = pw.data(); B.pu = pu.data(); B.D = D; B.DX = DX.data(); B.DY = DY.data();
     B.stims = (const fk::StimDev*)stims;
+    unsigned dummy_flags[1] = {0};
+    B.flags = dummy_flags;   // the emulation keeps its own flags
     fk::DriveOptions o;
     o.exact = options[0]; o.steps_per_launch = options[1]; o.kernel = options[2]; o.phys_top = options[3];
     o.phys_bottom = options[4]; o.cta_threads = options[5]; o.rows_per_cta = options[6]; o.uniform_diffusivity = options[7];
-    o.row0 = options[9]; o.row1 = options[10];
+    o.row0 = options[9]; o.row1 = options[10]; o.tiles_r = options[11]; o.tiles_c = options[12];
     EmuBackend be;
     be.reverse = options[8];
     const long long nsteps = rhs_mode ? 1 : fk::count_steps(t0, t1);
@@ -109,7 +119,7 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     const char* why = "";
     const int rc = fk::drive_euler(be, B, d_batched, H, W, batch, fk::make_consts(params14, dt, dx), n_stim, t0, nsteps, o,
                                    rhs_mode, &why);
-    if (info) { info[0] = be.launches_tile; info[1] = be.launches_stream + 1000 * be.launches_wide; }
+    if (info) { info[0] = be.launches_tile; info[1] = be.launches_stream + 1000 * be.launches_wide + 1000000 * be.launches_res; }
     return rc;
 }
 
@@ -131,6 +141,14 @@ extern "C" int fk_emu_plan(int H, int W, int batch, int T, int cta_threads, int 
     if (!ok) return 0;
     out[0] = P.G.NT; out[1] = P.G.nstrips; out[2] = P.G.cstride; out[3] = P.G.RH; out[4] = P.G.nchunks;
     out[5] = (int)P.smem_bytes;
+    return 1;
+}
+
+// resident planner probe (tests): {ntr, ntc, th_max, tw_max, threads, smem bytes}
+extern "C" int fk_emu_plan_resident(int H, int W, int batch, int* out) {
+    fk::ResPlan P;
+    if (!fk::plan_resident(H, W, batch, 148, 227 * 1024 - 64, 0, 0, 0, P)) return 0;
+    out[0] = P.G.ntr; out[1] = P.G.ntc; out[2] = P.G.th_max; out[3] = P.G.tw_max; out[4] = P.threads; out[5] = (int)P.smem_bytes;
     return 1;
 }
 

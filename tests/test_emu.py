@@ -42,11 +42,51 @@ def test_wide_kernel_exact(shape):
     assert info == (0, 6000)   # six launches of the wide kernel, nothing else
 
 
-def test_small_tissue_defaults_to_the_wide_kernel_and_fast_matches_other_kernels():
+@pytest.mark.parametrize("shape,nsteps,tiles", [
+    ((12, 16), 6, (0, 0)), ((3, 4), 5, (0, 0)), ((64, 96), 7, (0, 0)), ((64, 96), 7, (2, 3)), ((64, 96), 7, (4, 1)),
+    ((40, 64), 9, (3, 2)), ((37, 52), 8, (2, 2)), ((130, 20), 6, (0, 0)), ((9, 132), 6, (0, 0)), ((100, 200), 6, (5, 5)),
+    ((64, 96), 1, (2, 3)), ((64, 96), 2, (1, 1)), ((128, 128), 5, (0, 0)), ((33, 72), 6, (4, 9))])
+def test_resident_kernel_exact(shape, nsteps, tiles):
+    """Whole call in one resident launch (tiles in shared memory, halos through exchange planes): any tile grid, uneven
+    tiles, ring-only tiles, all four physical edges, stimuli -- bit-identical to the oracle."""
+    info = _exact(shape, 1, nsteps=nsteps, kernel=4, tiles=tiles)
+    assert info == (0, 1000000)   # one launch, nothing else
+
+
+def test_resident_kernel_exact_batched_per_tissue_inputs():
+    shape, batch = (40, 48), 3
+    cases = [common.random_case(shape, seed=20 + b, n_stim=2) for b in range(batch)]
+    st = [np.stack([c[0][k] for c in cases]) for k in range(3)]
+    D = np.stack([c[1] for c in cases])
+    stims = [c[2] for c in cases]
+    got, info = emu.euler(st, 0, 6, P3, D, stims, 0.01, 0.01, exact=True, kernel=4, tiles=(2, 2))
+    assert info == (0, 1000000)
+    for b in range(batch):
+        ref = C.forward_euler(cases[b][0], 0, 6, P3, cases[b][1], cases[b][2], 0.01, 0.01)
+        for a, r in zip(got, ref):
+            assert np.array_equal(a[b], r)
+
+
+def test_resident_planner():
+    p = emu.plan_resident(512, 512)
+    assert p and p["ntr"] * p["ntc"] <= 148 and p["smem_bytes"] <= 227 * 1024 and p["threads"] % 32 == 0
+    assert emu.plan_resident(1200, 1200) is None          # 40 MB of state + maps do not fit 148 x 227 KB
+    assert emu.plan_resident(64, 66) is None              # rows must be whole groups of 4 cells
+    p = emu.plan_resident(256, 256, batch=8)
+    assert p and p["ntr"] * p["ntc"] * 8 <= 148
+
+
+def test_small_tissue_defaults_and_fast_matches_other_kernels():
     (st, D) = common.smooth_case((64, 96), seed=6)
     _, _, stim = common.random_case((64, 96), seed=6, n_stim=2)
     a, info = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False)
+    assert info == (0, 1000000)   # >= 4 steps of a small tissue: the resident kernel
+    a3, info = emu.euler(st, 0, 3, P3, D, stim, 0.01, 0.01, exact=False)
+    assert info == (0, 3000)      # fewer: one wide launch per step
+    w7, info = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False, kernel=3)
     assert info == (0, 7000)
+    for x, y in zip(a, w7):
+        assert np.array_equal(x, y)
     b, _ = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False, kernel=1, T=2)
     c, _ = emu.euler(st, 0, 7, P3, D, stim, 0.01, 0.01, exact=False, kernel=2, T=2, cta_threads=32)
     for x, y, z in zip(a, b, c):

@@ -26,7 +26,8 @@ P3 = O.PARAMSETS["3"]
 @pytest.fixture(autouse=True)
 def _reset_options():
     from cardiax_b200 import options
-    saved = {k: getattr(options, k) for k in ("numerics", "steps_per_launch", "kernel", "cta_threads", "rows_per_cta")}
+    saved = {k: getattr(options, k) for k in ("numerics", "steps_per_launch", "kernel", "cta_threads", "rows_per_cta",
+                                              "tiles")}
     options.verbose = False
     yield
     for k, v in saved.items():
@@ -63,6 +64,55 @@ def test_exact_bitwise_vs_oracle(shape, T, kernel, extra):
     ref = C.forward_euler(st, 0, 9, P3, D, stim, 0.01, 0.01)
     got = run_gpu(st, 0, 9, P3, D, stim, numerics="exact", steps_per_launch=T, kernel=kernel, **extra)
     assert_exact(got, ref, "shape %s T %d kernel %d" % (shape, T, kernel))
+
+
+@pytest.mark.parametrize("shape,nsteps,tiles,threads", [
+    ((12, 16), 9, (0, 0), 0), ((3, 4), 5, (0, 0), 0), ((64, 96), 9, (2, 3), 0), ((64, 96), 9, (4, 1), 256),
+    ((128, 128), 9, (0, 0), 0), ((100, 200), 9, (5, 5), 0), ((256, 256), 40, (0, 0), 0), ((512, 512), 9, (0, 0), 0),
+    ((512, 512), 12, (16, 8), 512), ((33, 72), 6, (4, 9), 128), ((64, 96), 1, (2, 3), 0), ((1024, 1024), 6, (0, 0), 0)])
+def test_resident_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads):
+    """The resident kernel (whole call in one cooperative launch; halos exchanged through L2 with release/acquire
+    flags between co-resident CTAs): bit-identical to the oracle for any tile grid."""
+    from cardiax_b200 import _lib
+    st, D, stim = common.random_case(shape, seed=4, n_stim=3)
+    ref = C.forward_euler(st, 0, nsteps, P3, D, stim, 0.01, 0.01)
+    before = _lib.lib().fk_launch_count()
+    got = run_gpu(st, 0, nsteps, P3, D, stim, numerics="exact", kernel=4, tiles=tiles, cta_threads=threads)
+    assert _lib.lib().fk_launch_count() - before == 2   # D_x/D_y maps + ONE resident launch
+    assert_exact(got, ref, "resident %s tiles %s" % (shape, tiles))
+
+
+def test_resident_kernel_is_the_default_for_small_tissues_and_matches_the_other_kernels():
+    """Fast numerics are tiling- and kernel-independent: resident == wide == streaming, bit for bit, over 300 steps of
+    a smooth excitable field with stimuli firing on the way (BASELINE config 1/2 sized tissues)."""
+    from cardiax_b200 import _lib
+    st, D = common.smooth_case((256, 256), seed=8)
+    _, _, stim = common.random_case((256, 256), seed=8, n_stim=3)
+    before = _lib.lib().fk_launch_count()
+    a = run_gpu(st, 0, 300, P3, D, stim, numerics="fast")
+    assert _lib.lib().fk_launch_count() - before == 2
+    b = run_gpu(st, 0, 300, P3, D, stim, numerics="fast", kernel=3)
+    c = run_gpu(st, 0, 300, P3, D, stim, numerics="fast", kernel=2, steps_per_launch=2)
+    assert_exact(a, b, "resident vs wide")
+    assert_exact(a, c, "resident vs streaming")
+
+
+def test_resident_kernel_batched_and_repeated_calls():
+    """Several tissues in one resident launch, then the same call again (flags are re-zeroed per call)."""
+    shape, batch = (64, 64), 6
+    cases = [common.random_case(shape, seed=30 + b, n_stim=2) for b in range(batch)]
+    st = [np.stack([c[0][k] for c in cases]) for k in range(3)]
+    D = np.stack([c[1] for c in cases])
+    from cardiax_b200 import options, solve, stimulus
+    options.numerics, options.kernel = "exact", 4
+    gst = [[stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in c[2]] for c in cases]
+    state = solve.State(*[torch.as_tensor(x).cuda() for x in st])
+    for _ in range(2):
+        out = solve._forward_euler(state, 0, 11, P3, torch.as_tensor(D).cuda(), gst, 0.01, 0.01)
+        torch.cuda.synchronize()
+        for b in range(batch):
+            ref = C.forward_euler(cases[b][0], 0, 11, P3, cases[b][1], cases[b][2], 0.01, 0.01)
+            assert_exact([x[b].cpu().numpy() for x in out], ref, "tissue %d" % b)
 
 
 @pytest.mark.parametrize("pset", sorted(O.PARAMSETS))

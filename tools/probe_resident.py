@@ -1,0 +1,76 @@
+"""Sweep the resident kernel's tile grid / CTA size on the GPU (development tool).
+
+    python tools/probe_resident.py [fk128 fk256 fk512 fk1024]
+One line per (workload, tiles, threads): device microseconds per Euler step and Gcell-steps/s of one n-step call.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import oracle as O  # noqa: E402
+from cardiax_b200 import _lib, options, solve, stimulus  # noqa: E402
+
+
+def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=0):
+    options.verbose = False
+    options.numerics, options.kernel, options.steps_per_launch = numerics, kernel, T
+    options.cta_threads, options.rows_per_cta, options.tiles = threads, 0, tiles
+    st = solve.State(*[torch.as_tensor(work[k]).cuda() for k in "vwu"])
+    D = torch.as_tensor(work["D"]).cuda()
+    gs = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in work["stimuli"]]
+    P = O.PARAMSETS[work["params"]]
+    try:
+        s = solve._forward_euler(st, 0, n, P, D, gs, 0.01, 0.01)
+        torch.cuda.synchronize()
+        best = 1e30
+        for rep in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s2 = solve._forward_euler(s, n, 2 * n, P, D, gs, 0.01, 0.01)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / n)
+        cells = st.u.numel()
+        print("%-7s kernel=%d tiles=%-9s thr=%3d %-5s %7.2f us/step %7.1f Gcs/s  %s" % (
+            name, kernel, tiles, threads, numerics, best, cells / best / 1e3, _lib.last_plan()), flush=True)
+    except Exception as e:  # noqa: BLE001
+        print("%-7s kernel=%d tiles=%s thr=%d failed: %s" % (name, kernel, tiles, threads, str(e)[:120]), flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["fk128", "fk256", "fk512", "fk1024"]
+    sweeps = {
+        "fk128": [((0, 0), 0), ((16, 1), 256), ((16, 2), 128), ((8, 2), 256), ((8, 4), 128), ((4, 4), 256), ((4, 2), 512),
+                  ((16, 8), 128), ((2, 2), 512), ((1, 1), 512), ((12, 12), 128)],
+        "fk256": [((0, 0), 0), ((32, 4), 128), ((32, 2), 256), ((16, 8), 128), ((16, 4), 256), ((12, 12), 128),
+                  ((8, 8), 256), ((8, 16), 128), ((18, 8), 128), ((4, 4), 512)],
+        "fk512": [((0, 0), 0), ((64, 2), 512), ((37, 4), 512), ((18, 8), 320), ((18, 8), 512), ((16, 8), 512), ((16, 8), 256),
+                  ((12, 12), 512), ((9, 16), 512), ((32, 4), 512), ((24, 6), 384), ((8, 16), 512)],
+        "fk1024": [((0, 0), 0), ((37, 4), 512), ((21, 7), 512), ((18, 8), 512), ((12, 12), 512), ((74, 2), 512),
+                   ((16, 9), 512)],
+    }
+    for name in which:
+        if name == "fk128":
+            work = bench.make_fk128()
+        elif name == "fk512":
+            work = bench.make_fk512()
+        else:
+            n = int(name[2:])
+            work = bench.make_fk512()
+            from tests import common
+            _, D = common.smooth_case((n, n), 0)
+            work = dict(v=np.ones((n, n), np.float32), w=np.ones((n, n), np.float32), u=bench.make_fk4096(n, n)["u"], D=D,
+                        stimuli=[], params="3")
+        for tiles, thr in sweeps.get(name, [((0, 0), 0)]):
+            run(name, work, 4, tiles, thr)
+        run(name, work, 3, n=400)
+        run(name, work, 2, n=400, T=2)
+        run(name, work, 4, numerics="exact", n=500)
+
+
+if __name__ == "__main__":
+    main()
