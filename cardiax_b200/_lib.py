@@ -34,7 +34,8 @@ class FkOptions(ctypes.Structure):
     _fields_ = [("exact", ctypes.c_int), ("steps_per_launch", ctypes.c_int), ("kernel", ctypes.c_int),
                 ("phys_top", ctypes.c_int), ("phys_bottom", ctypes.c_int), ("cta_threads", ctypes.c_int),
                 ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("safe_division", ctypes.c_int),
-                ("tiles_r", ctypes.c_int), ("tiles_c", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
+                ("tiles_r", ctypes.c_int), ("tiles_c", ctypes.c_int), ("cells_per_thread", ctypes.c_int),
+                ("reserved", ctypes.c_int * 4)]
 
 
 def needs_build():
@@ -134,6 +135,8 @@ def lib():
     L.fk_last_plan.argtypes = [ctypes.POINTER(ci * 8)]
     L.fk_last_plan.restype = None
     L.fk_last_kernel.restype = ctypes.c_char_p
+    L.fk_resident_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong * 8)]
+    L.fk_resident_timing.restype = ci
     L.fk_profile_enable.argtypes = [ci]
     L.fk_profile_enable.restype = None
     L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll),
@@ -153,7 +156,7 @@ def last_plan():
     out = (ctypes.c_int * 8)()
     lib().fk_last_plan(ctypes.byref(out))
     if last_kernel() == "fk_resident_kernel":
-        return dict(zip(("steps", "cta_threads", "tile_cols", "tile_w", "tile_h", "tile_rows", "ctas_per_sm", "smem_bytes"),
+        return dict(zip(("steps", "cta_threads", "tile_cols", "tile_w", "tile_h", "tile_rows", "cells_per_thread", "smem_bytes"),
                         list(out)))
     return dict(zip(("T", "cta_threads", "strips", "cols_per_strip", "rows_per_cta", "row_chunks", "ctas_per_sm",
                      "smem_bytes"), list(out)))

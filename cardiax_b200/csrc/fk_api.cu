@@ -157,7 +157,8 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     float *DX, *DY, *pv, *pw, *pu;
     fk::StimDev* stims;
-    unsigned* flags;
+    fk::u64* xchg;
+    size_t xchg_bytes;
     size_t bytes;
 };
 
@@ -173,7 +174,8 @@ Workspace carve(void* base, int H, int W, int batch, int n_stim, int d_batched) 
     ws.pw = (float*)(p + off); off = align_up(off + plane * batch, 256);
     ws.pu = (float*)(p + off); off = align_up(off + plane * batch, 256);
     ws.stims = (fk::StimDev*)(p + off); off = align_up(off + sizeof(fk::StimDev) * (size_t)std::max(1, batch * n_stim), 256);
-    ws.flags = (unsigned*)(p + off); off = align_up(off + sizeof(unsigned) * fk::FK_RES_MAX_CTAS, 256);
+    ws.xchg_bytes = (size_t)fk::res_xchg_bytes(H, W, batch);
+    ws.xchg = ws.xchg_bytes ? (fk::u64*)(p + off) : nullptr; off = align_up(off + ws.xchg_bytes, 256);
     ws.bytes = off;
     return ws;
 }
@@ -256,11 +258,11 @@ struct CudaBackend {
         FK_CUDA(cudaGetLastError());
         return 0;
     }
-    long long resident_smem_limit() { return 227 * 1024 - 64; }
+    long long resident_smem_limit() { return 227 * 1024 - 256; }
     int resident(const fk::ResPlan& P, const fk::TileArgs& A, int exact, int batch) {
         g_last_plan[0] = P.G.nsteps; g_last_plan[1] = P.threads; g_last_plan[2] = P.G.ntc; g_last_plan[3] = P.G.tw_max;
-        g_last_plan[4] = P.G.th_max; g_last_plan[5] = P.G.ntr; g_last_plan[6] = 1; g_last_plan[7] = (int)P.smem_bytes;
-        const int cap = fk::resident_capacity(exact, P.threads, P.smem_bytes, num_sms());
+        g_last_plan[4] = P.G.th_max; g_last_plan[5] = P.G.ntr; g_last_plan[6] = P.G.nc; g_last_plan[7] = (int)P.smem_bytes;
+        const int cap = fk::resident_capacity(exact, P.G.nc, P.threads, P.smem_bytes, num_sms());
         if ((long long)P.G.ntr * P.G.ntc * batch > cap) return fail(-3, "resident kernel: the tiles are not co-resident on this device%s");
         ProfScope ps(0, st);
         g_last_kernel = "fk_resident_kernel";
@@ -307,6 +309,12 @@ void fk_last_plan(int* out8) {
 }
 
 const char* fk_last_kernel(void) { return g_last_kernel; }
+
+int fk_resident_timing(unsigned long long* out8) {
+    if (!out8) return fail(-1, "NULL pointer%s");
+    const int rc = fk::resident_timing(out8);
+    return rc ? cuda_fail((cudaError_t)rc, "fk_resident_timing") : 0;
+}
 
 void fk_profile_enable(int on) { g_prof.on = on != 0; }
 
@@ -423,7 +431,8 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     fk::DriveBuffers B;
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu; B.D = D; B.stims = ws.stims;
-    B.flags = rows_mode ? nullptr : ws.flags;
+    B.xchg = rows_mode ? nullptr : ws.xchg;
+    B.xchg_bytes = rows_mode ? 0 : (long long)ws.xchg_bytes;
     B.DX = DXext ? DXext : ws.DX;
     B.DY = DYext ? DYext : ws.DY;
     fk::DriveOptions o;
@@ -431,7 +440,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.phys_top = opt.phys_top; o.phys_bottom = opt.phys_bottom; o.cta_threads = opt.cta_threads;
     o.rows_per_cta = opt.rows_per_cta; o.uniform_diffusivity = opt.uniform_diffusivity;
     o.row0 = row0; o.row1 = row1;
-    o.tiles_r = opt.tiles_r; o.tiles_c = opt.tiles_c;
+    o.tiles_r = opt.tiles_r; o.tiles_c = opt.tiles_c; o.cells_per_thread = opt.cells_per_thread;
     CudaBackend be;
     be.st = st;
     const char* why = "";

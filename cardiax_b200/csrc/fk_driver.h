@@ -19,6 +19,7 @@ struct DriveOptions {
     int uniform_diffusivity;
     int row0, row1;         // output rows of a single-launch call (slab building block); row1 <= 0: all the rows owned
     int tiles_r, tiles_c;   // resident kernel: tile grid (0 = planner's choice)
+    int cells_per_thread;   // resident kernel: 1, 2 or 4 adjacent cells per thread (0 = planner's choice)
 };
 
 struct DriveBuffers {
@@ -27,10 +28,16 @@ struct DriveBuffers {
     float *pv, *pw, *pu;            // ping-pong scratch, (batch, H, W) each
     const float *D, *DX, *DY;
     const StimDev* stims;           // device/emulated copy of the stimulus table, or null
-    unsigned* flags;                // resident kernel: FK_RES_MAX_CTAS progress flags (zeroed by the backend), or null
+    u64* xchg;                      // resident kernel: mailboxes (zeroed by the backend), xchg_bytes long, or null
+    long long xchg_bytes;
 };
 
 enum { FK_DEFAULT_T = 2, FK_RES_MAX_CTAS = 1024 };
+// mailbox bytes fk_workspace_bytes provisions for the resident kernel: 32 per cell of problems it may take, else none
+inline long long res_xchg_bytes(int H, int W, int batch) {
+    const long long cells = (long long)H * W * batch;
+    return cells <= (1LL << 21) ? 32 * cells + 4096 : 0;
+}
 // Tissues (x batch) up to this many cells that fit the SMs' shared memory run whole calls in ONE resident launch.
 #ifndef FK_RES_MAX_CELLS
 #define FK_RES_MAX_CELLS (1LL << 20)
@@ -112,11 +119,12 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     // tissues that fit the machine's shared memory: the whole call in one resident launch (fk_resident.h)
     ResPlan rplan;
     bool use_res = false;
-    if (!rhs_mode && !slab && opt.row1 <= 0 && B.flags && nsteps < (1LL << 30) &&
+    if (!rhs_mode && !slab && opt.row1 <= 0 && B.xchg && nsteps < (1LL << 30) &&
         (opt.kernel == 4 || (opt.kernel == 0 && opt.steps_per_launch == 0 && nsteps >= 4 &&
                              (long long)H * W * batch <= FK_RES_MAX_CELLS))) {
         const int cap = be.num_sms() < FK_RES_MAX_CTAS ? be.num_sms() : FK_RES_MAX_CTAS;
-        use_res = plan_resident(H, W, batch, cap, be.resident_smem_limit(), opt.tiles_r, opt.tiles_c, opt.cta_threads, rplan);
+        use_res = plan_resident(H, W, batch, cap, be.resident_smem_limit(), B.xchg_bytes, opt.tiles_r, opt.tiles_c,
+                                opt.cta_threads, opt.cells_per_thread, rplan);
     }
     if (opt.kernel == 4 && !use_res) { *why = "resident kernel not applicable (needs W % 4 == 0, a whole tissue that fits shared memory)"; return -5; }
     // tissues too small to fill the machine: one launch of the barrier-free wide kernel per step
@@ -166,8 +174,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         A.u_out = B.u_out; A.v_out = B.v_out; A.w_out = B.w_out;
         A.T = 1; A.t0 = t0;
         rplan.G.nsteps = (int)nsteps;
-        rplan.G.xb[0] = B.pu; rplan.G.xb[1] = B.pv;
-        rplan.G.flags = B.flags;
+        rplan.G.xchg = B.xchg; rplan.G.timing = nullptr;
         rplan.G.spin_limit = 1u << 24;
         return be.resident(rplan, A, opt.exact, batch);
     }

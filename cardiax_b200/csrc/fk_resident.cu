@@ -1,5 +1,6 @@
 // fk_resident.cu -- the resident kernel (body: fk_resident.h) and its cooperative launcher.  sm_100a only.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "fk_resident.cuh"
 
@@ -7,69 +8,95 @@ namespace fk {
 
 namespace {
 
-__device__ __forceinline__ void flag_release(unsigned* p, unsigned v) {
-    __threadfence();   // the CTA's ring stores (ordered before this thread by the block barrier) become visible first
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned flag_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+// dynamic shared memory the kernel may ask for: the 227 KB opt-in limit minus its static shared memory (rounded up)
+enum { FK_RES_SMEM_OPTIN = 227 * 1024 - 256 };
 
-template <bool EXACT>
-__global__ void __launch_bounds__(512, 1)
+// development: cycle counters of CTA (0, 0), thread 0 (FK_RES_TIMING=1): ring, interior, halo, barrier; [6] = steps
+__device__ u64 g_res_timing[8];
+#define FK_TICK(k)                       \
+    if (timed) {                         \
+        const long long now_ = clock64();\
+        acc##k += (u64)(now_ - t_);      \
+        t_ = now_;                       \
+    }
+
+template <bool EXACT, int NC>
+__global__ void __launch_bounds__(FK_RES_MAX_THREADS, 1)
 fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ ResGeom G) {
     extern __shared__ __align__(16) float fk_res_smem[];
     __shared__ unsigned s_mask[2];
     ResCta X;
-    res_setup(A, G, blockIdx.x, blockIdx.y, fk_res_smem, X);
-    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    res_setup(A, G, blockIdx.x, blockIdx.y, gridDim.y, fk_res_smem, X);
+    const int tid = threadIdx.x, nthr = blockDim.x;
     res_load(A, G, X, tid, nthr);
     if (tid == 0) s_mask[0] = res_mask(A, X, 0);
     __syncthreads();
-    unsigned* const flags = G.flags + (long long)blockIdx.y * (G.ntr * G.ntc);
+    const bool timed = G.timing != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    u64 acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    long long t_ = timed ? clock64() : 0;
     for (int s = 0; s < G.nsteps; ++s) {
         const unsigned mask = s_mask[s & 1];
-        const bool last = s == G.nsteps - 1;
-        res_phase<EXACT>(A, G, X, s, 0, mask, tid, nthr);          // ring: new u also to the exchange plane
-        if (!last) {
-            __syncthreads();
-            if (tid == 0) {
-                flag_release(flags + X.tile, (unsigned)(s + 1));
-                s_mask[(s + 1) & 1] = res_mask(A, X, s + 1);
-            }
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            // phase 0: the ring, published to the neighbours' mailboxes as it is computed; phase 1: the interior, while
+            // those records travel.  ONE call site: the body exists once and stays inside the instruction cache.
+            res_phase<EXACT, NC>(A, G, X, s, phase, mask, tid, nthr);
+            if (phase == 0) { FK_TICK(0) } else { FK_TICK(1) }
         }
-        res_phase<EXACT>(A, G, X, s, 1, mask, tid, nthr);          // interior, while the flag travels
-        if (!last) {
-            for (int j = warp; j < FK_RES_JOBS; j += nwarps) {
-                const int nb = res_job_neighbour(G, X, j);
-                if (nb < 0) continue;
-                unsigned polls = 0;
-                while (flag_acquire(flags + nb) < (unsigned)(s + 1))
-                    if (++polls > G.spin_limit) __trap();           // a lost neighbour must not hang the device
-                res_job_load(A, G, X, s, j, lane, 32);
-            }
-            __syncthreads();
-        }
+        if (s == G.nsteps - 1) break;
+        if (tid == 0) s_mask[(s + 1) & 1] = res_mask(A, X, s + 1);
+        if (!res_halo(G, X, s, tid, nthr)) __trap();   // a lost neighbour must not hang the device
+        FK_TICK(2)
+        __syncthreads();
+        FK_TICK(3)
     }
+    if (timed) {
+        G.timing[0] = acc0; G.timing[1] = acc1; G.timing[2] = acc2; G.timing[3] = acc3;
+        G.timing[6] = (u64)G.nsteps;
+    }
+}
+
+template <bool EXACT, int NC>
+int launch_nc(const ResPlan& P, const TileArgs& A, const ResGeom& G, int batch, cudaStream_t st) {
+    static bool attr_set = false;
+    cudaError_t e;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    void* args[2] = {(void*)&A, (void*)&G};
+    return (int)cudaLaunchCooperativeKernel((const void*)fk_resident_kernel<EXACT, NC>, dim3(G.ntr * G.ntc, batch),
+                                            dim3(P.threads), args, (size_t)P.smem_bytes, st);
+}
+
+template <bool EXACT>
+int occupancy_nc(int nc, int threads, size_t smem) {
+    int n = 0;
+    cudaError_t e;
+#define FK_OCC(NC)                                                                                                       \
+    e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN); \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_resident_kernel<EXACT, NC>, threads, smem);
+    if (nc == 1) { FK_OCC(1) } else if (nc == 2) { FK_OCC(2) } else { FK_OCC(4) }
+#undef FK_OCC
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 template <bool EXACT>
 int launch_t(const ResPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
-    static bool attr_set = false;
-    cudaError_t e;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(fk_resident_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    e = cudaMemsetAsync(P.G.flags, 0, sizeof(unsigned) * (size_t)P.G.ntr * P.G.ntc * batch, st);
+    // tags start at zero: a record is valid from the step that writes tag >= 1
+    cudaError_t e = cudaMemsetAsync(P.G.xchg, 0, (size_t)P.xchg_bytes, st);
     if (e != cudaSuccess) return (int)e;
-    void* args[2] = {(void*)&A, (void*)&P.G};
-    e = cudaLaunchCooperativeKernel((const void*)fk_resident_kernel<EXACT>, dim3(P.G.ntr * P.G.ntc, batch), dim3(P.threads),
-                                    args, (size_t)P.smem_bytes, st);
-    return (int)e;
+    ResGeom G = P.G;
+    static const bool timing = getenv("FK_RES_TIMING") != nullptr;
+    if (timing) {
+        void* sym = nullptr;
+        if (cudaGetSymbolAddress(&sym, g_res_timing) == cudaSuccess) G.timing = (u64*)sym;
+    }
+    if (G.nc == 1) return launch_nc<EXACT, 1>(P, A, G, batch, st);
+    if (G.nc == 2) return launch_nc<EXACT, 2>(P, A, G, batch, st);
+    return launch_nc<EXACT, 4>(P, A, G, batch, st);
 }
 
 }  // namespace
@@ -78,16 +105,17 @@ int launch_resident(const ResPlan& P, const TileArgs& A, int exact, int batch, c
     return exact ? launch_t<true>(P, A, batch, st) : launch_t<false>(P, A, batch, st);
 }
 
+// development: the counters of the most recent timed launch (synchronises the device)
+int resident_timing(unsigned long long* out8) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out8, g_res_timing, sizeof(unsigned long long) * 8);
+    return (int)e;
+}
+
 // CTAs of the resident kernel the device can hold at once (cooperative launch limit) for this CTA shape
-int resident_capacity(int exact, int threads, long long smem_bytes, int num_sms) {
-    if (smem_bytes > 227 * 1024) return 0;
-    cudaError_t e = exact ? cudaFuncSetAttribute(fk_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                          : cudaFuncSetAttribute(fk_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int n = 0;
-    if (e == cudaSuccess)
-        e = exact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_resident_kernel<true>, threads, (size_t)smem_bytes)
-                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_resident_kernel<false>, threads, (size_t)smem_bytes);
-    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+int resident_capacity(int exact, int nc, int threads, long long smem_bytes, int num_sms) {
+    if (smem_bytes > FK_RES_SMEM_OPTIN) return 0;
+    const int n = exact ? occupancy_nc<true>(nc, threads, (size_t)smem_bytes) : occupancy_nc<false>(nc, threads, (size_t)smem_bytes);
     return n * num_sms;
 }
 

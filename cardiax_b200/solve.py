@@ -122,6 +122,7 @@ def _options(D=None, P=None, dx=None, **over):
     o.cta_threads = int(options.cta_threads)
     o.rows_per_cta = int(options.rows_per_cta)
     o.tiles_r, o.tiles_c = int(options.tiles[0]), int(options.tiles[1])
+    o.cells_per_thread = int(options.cells_per_thread)
     if D is not None and options.detect_uniform_diffusivity:
         o.uniform_diffusivity = int(_is_uniform(D))
     for k, v in over.items():

@@ -55,7 +55,8 @@ typedef struct FkOptions {
     int safe_division;    /* exact numerics only: 1 = every division through the IEEE sequence (__fdiv_rn) instead of the
                              3-instruction correctly rounded FMA division by constants (see fk_check_exact_division) */
     int tiles_r, tiles_c; /* resident kernel: tile grid rows x columns, one CTA per tile (0 = auto) */
-    int reserved[5];
+    int cells_per_thread; /* resident kernel: 1, 2 or 4 adjacent cells per thread (0 = auto) */
+    int reserved[4];
 } FkOptions;
 
 /* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */
@@ -128,9 +129,13 @@ long long fk_launch_count(void);
  * row chunks, resident CTAs per SM, dynamic shared memory bytes} */
 void fk_last_plan(int* out8);
 /* name of the step kernel launched most recently: "fk_stream_kernel", "fk_resident_kernel", "fk_wide_kernel",
- * "fk_tile_kernel" (resident launches report {steps, cta_threads, tile columns, tile width, tile height, tile rows, 1,
- * shared memory bytes} through fk_last_plan) */
+ * "fk_tile_kernel" (resident launches report {steps, cta_threads, tile columns, tile width, tile height, tile rows,
+ * cells per thread, shared memory bytes} through fk_last_plan) */
 const char* fk_last_kernel(void);
+/* Development aid: with FK_RES_TIMING=1 in the environment, CTA (0, 0) of every resident launch accumulates SM cycles
+ * spent in {ring groups, interior groups, waiting for and copying the halo, block barrier} (out8[0..3]) and the step
+ * count (out8[6]); this returns the counters of the last launch (synchronises the device). */
+int fk_resident_timing(unsigned long long* out8);
 void fk_profile_enable(int on);
 int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches,
                        double* stream_cell_steps);

@@ -42,14 +42,16 @@ def test_wide_kernel_exact(shape):
     assert info == (0, 6000)   # six launches of the wide kernel, nothing else
 
 
+@pytest.mark.parametrize("nc", [0, 1, 2, 4])
 @pytest.mark.parametrize("shape,nsteps,tiles", [
     ((12, 16), 6, (0, 0)), ((3, 4), 5, (0, 0)), ((64, 96), 7, (0, 0)), ((64, 96), 7, (2, 3)), ((64, 96), 7, (4, 1)),
     ((40, 64), 9, (3, 2)), ((37, 52), 8, (2, 2)), ((130, 20), 6, (0, 0)), ((9, 132), 6, (0, 0)), ((100, 200), 6, (5, 5)),
-    ((64, 96), 1, (2, 3)), ((64, 96), 2, (1, 1)), ((128, 128), 5, (0, 0)), ((33, 72), 6, (4, 9))])
-def test_resident_kernel_exact(shape, nsteps, tiles):
-    """Whole call in one resident launch (tiles in shared memory, halos through exchange planes): any tile grid, uneven
-    tiles, ring-only tiles, all four physical edges, stimuli -- bit-identical to the oracle."""
-    info = _exact(shape, 1, nsteps=nsteps, kernel=4, tiles=tiles)
+    ((64, 96), 1, (2, 3)), ((64, 96), 2, (1, 1)), ((128, 128), 5, (0, 0)), ((33, 72), 6, (4, 9)), ((7, 8), 5, (1, 1))])
+def test_resident_kernel_exact(shape, nsteps, tiles, nc):
+    """Whole call in one resident launch (tiles in shared memory, halos through tagged mailbox records): any tile grid,
+    uneven tiles, ring-only tiles, 1/2/4 cells per thread, all four physical edges (edge cells one per thread), stimuli
+    -- bit-identical to the oracle."""
+    info = _exact(shape, 1, nsteps=nsteps, kernel=4, tiles=tiles, nc=nc)
     assert info == (0, 1000000)   # one launch, nothing else
 
 

@@ -27,7 +27,7 @@ P3 = O.PARAMSETS["3"]
 def _reset_options():
     from cardiax_b200 import options
     saved = {k: getattr(options, k) for k in ("numerics", "steps_per_launch", "kernel", "cta_threads", "rows_per_cta",
-                                              "tiles")}
+                                              "tiles", "cells_per_thread")}
     options.verbose = False
     yield
     for k, v in saved.items():
@@ -66,18 +66,21 @@ def test_exact_bitwise_vs_oracle(shape, T, kernel, extra):
     assert_exact(got, ref, "shape %s T %d kernel %d" % (shape, T, kernel))
 
 
-@pytest.mark.parametrize("shape,nsteps,tiles,threads", [
-    ((12, 16), 9, (0, 0), 0), ((3, 4), 5, (0, 0), 0), ((64, 96), 9, (2, 3), 0), ((64, 96), 9, (4, 1), 256),
-    ((128, 128), 9, (0, 0), 0), ((100, 200), 9, (5, 5), 0), ((256, 256), 40, (0, 0), 0), ((512, 512), 9, (0, 0), 0),
-    ((512, 512), 12, (16, 8), 512), ((33, 72), 6, (4, 9), 128), ((64, 96), 1, (2, 3), 0), ((1024, 1024), 6, (0, 0), 0)])
-def test_resident_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads):
-    """The resident kernel (whole call in one cooperative launch; halos exchanged through L2 with release/acquire
-    flags between co-resident CTAs): bit-identical to the oracle for any tile grid."""
+@pytest.mark.parametrize("shape,nsteps,tiles,threads,nc", [
+    ((12, 16), 9, (0, 0), 0, 0), ((3, 4), 5, (0, 0), 0, 0), ((64, 96), 9, (2, 3), 0, 4), ((64, 96), 9, (4, 1), 256, 2),
+    ((128, 128), 9, (0, 0), 0, 0), ((100, 200), 9, (5, 5), 0, 0), ((256, 256), 40, (0, 0), 0, 0), ((512, 512), 9, (0, 0), 0, 0),
+    ((512, 512), 12, (16, 8), 512, 4), ((33, 72), 6, (4, 9), 128, 1), ((64, 96), 1, (2, 3), 0, 0), ((1024, 1024), 6, (0, 0), 0, 0),
+    ((256, 256), 30, (8, 8), 0, 2), ((128, 128), 50, (16, 1), 64, 4), ((200, 120), 25, (3, 3), 96, 1)])
+def test_resident_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads, nc):
+    """The resident kernel (whole call in one cooperative launch; halos exchanged between co-resident CTAs through
+    tagged 8-byte mailbox records in L2): bit-identical to the oracle for any tile grid, CTA size and cells per thread
+    (threads < groups: several rounds per step)."""
     from cardiax_b200 import _lib
     st, D, stim = common.random_case(shape, seed=4, n_stim=3)
     ref = C.forward_euler(st, 0, nsteps, P3, D, stim, 0.01, 0.01)
     before = _lib.lib().fk_launch_count()
-    got = run_gpu(st, 0, nsteps, P3, D, stim, numerics="exact", kernel=4, tiles=tiles, cta_threads=threads)
+    got = run_gpu(st, 0, nsteps, P3, D, stim, numerics="exact", kernel=4, tiles=tiles, cta_threads=threads,
+                  cells_per_thread=nc)
     assert _lib.lib().fk_launch_count() - before == 2   # D_x/D_y maps + ONE resident launch
     assert_exact(got, ref, "resident %s tiles %s" % (shape, tiles))
 

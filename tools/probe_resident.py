@@ -15,10 +15,10 @@ import oracle as O  # noqa: E402
 from cardiax_b200 import _lib, options, solve, stimulus  # noqa: E402
 
 
-def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=0):
+def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=0, nc=0):
     options.verbose = False
     options.numerics, options.kernel, options.steps_per_launch = numerics, kernel, T
-    options.cta_threads, options.rows_per_cta, options.tiles = threads, 0, tiles
+    options.cta_threads, options.rows_per_cta, options.tiles, options.cells_per_thread = threads, 0, tiles, nc
     st = solve.State(*[torch.as_tensor(work[k]).cuda() for k in "vwu"])
     D = torch.as_tensor(work["D"]).cuda()
     gs = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in work["stimuli"]]
@@ -37,21 +37,29 @@ def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=
         cells = st.u.numel()
         print("%-7s kernel=%d tiles=%-9s thr=%3d %-5s %7.2f us/step %7.1f Gcs/s  %s" % (
             name, kernel, tiles, threads, numerics, best, cells / best / 1e3, _lib.last_plan()), flush=True)
+        if kernel == 4 and os.environ.get("FK_RES_TIMING"):
+            import ctypes
+            out = (ctypes.c_ulonglong * 8)()
+            _lib.lib().fk_resident_timing(out)
+            ns = max(1, out[6])
+            print("        cycles/step of CTA 0: ring %.0f | interior %.0f | halo wait+copy %.0f | barrier %.0f | total %.0f"
+                  % tuple([out[k] / ns for k in range(4)] + [sum(out[:4]) / ns]), flush=True)
     except Exception as e:  # noqa: BLE001
         print("%-7s kernel=%d tiles=%s thr=%d failed: %s" % (name, kernel, tiles, threads, str(e)[:120]), flush=True)
 
 
 def main():
-    which = sys.argv[1:] or ["fk128", "fk256", "fk512", "fk1024"]
+    which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["fk128", "fk256", "fk512", "fk1024"]
+    short = "--short" in sys.argv
+    # (tiles, threads, cells per thread)
     sweeps = {
-        "fk128": [((0, 0), 0), ((16, 1), 256), ((16, 2), 128), ((8, 2), 256), ((8, 4), 128), ((4, 4), 256), ((4, 2), 512),
-                  ((16, 8), 128), ((2, 2), 512), ((1, 1), 512), ((12, 12), 128)],
-        "fk256": [((0, 0), 0), ((32, 4), 128), ((32, 2), 256), ((16, 8), 128), ((16, 4), 256), ((12, 12), 128),
-                  ((8, 8), 256), ((8, 16), 128), ((18, 8), 128), ((4, 4), 512)],
-        "fk512": [((0, 0), 0), ((64, 2), 512), ((37, 4), 512), ((18, 8), 320), ((18, 8), 512), ((16, 8), 512), ((16, 8), 256),
-                  ((12, 12), 512), ((9, 16), 512), ((32, 4), 512), ((24, 6), 384), ((8, 16), 512)],
-        "fk1024": [((0, 0), 0), ((37, 4), 512), ((21, 7), 512), ((18, 8), 512), ((12, 12), 512), ((74, 2), 512),
-                   ((16, 9), 512)],
+        "fk128": [((0, 0), 0, 0), ((8, 16), 0, 1), ((16, 8), 0, 1), ((12, 12), 0, 1), ((8, 8), 0, 1), ((8, 8), 0, 2), ((4, 4), 0, 2),
+                  ((16, 1), 0, 4), ((8, 16), 0, 2), ((4, 8), 0, 1), ((4, 4), 0, 4)],
+        "fk256": [((0, 0), 0, 0), ((12, 12), 0, 1), ((12, 12), 0, 2), ((16, 8), 0, 2), ((8, 16), 0, 2), ((8, 8), 0, 4),
+                  ((8, 8), 0, 2), ((16, 8), 0, 4), ((32, 4), 0, 4)],
+        "fk512": [((0, 0), 0, 0), ((12, 12), 0, 4), ((12, 12), 0, 2), ((18, 8), 0, 4), ((16, 8), 0, 4), ((9, 16), 0, 4),
+                  ((14, 10), 0, 2), ((24, 6), 0, 4), ((37, 4), 0, 4)],
+        "fk1024": [((0, 0), 0, 0), ((21, 7), 0, 4), ((12, 12), 0, 4), ((16, 9), 0, 4), ((18, 8), 0, 4)],
     }
     for name in which:
         if name == "fk128":
@@ -65,10 +73,11 @@ def main():
             _, D = common.smooth_case((n, n), 0)
             work = dict(v=np.ones((n, n), np.float32), w=np.ones((n, n), np.float32), u=bench.make_fk4096(n, n)["u"], D=D,
                         stimuli=[], params="3")
-        for tiles, thr in sweeps.get(name, [((0, 0), 0)]):
-            run(name, work, 4, tiles, thr)
-        run(name, work, 3, n=400)
-        run(name, work, 2, n=400, T=2)
+        for tiles, thr, nc in (sweeps.get(name, [((0, 0), 0, 0)])[:5] if short else sweeps.get(name, [((0, 0), 0, 0)])):
+            run(name, work, 4, tiles, thr, nc=nc)
+        if not short:
+            run(name, work, 3, n=400)
+            run(name, work, 2, n=400, T=2)
         run(name, work, 4, numerics="exact", n=500)
 
 
