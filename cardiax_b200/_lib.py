@@ -35,7 +35,7 @@ class FkOptions(ctypes.Structure):
                 ("phys_top", ctypes.c_int), ("phys_bottom", ctypes.c_int), ("cta_threads", ctypes.c_int),
                 ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("safe_division", ctypes.c_int),
                 ("tiles_r", ctypes.c_int), ("tiles_c", ctypes.c_int), ("cells_per_thread", ctypes.c_int),
-                ("reserved", ctypes.c_int * 4)]
+                ("edge_rows", ctypes.c_int), ("edge_colgroups", ctypes.c_int), ("reserved", ctypes.c_int * 2)]
 
 
 def needs_build():

@@ -441,6 +441,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.rows_per_cta = opt.rows_per_cta; o.uniform_diffusivity = opt.uniform_diffusivity;
     o.row0 = row0; o.row1 = row1;
     o.tiles_r = opt.tiles_r; o.tiles_c = opt.tiles_c; o.cells_per_thread = opt.cells_per_thread;
+    o.edge_rows = opt.edge_rows; o.edge_colgroups = opt.edge_colgroups;
     CudaBackend be;
     be.st = st;
     const char* why = "";

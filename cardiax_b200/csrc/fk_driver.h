@@ -20,6 +20,7 @@ struct DriveOptions {
     int row0, row1;         // output rows of a single-launch call (slab building block); row1 <= 0: all the rows owned
     int tiles_r, tiles_c;   // resident kernel: tile grid (0 = planner's choice)
     int cells_per_thread;   // resident kernel: 1, 2 or 4 adjacent cells per thread (0 = planner's choice)
+    int edge_rows, edge_colgroups;   // resident kernel: size of the tiles at the tissue's edges (0 auto, < 0 even split)
 };
 
 struct DriveBuffers {
@@ -124,7 +125,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
                              (long long)H * W * batch <= FK_RES_MAX_CELLS))) {
         const int cap = be.num_sms() < FK_RES_MAX_CTAS ? be.num_sms() : FK_RES_MAX_CTAS;
         use_res = plan_resident(H, W, batch, cap, be.resident_smem_limit(), B.xchg_bytes, opt.tiles_r, opt.tiles_c,
-                                opt.cta_threads, opt.cells_per_thread, rplan);
+                                opt.cta_threads, opt.cells_per_thread, opt.edge_rows, opt.edge_colgroups, rplan);
     }
     if (opt.kernel == 4 && !use_res) { *why = "resident kernel not applicable (needs W % 4 == 0, a whole tissue that fits shared memory)"; return -5; }
     // tissues too small to fill the machine: one launch of the barrier-free wide kernel per step

@@ -28,6 +28,8 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
     ResCta X;
     res_setup(A, G, blockIdx.x, blockIdx.y, gridDim.y, fk_res_smem, X);
     const int tid = threadIdx.x, nthr = blockDim.x;
+    ResThread T;
+    res_thread_setup<NC>(A, G, X, tid, nthr, T);
     res_load(A, G, X, tid, nthr);
     if (tid == 0) s_mask[0] = res_mask(A, X, 0);
     __syncthreads();
@@ -40,12 +42,12 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
         for (int phase = 0; phase < 2; ++phase) {
             // phase 0: the ring, published to the neighbours' mailboxes as it is computed; phase 1: the interior, while
             // those records travel.  ONE call site: the body exists once and stays inside the instruction cache.
-            res_phase<EXACT, NC>(A, G, X, s, phase, mask, tid, nthr);
+            res_phase<EXACT, NC>(A, G, X, T, s, phase, mask, tid, nthr);
             if (phase == 0) { FK_TICK(0) } else { FK_TICK(1) }
         }
         if (s == G.nsteps - 1) break;
         if (tid == 0) s_mask[(s + 1) & 1] = res_mask(A, X, s + 1);
-        if (!res_halo(G, X, s, tid, nthr)) __trap();   // a lost neighbour must not hang the device
+        if (!res_halo(G, X, T, s, tid, nthr)) __trap();   // a lost neighbour must not hang the device
         FK_TICK(2)
         __syncthreads();
         FK_TICK(3)

@@ -39,7 +39,9 @@ namespace fk {
 typedef unsigned long long u64;
 
 struct ResGeom {
-    int ntr, ntc;        // tiles along rows / columns: balanced split, columns in groups of 4 cells
+    int ntr, ntc;        // tiles along rows / columns (columns are cut in groups of 4 cells)
+    int eh, ewq;         // rows / column groups of the tiles at the tissue's edges (their one-sided formulas cost more,
+                         // so they get fewer cells); the rest is split evenly.  0 = split everything evenly
     int th_max, tw_max;  // largest tile
     int pitch;           // floats per row of a u buffer = tw_max + 8
     int nsteps;          // Euler steps of the launch
@@ -54,9 +56,11 @@ struct ResCta {
     int ti, tj, tile, sim;
     int r0, r1, c0, c1, th, tw, q;   // q = tw / nc groups per row
     int qe;                          // groups per row that lie within 4 cells of a tile edge, per side = 4 / nc
-    int nring, ninner;               // groups within 4 cells of a tile edge / the others
     int has_n, has_s, has_w, has_e;  // neighbours (0 at a physical edge)
-    int e_nt, e_nb, e_nl, e_nr, nedge;   // cells within 4 of a PHYSICAL edge: top/bottom rows, left/right columns, total
+    int ir0, ir1, ig0, ig1;          // INTERIOR = rows [ir0, ir1) x groups [ig0, ig1): no cell a neighbour needs
+    int nring, ninner;               // RING groups (the rest: within 4 cells of a side that has a neighbour) / interior
+    int e_nt, e_nb, e_nl, e_nr;      // cells within 4 of a PHYSICAL edge: top/bottom rows, left/right columns of the rest
+    int nedge;                       // ... their number
     int nhalo[4];                    // 16-byte units (2 records) of the north, south, west, east halo
     float *U0, *V, *Wd, *Dm, *DXm, *DYm;   // u buffer of parity p: U0 + p * nu
     int nu;                                // floats per u buffer
@@ -83,21 +87,37 @@ FK_HD int res_edge_counts(int H, int W, int r0, int r1, int c0, int c1, int& nt,
     return (nt + nb) * tw + (th - nt - nb) * (nl + nr);
 }
 
-FK_HD void res_setup(const TileArgs& A, const ResGeom& G, int tile, int sim, int batch, float* smem, ResCta& X) {
-    X.tile = tile; X.sim = sim;
+// split of n units into nt parts with e units in the first and last part (0: all parts even): start of part t
+FK_HD int res_split(int n, int nt, int e, int t) {
+    if (e <= 0 || nt < 3) return (int)((long long)n * t / nt);
+    if (t == 0) return 0;
+    if (t == nt) return n;
+    return e + (int)((long long)(n - 2 * e) * (t - 1) / (nt - 2));
+}
+
+// geometry of one tile (no pointers): shared by the kernel and the planner
+FK_HD void res_tile_geom(int H, int W, const ResGeom& G, int tile, ResCta& X) {
+    X.tile = tile;
     X.ti = tile / G.ntc; X.tj = tile - X.ti * G.ntc;
-    const int Q = A.W >> 2;
-    X.r0 = (int)((long long)A.H * X.ti / G.ntr);
-    X.r1 = (int)((long long)A.H * (X.ti + 1) / G.ntr);
-    X.c0 = 4 * (int)((long long)Q * X.tj / G.ntc);
-    X.c1 = 4 * (int)((long long)Q * (X.tj + 1) / G.ntc);
+    X.r0 = res_split(H, G.ntr, G.eh, X.ti);
+    X.r1 = res_split(H, G.ntr, G.eh, X.ti + 1);
+    X.c0 = 4 * res_split(W >> 2, G.ntc, G.ewq, X.tj);
+    X.c1 = 4 * res_split(W >> 2, G.ntc, G.ewq, X.tj + 1);
     X.th = X.r1 - X.r0; X.tw = X.c1 - X.c0; X.q = X.tw / G.nc; X.qe = 4 / G.nc;
-    if (X.th <= 8 || X.tw <= 8) { X.nring = X.th * X.q; X.ninner = 0; }
-    else { X.nring = 8 * X.q + 2 * X.qe * (X.th - 8); X.ninner = (X.th - 8) * (X.q - 2 * X.qe); }
-    X.nedge = res_edge_counts(A.H, A.W, X.r0, X.r1, X.c0, X.c1, X.e_nt, X.e_nb, X.e_nl, X.e_nr);
     X.has_n = X.ti > 0; X.has_s = X.ti < G.ntr - 1; X.has_w = X.tj > 0; X.has_e = X.tj < G.ntc - 1;
+    X.ir0 = X.has_n ? 4 : 0; X.ir1 = X.has_s ? X.th - 4 : X.th;
+    X.ig0 = X.has_w ? X.qe : 0; X.ig1 = X.has_e ? X.q - X.qe : X.q;
+    if (X.ir1 <= X.ir0 || X.ig1 <= X.ig0) { X.ir0 = X.ir1 = 0; X.ig0 = X.ig1 = 0; }   // no interior: all ring
+    X.ninner = (X.ir1 - X.ir0) * (X.ig1 - X.ig0);
+    X.nring = X.th * X.q - X.ninner;
+    X.nedge = res_edge_counts(H, W, X.r0, X.r1, X.c0, X.c1, X.e_nt, X.e_nb, X.e_nl, X.e_nr);
     X.nhalo[0] = X.has_n ? 2 * X.tw : 0; X.nhalo[1] = X.has_s ? 2 * X.tw : 0;
     X.nhalo[2] = X.has_w ? 2 * X.th : 0; X.nhalo[3] = X.has_e ? 2 * X.th : 0;
+}
+
+FK_HD void res_setup(const TileArgs& A, const ResGeom& G, int tile, int sim, int batch, float* smem, ResCta& X) {
+    res_tile_geom(A.H, A.W, G, tile, X);
+    X.sim = sim;
     const long long nu = (long long)(G.th_max + 8) * G.pitch, nv = (long long)G.th_max * G.tw_max;
     X.U0 = smem; X.nu = (int)nu;
     X.V = smem + 2 * nu; X.Wd = X.V + nv; X.Dm = X.Wd + nv; X.DXm = X.Dm + nv; X.DYm = X.DXm + nv;
@@ -109,18 +129,28 @@ FK_HD void res_setup(const TileArgs& A, const ResGeom& G, int tile, int sim, int
     X.stims = A.stims ? A.stims + (long long)sim * A.n_stim : nullptr;
 }
 
-// group i of the ring (phase 0) or of the interior (phase 1) -> local row and column of its first cell
-FK_HD void res_locate(const ResGeom& G, const ResCta& X, int phase, int i, int& lr, int& lc) {
-    const int q = X.q, qe = X.qe, nc = G.nc;
-    if (phase) { const int qi = q - 2 * qe, r = i / qi; lr = 4 + r; lc = nc * (qe + i - r * qi); return; }
-    if (X.ninner == 0 || i < 4 * q) { const int r = i / q; lr = r; lc = nc * (i - r * q); return; }
-    if (i < 8 * q) { const int j = i - 4 * q, r = j / q; lr = X.th - 4 + r; lc = nc * (j - r * q); return; }
-    const int j = i - 8 * q, r = j / (2 * qe), k = j - r * 2 * qe;   // middle rows: qe groups at each end
-    lr = 4 + r;
-    lc = nc * (k < qe ? k : q - 2 * qe + k);
+// does a neighbour need cell (lr, lc)'s new u (is it within 4 cells of a side that has a neighbour)?
+FK_HD bool res_publishes(const ResCta& X, int lr, int lc) {
+    return (X.has_n && lr < 4) || (X.has_s && lr >= X.th - 4) || (X.has_w && lc < 4) || (X.has_e && lc >= X.tw - 4);
 }
 
-// edge cell e (see res_edge_counts) -> local row and column
+// group i of the ring (phase 0) or of the interior (phase 1) -> local row and column of its first cell
+FK_HD void res_locate(const ResGeom& G, const ResCta& X, int phase, int i, int& lr, int& lc) {
+    const int q = X.q, nc = G.nc;
+    if (phase) { const int qi = X.ig1 - X.ig0, r = i / qi; lr = X.ir0 + r; lc = nc * (X.ig0 + i - r * qi); return; }
+    if (X.ninner == 0) { const int r = i / q; lr = r; lc = nc * (i - r * q); return; }
+    const int ntop = X.ir0 * q;
+    if (i < ntop) { const int r = i / q; lr = r; lc = nc * (i - r * q); return; }
+    i -= ntop;
+    const int nbot = (X.th - X.ir1) * q;
+    if (i < nbot) { const int r = i / q; lr = X.ir1 + r; lc = nc * (i - r * q); return; }
+    i -= nbot;
+    const int m = X.ig0 + q - X.ig1, r = i / m, k = i - r * m;   // middle rows: the groups left and right of the interior
+    lr = X.ir0 + r;
+    lc = nc * (k < X.ig0 ? k : X.ig1 + (k - X.ig0));
+}
+
+// edge cell e (of the set res_edge_counts describes) -> local row and column
 FK_HD void res_locate_edge(const ResCta& X, int e, int& lr, int& lc) {
     const int band = (X.e_nt + X.e_nb) * X.tw;
     if (e < band) {
@@ -200,70 +230,82 @@ FK_HD void res_publish(const ResGeom& G, const ResCta& X, u64* box, int lr, int 
     if (X.has_e && lc >= X.tw - 4) put(box + 8 * G.tw_max + 8 * lr + 4 + lc - (X.tw - 4));
 }
 
-// halo unit i (2 records) of step s: where it comes from (the neighbour's mailbox) and where it goes (next u buffer)
-FK_HD void res_halo_unit(const ResGeom& G, const ResCta& X, float* nxt, const u64* xp, int i, const u64*& src, float*& dst) {
+// halo unit i (2 records): where it comes from (offset into a parity's mailboxes) and where it goes (offset into a u
+// buffer).  The same for every step, so each thread works its first two units out once, before the step loop.
+FK_HD void res_halo_unit(const ResGeom& G, const ResCta& X, int i, long long& src, int& dst) {
     const int P = G.pitch, hw = X.tw >> 1;
     if (i < X.nhalo[0]) {          // north halo rows -4 .. -1  <-  bottom rows (rr = 4 .. 7) of the tile above
         const int j = i / hw, k = 2 * (i - j * hw);
-        src = xp + (X.mbox - (long long)G.ntc * G.slots) + (4 + j) * G.tw_max + k;
-        dst = nxt + j * P + 4 + k;
+        src = (X.mbox - (long long)G.ntc * G.slots) + (4 + j) * G.tw_max + k;
+        dst = j * P + 4 + k;
         return;
     }
     i -= X.nhalo[0];
     if (i < X.nhalo[1]) {          // south halo rows th .. th+3  <-  top rows (rr = 0 .. 3) of the tile below
         const int j = i / hw, k = 2 * (i - j * hw);
-        src = xp + (X.mbox + (long long)G.ntc * G.slots) + j * G.tw_max + k;
-        dst = nxt + (X.th + 4 + j) * P + 4 + k;
+        src = (X.mbox + (long long)G.ntc * G.slots) + j * G.tw_max + k;
+        dst = (X.th + 4 + j) * P + 4 + k;
         return;
     }
     i -= X.nhalo[1];
     if (i < X.nhalo[2]) {          // west halo columns -4 .. -1  <-  last columns (cc = 4 .. 7) of the tile to the left
         const int r = i >> 1, k = 2 * (i & 1);
-        src = xp + (X.mbox - G.slots) + 8 * G.tw_max + 8 * r + 4 + k;
-        dst = nxt + (r + 4) * P + k;
+        src = (X.mbox - G.slots) + 8 * G.tw_max + 8 * r + 4 + k;
+        dst = (r + 4) * P + k;
         return;
     }
     i -= X.nhalo[2];               // east halo columns tw .. tw+3  <-  first columns (cc = 0 .. 3) of the tile to the right
     const int r = i >> 1, k = 2 * (i & 1);
-    src = xp + (X.mbox + G.slots) + 8 * G.tw_max + 8 * r + k;
-    dst = nxt + (r + 4) * P + X.tw + 4 + k;
+    src = (X.mbox + G.slots) + 8 * G.tw_max + 8 * r + k;
+    dst = (r + 4) * P + X.tw + 4 + k;
 }
 
+// what a thread does first in each phase and in the halo copy: the same every step, worked out once (the integer
+// divisions of the item -> cell maps would otherwise sit on the critical path of every step)
+struct ResThread {
+    int ty0, lr0, lc0;   // first item of the ring phase: type (0 nothing, 1 central group of NC cells, 2 one general cell)
+    int ty1, lr1, lc1;   // first item of the interior phase
+    long long hs0, hs1;  // first two halo units: source offsets
+    int hd0, hd1;        //                       destination offsets
+};
+
 // receive the halo of step s (tag s + 1) into the next u buffer; returns false if a record never arrived
-FK_HD bool res_halo(const ResGeom& G, const ResCta& X, int s, int tid, int nthr) {
+FK_HD bool res_halo(const ResGeom& G, const ResCta& X, const ResThread& T, int s, int tid, int nthr) {
     float* nxt = X.U0 + ((s + 1) & 1) * X.nu;
     const u64* xp = G.xchg + ((s + 1) & 1) * X.pstride;
     const unsigned tag = (unsigned)(s + 1);
     const int U = X.nhalo[0] + X.nhalo[1] + X.nhalo[2] + X.nhalo[3];
     for (int i = tid; i < U; i += 2 * nthr) {   // two units in flight per thread
-        const u64 *s0, *s1 = nullptr;
-        float *d0, *d1 = nullptr;
-        res_halo_unit(G, X, nxt, xp, i, s0, d0);
+        long long s0 = T.hs0, s1 = T.hs1;
+        int d0 = T.hd0, d1 = T.hd1;
         const bool two = i + nthr < U;
-        if (two) res_halo_unit(G, X, nxt, xp, i + nthr, s1, d1);
+        if (i != tid) {
+            res_halo_unit(G, X, i, s0, d0);
+            if (two) res_halo_unit(G, X, i + nthr, s1, d1);
+        }
         u64 a0, b0, a1 = 0, b1 = 0;
-        ll_load2(s0, a0, b0);
-        if (two) ll_load2(s1, a1, b1);
+        ll_load2(xp + s0, a0, b0);
+        if (two) ll_load2(xp + s1, a1, b1);
         unsigned spins = 0;
         while (ll_tag(a0) != tag || ll_tag(b0) != tag) {
 #if defined(__CUDA_ARCH__)
             if (++spins > G.spin_limit) return false;
-            ll_load2(s0, a0, b0);
+            ll_load2(xp + s0, a0, b0);
 #else
             return false;   // the emulation runs the CTAs in lock step: the record must be there
 #endif
         }
-        d0[0] = ll_value(a0); d0[1] = ll_value(b0);
+        nxt[d0] = ll_value(a0); nxt[d0 + 1] = ll_value(b0);
         if (two) {
             while (ll_tag(a1) != tag || ll_tag(b1) != tag) {
 #if defined(__CUDA_ARCH__)
                 if (++spins > G.spin_limit) return false;
-                ll_load2(s1, a1, b1);
+                ll_load2(xp + s1, a1, b1);
 #else
                 return false;
 #endif
             }
-            d1[0] = ll_value(a1); d1[1] = ll_value(b1);
+            nxt[d1] = ll_value(a1); nxt[d1 + 1] = ll_value(b1);
         }
     }
     return true;
@@ -330,31 +372,33 @@ FK_HD void stn(float* p, const float* v) {
     else p[0] = v[0];
 }
 
-// first derivative / dx of whichever kind (solve.py:232-249) from a window a[0..6] centred on a[3]
+// first derivative / dx of whichever kind (solve.py:232-249) from a window a[0..6] centred on a[3].  Branch free: the
+// central value and ONE one-sided value (coefficients and operands selected) are both computed and one is kept -- a
+// cell at a physical edge is a lone dependent chain on the step's critical path, and straight-line code lets its
+// eight derivatives overlap.  Same operations on the same operands as fk_core.h's deriv(): identical bits.
 template <bool EXACT>
 FK_HD float res_deriv(const Consts& K, int kind, const float* a) {
-    if (kind == CEN) return dcen<EXACT>(K, a[1], a[2], a[4], a[5]);
-    if (kind == FWD)
-        return deriv<EXACT>(K, FWD, (float)(-11.0 / 6.0), 3.0f, -(float)(3.0 / 2.0), (float)(1.0 / 3.0), a[3], a[4], a[5], a[6]);
-    return deriv<EXACT>(K, BWD, (float)(-1.0 / 3.0), (float)(3.0 / 2.0), -3.0f, (float)(11.0 / 6.0), a[0], a[1], a[2], a[3]);
+    const float cen = dcen<EXACT>(K, a[1], a[2], a[4], a[5]);
+    const bool f = kind == FWD;
+    const float k0 = f ? (float)(-11.0 / 6.0) : (float)(-1.0 / 3.0), k1 = f ? 3.0f : (float)(3.0 / 2.0);
+    const float k2 = f ? -(float)(3.0 / 2.0) : -3.0f, k3 = f ? (float)(1.0 / 3.0) : (float)(11.0 / 6.0);
+    const float t = tap4<EXACT>(k0, k1, k2, k3, f ? a[3] : a[0], f ? a[4] : a[1], f ? a[5] : a[2], f ? a[6] : a[3]);
+    float one;
+    if (EXACT) one = Num<true>::divc(t, K.dx, K.y_dx, K.div_lo, K.div_hi);
+    else one = Num<false>::mul(t, K.r_dx);
+    return kind == CEN ? cen : one;
 }
 
 // First and second derivative along one axis of the edge-padded array (solve.py:29-31, 49-52, crop :61-65) at padded
-// index P of an axis of n cells, anywhere on the axis: up[0..12] are the padded values P-6 .. P+6.  Only the first
-// derivatives the second pass reads are evaluated (same values as fk_wide.h's wide_axis_general).
+// index P of an axis of n cells, anywhere on the axis: up[0..12] are the padded values P-6 .. P+6 (entries beyond the
+// pad are never used by the formulas that apply).  Same values as fk_wide.h's wide_axis_general.
 template <bool EXACT>
 FK_HD void res_axis_general(const Consts& K, const float* up, int P, int n, float& d1, float& d2) {
-    const int kind = kind_of(P, n, 1, 1);
-    // the second pass reads g[1], g[2], g[4], g[5] (central; d1 = g[3]), g[3..6] (forward) or g[0..3] (backward)
-    const int lo = kind == BWD ? 0 : (kind == CEN ? 1 : 3), hi = kind == FWD ? 6 : (kind == CEN ? 5 : 3);
-    float g[7];
+    float g[7];   // first derivative at padded P-3 .. P+3
 #pragma unroll
-    for (int m = 0; m < 7; ++m) {   // ONE inlined copy of the derivative per slot keeps the kernel small
-        g[m] = 0.0f;
-        if (m >= lo && m <= hi) g[m] = res_deriv<EXACT>(K, kind_of(P - 3 + m, n, 1, 1), up + m);
-    }
+    for (int m = 0; m < 7; ++m) g[m] = res_deriv<EXACT>(K, kind_of(P - 3 + m, n, 1, 1), up + m);
     d1 = g[3];
-    d2 = res_deriv<EXACT>(K, kind, g);
+    d2 = res_deriv<EXACT>(K, kind_of(P, n, 1, 1), g);
 }
 
 // one Euler step of NC cells (row, c .. c+NC-1), local (lr, lc): reads `cur` (+ halo), writes `nxt`, v, w in place; ring
@@ -403,13 +447,13 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
             u_xx[k] = dcen<EXACT>(A.K, gx[0], gx[1], gx[3], gx[4]);
         }
     } else {
-        // padded rows P-6 .. P+6 = tissue rows row-6 .. row+6 clamped (solve.py:31); entries the applicable formulas
-        // never use may fall outside the tile's buffer rows and are clamped into it
+        // padded rows P-6 .. P+6 = tissue rows row-6 .. row+6 clamped to the tissue (solve.py:31).  They all lie in the
+        // tile's buffer: a tile with a neighbour above/below is >= 8 rows, so a cell within 4 rows of a physical edge
+        // sits in the tile AT that edge, and 6 rows the other way is inside the tile or its 4-row halo.
         float ur[13][NC];
-        const int nrows = G.th_max + 8;
+        const int lo = -row, hi = H - 1 - row;
 #pragma unroll
-        for (int j = 0; j < 13; ++j)
-            ldn<NC>(cur + clampi(clampi(row + j - 6, 0, H - 1) - X.r0 + 4, 0, nrows - 1) * P + (lc + 4), ur[j]);
+        for (int j = 0; j < 13; ++j) ldn<NC>(uc0 + clampi(j - 6, lo, hi) * P, ur[j]);
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             float col[13];
@@ -442,12 +486,12 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
             u_yy[k] = dcen<EXACT>(A.K, gy[k], gy[k + 1], gy[k + 3], gy[k + 4]);
         }
     } else {
-        const float* urow = cur + (lr + 4) * P;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             float win[13];   // padded columns Q-6 .. Q+6 of cell c + k, clamped like the rows above
+            const int lo = -(c + k), hi = W - 1 - (c + k);
 #pragma unroll
-            for (int j = 0; j < 13; ++j) win[j] = urow[clampi(clampi(c + k + j - 6, 0, W - 1) - X.c0 + 4, 0, P - 1)];
+            for (int j = 0; j < 13; ++j) win[j] = uc0[k + clampi(j - 6, lo, hi)];
             res_axis_general<EXACT>(A.K, win, c + k + 1, W, u_y[k], u_yy[k]);
         }
     }
@@ -473,34 +517,56 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     }
 }
 
-// The ring (phase 0) or interior (phase 1) groups of step s, strided over the CTA's threads.  With NC > 1 the groups
-// that touch a physical edge are skipped and their cells done ONE PER THREAD as extra items of phase 0: the one-sided
-// formulas cost several times the central ones, and a tile at the tissue's edge must not be slower than the others
-// (every CTA waits for its neighbours each step).
+// item i of a phase -> its cell(s) and what to do with them: 1 = a group of NC cells whose formulas are all central,
+// 2 = ONE cell through the general formulas, 0 = nothing.  Phase 0 = what the neighbours wait for (the ring), published
+// as it is computed; phase 1 = everything else, computed while those records travel.  With NC > 1 the groups that
+// touch a physical edge are skipped and their cells done ONE PER THREAD as extra items (of phase 0 if a neighbour needs
+// them, else of phase 1): the one-sided formulas cost several times the central ones and the step's critical path is
+// the slowest thread of the slowest tile.
+template <int NC>
+FK_HD int res_item(const TileArgs& A, const ResGeom& G, const ResCta& X, int phase, int i, int& lr, int& lc) {
+    const int n = phase ? X.ninner : X.nring;
+    if (NC == 1) {
+        if (i >= n) return 0;
+        res_locate(G, X, phase, i, lr, lc);
+        return 2;
+    }
+    if (i < n) {
+        res_locate(G, X, phase, i, lr, lc);
+        const int row = X.r0 + lr, c = X.c0 + lc;
+        return (row >= 4 && row + 5 <= A.H && c >= 4 && c + NC + 4 <= A.W) ? 1 : 0;
+    }
+    if (i >= n + X.nedge) return 0;
+    res_locate_edge(X, i - n, lr, lc);
+    return res_publishes(X, lr, lc) == (phase == 0) ? 2 : 0;
+}
+
+template <int NC>
+FK_HD void res_thread_setup(const TileArgs& A, const ResGeom& G, const ResCta& X, int tid, int nthr, ResThread& T) {
+    T.lr0 = T.lc0 = T.lr1 = T.lc1 = 0;
+    T.ty0 = res_item<NC>(A, G, X, 0, tid, T.lr0, T.lc0);
+    T.ty1 = res_item<NC>(A, G, X, 1, tid, T.lr1, T.lc1);
+    const int U = X.nhalo[0] + X.nhalo[1] + X.nhalo[2] + X.nhalo[3];
+    T.hs0 = T.hs1 = 0; T.hd0 = T.hd1 = 0;
+    if (tid < U) res_halo_unit(G, X, tid, T.hs0, T.hd0);
+    if (tid + nthr < U) res_halo_unit(G, X, tid + nthr, T.hs1, T.hd1);
+}
+
+// one phase of step s, its items strided over the CTA's threads
 template <bool EXACT, int NC>
-FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, int s, int phase, unsigned mask, int tid,
-                     int nthr) {   // (the kernel calls this from ONE site, in a phase loop: a single copy of the body)
+FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
+                     unsigned mask, int tid, int nthr) {   // (called from ONE site, in a phase loop: a single copy)
     const float* cur = X.U0 + (s & 1) * X.nu;
     float* nxt = X.U0 + ((s + 1) & 1) * X.nu;
     const bool last = s == G.nsteps - 1;
     u64* box = (last || phase) ? nullptr : G.xchg + ((s + 1) & 1) * X.pstride + X.mbox;
     const unsigned tag = (unsigned)(s + 1);
-    const int n = phase ? X.ninner : X.nring;
-    const int ne = (phase || NC == 1) ? 0 : X.nedge;
-    for (int i = tid; i < n + ne; i += nthr) {
-        int lr, lc;
-        if (NC == 1) {
-            res_locate(G, X, phase, i, lr, lc);
-            res_group<EXACT, 1, true>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
-        } else if (i < n) {
-            res_locate(G, X, phase, i, lr, lc);
-            const int row = X.r0 + lr, c = X.c0 + lc;
-            if (row >= 4 && row + 5 <= A.H && c >= 4 && c + NC + 4 <= A.W)
-                res_group<EXACT, NC, false>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
-        } else {
-            res_locate_edge(X, i - n, lr, lc);
-            res_group<EXACT, 1, true>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
-        }
+    const int n = (phase ? X.ninner : X.nring) + (NC == 1 ? 0 : X.nedge);
+    for (int i = tid; i < n; i += nthr) {
+        int lr = phase ? T.lr1 : T.lr0, lc = phase ? T.lc1 : T.lc0, ty = phase ? T.ty1 : T.ty0;
+        if (i != tid) ty = res_item<NC>(A, G, X, phase, i, lr, lc);
+        if (ty == 2) res_group<EXACT, 1, true>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        else if (NC > 1 && ty == 1) res_group<EXACT, NC, false>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
     }
 }
 
@@ -514,21 +580,56 @@ struct ResPlan {
 
 enum { FK_RES_MAX_THREADS = 512 };
 
-FK_HD void res_group_counts(int th, int tw, int nc, int& nring, int& ninner) {
-    const int q = tw / nc, qe = 4 / nc;
-    if (th <= 8 || tw <= 8) { nring = th * q; ninner = 0; }
-    else { nring = 8 * q + 2 * qe * (th - 8); ninner = (th - 8) * (q - 2 * qe); }
+// Modelled time (SM cycles) one tile class spends per step, and the items of its busiest phase.  Latencies and
+// instruction counts of the item kinds are measured figures (profiles/probe_resident_r01.log): a central group of
+// 1 / 2 / 4 cells is a dependent chain of ~650 / 900 / 1100 cycles and ~220 / 300 / 450 instructions, a general cell
+// ~1750 cycles and ~700 instructions; a phase lasts as long as its rounds of chains or as the issue of its warps on 4
+// schedulers at ~0.6 IPC, whichever is longer.
+inline double res_tile_cost(int H, int W, const ResGeom& G, int tile, int threads, int& items) {
+    ResCta X;
+    res_tile_geom(H, W, G, tile, X);
+    const int nc = G.nc;
+    const double lat_f = nc == 1 ? 650 : (nc == 2 ? 900 : 1100), ins_f = nc == 1 ? 220 : (nc == 2 ? 300 : 450);
+    const double lat_g = 1750, ins_g = 700;
+    // edge cells a neighbour needs (estimate: rows of the physical bands times published columns and vice versa)
+    int pub = (X.e_nt + X.e_nb) * 4 * (X.has_w + X.has_e) + (X.e_nl + X.e_nr) * 4 * (X.has_n + X.has_s);
+    if (pub > X.nedge) pub = X.nedge;
+    double total = 0;
+    items = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        const int ngen = phase ? X.nedge - pub : pub;
+        int ngrp = phase ? X.ninner : X.nring;
+        int nfast = ngrp - (nc == 1 ? ngen : (ngen + nc - 1) / nc);
+        if (nfast < 0) nfast = 0;
+        const int n = nc == 1 ? ngrp : ngrp + X.nedge;   // thread slots the phase walks through
+        if (n > items) items = n;
+        if (nfast + ngen == 0) continue;
+        const int rounds = (n + threads - 1) / threads;
+        const double chain = rounds * (ngen ? lat_g : lat_f);
+        const double issue = (((nfast + 31) / 32) * ins_f + ((ngen + 31) / 32) * ins_g) / (4 * 0.6);
+        total += chain > issue ? chain : issue;
+    }
+    return total + 900;   // + the halo's trip through L2 and the barrier
 }
 
 // Tiles for a (batch, H, W) problem on `capacity` co-resident CTAs with `smem_limit` bytes each and `xchg_limit` bytes
 // of mailboxes.  A tile next to another tile is at least 8 cells wide/tall (a halo comes from ONE tile, and the edge
 // formulas reach 7 cells into the tissue).  Cells per thread group: the smallest NC whose groups fit one round of 512
 // threads -- a small tile is latency bound and wants every lane busy; a large one wants the fewest instructions.
-// Cost of a plan: the serial rounds a CTA runs per step, ring and interior separately (the halo travels in between),
-// each at least a lone warp's dependent chain, then the tile size; ties go to fewer tiles.
+// The step lasts as long as its slowest tile: the plan's cost is the largest modelled time of the corner, edge and
+// interior tile classes, with the tiles at the tissue's edges shrunk (several ratios tried) to even them out.
+// force_eh / force_ewq: > 0 that many rows / column groups in the edge tiles, < 0 even split, 0 planner's choice.
 inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_limit, long long xchg_limit, int force_ntr,
-                          int force_ntc, int force_threads, int force_nc, ResPlan& P) {
+                          int force_ntc, int force_threads, int force_nc, int force_eh, int force_ewq, ResPlan& P) {
     if (W % 4 != 0 || H < 3 || W < 4 || batch < 1) return false;
+    // the last plan is kept: a run calls this once per segment with the same problem
+    struct Memo { int key[8]; bool ok; ResPlan plan; };
+    static Memo memo = {{-1, 0, 0, 0, 0, 0, 0, 0}, false, ResPlan()};
+    const int key[8] = {H, W, batch, capacity, force_ntr * 4096 + force_ntc, force_eh * 4096 + force_ewq,
+                        force_threads * 8 + force_nc, (int)(smem_limit / 64) + (int)((xchg_limit / 4096) % 1000003)};
+    bool same = true;
+    for (int i = 0; i < 8; ++i) same = same && memo.key[i] == key[i];
+    if (same) { if (memo.ok) P = memo.plan; return memo.ok; }
     const int Q = W >> 2;
     double best = 1e300;
     bool found = false;
@@ -539,46 +640,72 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
             if (ntc > 1 && Q / ntc < 2) break;
             if ((long long)ntr * ntc * batch > capacity) break;
             if (force_ntc > 0 && ntc != force_ntc) continue;
-            const int th = (H + ntr - 1) / ntr, tw = 4 * ((Q + ntc - 1) / ntc);
-            const long long smem = res_smem_floats(th, tw) * 4;
-            if (smem > smem_limit) continue;
-            const int slots = 8 * tw + 8 * th;
-            const long long xbytes = 2LL * batch * ntr * ntc * slots * (long long)sizeof(u64);
-            if (xbytes > xchg_limit) continue;
-            int nc = force_nc;
-            if (nc != 1 && nc != 2 && nc != 4) nc = th * tw <= FK_RES_MAX_THREADS ? 1 : (th * tw <= 2 * FK_RES_MAX_THREADS ? 2 : 4);
-            int nring, ninner;
-            res_group_counts(th, tw, nc, nring, ninner);
-            if (nc > 1) {   // the corner tile's cells next to a physical edge are extra one-cell items of the ring phase
-                int nt, nb, nl, nr;
-                nring += res_edge_counts(H, W, 0, th, 0, tw, nt, nb, nl, nr);
-            }
-            int threads = force_threads;
-            if (threads <= 0) {
-                const int m = nring > ninner ? nring : ninner;
-                threads = (m + 31) / 32 * 32;
-                if (threads < 64) threads = 64;
-                if (threads > FK_RES_MAX_THREADS) threads = FK_RES_MAX_THREADS;
-            }
-            // a round of one group per thread: a dependent chain ~ (4 + 3 nc) units long, or the issue time of its warps
-            auto phase_cost = [&](int n) {
-                if (n == 0) return 0.0;
-                const int rounds = (n + threads - 1) / threads;
-                const double chain = 4.0 + 3.0 * nc, issue = (double)((n + 31) / 32) * (2.0 + 2.5 * nc) / 4.0;
-                return rounds * chain > issue ? rounds * chain : issue;
-            };
-            const double cost = phase_cost(nring) + phase_cost(ninner) + 1e-3 * ntr * ntc + 1e-4 * (th + tw);
-            if (cost < best) {
-                best = cost;
-                found = true;
-                P.G.ntr = ntr; P.G.ntc = ntc; P.G.th_max = th; P.G.tw_max = tw; P.G.pitch = tw + 8;
-                P.G.nc = nc; P.G.slots = slots;
-                P.threads = threads;
-                P.smem_bytes = smem;
-                P.xchg_bytes = xbytes;
+            for (int shrink = 0; shrink < 4; ++shrink) {
+                // edge tiles get f times the rows / column groups of the others: n = (nt - 2 + 2 f) * inner
+                static const double fs[4] = {1.0, 0.85, 0.7, 0.55};
+                ResGeom G = ResGeom();
+                G.ntr = ntr; G.ntc = ntc;
+                if (force_eh || force_ewq) {
+                    if (shrink) break;
+                    if (force_eh > 0 && ntr >= 3) G.eh = force_eh;
+                    if (force_ewq > 0 && ntc >= 3) G.ewq = force_ewq;
+                    if (G.eh && (G.eh < 8 || (H - 2 * G.eh) / (ntr - 2) < 8)) continue;
+                    if (G.ewq && (G.ewq < 2 || (Q - 2 * G.ewq) / (ntc - 2) < 2)) continue;
+                } else if (shrink) {
+                    if (ntr >= 3) { G.eh = (int)(fs[shrink] * H / (ntr - 2 + 2 * fs[shrink]) + 0.5); if (G.eh < 8) G.eh = 8; }
+                    if (ntc >= 3) { G.ewq = (int)(fs[shrink] * Q / (ntc - 2 + 2 * fs[shrink]) + 0.5); if (G.ewq < 2) G.ewq = 2; }
+                    if (!G.eh && !G.ewq) break;
+                    if (G.eh && (H - 2 * G.eh) / (ntr - 2) < 8) continue;
+                    if (G.ewq && (Q - 2 * G.ewq) / (ntc - 2) < 2) continue;
+                }
+                int th = 0, tw = 0;
+                for (int t = 0; t < ntr; ++t) { const int h = res_split(H, ntr, G.eh, t + 1) - res_split(H, ntr, G.eh, t); if (h > th) th = h; }
+                for (int t = 0; t < ntc; ++t) { const int w = 4 * (res_split(Q, ntc, G.ewq, t + 1) - res_split(Q, ntc, G.ewq, t)); if (w > tw) tw = w; }
+                const long long smem = res_smem_floats(th, tw) * 4;
+                if (smem > smem_limit) continue;
+                G.th_max = th; G.tw_max = tw; G.pitch = tw + 8; G.slots = 8 * tw + 8 * th;
+                const long long xbytes = 2LL * batch * ntr * ntc * G.slots * (long long)sizeof(u64);
+                if (xbytes > xchg_limit) continue;
+                G.nc = force_nc;
+                if (G.nc != 1 && G.nc != 2 && G.nc != 4)
+                    G.nc = th * tw <= FK_RES_MAX_THREADS ? 1 : (th * tw <= 2 * FK_RES_MAX_THREADS ? 2 : 4);
+                // tile classes: corner, top edge, left edge, interior (those that exist)
+                const int rows[2] = {0, ntr > 2 ? 1 : ntr - 1}, cols[2] = {0, ntc > 2 ? 1 : ntc - 1};
+                int threads = force_threads;
+                if (threads <= 0) {
+                    int m = 0;
+                    for (int a = 0; a < 2; ++a)
+                        for (int b = 0; b < 2; ++b) {
+                            int items;
+                            res_tile_cost(H, W, G, rows[a] * ntc + cols[b], FK_RES_MAX_THREADS, items);
+                            if (items > m) m = items;
+                        }
+                    threads = (m + 31) / 32 * 32;
+                    if (threads < 64) threads = 64;
+                    if (threads > FK_RES_MAX_THREADS) threads = FK_RES_MAX_THREADS;
+                }
+                double cost = 0;
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        int items;
+                        const double c = res_tile_cost(H, W, G, rows[a] * ntc + cols[b], threads, items);
+                        if (c > cost) cost = c;
+                    }
+                cost += 0.5 * ntr * ntc;   // ties: fewer tiles
+                if (cost < best) {
+                    best = cost;
+                    found = true;
+                    P.G = G;
+                    P.threads = threads;
+                    P.smem_bytes = smem;
+                    P.xchg_bytes = xbytes;
+                }
             }
         }
     }
+    for (int i = 0; i < 8; ++i) memo.key[i] = key[i];
+    memo.ok = found;
+    if (found) memo.plan = P;
     return found;
 }
 
@@ -588,10 +715,11 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
 #include <vector>
 namespace fk {
 template <bool EXACT>
-inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, int s, int phase, unsigned mask) {
-    if (G.nc == 1) res_phase<EXACT, 1>(A, G, X, s, phase, mask, 0, 1);
-    else if (G.nc == 2) res_phase<EXACT, 2>(A, G, X, s, phase, mask, 0, 1);
-    else res_phase<EXACT, 4>(A, G, X, s, phase, mask, 0, 1);
+inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
+                          unsigned mask) {
+    if (G.nc == 1) res_phase<EXACT, 1>(A, G, X, T, s, phase, mask, 0, 1);
+    else if (G.nc == 2) res_phase<EXACT, 2>(A, G, X, T, s, phase, mask, 0, 1);
+    else res_phase<EXACT, 4>(A, G, X, T, s, phase, mask, 0, 1);
 }
 // CTAs advance in lock step, phase by phase, which is one legal interleaving of the mailbox protocol; shared memory is
 // poisoned with NaN so that a read of a halo nobody filled shows up in the result, and a record that has not arrived
@@ -604,23 +732,28 @@ inline int emu_resident_launch(const ResPlan& P, const TileArgs& A, int batch, i
     std::vector<u64> xchg((size_t)(P.xchg_bytes / sizeof(u64)), 0ull);
     G.xchg = xchg.data();
     std::vector<ResCta> X((size_t)ntiles * batch);
+    std::vector<ResThread> T((size_t)ntiles * batch);
     for (int sim = 0; sim < batch; ++sim)
         for (int t = 0; t < ntiles; ++t) {
             ResCta& x = X[(size_t)sim * ntiles + t];
             res_setup(A, G, t, sim, batch, smem[(size_t)sim * ntiles + t].data(), x);
             res_load(A, G, x, 0, 1);
+            ResThread& th = T[(size_t)sim * ntiles + t];
+            if (G.nc == 1) res_thread_setup<1>(A, G, x, 0, 1, th);
+            else if (G.nc == 2) res_thread_setup<2>(A, G, x, 0, 1, th);
+            else res_thread_setup<4>(A, G, x, 0, 1, th);
         }
     for (int s = 0; s < G.nsteps; ++s) {
         for (size_t i = 0; i < X.size(); ++i) {
             const unsigned mask = res_mask(A, X[i], s);
             for (int phase = 0; phase < 2; ++phase) {
-                if (exact) emu_res_phase<true>(A, G, X[i], s, phase, mask);
-                else emu_res_phase<false>(A, G, X[i], s, phase, mask);
+                if (exact) emu_res_phase<true>(A, G, X[i], T[i], s, phase, mask);
+                else emu_res_phase<false>(A, G, X[i], T[i], s, phase, mask);
             }
         }
         if (s == G.nsteps - 1) break;
         for (size_t i = 0; i < X.size(); ++i)
-            if (!res_halo(G, X[i], s, 0, 1)) return -7;
+            if (!res_halo(G, X[i], T[i], s, 0, 1)) return -7;
     }
     return 0;
 }

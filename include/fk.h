@@ -56,7 +56,9 @@ typedef struct FkOptions {
                              3-instruction correctly rounded FMA division by constants (see fk_check_exact_division) */
     int tiles_r, tiles_c; /* resident kernel: tile grid rows x columns, one CTA per tile (0 = auto) */
     int cells_per_thread; /* resident kernel: 1, 2 or 4 adjacent cells per thread (0 = auto) */
-    int reserved[4];
+    int edge_rows, edge_colgroups; /* resident kernel: rows / 4-column groups of the tiles at the tissue's edges
+                                      (0 = auto, < 0 = even split) */
+    int reserved[2];
 } FkOptions;
 
 /* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */

@@ -55,6 +55,14 @@ def test_resident_kernel_exact(shape, nsteps, tiles, nc):
     assert info == (0, 1000000)   # one launch, nothing else
 
 
+@pytest.mark.parametrize("shape,tiles,edge,nc", [((96, 160), (5, 6), (12, 4), 4), ((96, 160), (5, 6), (12, 4), 1),
+                                                 ((120, 96), (4, 3), (20, 6), 2), ((120, 96), (6, 1), (10, 0), 4)])
+def test_resident_kernel_uneven_edge_tiles(shape, tiles, edge, nc):
+    """Smaller tiles at the tissue's edges (their one-sided formulas cost more): same bits."""
+    info = _exact(shape, 1, nsteps=6, kernel=4, tiles=tiles, nc=nc, edge_tile=edge)
+    assert info == (0, 1000000)
+
+
 def test_resident_kernel_exact_batched_per_tissue_inputs():
     shape, batch = (40, 48), 3
     cases = [common.random_case(shape, seed=20 + b, n_stim=2) for b in range(batch)]

@@ -70,7 +70,7 @@ def test_exact_bitwise_vs_oracle(shape, T, kernel, extra):
     ((12, 16), 9, (0, 0), 0, 0), ((3, 4), 5, (0, 0), 0, 0), ((64, 96), 9, (2, 3), 0, 4), ((64, 96), 9, (4, 1), 256, 2),
     ((128, 128), 9, (0, 0), 0, 0), ((100, 200), 9, (5, 5), 0, 0), ((256, 256), 40, (0, 0), 0, 0), ((512, 512), 9, (0, 0), 0, 0),
     ((512, 512), 12, (16, 8), 512, 4), ((33, 72), 6, (4, 9), 128, 1), ((64, 96), 1, (2, 3), 0, 0), ((1024, 1024), 6, (0, 0), 0, 0),
-    ((256, 256), 30, (8, 8), 0, 2), ((128, 128), 50, (16, 1), 64, 4), ((200, 120), 25, (3, 3), 96, 1)])
+    ((256, 256), 30, (8, 8), 0, 2), ((128, 128), 20, (16, 1), 64, 4), ((200, 120), 25, (3, 3), 96, 1)])
 def test_resident_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads, nc):
     """The resident kernel (whole call in one cooperative launch; halos exchanged between co-resident CTAs through
     tagged 8-byte mailbox records in L2): bit-identical to the oracle for any tile grid, CTA size and cells per thread

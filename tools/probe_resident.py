@@ -15,10 +15,11 @@ import oracle as O  # noqa: E402
 from cardiax_b200 import _lib, options, solve, stimulus  # noqa: E402
 
 
-def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=0, nc=0):
+def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=0, nc=0, edge=(0, 0)):
     options.verbose = False
     options.numerics, options.kernel, options.steps_per_launch = numerics, kernel, T
     options.cta_threads, options.rows_per_cta, options.tiles, options.cells_per_thread = threads, 0, tiles, nc
+    options.edge_tile = edge
     st = solve.State(*[torch.as_tensor(work[k]).cuda() for k in "vwu"])
     D = torch.as_tensor(work["D"]).cuda()
     gs = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in work["stimuli"]]
@@ -35,8 +36,8 @@ def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) * 1e3 / n)
         cells = st.u.numel()
-        print("%-7s kernel=%d tiles=%-9s thr=%3d %-5s %7.2f us/step %7.1f Gcs/s  %s" % (
-            name, kernel, tiles, threads, numerics, best, cells / best / 1e3, _lib.last_plan()), flush=True)
+        print("%-7s kernel=%d tiles=%-9s edge=%-9s %-5s %7.2f us/step %7.1f Gcs/s  %s" % (
+            name, kernel, tiles, edge, numerics, best, cells / best / 1e3, _lib.last_plan()), flush=True)
         if kernel == 4 and os.environ.get("FK_RES_TIMING"):
             import ctypes
             out = (ctypes.c_ulonglong * 8)()
@@ -51,15 +52,18 @@ def run(name, work, kernel, tiles=(0, 0), threads=0, n=2000, numerics="fast", T=
 def main():
     which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["fk128", "fk256", "fk512", "fk1024"]
     short = "--short" in sys.argv
-    # (tiles, threads, cells per thread)
+    one = "--one" in sys.argv   # a single run of the planner's choice (for ncu)
+    # (tiles, cells per thread, (edge tile rows, edge tile column groups); -1 = even split)
+    E = (-1, -1)
     sweeps = {
-        "fk128": [((0, 0), 0, 0), ((8, 16), 0, 1), ((16, 8), 0, 1), ((12, 12), 0, 1), ((8, 8), 0, 1), ((8, 8), 0, 2), ((4, 4), 0, 2),
-                  ((16, 1), 0, 4), ((8, 16), 0, 2), ((4, 8), 0, 1), ((4, 4), 0, 4)],
-        "fk256": [((0, 0), 0, 0), ((12, 12), 0, 1), ((12, 12), 0, 2), ((16, 8), 0, 2), ((8, 16), 0, 2), ((8, 8), 0, 4),
-                  ((8, 8), 0, 2), ((16, 8), 0, 4), ((32, 4), 0, 4)],
-        "fk512": [((0, 0), 0, 0), ((12, 12), 0, 4), ((12, 12), 0, 2), ((18, 8), 0, 4), ((16, 8), 0, 4), ((9, 16), 0, 4),
-                  ((14, 10), 0, 2), ((24, 6), 0, 4), ((37, 4), 0, 4)],
-        "fk1024": [((0, 0), 0, 0), ((21, 7), 0, 4), ((12, 12), 0, 4), ((16, 9), 0, 4), ((18, 8), 0, 4)],
+        "fk128": [((0, 0), 0, (0, 0)), ((8, 16), 2, E), ((8, 16), 1, E), ((16, 8), 2, E), ((8, 16), 2, (13, -1)), ((8, 12), 2, E),
+                  ((10, 14), 2, E), ((10, 14), 2, (10, -1)), ((5, 4), 4, E), ((6, 8), 2, E)],
+        "fk256": [((0, 0), 0, (0, 0)), ((16, 8), 2, E), ((16, 8), 2, (12, -1)), ((16, 8), 2, (12, 6)), ((12, 12), 2, E),
+                  ((12, 12), 2, (16, 4)), ((9, 7), 4, E), ((16, 9), 2, (12, 5)), ((18, 8), 2, (10, 6))],
+        "fk512": [((0, 0), 0, (0, 0)), ((14, 10), 4, E), ((14, 10), 4, (28, 10)), ((14, 10), 4, (22, 8)), ((12, 12), 4, E),
+                  ((12, 12), 4, (32, 8)), ((12, 12), 2, (32, 8)), ((16, 9), 4, (24, 10)), ((18, 8), 4, (20, 12))],
+        "fk1024": [((0, 0), 0, (0, 0)), ((16, 9), 4, E), ((16, 9), 4, (48, 22)), ((16, 9), 4, (40, 20)), ((21, 7), 4, E),
+                   ((21, 7), 4, (36, 28)), ((18, 8), 4, (40, 24))],
     }
     for name in which:
         if name == "fk128":
@@ -73,8 +77,11 @@ def main():
             _, D = common.smooth_case((n, n), 0)
             work = dict(v=np.ones((n, n), np.float32), w=np.ones((n, n), np.float32), u=bench.make_fk4096(n, n)["u"], D=D,
                         stimuli=[], params="3")
-        for tiles, thr, nc in (sweeps.get(name, [((0, 0), 0, 0)])[:5] if short else sweeps.get(name, [((0, 0), 0, 0)])):
-            run(name, work, 4, tiles, thr, nc=nc)
+        if one:
+            run(name, work, 4, n=500)
+            continue
+        for tiles, nc, edge in (sweeps[name][:5] if short else sweeps[name]):
+            run(name, work, 4, tiles, 0, nc=nc, edge=edge)
         if not short:
             run(name, work, 3, n=400)
             run(name, work, 2, n=400, T=2)
