@@ -46,6 +46,7 @@ struct ResGeom {
     int pitch;           // floats per row of a u buffer = tw_max + 8
     int nsteps;          // Euler steps of the launch
     int nc;              // adjacent cells per thread group: 1, 2 or 4
+    int single;          // 1: every tile's items fit one round of the CTA's threads -- no interior phase (all "ring")
     int slots;           // mailbox records per tile and parity: 8 * tw_max (4 top + 4 bottom rows) + 8 * th_max (columns)
     u64* xchg;           // mailboxes [2 parities][batch * ntr * ntc tiles][slots], tags zero at launch
     u64* timing;         // null, or cycle counters CTA (0, 0) fills (development: FK_RES_TIMING=1)
@@ -57,8 +58,8 @@ struct ResCta {
     int r0, r1, c0, c1, th, tw, q;   // q = tw / nc groups per row
     int qe;                          // groups per row that lie within 4 cells of a tile edge, per side = 4 / nc
     int has_n, has_s, has_w, has_e;  // neighbours (0 at a physical edge)
-    int ir0, ir1, ig0, ig1;          // INTERIOR = rows [ir0, ir1) x groups [ig0, ig1): no cell a neighbour needs
-    int nring, ninner;               // RING groups (the rest: within 4 cells of a side that has a neighbour) / interior
+    int ir0, ir1, ig0, ig1;          // INTERIOR = rows [ir0, ir1) x groups [ig0, ig1): 4 cells away from every side
+    int nring, ninner;               // RING groups (the rest) / interior groups
     int e_nt, e_nb, e_nl, e_nr;      // cells within 4 of a PHYSICAL edge: top/bottom rows, left/right columns of the rest
     int nedge;                       // ... their number
     int nhalo[4];                    // 16-byte units (2 records) of the north, south, west, east halo
@@ -105,9 +106,11 @@ FK_HD void res_tile_geom(int H, int W, const ResGeom& G, int tile, ResCta& X) {
     X.c1 = 4 * res_split(W >> 2, G.ntc, G.ewq, X.tj + 1);
     X.th = X.r1 - X.r0; X.tw = X.c1 - X.c0; X.q = X.tw / G.nc; X.qe = 4 / G.nc;
     X.has_n = X.ti > 0; X.has_s = X.ti < G.ntr - 1; X.has_w = X.tj > 0; X.has_e = X.tj < G.ntc - 1;
-    X.ir0 = X.has_n ? 4 : 0; X.ir1 = X.has_s ? X.th - 4 : X.th;
-    X.ig0 = X.has_w ? X.qe : 0; X.ig1 = X.has_e ? X.q - X.qe : X.q;
-    if (X.ir1 <= X.ir0 || X.ig1 <= X.ig0) { X.ir0 = X.ir1 = 0; X.ig0 = X.ig1 = 0; }   // no interior: all ring
+    // The ring is geometric -- 4 cells along EVERY side, physical edges included -- and the cells at a physical edge
+    // all belong to phase 0.  (Tried: ring = only what a neighbour needs, the rest in phase 1.  Slower at every size:
+    // the expensive one-sided cells then queue up behind the interior as a second, nearly empty round.)
+    X.ir0 = 4; X.ir1 = X.th - 4; X.ig0 = X.qe; X.ig1 = X.q - X.qe;
+    if (G.single || X.ir1 <= X.ir0 || X.ig1 <= X.ig0) { X.ir0 = X.ir1 = 0; X.ig0 = X.ig1 = 0; }   // no interior: all ring
     X.ninner = (X.ir1 - X.ir0) * (X.ig1 - X.ig0);
     X.nring = X.th * X.q - X.ninner;
     X.nedge = res_edge_counts(H, W, X.r0, X.r1, X.c0, X.c1, X.e_nt, X.e_nb, X.e_nl, X.e_nr);
@@ -518,11 +521,10 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
 }
 
 // item i of a phase -> its cell(s) and what to do with them: 1 = a group of NC cells whose formulas are all central,
-// 2 = ONE cell through the general formulas, 0 = nothing.  Phase 0 = what the neighbours wait for (the ring), published
-// as it is computed; phase 1 = everything else, computed while those records travel.  With NC > 1 the groups that
-// touch a physical edge are skipped and their cells done ONE PER THREAD as extra items (of phase 0 if a neighbour needs
-// them, else of phase 1): the one-sided formulas cost several times the central ones and the step's critical path is
-// the slowest thread of the slowest tile.
+// 2 = ONE cell through the general formulas, 0 = nothing.  Phase 0 = the ring (what the neighbours wait for), published
+// as it is computed; phase 1 = the interior, computed while those records travel.  With NC > 1 the groups that touch a
+// physical edge are skipped and their cells done ONE PER THREAD as extra items of phase 0: the one-sided formulas cost
+// several times the central ones and the step's critical path is the slowest thread of the slowest tile.
 template <int NC>
 FK_HD int res_item(const TileArgs& A, const ResGeom& G, const ResCta& X, int phase, int i, int& lr, int& lc) {
     const int n = phase ? X.ninner : X.nring;
@@ -536,9 +538,9 @@ FK_HD int res_item(const TileArgs& A, const ResGeom& G, const ResCta& X, int pha
         const int row = X.r0 + lr, c = X.c0 + lc;
         return (row >= 4 && row + 5 <= A.H && c >= 4 && c + NC + 4 <= A.W) ? 1 : 0;
     }
-    if (i >= n + X.nedge) return 0;
+    if (phase || i >= n + X.nedge) return 0;
     res_locate_edge(X, i - n, lr, lc);
-    return res_publishes(X, lr, lc) == (phase == 0) ? 2 : 0;
+    return 2;
 }
 
 template <int NC>
@@ -561,7 +563,7 @@ FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     const bool last = s == G.nsteps - 1;
     u64* box = (last || phase) ? nullptr : G.xchg + ((s + 1) & 1) * X.pstride + X.mbox;
     const unsigned tag = (unsigned)(s + 1);
-    const int n = (phase ? X.ninner : X.nring) + (NC == 1 ? 0 : X.nedge);
+    const int n = phase ? X.ninner : (NC == 1 ? X.nring : X.nring + X.nedge);
     for (int i = tid; i < n; i += nthr) {
         int lr = phase ? T.lr1 : T.lr0, lc = phase ? T.lc1 : T.lc0, ty = phase ? T.ty1 : T.ty0;
         if (i != tid) ty = res_item<NC>(A, G, X, phase, i, lr, lc);
@@ -580,44 +582,32 @@ struct ResPlan {
 
 enum { FK_RES_MAX_THREADS = 512 };
 
-// Modelled time (SM cycles) one tile class spends per step, and the items of its busiest phase.  Latencies and
-// instruction counts of the item kinds are measured figures (profiles/probe_resident_r01.log): a central group of
-// 1 / 2 / 4 cells is a dependent chain of ~650 / 900 / 1100 cycles and ~220 / 300 / 450 instructions, a general cell
-// ~1750 cycles and ~700 instructions; a phase lasts as long as its rounds of chains or as the issue of its warps on 4
-// schedulers at ~0.6 IPC, whichever is longer.
-inline double res_tile_cost(int H, int W, const ResGeom& G, int tile, int threads, int& items) {
+// thread slots the busiest phase of a tile walks through
+inline int res_tile_items(int H, int W, const ResGeom& G, int tile) {
     ResCta X;
     res_tile_geom(H, W, G, tile, X);
-    const int nc = G.nc;
-    const double lat_f = nc == 1 ? 650 : (nc == 2 ? 900 : 1100), ins_f = nc == 1 ? 220 : (nc == 2 ? 300 : 450);
-    const double lat_g = 1750, ins_g = 700;
-    // edge cells a neighbour needs (estimate: rows of the physical bands times published columns and vice versa)
-    int pub = (X.e_nt + X.e_nb) * 4 * (X.has_w + X.has_e) + (X.e_nl + X.e_nr) * 4 * (X.has_n + X.has_s);
-    if (pub > X.nedge) pub = X.nedge;
-    double total = 0;
-    items = 0;
-    for (int phase = 0; phase < 2; ++phase) {
-        const int ngen = phase ? X.nedge - pub : pub;
-        int ngrp = phase ? X.ninner : X.nring;
-        int nfast = ngrp - (nc == 1 ? ngen : (ngen + nc - 1) / nc);
-        if (nfast < 0) nfast = 0;
-        const int n = nc == 1 ? ngrp : ngrp + X.nedge;   // thread slots the phase walks through
-        if (n > items) items = n;
-        if (nfast + ngen == 0) continue;
-        const int rounds = (n + threads - 1) / threads;
-        const double chain = rounds * (ngen ? lat_g : lat_f);
-        const double issue = (((nfast + 31) / 32) * ins_f + ((ngen + 31) / 32) * ins_g) / (4 * 0.6);
-        total += chain > issue ? chain : issue;
-    }
-    return total + 900;   // + the halo's trip through L2 and the barrier
+    const int p0 = G.nc == 1 ? X.nring : X.nring + X.nedge;
+    return p0 > X.ninner ? p0 : X.ninner;
+}
+
+// work of a tile in central-cell units: a cell at a physical edge (one-sided formulas, one cell per thread) costs ~6
+inline double res_tile_work(int H, int W, const ResGeom& G, int tile) {
+    ResCta X;
+    res_tile_geom(H, W, G, tile, X);
+    return (double)X.th * X.tw + 5.0 * X.nedge;
 }
 
 // Tiles for a (batch, H, W) problem on `capacity` co-resident CTAs with `smem_limit` bytes each and `xchg_limit` bytes
 // of mailboxes.  A tile next to another tile is at least 8 cells wide/tall (a halo comes from ONE tile, and the edge
-// formulas reach 7 cells into the tissue).  Cells per thread group: the smallest NC whose groups fit one round of 512
-// threads -- a small tile is latency bound and wants every lane busy; a large one wants the fewest instructions.
-// The step lasts as long as its slowest tile: the plan's cost is the largest modelled time of the corner, edge and
-// interior tile classes, with the tiles at the tissue's edges shrunk (several ratios tried) to even them out.
+// formulas reach 7 cells into the tissue).  Distilled from sweeps on B200 (profiles/probe_resident_r01.log):
+//  * cells per thread: 2 up to 1024-cell tiles (such tiles are latency bound: every lane busy), 4 above (fewest
+//    instructions); 1 only for tiles of a few dozen cells;
+//  * small tiles (nc < 4): the step time follows th * tw + 6 (th + tw) of the largest tile -- its cells plus its
+//    perimeter (ring work, halo records) --, grids that divide the tissue evenly are ~15 % faster than ragged ones,
+//    and if everything fits one round of <= 512 threads there is no interior phase at all;
+//  * large tiles (nc = 4) are issue bound and the step lasts as long as the slowest tile: the tiles at the tissue's
+//    edges, whose one-sided cells cost ~6 central ones, get f = 1, .85, .7, .55 or .45 of the others' rows / columns,
+//    whichever evens out the work of corner, edge and interior tiles best within shared memory.
 // force_eh / force_ewq: > 0 that many rows / column groups in the edge tiles, < 0 even split, 0 planner's choice.
 inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_limit, long long xchg_limit, int force_ntr,
                           int force_ntc, int force_threads, int force_nc, int force_eh, int force_ewq, ResPlan& P) {
@@ -631,6 +621,7 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
     for (int i = 0; i < 8; ++i) same = same && memo.key[i] == key[i];
     if (same) { if (memo.ok) P = memo.plan; return memo.ok; }
     const int Q = W >> 2;
+    static const double fs[5] = {1.0, 0.85, 0.7, 0.55, 0.45};
     double best = 1e300;
     bool found = false;
     for (int ntr = 1; ntr <= H; ++ntr) {
@@ -640,24 +631,23 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
             if (ntc > 1 && Q / ntc < 2) break;
             if ((long long)ntr * ntc * batch > capacity) break;
             if (force_ntc > 0 && ntc != force_ntc) continue;
-            for (int shrink = 0; shrink < 4; ++shrink) {
-                // edge tiles get f times the rows / column groups of the others: n = (nt - 2 + 2 f) * inner
-                static const double fs[4] = {1.0, 0.85, 0.7, 0.55};
+            const int th_even = (H + ntr - 1) / ntr, tw_even = 4 * ((Q + ntc - 1) / ntc);
+            int nc = force_nc;
+            if (nc != 1 && nc != 2 && nc != 4) nc = th_even * tw_even <= 64 ? 1 : (th_even * tw_even <= 1024 ? 2 : 4);
+            const bool forced_edge = force_eh != 0 || force_ewq != 0;
+            for (int k = 0; k < ((nc == 4 && !forced_edge) ? 5 : 1); ++k) {
                 ResGeom G = ResGeom();
-                G.ntr = ntr; G.ntc = ntc;
-                if (force_eh || force_ewq) {
-                    if (shrink) break;
+                G.ntr = ntr; G.ntc = ntc; G.nc = nc;
+                if (forced_edge) {
                     if (force_eh > 0 && ntr >= 3) G.eh = force_eh;
                     if (force_ewq > 0 && ntc >= 3) G.ewq = force_ewq;
-                    if (G.eh && (G.eh < 8 || (H - 2 * G.eh) / (ntr - 2) < 8)) continue;
-                    if (G.ewq && (G.ewq < 2 || (Q - 2 * G.ewq) / (ntc - 2) < 2)) continue;
-                } else if (shrink) {
-                    if (ntr >= 3) { G.eh = (int)(fs[shrink] * H / (ntr - 2 + 2 * fs[shrink]) + 0.5); if (G.eh < 8) G.eh = 8; }
-                    if (ntc >= 3) { G.ewq = (int)(fs[shrink] * Q / (ntc - 2 + 2 * fs[shrink]) + 0.5); if (G.ewq < 2) G.ewq = 2; }
+                } else if (k) {
+                    if (ntr >= 3) G.eh = (int)(fs[k] * H / (ntr - 2 + 2 * fs[k]) + 0.5);
+                    if (ntc >= 3) G.ewq = (int)(fs[k] * Q / (ntc - 2 + 2 * fs[k]) + 0.5);
                     if (!G.eh && !G.ewq) break;
-                    if (G.eh && (H - 2 * G.eh) / (ntr - 2) < 8) continue;
-                    if (G.ewq && (Q - 2 * G.ewq) / (ntc - 2) < 2) continue;
                 }
+                if (G.eh && (G.eh < 8 || (H - 2 * G.eh) / (ntr - 2) < 8)) continue;
+                if (G.ewq && (G.ewq < 2 || (Q - 2 * G.ewq) / (ntc - 2) < 2)) continue;
                 int th = 0, tw = 0;
                 for (int t = 0; t < ntr; ++t) { const int h = res_split(H, ntr, G.eh, t + 1) - res_split(H, ntr, G.eh, t); if (h > th) th = h; }
                 for (int t = 0; t < ntc; ++t) { const int w = 4 * (res_split(Q, ntc, G.ewq, t + 1) - res_split(Q, ntc, G.ewq, t)); if (w > tw) tw = w; }
@@ -666,40 +656,57 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
                 G.th_max = th; G.tw_max = tw; G.pitch = tw + 8; G.slots = 8 * tw + 8 * th;
                 const long long xbytes = 2LL * batch * ntr * ntc * G.slots * (long long)sizeof(u64);
                 if (xbytes > xchg_limit) continue;
-                G.nc = force_nc;
-                if (G.nc != 1 && G.nc != 2 && G.nc != 4)
-                    G.nc = th * tw <= FK_RES_MAX_THREADS ? 1 : (th * tw <= 2 * FK_RES_MAX_THREADS ? 2 : 4);
-                // tile classes: corner, top edge, left edge, interior (those that exist)
+                // corner, top-edge, left-edge and interior tile (those that exist)
                 const int rows[2] = {0, ntr > 2 ? 1 : ntr - 1}, cols[2] = {0, ntc > 2 ? 1 : ntc - 1};
-                int threads = force_threads;
-                if (threads <= 0) {
-                    int m = 0;
+                double cost;
+                if (nc == 4) {
+                    cost = 0;
                     for (int a = 0; a < 2; ++a)
                         for (int b = 0; b < 2; ++b) {
-                            int items;
-                            res_tile_cost(H, W, G, rows[a] * ntc + cols[b], FK_RES_MAX_THREADS, items);
-                            if (items > m) m = items;
+                            const double w = res_tile_work(H, W, G, rows[a] * ntc + cols[b]);
+                            if (w > cost) cost = w;
                         }
-                    threads = (m + 31) / 32 * 32;
-                    if (threads < 64) threads = 64;
-                    if (threads > FK_RES_MAX_THREADS) threads = FK_RES_MAX_THREADS;
+                    cost += 6.0 * (th + tw);
+                } else {
+                    cost = (double)th * tw + 6.0 * (th + tw);
+                    if (H % ntr != 0 || Q % ntc != 0) cost *= 1.15;
                 }
-                double cost = 0;
+                cost += 0.01 * th + 1e-3 * ntr * ntc;
+                if (cost >= best) continue;
+                best = cost;
+                found = true;
+                // one round where <= 512 threads allow it; if even ring + interior + edge items together fit: one phase
+                G.single = 1;
+                int all = 0, two = 0;
                 for (int a = 0; a < 2; ++a)
                     for (int b = 0; b < 2; ++b) {
-                        int items;
-                        const double c = res_tile_cost(H, W, G, rows[a] * ntc + cols[b], threads, items);
-                        if (c > cost) cost = c;
+                        G.single = 1;
+                        const int i1 = res_tile_items(H, W, G, rows[a] * ntc + cols[b]);
+                        G.single = 0;
+                        const int i2 = res_tile_items(H, W, G, rows[a] * ntc + cols[b]);
+                        if (i1 > all) all = i1;
+                        if (i2 > two) two = i2;
                     }
-                cost += 0.5 * ntr * ntc;   // ties: fewer tiles
-                if (cost < best) {
-                    best = cost;
-                    found = true;
-                    P.G = G;
-                    P.threads = threads;
-                    P.smem_bytes = smem;
-                    P.xchg_bytes = xbytes;
+                {   // the largest tile (tiles of a class differ by a row / a column group)
+                    const int q = tw / nc, qe = 4 / nc, g = th * q;
+                    const int inner = (th > 8 && tw > 8) ? (th - 8) * (q - 2 * qe) : 0, ring = g - inner;
+                    if (g > all) all = g;
+                    if (ring > two) two = ring;
+                    if (inner > two) two = inner;
                 }
+                G.single = all <= FK_RES_MAX_THREADS;
+                int threads = force_threads;
+                if (threads <= 0) {
+                    threads = ((G.single ? all : two) + 31) / 32 * 32;
+                    if (threads < 64) threads = 64;
+                    if (threads > FK_RES_MAX_THREADS) threads = FK_RES_MAX_THREADS;
+                } else if (all > threads) {
+                    G.single = 0;
+                }
+                P.G = G;
+                P.threads = threads;
+                P.smem_bytes = smem;
+                P.xchg_bytes = xbytes;
             }
         }
     }

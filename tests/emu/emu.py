@@ -75,10 +75,11 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
     return (vo, wo, uo), (info[0], info[1])
 
 
-def plan_resident(H, W, batch=1):
+def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0)):
     """The resident kernel's geometry for a problem: dict or None."""
-    out = (ctypes.c_int * 10)()
-    if not lib().fk_emu_plan_resident(H, W, batch, out):
+    out = (ctypes.c_int * 11)()
+    force = (ctypes.c_int * 6)(int(tiles[0]), int(tiles[1]), threads, nc, int(edge_tile[0]), int(edge_tile[1]))
+    if not lib().fk_emu_plan_resident(H, W, batch, out, force):
         return None
     return dict(zip(("ntr", "ntc", "th_max", "tw_max", "threads", "smem_bytes", "nc", "xchg_bytes", "edge_rows",
-                     "edge_colgroups"), list(out)))
+                     "edge_colgroups", "single_phase"), list(out)))

@@ -56,14 +56,12 @@ def main():
     # (tiles, cells per thread, (edge tile rows, edge tile column groups); -1 = even split)
     E = (-1, -1)
     sweeps = {
-        "fk128": [((0, 0), 0, (0, 0)), ((8, 16), 2, E), ((8, 16), 1, E), ((16, 8), 2, E), ((8, 16), 2, (13, -1)), ((8, 12), 2, E),
-                  ((10, 14), 2, E), ((10, 14), 2, (10, -1)), ((5, 4), 4, E), ((6, 8), 2, E)],
-        "fk256": [((0, 0), 0, (0, 0)), ((16, 8), 2, E), ((16, 8), 2, (12, -1)), ((16, 8), 2, (12, 6)), ((12, 12), 2, E),
-                  ((12, 12), 2, (16, 4)), ((9, 7), 4, E), ((16, 9), 2, (12, 5)), ((18, 8), 2, (10, 6))],
-        "fk512": [((0, 0), 0, (0, 0)), ((14, 10), 4, E), ((14, 10), 4, (28, 10)), ((14, 10), 4, (22, 8)), ((12, 12), 4, E),
-                  ((12, 12), 4, (32, 8)), ((12, 12), 2, (32, 8)), ((16, 9), 4, (24, 10)), ((18, 8), 4, (20, 12))],
-        "fk1024": [((0, 0), 0, (0, 0)), ((16, 9), 4, E), ((16, 9), 4, (48, 22)), ((16, 9), 4, (40, 20)), ((21, 7), 4, E),
-                   ((21, 7), 4, (36, 28)), ((18, 8), 4, (40, 24))],
+        "fk128": [((0, 0), 0, (0, 0)), ((8, 16), 2, E), ((8, 8), 2, E), ((12, 12), 2, E), ((16, 8), 1, E), ((8, 8), 4, E)],
+        "fk256": [((0, 0), 0, (0, 0)), ((8, 16), 2, E), ((12, 12), 2, E), ((16, 8), 4, E), ((8, 8), 2, E), ((8, 8), 4, E)],
+        "fk512": [((0, 0), 0, (0, 0)), ((14, 10), 4, (22, 8)), ((14, 10), 4, (18, 6)), ((12, 12), 4, (20, 5)), ((16, 9), 4, (20, 8)),
+                  ((12, 12), 4, (32, 8)), ((14, 10), 4, (0, 0)), ((16, 9), 4, (0, 0))],
+        "fk1024": [((0, 0), 0, (0, 0)), ((21, 7), 4, (40, 32)), ((21, 7), 4, (0, 0)), ((16, 9), 4, (0, 0)), ((24, 6), 4, (0, 0)),
+                   ((12, 12), 4, (0, 0)), ((18, 8), 4, (0, 0))],
     }
     for name in which:
         if name == "fk128":
