@@ -117,6 +117,10 @@ def lib():
     L.fk_forward_euler.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci,
                                               cd, cd, cf, cf, ctypes.POINTER(FkOptions), vp, sz, vp]
     L.fk_forward_euler.restype = ci
+    L.fk_forward_heun.argtypes = L.fk_forward_euler.argtypes
+    L.fk_forward_heun.restype = ci
+    L.fk_heun_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+    L.fk_heun_workspace_bytes.restype = sz
     L.fk_euler_rows.argtypes = [vp] * 6 + [vp, vp, vp, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd,
                                            ci, cf, cf, ctypes.POINTER(FkOptions), ci, ci, vp, sz, vp]
     L.fk_euler_rows.restype = ci

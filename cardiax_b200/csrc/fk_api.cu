@@ -126,6 +126,22 @@ __global__ void fk_stimulate_kernel(const float* __restrict__ x, float* __restri
     }
 }
 
+// Heun stages (solve.py:73-85): out = y + k * h, or out = y + (k1 + k2) * h, on the three state arrays at once
+template <bool EXACT>
+__global__ void fk_heun_stage_kernel(const float* __restrict__ yv, const float* __restrict__ yw, const float* __restrict__ yu,
+                                     const float* __restrict__ av, const float* __restrict__ aw, const float* __restrict__ au,
+                                     const float* __restrict__ bv, const float* __restrict__ bw, const float* __restrict__ bu,
+                                     float h, float* __restrict__ ov, float* __restrict__ ow, float* __restrict__ ou, long long n) {
+    typedef fk::Num<EXACT> N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float kv = av[i], kw = aw[i], ku = au[i];
+        if (bv) { kv = N::add(kv, bv[i]); kw = N::add(kw, bw[i]); ku = N::add(ku, bu[i]); }
+        ov[i] = fk::euler<EXACT>(yv[i], kv, h);
+        ow[i] = fk::euler<EXACT>(yw[i], kw, h);
+        ou[i] = fk::euler<EXACT>(yu[i], ku, h);
+    }
+}
+
 // exhaustive check of Num<true>::divc against __fdiv_rn: every significand, three exponents, every divisor of a run
 __global__ void fk_divcheck_kernel(fk::Consts K, unsigned long long* bad) {
     const float divisors[10] = {K.tau_d, K.tau_0, K.two_tau_si, K.Cm, K.tau_v_plus, K.tau_v1_minus, K.tau_v2_minus,
@@ -459,6 +475,83 @@ int fk_forward_euler(const float* v_in, const float* w_in, const float* u_in, fl
     const long long nsteps = fk::count_steps(t0, t1);
     return run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, d_batched, H, W, batch, params, stimuli, n_stim, t0, nsteps,
                      dt, dx, opt, 0, workspace, workspace_bytes, stream);
+}
+
+size_t fk_heun_workspace_bytes(int H, int W, int batch, int n_stim, int d_batched) {
+    const size_t base = fk_workspace_bytes(H, W, batch, n_stim, d_batched);
+    if (!base) return 0;
+    return base + 9 * align_up((size_t)H * W * sizeof(float) * batch, 256);   // k1, the predictor state, k2
+}
+
+int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                    const float* D, int d_batched, int H, int W, int batch, const FkParams* params,
+                    const FkStimulus* stimuli, int n_stim, double t0, double t1, float dt, float dx, const FkOptions* opt_in,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(H, W, batch, params, n_stim, stimuli);
+    if (rc) return rc;
+    if (!v_in || !w_in || !u_in || !v_out || !w_out || !u_out || !D) return fail(-1, "NULL pointer%s");
+    FkOptions opt;
+    if (opt_in) opt = *opt_in; else fk_default_options(&opt);
+    if (!opt.phys_top || !opt.phys_bottom) return fail(-1, "fk_forward_heun works on whole tissues%s");
+    const size_t need = fk_heun_workspace_bytes(H, W, batch, n_stim, d_batched);
+    if (!workspace || workspace_bytes < need) return fail(-4, "workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nsteps = fk::count_steps(t0, t1);
+    const size_t plane_bytes = (size_t)H * W * sizeof(float) * batch;
+    if (nsteps <= 0) {
+        FK_CUDA(cudaMemcpyAsync(v_out, v_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
+        FK_CUDA(cudaMemcpyAsync(w_out, w_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
+        FK_CUDA(cudaMemcpyAsync(u_out, u_in, plane_bytes, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    Workspace ws = carve(workspace, H, W, batch, n_stim, d_batched);
+    float* extra[9];
+    {
+        char* p = (char*)workspace + ws.bytes;
+        const size_t stride = align_up(plane_bytes, 256);
+        for (int i = 0; i < 9; ++i) extra[i] = (float*)(p + i * stride);
+    }
+    float *k1[3] = {extra[0], extra[1], extra[2]}, *y1[3] = {extra[3], extra[4], extra[5]}, *k2[3] = {extra[6], extra[7], extra[8]};
+    rc = upload_stims(stimuli, batch * n_stim, ws.stims, st);
+    if (rc) return rc;
+    rc = launch_dgrad(D, ws.DX, ws.DY, H, W, d_batched ? batch : 1, dx, 1, 1, st);
+    if (rc) return rc;
+    fk::DriveOptions o;
+    memset(&o, 0, sizeof(o));
+    o.exact = opt.exact; o.phys_top = 1; o.phys_bottom = 1; o.kernel = 1;
+    CudaBackend be;
+    be.st = st;
+    fk::Consts K = make_consts(*params, dt, dx);
+    if (opt.safe_division) K.div_lo = INFINITY;
+    const long long n = (long long)H * W * batch;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 16);
+    const float h_half = (float)((double)dt * 0.5);   // `dt * 0.5` of solve.py:83: exact halving of fl32(dt)
+    const float *yv = v_in, *yw = w_in, *yu = u_in;
+    const char* why = "";
+    auto rhs = [&](const float* sv, const float* sw, const float* su, float** k, double t) {
+        fk::DriveBuffers B;
+        memset(&B, 0, sizeof(B));
+        B.v_in = sv; B.w_in = sw; B.u_in = su; B.v_out = k[0]; B.w_out = k[1]; B.u_out = k[2];
+        B.D = D; B.DX = ws.DX; B.DY = ws.DY; B.stims = ws.stims;
+        return fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 1, o, 1, &why);
+    };
+    for (long long l = 0; l < nsteps; ++l) {
+        const double t = t0 + (double)l;   // both stages at the same counter (solve.py:78, 80)
+        const bool to_out = ((nsteps - 1 - l) % 2 == 0);
+        float *nv = to_out ? v_out : ws.pv, *nw = to_out ? w_out : ws.pw, *nu = to_out ? u_out : ws.pu;
+        rc = rhs(yv, yw, yu, k1, t);
+        if (rc) return why[0] ? fail(rc, "%s", why) : rc;
+        g_launches += 2;
+        if (opt.exact) fk_heun_stage_kernel<true><<<blocks, 256, 0, st>>>(yv, yw, yu, k1[0], k1[1], k1[2], nullptr, nullptr, nullptr, dt, y1[0], y1[1], y1[2], n);
+        else fk_heun_stage_kernel<false><<<blocks, 256, 0, st>>>(yv, yw, yu, k1[0], k1[1], k1[2], nullptr, nullptr, nullptr, dt, y1[0], y1[1], y1[2], n);
+        rc = rhs(y1[0], y1[1], y1[2], k2, t);
+        if (rc) return why[0] ? fail(rc, "%s", why) : rc;
+        if (opt.exact) fk_heun_stage_kernel<true><<<blocks, 256, 0, st>>>(yv, yw, yu, k1[0], k1[1], k1[2], k2[0], k2[1], k2[2], h_half, nv, nw, nu, n);
+        else fk_heun_stage_kernel<false><<<blocks, 256, 0, st>>>(yv, yw, yu, k1[0], k1[1], k1[2], k2[0], k2[1], k2[2], h_half, nv, nw, nu, n);
+        FK_CUDA(cudaGetLastError());
+        yv = nv; yw = nw; yu = nu;
+    }
+    return 0;
 }
 
 int fk_check_exact_division(const FkParams* params, float dx, long long* mismatches, void* stream) {

@@ -201,23 +201,25 @@ def step_euler(state, t, params, diffusivity, stimuli, dt, dx):
 
 def step_heun(state, t, params, diffusivity, stimuli, dt, dx):
     """cardiax/solve.py:73-85 -- Heun: both stages evaluated at the same counter ``t``."""
-    dt32 = float(np.float32(_scalar(dt)))
-    k1 = step(state, t, params, diffusivity, stimuli, dx)
-    pred = State(*[torch.add(x, d * dt32) for x, d in zip(state, k1)])
-    k2 = step(pred, t, params, diffusivity, stimuli, dx)
-    half = float(np.float32(dt32 * 0.5))
-    return State(*[torch.add(x, torch.add(a, b) * half) for x, a, b in zip(state, k1, k2)])
+    t = _scalar(t)
+    return _forward_heun(state, t, t + 1.0, params, diffusivity, stimuli, dt, dx)
 
 
 def _forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx):
-    """cardiax/solve.py:103-111."""
-    i = _scalar(t)
-    t_end = _scalar(t_end)
-    state = State(*state)
-    while i < t_end:
-        state = step_heun(state, i, params, diffusivity, stimuli, dt, dx)
-        i += 1.0
-    return state
+    """cardiax/solve.py:103-111 -- ``lax.fori_loop(t, t_end, step_heun)``; the whole loop runs on the device."""
+    L = _lib.lib()
+    dev, v, w, u, D, batch, H, W = _prep(state, diffusivity)
+    arr, n_stim, keep = _pack_stimuli(stimuli, batch, (H, W), dev)
+    nbytes = L.fk_heun_workspace_bytes(H, W, batch, n_stim, int(D.dim() == 3))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    vo, wo, uo = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
+    P = _params_struct(params)
+    o = _options(None, P, dx)
+    _lib.check(L.fk_forward_heun(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
+                                 D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
+                                 _scalar(t), _scalar(t_end), np.float32(_scalar(dt)), np.float32(_scalar(dx)),
+                                 ctypes.byref(o), ws.data_ptr(), nbytes, _stream()))
+    return State(vo, wo, uo)
 
 
 def _forward_dormandprince(state, ts, params, diffusivity, stimuli, dt, dx):

@@ -83,6 +83,16 @@ int fk_forward_euler(const float* v_in_dev, const float* w_in_dev, const float* 
                      double t1, float dt, float dx, const FkOptions* opt, void* workspace_dev, size_t workspace_bytes,
                      void* stream);
 
+/* solve._forward_heun (cardiax/solve.py:73-85, 103-111): Heun steps for counter in [t0, t1) -- both stages evaluated at
+ * the same counter, new = y + (k1 + k2) * (dt * 0.5) -- with the whole loop on the device (two right-hand-side launches
+ * and two fused stage kernels per step).  Same arguments as fk_forward_euler; workspace: fk_heun_workspace_bytes. */
+size_t fk_heun_workspace_bytes(int H, int W, int batch, int n_stim, int diffusivity_batched);
+int fk_forward_heun(const float* v_in_dev, const float* w_in_dev, const float* u_in_dev, float* v_out_dev,
+                    float* w_out_dev, float* u_out_dev, const float* diffusivity_dev, int diffusivity_batched, int H,
+                    int W, int batch, const FkParams* params, const FkStimulus* stimuli, int n_stim, double t0,
+                    double t1, float dt, float dx, const FkOptions* opt, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
+
 /* Building block of the row-slab decomposition of one large tissue over several GPUs (no reference counterpart: the
  * reference runs a tissue on one device).  ONE launch of nsteps (1..4) Euler steps that writes output rows
  * [row0, row1) of a local (H, W) buffer and nothing else; it reads input rows [row0 - 4 nsteps, row1 + 4 nsteps)

@@ -13,7 +13,7 @@ and on the ``tests/unittests/stimulus_test.py:23`` expectation; see DESIGN.md.
 """
 from .fk_oracle import (  # noqa: F401
     Params, State, Protocol, Stimulus,
-    init, gradient, stimulate, stimulus_active, step, step_euler, forward_euler,
+    init, gradient, stimulate, stimulus_active, step, step_euler, forward_euler, step_heun, forward_heun,
     tanh_xla_f32, PARAMSETS,
     rectangular, linear, triangular,
 )

@@ -224,6 +224,26 @@ def forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx, dtype=n
     return state
 
 
+def step_heun(state, t, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla"):
+    """cardiax/solve.py:73-85 -- Heun: k1 at y, k2 at y + k1*dt (SAME counter t), y + (k1 + k2) * (dt * 0.5)."""
+    def euler(y, dy, h):  # :74-75  jnp.add(v, dv * h)
+        return State(*[np.add(np.asarray(a, dtype), b * h) for a, b in zip(y, dy)])
+    d_state = step(state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh)
+    new_state = euler(state, d_state, dtype(dt))
+    d_new_state = step(new_state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh)
+    summed = State(*[np.add(a, b) for a, b in zip(d_state, d_new_state)])
+    return euler(state, summed, dtype(float(dt) * 0.5))   # `dt * 0.5` is a Python-float product, then weak-typed
+
+
+def forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla"):
+    """cardiax/solve.py:103-111."""
+    i = float(t)
+    while i < float(t_end):
+        state = step_heun(state, i, params, diffusivity, stimuli, dt, dx, dtype=dtype, tanh=tanh)
+        i += 1.0
+    return state
+
+
 # --------------------------------------------------------------------------- stimulus.py
 def rectangular(shape, centre, size, modulus, protocol):
     """cardiax/stimulus.py:31-60."""

@@ -118,6 +118,29 @@ def test_resident_kernel_batched_and_repeated_calls():
             assert_exact([x[b].cpu().numpy() for x in out], ref, "tissue %d" % b)
 
 
+@pytest.mark.parametrize("shape,n", [((48, 64), 5), ((37, 53), 3), ((128, 128), 4)])
+def test_heun_exact_bitwise_vs_oracle(shape, n):
+    """solve._forward_heun / step_heun (cardiax/solve.py:73-85, 103-111): the device-side Heun loop (two right-hand sides
+    at the same counter + fused stage kernels) is bit-identical to the oracle's literal restatement."""
+    from cardiax_b200 import options, solve, stimulus
+    st, D, stim = common.random_case(shape, seed=9, n_stim=3)
+    ref = O.forward_heun(st, 0, n, P3, D, stim, 0.01, 0.01)
+    options.numerics = "exact"
+    gst = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in stim]
+    gstate = solve.State(*[torch.as_tensor(x).cuda() for x in st])
+    got = solve._forward_heun(gstate, 0, n, P3, torch.as_tensor(D).cuda(), gst, 0.01, 0.01)
+    assert_exact([x.cpu().numpy() for x in got], ref, "heun %s" % (shape,))
+    one = solve.step_heun(gstate, 0, P3, torch.as_tensor(D).cuda(), gst, 0.01, 0.01)
+    assert_exact([x.cpu().numpy() for x in one], O.step_heun(st, 0, P3, D, stim, 0.01, 0.01), "step_heun")
+    # through the checkpoint loop with the integrator selected like the reference does (TimeIntegrator.HEUN)
+    states = solve.forward(gstate, [0, 2, n], P3, torch.as_tensor(D).cuda(), gst, 0.01, 0.01, solve.TimeIntegrator.HEUN)
+    assert_exact([x.cpu().numpy() for x in states[-1]], ref, "forward(HEUN)")
+    options.numerics = "fast"
+    fast = solve._forward_heun(gstate, 0, n, P3, torch.as_tensor(D).cuda(), gst, 0.01, 0.01)
+    for a, b in zip(fast, ref):
+        assert float(np.abs(a.cpu().numpy() - b).max()) <= TOL_FAST * max(1.0, float(np.abs(b).max()))
+
+
 @pytest.mark.parametrize("pset", sorted(O.PARAMSETS))
 def test_exact_all_paramsets(pset):
     st, D, stim = common.random_case((64, 96), seed=5)

@@ -182,3 +182,25 @@ def test_fp32_drift_envelope_defines_the_tolerance():
     # the libm-tanh variant of the oracle is another legitimate fp32 implementation: same order of magnitude
     c = C.forward_euler(O.init(shape), 0, 1000, P3, D, stim, 0.01, 0.01, tanh="libm")
     assert max(float(np.abs(x - y).max()) for x, y in zip(a, c)) < 1e-4
+
+
+def test_heun_restatement_is_second_order_and_matches_its_definition():
+    """oracle.step_heun (cardiax/solve.py:73-85): the mean of the two slopes, both taken at the same counter; against the
+    fp64 twin of a run with half the time step it converges with order 2 where Euler converges with order 1."""
+    from tests import common
+    st, D = common.smooth_case((24, 32), seed=1)
+    P = O.PARAMSETS["3"]
+    k1 = O.step(st, 0, P, D, [], 0.01)
+    y1 = O.State(*[a + b * np.float32(0.01) for a, b in zip(st, k1)])
+    k2 = O.step(y1, 0, P, D, [], 0.01)
+    ref = O.State(*[a + (b + c) * np.float32(0.005) for a, b, c in zip(st, k1, k2)])
+    got = O.step_heun(st, 0, P, D, [], 0.01, 0.01)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    # order of convergence on u over a fixed horizon (fp64)
+    def run(fn, dt, n):
+        return fn(st, 0, n, P, D, [], dt, 0.01, dtype=np.float64)[2]
+    exact = run(O.forward_heun, 0.00125, 64)
+    e_h = [np.abs(run(O.forward_heun, dt, n) - exact).max() for dt, n in ((0.01, 8), (0.005, 16))]
+    e_e = [np.abs(run(O.forward_euler, dt, n) - exact).max() for dt, n in ((0.01, 8), (0.005, 16))]
+    assert e_h[0] / e_h[1] > 3.0 and 1.6 < e_e[0] / e_e[1] < 2.6 and e_h[0] < e_e[0]
