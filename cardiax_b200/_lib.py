@@ -35,7 +35,8 @@ class FkOptions(ctypes.Structure):
                 ("phys_top", ctypes.c_int), ("phys_bottom", ctypes.c_int), ("cta_threads", ctypes.c_int),
                 ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("safe_division", ctypes.c_int),
                 ("tiles_r", ctypes.c_int), ("tiles_c", ctypes.c_int), ("cells_per_thread", ctypes.c_int),
-                ("edge_rows", ctypes.c_int), ("edge_colgroups", ctypes.c_int), ("reserved", ctypes.c_int * 2)]
+                ("edge_rows", ctypes.c_int), ("edge_colgroups", ctypes.c_int), ("maps_global", ctypes.c_int),
+                ("reserved", ctypes.c_int * 1)]
 
 
 def needs_build():
@@ -160,8 +161,10 @@ def last_plan():
     out = (ctypes.c_int * 8)()
     lib().fk_last_plan(ctypes.byref(out))
     if last_kernel() == "fk_resident_kernel":
-        return dict(zip(("steps", "cta_threads", "tile_cols", "tile_w", "tile_h", "tile_rows", "cells_per_thread", "smem_bytes"),
-                        list(out)))
+        d = dict(zip(("steps", "cta_threads", "tile_cols", "tile_w", "tile_h", "tile_rows", "cells_per_thread", "smem_bytes"),
+                     list(out)))
+        d["maps_in_l2"], d["cells_per_thread"] = d["cells_per_thread"] >> 3, d["cells_per_thread"] & 7
+        return d
     return dict(zip(("T", "cta_threads", "strips", "cols_per_strip", "rows_per_cta", "row_chunks", "ctas_per_sm",
                      "smem_bytes"), list(out)))
 

@@ -277,8 +277,8 @@ struct CudaBackend {
     long long resident_smem_limit() { return 227 * 1024 - 256; }
     int resident(const fk::ResPlan& P, const fk::TileArgs& A, int exact, int batch) {
         g_last_plan[0] = P.G.nsteps; g_last_plan[1] = P.threads; g_last_plan[2] = P.G.ntc; g_last_plan[3] = P.G.tw_max;
-        g_last_plan[4] = P.G.th_max; g_last_plan[5] = P.G.ntr; g_last_plan[6] = P.G.nc; g_last_plan[7] = (int)P.smem_bytes;
-        const int cap = fk::resident_capacity(exact, P.G.nc, P.threads, P.smem_bytes, num_sms());
+        g_last_plan[4] = P.G.th_max; g_last_plan[5] = P.G.ntr; g_last_plan[6] = P.G.nc + 8 * P.G.mg; g_last_plan[7] = (int)P.smem_bytes;
+        const int cap = fk::resident_capacity(exact, P.G.nc, P.G.mg, P.threads, P.smem_bytes, num_sms());
         if ((long long)P.G.ntr * P.G.ntc * batch > cap) return fail(-3, "resident kernel: the tiles are not co-resident on this device%s");
         ProfScope ps(0, st);
         g_last_kernel = "fk_resident_kernel";
@@ -457,7 +457,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.rows_per_cta = opt.rows_per_cta; o.uniform_diffusivity = opt.uniform_diffusivity;
     o.row0 = row0; o.row1 = row1;
     o.tiles_r = opt.tiles_r; o.tiles_c = opt.tiles_c; o.cells_per_thread = opt.cells_per_thread;
-    o.edge_rows = opt.edge_rows; o.edge_colgroups = opt.edge_colgroups;
+    o.edge_rows = opt.edge_rows; o.edge_colgroups = opt.edge_colgroups; o.maps_global = opt.maps_global;
     CudaBackend be;
     be.st = st;
     const char* why = "";

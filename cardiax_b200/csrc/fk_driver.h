@@ -21,6 +21,7 @@ struct DriveOptions {
     int tiles_r, tiles_c;   // resident kernel: tile grid (0 = planner's choice)
     int cells_per_thread;   // resident kernel: 1, 2 or 4 adjacent cells per thread (0 = planner's choice)
     int edge_rows, edge_colgroups;   // resident kernel: size of the tiles at the tissue's edges (0 auto, < 0 even split)
+    int maps_global;        // resident kernel: 1 = diffusivity maps read from global memory (L2), 0 = planner's choice
 };
 
 struct DriveBuffers {
@@ -41,7 +42,7 @@ inline long long res_xchg_bytes(int H, int W, int batch) {
 }
 // Tissues (x batch) up to this many cells that fit the SMs' shared memory run whole calls in ONE resident launch.
 #ifndef FK_RES_MAX_CELLS
-#define FK_RES_MAX_CELLS (1LL << 20)
+#define FK_RES_MAX_CELLS (1LL << 21)
 #endif
 
 // finalises the tile counts of A.reg[0..nreg)
@@ -125,7 +126,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
                              (long long)H * W * batch <= FK_RES_MAX_CELLS))) {
         const int cap = be.num_sms() < FK_RES_MAX_CTAS ? be.num_sms() : FK_RES_MAX_CTAS;
         use_res = plan_resident(H, W, batch, cap, be.resident_smem_limit(), B.xchg_bytes, opt.tiles_r, opt.tiles_c,
-                                opt.cta_threads, opt.cells_per_thread, opt.edge_rows, opt.edge_colgroups, rplan);
+                                opt.cta_threads, opt.cells_per_thread, opt.edge_rows, opt.edge_colgroups, opt.maps_global, rplan);
     }
     if (opt.kernel == 4 && !use_res) { *why = "resident kernel not applicable (needs W % 4 == 0, a whole tissue that fits shared memory)"; return -5; }
     // tissues too small to fill the machine: one launch of the barrier-free wide kernel per step

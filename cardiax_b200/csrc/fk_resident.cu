@@ -20,7 +20,7 @@ __device__ u64 g_res_timing[8];
         t_ = now_;                       \
     }
 
-template <bool EXACT, int NC>
+template <bool EXACT, int NC, bool MG>
 __global__ void __launch_bounds__(FK_RES_MAX_THREADS, 1)
 fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ ResGeom G) {
     extern __shared__ __align__(16) float fk_res_smem[];
@@ -42,7 +42,7 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
         for (int phase = 0; phase < 2; ++phase) {
             // phase 0: the ring, published to the neighbours' mailboxes as it is computed; phase 1: the interior, while
             // those records travel.  ONE call site: the body exists once and stays inside the instruction cache.
-            res_phase<EXACT, NC>(A, G, X, T, s, phase, mask, tid, nthr);
+            res_phase<EXACT, NC, MG>(A, G, X, T, s, phase, mask, tid, nthr);
             if (phase == 0) { FK_TICK(0) } else { FK_TICK(1) }
         }
         if (s == G.nsteps - 1) break;
@@ -58,28 +58,29 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
     }
 }
 
-template <bool EXACT, int NC>
+template <bool EXACT, int NC, bool MG>
 int launch_nc(const ResPlan& P, const TileArgs& A, const ResGeom& G, int batch, cudaStream_t st) {
     static bool attr_set = false;
     cudaError_t e;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN);
+        e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     void* args[2] = {(void*)&A, (void*)&G};
-    return (int)cudaLaunchCooperativeKernel((const void*)fk_resident_kernel<EXACT, NC>, dim3(G.ntr * G.ntc, batch),
+    return (int)cudaLaunchCooperativeKernel((const void*)fk_resident_kernel<EXACT, NC, MG>, dim3(G.ntr * G.ntc, batch),
                                             dim3(P.threads), args, (size_t)P.smem_bytes, st);
 }
 
 template <bool EXACT>
-int occupancy_nc(int nc, int threads, size_t smem) {
+int occupancy_nc(int nc, int mg, int threads, size_t smem) {
     int n = 0;
     cudaError_t e;
-#define FK_OCC(NC)                                                                                                       \
-    e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN); \
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_resident_kernel<EXACT, NC>, threads, smem);
-    if (nc == 1) { FK_OCC(1) } else if (nc == 2) { FK_OCC(2) } else { FK_OCC(4) }
+#define FK_OCC(NC, MG)                                                                                                       \
+    e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN); \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fk_resident_kernel<EXACT, NC, MG>, threads, smem);
+    if (mg) { if (nc == 1) { FK_OCC(1, true) } else if (nc == 2) { FK_OCC(2, true) } else { FK_OCC(4, true) } }
+    else { if (nc == 1) { FK_OCC(1, false) } else if (nc == 2) { FK_OCC(2, false) } else { FK_OCC(4, false) } }
 #undef FK_OCC
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
@@ -96,9 +97,14 @@ int launch_t(const ResPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
         void* sym = nullptr;
         if (cudaGetSymbolAddress(&sym, g_res_timing) == cudaSuccess) G.timing = (u64*)sym;
     }
-    if (G.nc == 1) return launch_nc<EXACT, 1>(P, A, G, batch, st);
-    if (G.nc == 2) return launch_nc<EXACT, 2>(P, A, G, batch, st);
-    return launch_nc<EXACT, 4>(P, A, G, batch, st);
+    if (G.mg) {
+        if (G.nc == 1) return launch_nc<EXACT, 1, true>(P, A, G, batch, st);
+        if (G.nc == 2) return launch_nc<EXACT, 2, true>(P, A, G, batch, st);
+        return launch_nc<EXACT, 4, true>(P, A, G, batch, st);
+    }
+    if (G.nc == 1) return launch_nc<EXACT, 1, false>(P, A, G, batch, st);
+    if (G.nc == 2) return launch_nc<EXACT, 2, false>(P, A, G, batch, st);
+    return launch_nc<EXACT, 4, false>(P, A, G, batch, st);
 }
 
 }  // namespace
@@ -115,9 +121,9 @@ int resident_timing(unsigned long long* out8) {
 }
 
 // CTAs of the resident kernel the device can hold at once (cooperative launch limit) for this CTA shape
-int resident_capacity(int exact, int nc, int threads, long long smem_bytes, int num_sms) {
+int resident_capacity(int exact, int nc, int mg, int threads, long long smem_bytes, int num_sms) {
     if (smem_bytes > FK_RES_SMEM_OPTIN) return 0;
-    const int n = exact ? occupancy_nc<true>(nc, threads, (size_t)smem_bytes) : occupancy_nc<false>(nc, threads, (size_t)smem_bytes);
+    const int n = exact ? occupancy_nc<true>(nc, mg, threads, (size_t)smem_bytes) : occupancy_nc<false>(nc, mg, threads, (size_t)smem_bytes);
     return n * num_sms;
 }
 

@@ -47,6 +47,7 @@ struct ResGeom {
     int nsteps;          // Euler steps of the launch
     int nc;              // adjacent cells per thread group: 1, 2 or 4
     int single;          // 1: every tile's items fit one round of the CTA's threads -- no interior phase (all "ring")
+    int mg;              // 1: the diffusivity maps stay in global memory (L2) instead of shared memory (larger tissues)
     int slots;           // mailbox records per tile and parity: 8 * tw_max (4 top + 4 bottom rows) + 8 * th_max (columns)
     u64* xchg;           // mailboxes [2 parities][batch * ntr * ntc tiles][slots], tags zero at launch
     u64* timing;         // null, or cycle counters CTA (0, 0) fills (development: FK_RES_TIMING=1)
@@ -71,8 +72,8 @@ struct ResCta {
     const StimDev* stims;
 };
 
-FK_HD long long res_smem_floats(int th_max, int tw_max) {
-    return 2LL * (th_max + 8) * (tw_max + 8) + 5LL * th_max * tw_max;
+FK_HD long long res_smem_floats(int th_max, int tw_max, int mg) {
+    return 2LL * (th_max + 8) * (tw_max + 8) + (mg ? 2LL : 5LL) * th_max * tw_max;
 }
 
 // the cells of tile rows [r0, r1) x columns [c0, c1) that lie within 4 cells of a physical edge of the H x W tissue
@@ -123,7 +124,7 @@ FK_HD void res_setup(const TileArgs& A, const ResGeom& G, int tile, int sim, int
     X.sim = sim;
     const long long nu = (long long)(G.th_max + 8) * G.pitch, nv = (long long)G.th_max * G.tw_max;
     X.U0 = smem; X.nu = (int)nu;
-    X.V = smem + 2 * nu; X.Wd = X.V + nv; X.Dm = X.Wd + nv; X.DXm = X.Dm + nv; X.DYm = X.DXm + nv;
+    X.V = smem + 2 * nu; X.Wd = X.V + nv; X.Dm = X.Wd + nv; X.DXm = X.Dm + nv; X.DYm = X.DXm + nv;   // (maps: only if !G.mg)
     X.boff = (long long)sim * A.plane;
     X.boffD = (long long)sim * A.plane_D;
     const long long ntiles = (long long)G.ntr * G.ntc;
@@ -333,9 +334,11 @@ FK_HD void res_load(const TileArgs& A, const ResGeom& G, const ResCta& X, int ti
         float t[4];
         unpack4(ldg4(A.v_in + X.boff + g), t); st4(X.V + o, t);
         unpack4(ldg4(A.w_in + X.boff + g), t); st4(X.Wd + o, t);
-        unpack4(ldg4(A.D + X.boffD + g), t); st4(X.Dm + o, t);
-        unpack4(ldg4(A.DX + X.boffD + g), t); st4(X.DXm + o, t);
-        unpack4(ldg4(A.DY + X.boffD + g), t); st4(X.DYm + o, t);
+        if (!G.mg) {
+            unpack4(ldg4(A.D + X.boffD + g), t); st4(X.Dm + o, t);
+            unpack4(ldg4(A.DX + X.boffD + g), t); st4(X.DXm + o, t);
+            unpack4(ldg4(A.DY + X.boffD + g), t); st4(X.DYm + o, t);
+        }
     }
 }
 
@@ -367,6 +370,15 @@ FK_HD void ldn(const float* p, float* v) {
     if (NC == 4) unpack4(ld4(p), v);
     else if (NC == 2) { const F2 t = ld2(p); v[0] = t.x; v[1] = t.y; }
     else v[0] = p[0];
+}
+// NC-wide read-only global load (diffusivity maps kept in L2)
+template <int NC>
+FK_HD void ldgn(const float* p, float* v) {
+    if (NC == 4) unpack4(ldg4(p), v);
+    else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) v[k] = ldg1(p + k);
+    }
 }
 template <int NC>
 FK_HD void stn(float* p, const float* v) {
@@ -408,7 +420,8 @@ FK_HD void res_axis_general(const Consts& K, const float* up, int P, int n, floa
 // groups (box != null) also publish the new u; the last step writes the caller's output instead
 // GENERAL = false: the caller guarantees that every formula of the group is central (no cell within 4 of a physical
 // edge) and only that path is compiled.
-template <bool EXACT, int NC, bool GENERAL>
+// MG: the diffusivity maps are read from global memory (L2 resident) instead of shared memory.
+template <bool EXACT, int NC, bool GENERAL, bool MG>
 FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const float* cur, float* nxt, int lr, int lc,
                      unsigned mask, bool last, u64* box, unsigned tag) {
     const int H = A.H, W = A.W, P = G.pitch, row = X.r0 + lr, c = X.c0 + lc;
@@ -417,12 +430,18 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     ldn<NC>(uc0, uc);
     const int o = lr * G.tw_max + lc;
     float v[NC], w[NC], Dv[NC], DXv[NC], DYv[NC], stim[NC];
+    const long long g = (long long)row * W + c;
+    if (MG) {   // requested first: the longest latency of the group
+        ldgn<NC>(A.D + X.boffD + g, Dv);
+        ldgn<NC>(A.DX + X.boffD + g, DXv);
+        ldgn<NC>(A.DY + X.boffD + g, DYv);
+    } else {
+        ldn<NC>(X.Dm + o, Dv);
+        ldn<NC>(X.DXm + o, DXv);
+        ldn<NC>(X.DYm + o, DYv);
+    }
     ldn<NC>(X.V + o, v);
     ldn<NC>(X.Wd + o, w);
-    ldn<NC>(X.Dm + o, Dv);
-    ldn<NC>(X.DXm + o, DXv);
-    ldn<NC>(X.DYm + o, DYv);
-    const long long g = (long long)row * W + c;
 #pragma unroll
     for (int k = 0; k < NC; ++k) stim[k] = 0.0f;
     if (mask) {
@@ -555,7 +574,7 @@ FK_HD void res_thread_setup(const TileArgs& A, const ResGeom& G, const ResCta& X
 }
 
 // one phase of step s, its items strided over the CTA's threads
-template <bool EXACT, int NC>
+template <bool EXACT, int NC, bool MG>
 FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
                      unsigned mask, int tid, int nthr) {   // (called from ONE site, in a phase loop: a single copy)
     const float* cur = X.U0 + (s & 1) * X.nu;
@@ -567,8 +586,8 @@ FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     for (int i = tid; i < n; i += nthr) {
         int lr = phase ? T.lr1 : T.lr0, lc = phase ? T.lc1 : T.lc0, ty = phase ? T.ty1 : T.ty0;
         if (i != tid) ty = res_item<NC>(A, G, X, phase, i, lr, lc);
-        if (ty == 2) res_group<EXACT, 1, true>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
-        else if (NC > 1 && ty == 1) res_group<EXACT, NC, false>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        if (ty == 2) res_group<EXACT, 1, true, MG>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        else if (NC > 1 && ty == 1) res_group<EXACT, NC, false, MG>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
     }
 }
 
@@ -609,14 +628,17 @@ inline double res_tile_work(int H, int W, const ResGeom& G, int tile) {
 //    edges, whose one-sided cells cost ~6 central ones, get f = 1, .85, .7, .55 or .45 of the others' rows / columns,
 //    whichever evens out the work of corner, edge and interior tiles best within shared memory.
 // force_eh / force_ewq: > 0 that many rows / column groups in the edge tiles, < 0 even split, 0 planner's choice.
+// maps_global: 1 = keep the diffusivity maps in global memory (L2), 0 = in shared memory if any plan fits, else global.
 inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_limit, long long xchg_limit, int force_ntr,
-                          int force_ntc, int force_threads, int force_nc, int force_eh, int force_ewq, ResPlan& P) {
+                          int force_ntc, int force_threads, int force_nc, int force_eh, int force_ewq, int maps_global,
+                          ResPlan& P) {
     if (W % 4 != 0 || H < 3 || W < 4 || batch < 1) return false;
     // the last plan is kept: a run calls this once per segment with the same problem
     struct Memo { int key[8]; bool ok; ResPlan plan; };
     static Memo memo = {{-1, 0, 0, 0, 0, 0, 0, 0}, false, ResPlan()};
     const int key[8] = {H, W, batch, capacity, force_ntr * 4096 + force_ntc, force_eh * 4096 + force_ewq,
-                        force_threads * 8 + force_nc, (int)(smem_limit / 64) + (int)((xchg_limit / 4096) % 1000003)};
+                        force_threads * 16 + force_nc * 2 + (maps_global ? 1 : 0),
+                        (int)(smem_limit / 64) + (int)((xchg_limit / 4096) % 1000003)};
     bool same = true;
     for (int i = 0; i < 8; ++i) same = same && memo.key[i] == key[i];
     if (same) { if (memo.ok) P = memo.plan; return memo.ok; }
@@ -624,6 +646,7 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
     static const double fs[5] = {1.0, 0.85, 0.7, 0.55, 0.45};
     double best = 1e300;
     bool found = false;
+    for (int mg = maps_global ? 1 : 0; mg < 2 && !found; ++mg)
     for (int ntr = 1; ntr <= H; ++ntr) {
         if (ntr > 1 && H / ntr < 8) break;
         if (force_ntr > 0 && ntr != force_ntr) continue;
@@ -637,7 +660,7 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
             const bool forced_edge = force_eh != 0 || force_ewq != 0;
             for (int k = 0; k < ((nc == 4 && !forced_edge) ? 5 : 1); ++k) {
                 ResGeom G = ResGeom();
-                G.ntr = ntr; G.ntc = ntc; G.nc = nc;
+                G.ntr = ntr; G.ntc = ntc; G.nc = nc; G.mg = mg;
                 if (forced_edge) {
                     if (force_eh > 0 && ntr >= 3) G.eh = force_eh;
                     if (force_ewq > 0 && ntc >= 3) G.ewq = force_ewq;
@@ -651,7 +674,7 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
                 int th = 0, tw = 0;
                 for (int t = 0; t < ntr; ++t) { const int h = res_split(H, ntr, G.eh, t + 1) - res_split(H, ntr, G.eh, t); if (h > th) th = h; }
                 for (int t = 0; t < ntc; ++t) { const int w = 4 * (res_split(Q, ntc, G.ewq, t + 1) - res_split(Q, ntc, G.ewq, t)); if (w > tw) tw = w; }
-                const long long smem = res_smem_floats(th, tw) * 4;
+                const long long smem = res_smem_floats(th, tw, mg) * 4;
                 if (smem > smem_limit) continue;
                 G.th_max = th; G.tw_max = tw; G.pitch = tw + 8; G.slots = 8 * tw + 8 * th;
                 const long long xbytes = 2LL * batch * ntr * ntc * G.slots * (long long)sizeof(u64);
@@ -724,9 +747,15 @@ namespace fk {
 template <bool EXACT>
 inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
                           unsigned mask) {
-    if (G.nc == 1) res_phase<EXACT, 1>(A, G, X, T, s, phase, mask, 0, 1);
-    else if (G.nc == 2) res_phase<EXACT, 2>(A, G, X, T, s, phase, mask, 0, 1);
-    else res_phase<EXACT, 4>(A, G, X, T, s, phase, mask, 0, 1);
+    if (G.mg) {
+        if (G.nc == 1) res_phase<EXACT, 1, true>(A, G, X, T, s, phase, mask, 0, 1);
+        else if (G.nc == 2) res_phase<EXACT, 2, true>(A, G, X, T, s, phase, mask, 0, 1);
+        else res_phase<EXACT, 4, true>(A, G, X, T, s, phase, mask, 0, 1);
+    } else {
+        if (G.nc == 1) res_phase<EXACT, 1, false>(A, G, X, T, s, phase, mask, 0, 1);
+        else if (G.nc == 2) res_phase<EXACT, 2, false>(A, G, X, T, s, phase, mask, 0, 1);
+        else res_phase<EXACT, 4, false>(A, G, X, T, s, phase, mask, 0, 1);
+    }
 }
 // CTAs advance in lock step, phase by phase, which is one legal interleaving of the mailbox protocol; shared memory is
 // poisoned with NaN so that a read of a halo nobody filled shows up in the result, and a record that has not arrived
@@ -734,7 +763,7 @@ inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, 
 inline int emu_resident_launch(const ResPlan& P, const TileArgs& A, int batch, int exact) {
     ResGeom G = P.G;
     const int ntiles = G.ntr * G.ntc;
-    const long long floats = res_smem_floats(G.th_max, G.tw_max);
+    const long long floats = res_smem_floats(G.th_max, G.tw_max, G.mg);
     std::vector<std::vector<float>> smem((size_t)ntiles * batch, std::vector<float>((size_t)floats, __builtin_nanf("")));
     std::vector<u64> xchg((size_t)(P.xchg_bytes / sizeof(u64)), 0ull);
     G.xchg = xchg.data();

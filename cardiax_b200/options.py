@@ -15,6 +15,7 @@ cta_threads = 0
 rows_per_cta = 0
 tiles = (0, 0)
 cells_per_thread = 0   # resident kernel: 1, 2 or 4 (0 = planner's choice)
+maps_global = 0        # resident kernel: 1 = diffusivity maps read from L2 instead of shared memory (0 = only if needed)
 edge_tile = (0, 0)     # resident kernel: (rows, 4-column groups) of the tiles at the tissue's edges (0 auto, < 0 even)
 detect_uniform_diffusivity = True
 safe_division = False   # exact numerics: force every division through __fdiv_rn

@@ -124,6 +124,7 @@ def _options(D=None, P=None, dx=None, **over):
     o.tiles_r, o.tiles_c = int(options.tiles[0]), int(options.tiles[1])
     o.cells_per_thread = int(options.cells_per_thread)
     o.edge_rows, o.edge_colgroups = int(options.edge_tile[0]), int(options.edge_tile[1])
+    o.maps_global = int(options.maps_global)
     if D is not None and options.detect_uniform_diffusivity:
         o.uniform_diffusivity = int(_is_uniform(D))
     for k, v in over.items():

@@ -58,7 +58,9 @@ typedef struct FkOptions {
     int cells_per_thread; /* resident kernel: 1, 2 or 4 adjacent cells per thread (0 = auto) */
     int edge_rows, edge_colgroups; /* resident kernel: rows / 4-column groups of the tiles at the tissue's edges
                                       (0 = auto, < 0 = even split) */
-    int reserved[2];
+    int maps_global;      /* resident kernel: 1 = read the diffusivity maps from global memory (L2) instead of keeping
+                             them in shared memory (0 = only when the tissue would not fit otherwise) */
+    int reserved[1];
 } FkOptions;
 
 /* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */
@@ -142,7 +144,7 @@ long long fk_launch_count(void);
 void fk_last_plan(int* out8);
 /* name of the step kernel launched most recently: "fk_stream_kernel", "fk_resident_kernel", "fk_wide_kernel",
  * "fk_tile_kernel" (resident launches report {steps, cta_threads, tile columns, tile width, tile height, tile rows,
- * cells per thread, shared memory bytes} through fk_last_plan) */
+ * cells per thread (+ 8 if the diffusivity maps stay in L2), shared memory bytes} through fk_last_plan) */
 const char* fk_last_kernel(void);
 /* Development aid: with FK_RES_TIMING=1 in the environment, CTA (0, 0) of every resident launch accumulates SM cycles
  * spent in {ring groups, interior groups, waiting for and copying the halo, block barrier} (out8[0..3]) and the step

@@ -42,7 +42,7 @@ def stim_active(t, start, duration, period):
 
 
 def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, cta_threads=0, rows_per_cta=0,
-          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0, tiles=(0, 0), nc=0, edge_tile=(0, 0)):
+          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0, tiles=(0, 0), nc=0, edge_tile=(0, 0), maps_global=0):
     """state: (v, w, u) arrays of shape (H, W) or (batch, H, W).  Returns (v, w, u) and launch counts."""
     v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
     batched = u.ndim == 3
@@ -63,8 +63,9 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
             f = np.ascontiguousarray(s.field, dtype=np.float32)
             keep.append(f)
             arr[b * n_stim + i] = _Stim(f.ctypes.data, *[float(np.asarray(x).reshape(-1)[0]) for x in s.protocol])
-    opts = (ctypes.c_int * 16)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse,
-                               row0, row1, int(tiles[0]), int(tiles[1]), int(nc), int(edge_tile[0]), int(edge_tile[1]))
+    opts = (ctypes.c_int * 17)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse,
+                               row0, row1, int(tiles[0]), int(tiles[1]), int(nc), int(edge_tile[0]), int(edge_tile[1]),
+                               int(maps_global))
     info = (ctypes.c_int * 2)()
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib().fk_emu_euler(p(v), p(w), p(u), p(vo), p(wo), p(uo), p(D), d_batched, H, W, batch, p(par), arr, n_stim,
@@ -75,11 +76,11 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
     return (vo, wo, uo), (info[0], info[1])
 
 
-def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0)):
+def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0), maps_global=0):
     """The resident kernel's geometry for a problem: dict or None."""
-    out = (ctypes.c_int * 11)()
-    force = (ctypes.c_int * 6)(int(tiles[0]), int(tiles[1]), threads, nc, int(edge_tile[0]), int(edge_tile[1]))
+    out = (ctypes.c_int * 12)()
+    force = (ctypes.c_int * 7)(int(tiles[0]), int(tiles[1]), threads, nc, int(edge_tile[0]), int(edge_tile[1]), maps_global)
     if not lib().fk_emu_plan_resident(H, W, batch, out, force):
         return None
     return dict(zip(("ntr", "ntc", "th_max", "tw_max", "threads", "smem_bytes", "nc", "xchg_bytes", "edge_rows",
-                     "edge_colgroups", "single_phase"), list(out)))
+                     "edge_colgroups", "single_phase", "maps_in_l2"), list(out)))

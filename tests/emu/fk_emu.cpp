@@ -85,7 +85,7 @@ struct EmuStim {
 };
 
 // options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse,
-//           row0, row1, tiles_r, tiles_c, cells_per_thread, edge_rows, edge_colgroups}
+//           row0, row1, tiles_r, tiles_c, cells_per_thread, edge_rows, edge_colgroups, maps_global}
 // info (optional, 2 ints): tile launches, stream launches + 1000 * wide launches + 1000000 * resident launches
 int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
                  const float* D, int d_batched, int H, int W, int batch, const float* params14, const EmuStim* stims,
@@ -109,7 +109,7 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     fk::DriveOptions o;
     o.exact = options[0]; o.steps_per_launch = options[1]; o.kernel = options[2]; o.phys_top = options[3];
     o.phys_bottom = options[4]; o.cta_threads = options[5]; o.rows_per_cta = options[6]; o.uniform_diffusivity = options[7];
-    o.row0 = options[9]; o.row1 = options[10]; o.tiles_r = options[11]; o.tiles_c = options[12]; o.cells_per_thread = options[13]; o.edge_rows = options[14]; o.edge_colgroups = options[15];
+    o.row0 = options[9]; o.row1 = options[10]; o.tiles_r = options[11]; o.tiles_c = options[12]; o.cells_per_thread = options[13]; o.edge_rows = options[14]; o.edge_colgroups = options[15]; o.maps_global = options[16];
     EmuBackend be;
     be.reverse = options[8];
     const long long nsteps = rhs_mode ? 1 : fk::count_steps(t0, t1);
@@ -146,12 +146,12 @@ extern "C" int fk_emu_plan(int H, int W, int batch, int T, int cta_threads, int 
 }
 
 // resident planner probe (tests): {ntr, ntc, th_max, tw_max, threads, smem bytes, cells per thread, mailbox bytes}
-extern "C" int fk_emu_plan_resident(int H, int W, int batch, int* out, const int* force6) {
+extern "C" int fk_emu_plan_resident(int H, int W, int batch, int* out, const int* force6) {   // force6[6] = maps_global
     fk::ResPlan P;
     if (!fk::plan_resident(H, W, batch, 148, 227 * 1024 - 256, fk::res_xchg_bytes(H, W, batch), force6[0], force6[1], force6[2],
-                           force6[3], force6[4], force6[5], P)) return 0;
+                           force6[3], force6[4], force6[5], force6[6], P)) return 0;
     out[0] = P.G.ntr; out[1] = P.G.ntc; out[2] = P.G.th_max; out[3] = P.G.tw_max; out[4] = P.threads; out[5] = (int)P.smem_bytes;
-    out[6] = P.G.nc; out[7] = (int)P.xchg_bytes; out[8] = P.G.eh; out[9] = P.G.ewq; out[10] = P.G.single;
+    out[6] = P.G.nc; out[7] = (int)P.xchg_bytes; out[8] = P.G.eh; out[9] = P.G.ewq; out[10] = P.G.single; out[11] = P.G.mg;
     return 1;
 }
 

@@ -63,6 +63,13 @@ def test_resident_kernel_uneven_edge_tiles(shape, tiles, edge, nc):
     assert info == (0, 1000000)
 
 
+@pytest.mark.parametrize("shape,tiles,nc", [((64, 96), (2, 3), 4), ((40, 64), (3, 2), 2), ((33, 72), (1, 1), 1)])
+def test_resident_kernel_maps_in_global_memory(shape, tiles, nc):
+    """Larger tissues keep only u, v, w in shared memory and read D, D_x, D_y from L2: same bits."""
+    info = _exact(shape, 1, nsteps=6, kernel=4, tiles=tiles, nc=nc, maps_global=1)
+    assert info == (0, 1000000)
+
+
 def test_resident_kernel_exact_batched_per_tissue_inputs():
     shape, batch = (40, 48), 3
     cases = [common.random_case(shape, seed=20 + b, n_stim=2) for b in range(batch)]
@@ -80,7 +87,9 @@ def test_resident_kernel_exact_batched_per_tissue_inputs():
 def test_resident_planner():
     p = emu.plan_resident(512, 512)
     assert p and p["ntr"] * p["ntc"] <= 148 and p["smem_bytes"] <= 227 * 1024 and p["threads"] % 32 == 0
-    assert emu.plan_resident(1200, 1200) is None          # 40 MB of state + maps do not fit 148 x 227 KB
+    p = emu.plan_resident(1200, 1200)                      # the reference's data-generation tissue: 40 MB of state + maps
+    assert p and p["maps_in_l2"] == 1 and p["smem_bytes"] <= 227 * 1024   # do not fit 148 x 227 KB; u, v, w alone do
+    assert emu.plan_resident(1600, 1600) is None
     assert emu.plan_resident(64, 66) is None              # rows must be whole groups of 4 cells
     p = emu.plan_resident(256, 256, batch=8)
     assert p and p["ntr"] * p["ntc"] * 8 <= 148

@@ -27,7 +27,7 @@ P3 = O.PARAMSETS["3"]
 def _reset_options():
     from cardiax_b200 import options
     saved = {k: getattr(options, k) for k in ("numerics", "steps_per_launch", "kernel", "cta_threads", "rows_per_cta",
-                                              "tiles", "cells_per_thread")}
+                                              "tiles", "cells_per_thread", "edge_tile", "maps_global")}
     options.verbose = False
     yield
     for k, v in saved.items():
@@ -83,6 +83,21 @@ def test_resident_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads, 
                   cells_per_thread=nc)
     assert _lib.lib().fk_launch_count() - before == 2   # D_x/D_y maps + ONE resident launch
     assert_exact(got, ref, "resident %s tiles %s" % (shape, tiles))
+
+
+@pytest.mark.parametrize("shape,nsteps,tiles,edge,mg", [((1200, 1200), 5, (0, 0), (0, 0), 0), ((96, 160), 9, (5, 6), (12, 4), 1),
+                                                        ((200, 120), 12, (3, 3), (0, 0), 1), ((512, 512), 8, (0, 0), (0, 0), 0)])
+def test_resident_kernel_maps_in_l2_and_uneven_edge_tiles(shape, nsteps, tiles, edge, mg):
+    """The reference's data-generation tissue (1200 x 1200, heterogeneous D: deepx/generate.py:92) keeps u, v, w in
+    shared memory and reads D, D_x, D_y from L2; smaller tiles at the tissue's edges.  Bit-identical to the oracle."""
+    from cardiax_b200 import _lib
+    st, D, stim = common.random_case(shape, seed=6, n_stim=2)
+    ref = C.forward_euler(st, 0, nsteps, P3, D, stim, 0.01, 0.01)
+    got = run_gpu(st, 0, nsteps, P3, D, stim, numerics="exact", kernel=4, tiles=tiles, edge_tile=edge, maps_global=mg)
+    assert _lib.last_kernel() == "fk_resident_kernel"
+    if shape == (1200, 1200):
+        assert _lib.last_plan()["maps_in_l2"] == 1
+    assert_exact(got, ref, "resident %s" % (shape,))
 
 
 def test_resident_kernel_is_the_default_for_small_tissues_and_matches_the_other_kernels():
