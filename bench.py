@@ -214,7 +214,8 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--halo-launches", type=int, default=8)
-    ap.add_argument("--no-extra", action="store_true", help="skip the quick fk512 / fk128 lines (BASELINE configs 2, 1)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the quick fk512 / fk128 / fk1200 lines (BASELINE configs 2, 1; the reference's data-generation tissue)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -413,7 +414,13 @@ def main():
     if world == 1 and workload == "fk4096" and not args.no_extra:
         other = {}
         fl = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-        for name, mk in (("fk512", make_fk512), ("fk128", make_fk128)):
+        def make_fk1200():   # the reference's data-generation tissue: 1200 x 1200, scar-map D (deepx/generate.py:92)
+            from tests import common
+            _, Dm = common.smooth_case((1200, 1200), 0)
+            wq = make_fk4096(1200, 1200)
+            wq.update(D=Dm, params="3")
+            return wq
+        for name, mk in (("fk512", make_fk512), ("fk128", make_fk128), ("fk1200", make_fk1200)):
             wk = mk()
             gs, Dk = dev_stim(wk["stimuli"]), torch.as_tensor(wk["D"]).to(dev)
             pk = O.PARAMSETS[wk["params"]]
