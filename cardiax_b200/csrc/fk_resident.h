@@ -125,7 +125,7 @@ FK_HD void res_tile_geom(int H, int W, const ResGeom& G, int tile, ResCta& X) {
     X.ninner = (X.ir1 - X.ir0) * (X.ig1 - X.ig0);
     X.nring = X.th * X.q - X.ninner;
     X.npair = 0;
-    if (G.r2 && G.nc == 4) {   // interior rows in pairs; an odd last row stays a row of plain groups
+    if (FK_RES_R2 && G.r2 && G.nc == 4) {   // interior rows in pairs; an odd last row stays a row of plain groups
         const int rows = X.ir1 - X.ir0, qi = X.ig1 - X.ig0;
         X.npair = (rows / 2) * qi;
         X.ninner = X.npair + (rows & 1) * qi;
@@ -159,7 +159,7 @@ FK_HD void res_locate(const ResGeom& G, const ResCta& X, int phase, int i, int& 
     const int q = X.q, nc = G.nc;
     if (phase) {
         const int qi = X.ig1 - X.ig0;
-        if (X.npair) {   // 2-row blocks first, then the odd last row
+        if (FK_RES_R2 && X.npair) {   // 2-row blocks first, then the odd last row
             if (i >= X.npair) { lr = X.ir1 - 1; lc = nc * (X.ig0 + i - X.npair); return; }
             const int r = i / qi;
             lr = X.ir0 + 2 * r; lc = nc * (X.ig0 + i - r * qi);
@@ -654,7 +654,7 @@ FK_HD int res_item(const TileArgs& A, const ResGeom& G, const ResCta& X, int pha
     }
     if (i < n) {
         res_locate(G, X, phase, i, lr, lc);
-        if (phase && i < X.npair) return 3;   // a 2-row block of the interior: central by construction
+        if (FK_RES_R2 && phase && i < X.npair) return 3;   // a 2-row block of the interior: central by construction
         const int row = X.r0 + lr, c = X.c0 + lc;
         return (row >= 4 && row + 5 <= A.H && c >= 4 && c + NC + 4 <= A.W) ? 1 : 0;
     }
