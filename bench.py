@@ -441,6 +441,31 @@ def main():
                            "kernel": _lib.last_kernel(), "launch_geometry": _lib.last_plan(), "segments": n_seg,
                            "euler_steps_per_segment": seg}
         del fl
+        # the reference's README table (README.md:25-31): wall seconds of forward() over 1e3 steps, field size varied,
+        # two stimuli (cardiax's fenton_karma notebooks); host wall clock, call + synchronize, best of 3
+        import time as _t
+        table = {}
+        for n in (64, 128, 256, 512, 1024):
+            shp = (n, n)
+            s1 = stimulus.Stimulus(stimulus.Protocol(0, 2, 1e9), torch.as_tensor(O.linear(shp, 0, 0.2, 20.0, O.Protocol(0, 2, 1e9)).field).to(dev))
+            s2 = stimulus.Stimulus(stimulus.Protocol(200, 2, 1e9), torch.as_tensor(O.linear(shp, 1, 0.2, 20.0, O.Protocol(200, 2, 1e9)).field).to(dev))
+            Dn = torch.full(shp, 1e-3, device=dev)
+            best = 1e30
+            for _ in range(4):
+                s0 = solve.init(shp)
+                torch.cuda.synchronize()
+                w0 = _t.perf_counter()
+                out_states = solve.forward(s0, [0, 1000], O.PARAMSETS["3"], Dn, [s1, s2], 0.01, 0.01)
+                torch.cuda.synchronize()
+                best = min(best, _t.perf_counter() - w0)
+            assert bool(torch.isfinite(out_states[-1].u).all())
+            table[str(n)] = best
+        other["readme_table_seconds_1e3_steps"] = {
+            "ours_b200": table,
+            "reference_published": {"jax_cpu_2vcpu": {"64": 0.336, "128": 0.904, "256": 2.94, "512": 11.1, "1024": 45.0},
+                                    "jax_gpu_t4": {"64": 0.193, "128": 0.189, "256": 0.199, "512": 0.237, "1024": 0.613},
+                                    "jax_tpu": {"64": 0.059, "128": 0.074, "256": 0.119, "512": 0.272, "1024": 0.842},
+                                    "source": "reference README.md:28-31 (older API, other hardware: context only)"}}
 
     peak, peak_kind = peaks()
     roof = None
