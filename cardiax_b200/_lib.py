@@ -11,8 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("FK_SO") or os.path.join(CSRC, "libfk.so")   # FK_SO: development A/B of two builds
-_SOURCES = ["fk_api.cu", "fk_stream_tu.cu", "fk_resident.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh",
-            "fk_driver.h", "fk_wide.h", "fk_resident.h", "fk_resident.cuh"]
+_SOURCES = ["fk_api.cu", "fk_stream_tu.cu", "fk_resident.cu", "fk_aux.cu", "fk_core.h", "fk_tile.h", "fk_stream.h", "fk_stream.cuh",
+            "fk_driver.h", "fk_wide.h", "fk_resident.h", "fk_resident.cuh", "fk_aux.h", "fk_aux.cuh", "fk_ode.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 STREAM_DEPTHS = (1, 2, 3, 4)   # one translation unit per (temporal-blocking depth, numerics), compiled in parallel
 
@@ -65,18 +65,21 @@ def build(force=False, verbose=False):
     mask = sum(1 << t for t in depths)
     jobs = [(os.path.join(objdir, "fk_api.o"), ["-DFK_DEPTH_MASK=%d" % mask, "-c", os.path.join(CSRC, "fk_api.cu")])]
     jobs.append((os.path.join(objdir, "fk_resident.o"), ["-c", os.path.join(CSRC, "fk_resident.cu")]))
+    jobs.append((os.path.join(objdir, "fk_aux.o"), ["-c", os.path.join(CSRC, "fk_aux.cu")]))
     for t in reversed(depths):   # the deepest (slowest to compile) first
         for e in (1, 0):
             jobs.append((os.path.join(objdir, "fk_stream_T%d_E%d.o" % (t, e)),
                          ["-DFK_TU_T=%d" % t, "-DFK_TU_EXACT=%d" % e, "-c", os.path.join(CSRC, "fk_stream_tu.cu")]))
     ptxas = ["-Xptxas", "-v"] if verbose else []
+    aux_deps = ["fk_aux.cu", "fk_aux.cuh", "fk_aux.h", "fk_ode.h", "fk_core.h"]
+    res_deps = [d for d in _SOURCES if d not in ("fk_aux.cu", "fk_aux.cuh", "fk_aux.h", "fk_ode.h")]
     stream_deps = ["fk_stream_tu.cu", "fk_stream.cuh", "fk_stream.h", "fk_tile.h", "fk_core.h"]
 
     def fresh(job):   # an object newer than everything its translation unit includes is kept (FK_DEPTHS changes: force)
         obj, args = job
         if force or not os.path.exists(obj) or "fk_api.cu" in args[-1]:
             return False
-        deps = stream_deps if "fk_stream_tu.cu" in args[-1] else _SOURCES
+        deps = stream_deps if "fk_stream_tu.cu" in args[-1] else aux_deps if "fk_aux.cu" in args[-1] else res_deps
         return all(os.path.getmtime(obj) >= os.path.getmtime(os.path.join(CSRC, d)) for d in deps)
 
     def run(job):
@@ -136,6 +139,18 @@ def lib():
     L.fk_stimulate.restype = ci
     L.fk_diffusivity_gradients.argtypes = [vp, vp, vp, ci, ci, ci, cf, ci, ci, vp]
     L.fk_diffusivity_gradients.restype = ci
+    L.fk_dopri5_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+    L.fk_dopri5_workspace_bytes.restype = sz
+    L.fk_odeint_dopri5.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci,
+                                              ctypes.POINTER(cf), ci, cf, cf, cf, cd, ctypes.POINTER(FkOptions), vp, sz, vp,
+                                              ctypes.POINTER(ll * 3)]
+    L.fk_odeint_dopri5.restype = ci
+    L.fk_resize_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+    L.fk_resize_workspace_bytes.restype = sz
+    L.fk_resize_bilinear.argtypes = [ctypes.POINTER(vp), ci, ci, ci, vp, ci, ci, vp, sz, vp]
+    L.fk_resize_bilinear.restype = ci
+    L.fk_electrogram.argtypes = [vp, ci, ci, ci, cf, cf, vp, vp]
+    L.fk_electrogram.restype = ci
     L.fk_launch_count.restype = ll
     L.fk_last_plan.argtypes = [ctypes.POINTER(ci * 8)]
     L.fk_last_plan.restype = None

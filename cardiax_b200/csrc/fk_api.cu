@@ -12,6 +12,7 @@
 #include "fk_stream.cuh"
 #include "fk_resident.cuh"
 #include "fk_driver.h"
+#include "fk_aux.cuh"
 
 namespace {
 
@@ -44,6 +45,16 @@ int num_sms() {
     }
     return g_num_sms;
 }
+
+}  // namespace
+
+namespace fk {
+int api_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+int api_cuda_fail(int e, const char* where) { return cuda_fail((cudaError_t)e, where); }
+void api_count_launch(int n) { g_launches += n; }
+}  // namespace fk
+
+namespace {
 
 // ------------------------------------------------------------------ kernels
 template <bool EXACT>
@@ -551,6 +562,101 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
         FK_CUDA(cudaGetLastError());
         yv = nv; yw = nw; yu = nu;
     }
+    return 0;
+}
+
+// ---- solve._forward_dormandprince: the CUDA backend of fk::drive_dopri5 (fk_ode.h)
+size_t fk_dopri5_workspace_bytes(int H, int W, int batch, int n_stim, int d_batched) {
+    const size_t base = fk_workspace_bytes(H, W, batch, n_stim, d_batched);
+    if (!base) return 0;
+    // y, stage, candidate, k[7], two sets of five interpolation coefficients: 20 States
+    return base + 60 * align_up((size_t)H * W * sizeof(float) * batch, 256) + align_up(fk::ode_scratch_bytes(), 256);
+}
+
+int fk_odeint_dopri5(const float* v0, const float* w0, const float* u0, float* v_out, float* w_out, float* u_out,
+                     const float* D, int d_batched, int H, int W, int batch, const FkParams* params,
+                     const FkStimulus* stimuli, int n_stim, const float* ts, int n_ts, float dx, float rtol, float atol,
+                     double mxstep, const FkOptions* opt_in, void* workspace, size_t workspace_bytes, void* stream,
+                     long long* stats3) {
+    int rc = check_common(H, W, batch, params, n_stim, stimuli);
+    if (rc) return rc;
+    if (!v0 || !w0 || !u0 || !v_out || !w_out || !u_out || !D || !ts) return fail(-1, "NULL pointer%s");
+    if (n_ts < 1) return fail(-1, "fk_odeint_dopri5 needs at least one output time%s");
+    FkOptions opt;
+    if (opt_in) opt = *opt_in; else fk_default_options(&opt);
+    const size_t need = fk_dopri5_workspace_bytes(H, W, batch, n_stim, d_batched);
+    if (!workspace || workspace_bytes < need) return fail(-4, "workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace ws = carve(workspace, H, W, batch, n_stim, d_batched);
+    const size_t plane_bytes = (size_t)H * W * sizeof(float) * batch;
+    const size_t stride = align_up(plane_bytes, 256);
+    char* p = (char*)workspace + ws.bytes;
+    auto next3 = [&]() { fk::P3 r; for (int a = 0; a < 3; ++a) { r.a[a] = (float*)p; p += stride; } return r; };
+    fk::OdeBuffers B;
+    B.n = (long long)H * W * batch;
+    B.y = next3(); B.ys = next3(); B.yn = next3();
+    for (int s = 0; s < 7; ++s) B.k[s] = next3();
+    for (int c = 0; c < 2; ++c) for (int j = 0; j < 5; ++j) B.c[c][j] = next3();
+    B.out.a[0] = v_out; B.out.a[1] = w_out; B.out.a[2] = u_out;
+    fk::OdeScratch scratch;
+    scratch.partial = (double*)p;
+    FK_CUDA(cudaMemcpyAsync(B.y.a[0], v0, plane_bytes, cudaMemcpyDeviceToDevice, st));
+    FK_CUDA(cudaMemcpyAsync(B.y.a[1], w0, plane_bytes, cudaMemcpyDeviceToDevice, st));
+    FK_CUDA(cudaMemcpyAsync(B.y.a[2], u0, plane_bytes, cudaMemcpyDeviceToDevice, st));
+    rc = upload_stims(stimuli, batch * n_stim, ws.stims, st);
+    if (rc) return rc;
+    rc = launch_dgrad(D, ws.DX, ws.DY, H, W, d_batched ? batch : 1, dx, 1, 1, st);
+    if (rc) return rc;
+
+    struct Backend {
+        CudaBackend be;
+        fk::DriveOptions o;
+        fk::Consts K;
+        fk::Dopri T;
+        fk::OdeScratch S;
+        const float *D, *DX, *DY;
+        const fk::StimDev* stims;
+        int d_batched, H, W, batch, n_stim, exact;
+        long long n;
+        const char* why;
+        int rhs(const fk::P3& y, const fk::P3& k, float t) {
+            fk::DriveBuffers Bf;
+            memset(&Bf, 0, sizeof(Bf));
+            Bf.v_in = y.a[0]; Bf.w_in = y.a[1]; Bf.u_in = y.a[2]; Bf.v_out = k.a[0]; Bf.w_out = k.a[1]; Bf.u_out = k.a[2];
+            Bf.D = D; Bf.DX = DX; Bf.DY = DY; Bf.stims = stims;
+            const int rc = fk::drive_euler(be, Bf, d_batched, H, W, batch, K, n_stim, (double)t, 1, o, 1, &why);
+            return rc ? (why[0] ? fail(rc, "%s", why) : rc) : 0;
+        }
+        int copy(const fk::P3& dst, long long off, const fk::P3& src) { return fk::launch_ode_copy(dst, off, src, n, be.st); }
+        int init_norms(const fk::P3& y, const fk::P3& f, float rtol, float atol, double* s2) {
+            return fk::launch_ode_init_norms(exact, y, f, rtol, atol, n, S, s2, be.st);
+        }
+        int axpy(const fk::P3& y, float h, const fk::P3& f, const fk::P3& out) { return fk::launch_ode_axpy(exact, y, h, f, out, n, be.st); }
+        int diff_norm(const fk::P3& f1, const fk::P3& f0, const fk::P3& y, float rtol, float atol, double* s) {
+            return fk::launch_ode_diff_norm(exact, f1, f0, y, rtol, atol, n, S, s, be.st);
+        }
+        int stage(int i, const fk::P3& y, const fk::P3* k, float dt, const fk::P3& ys) {
+            return fk::launch_ode_stage(exact, T, i, y, k, dt, ys, n, be.st);
+        }
+        int finish(const fk::P3& y, const fk::P3* k, float dt, float rtol, float atol, const fk::P3& yn, const fk::P3* c, double* s) {
+            return fk::launch_ode_finish(exact, T, y, k, dt, rtol, atol, yn, c, n, S, s, be.st);
+        }
+        int interp(const fk::P3* c, float r, const fk::P3& out, long long off) { return fk::launch_ode_interp(exact, c, r, out, off, n, be.st); }
+    } be;
+    be.be.st = st;
+    memset(&be.o, 0, sizeof(be.o));
+    be.o.exact = opt.exact; be.o.phys_top = 1; be.o.phys_bottom = 1; be.o.kernel = 1;
+    be.K = make_consts(*params, 0.0f, dx);
+    if (opt.safe_division) be.K.div_lo = INFINITY;
+    be.T = fk::make_dopri();
+    be.S = scratch;
+    be.D = D; be.DX = ws.DX; be.DY = ws.DY; be.stims = ws.stims;
+    be.d_batched = d_batched; be.H = H; be.W = W; be.batch = batch; be.n_stim = n_stim; be.exact = opt.exact;
+    be.n = B.n; be.why = "";
+    fk::OdeStats S = {0, 0, 0};
+    rc = fk::drive_dopri5(be, B, n_ts, ts, rtol, atol, mxstep, &S);
+    if (rc) return rc;
+    if (stats3) { stats3[0] = S.attempts; stats3[1] = S.accepted; stats3[2] = S.rhs_evals; }
     return 0;
 }
 

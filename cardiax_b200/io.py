@@ -217,42 +217,41 @@ def load_diffusivity(filepath):
 
 
 # --------------------------------------------------------------------------- jax.image.resize(..., "bilinear")
-_weights_cache = {}
-
-
-def _weight_matrix(n_in, n_out, device):
-    """(n_in, n_out) weights of jax.image.resize's separable triangle filter with anti-aliasing."""
-    key = (n_in, n_out, str(device))
-    w = _weights_cache.get(key)
-    if w is None:
-        scale = n_out / n_in
-        inv_scale = 1.0 / scale
-        kernel_scale = max(inv_scale, 1.0)
-        sample_f = (np.arange(n_out, dtype=np.float64) + 0.5) * inv_scale - 0.5
-        x = np.abs(sample_f[None, :] - np.arange(n_in, dtype=np.float64)[:, None]) / kernel_scale
-        wt = np.maximum(0.0, 1.0 - x)
-        total = wt.sum(axis=0, keepdims=True)
-        wt = np.where(np.abs(total) > 1000.0 * np.finfo(np.float32).eps, wt / np.where(total == 0, 1, total), 0.0)
-        inside = (sample_f >= -0.5) & (sample_f <= n_in - 0.5)
-        wt = np.where(inside[None, :], wt, 0.0).astype(np.float32)
-        w = torch.from_numpy(wt).to(device)
-        _weights_cache[key] = w
-    return w
+def _resize_planes(planes, H, W, size, out=None):
+    """``planes``: list of contiguous fp32 CUDA (H, W) tensors -> packed (len(planes), H', W') tensor, ONE launch of
+    ``fk_resize_kernel`` on the current stream (weights built by the library: csrc/fk_aux.h)."""
+    import ctypes
+    from . import _lib
+    L = _lib.lib()
+    dev = planes[0].device
+    Ho, Wo = int(size[0]), int(size[1])
+    n = len(planes)
+    if out is None:
+        out = torch.empty((n, Ho, Wo), dtype=torch.float32, device=dev)
+    nbytes = L.fk_resize_workspace_bytes(H, W, Ho, Wo, n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in planes])
+    _lib.check(L.fk_resize_bilinear(ptrs, n, H, W, out.data_ptr(), Ho, Wo, ws.data_ptr(), nbytes,
+                                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
 
 
 def imresize(a, size, method="bilinear"):
-    """io.py:118-124 -- resize the last two axes of a 2-D or 3-D array to ``size``."""
+    """io.py:118-124 -- ``jax.image.resize(a, a.shape[:-2] + size, "bilinear")`` of a 2-D or 3-D (or deeper) array:
+    anti-aliased triangle filter, half-pixel centres.  Runs on the GPU (host arrays are uploaded; no CPU fallback)."""
     if method != "bilinear":
         raise NotImplementedError("only the reference's default 'bilinear' is provided")
+    from . import solve
     if not isinstance(a, torch.Tensor):
         a = torch.as_tensor(np.asarray(a))
-    a = a.to(torch.float32)
     H, W = a.shape[-2:]
     if (H, W) == tuple(size):
-        return a.clone()
-    wh = _weight_matrix(H, int(size[0]), a.device)  # (H, H')
-    ww = _weight_matrix(W, int(size[1]), a.device)  # (W, W')
-    return torch.matmul(wh.t(), torch.matmul(a, ww))
+        return a.to(torch.float32).clone()
+    a = solve._as_f32(a)
+    lead = tuple(a.shape[:-2])
+    flat = a.reshape((-1, H, W))
+    out = _resize_planes([flat[i] for i in range(flat.shape[0])], H, W, size)
+    return out.reshape(lead + (int(size[0]), int(size[1])))
 
 
 # --------------------------------------------------------------------------- asynchronous snapshots
@@ -287,9 +286,12 @@ class AsyncSnapshotWriter:
         keep = tuple(state)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            arr = torch.stack(keep)
-            if tuple(arr.shape[-2:]) != self.shape[-2:]:
-                arr = imresize(arr, self.shape[-2:])
+            H, W = keep[0].shape[-2:]
+            if (H, W) != self.shape[-2:]:   # v, w, u (of every tissue of a batch) in one launch
+                planes = [p for x in keep for p in x.contiguous().reshape(-1, H, W)]
+                arr = _resize_planes(planes, H, W, self.shape[-2:]).reshape(self.shape)
+            else:
+                arr = torch.stack(keep)
             self.pinned[slot].copy_(arr, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.stream)

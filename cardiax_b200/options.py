@@ -20,3 +20,7 @@ edge_tile = (0, 0)     # resident kernel: (rows, 4-column groups) of the tiles a
 detect_uniform_diffusivity = True
 safe_division = False   # exact numerics: force every division through __fdiv_rn
 verbose = True
+# TimeIntegrator.DORMANDPRINCE: the keyword defaults of jax.experimental.ode.odeint, which the reference never overrides
+ode_rtol = 1.4e-8
+ode_atol = 1.4e-8
+ode_mxstep = float("inf")

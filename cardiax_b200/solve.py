@@ -224,8 +224,40 @@ def _forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx):
 
 
 def _forward_dormandprince(state, ts, params, diffusivity, stimuli, dt, dx):
-    """cardiax/solve.py:114-124 -- adaptive Dopri5 through jax.experimental.ode; not on the accelerated path."""
-    raise NotImplementedError("the adaptive Dormand-Prince integrator is outside the accelerated hot path")
+    """cardiax/solve.py:114-124 -- ``jax.experimental.ode.odeint(step, state, ts, params, diffusivity, stimuli, dx)``:
+    adaptive Dormand-Prince with jax's controller and dense output; ``ts`` are continuous times in the same (step)
+    units the checkpoints are given in and ``dt`` is unused, exactly like the reference.  Returns a State of stacked
+    arrays ``(len(ts), H, W)`` whose first entry is the initial state.  The arrays stay on the device; the step-size
+    controller runs on the host, so this call synchronises the current stream (options.ode_* = odeint's keywords)."""
+    L = _lib.lib()
+    dev, v, w, u, D, batch, H, W = _prep(state, diffusivity)
+    arr, n_stim, keep = _pack_stimuli(stimuli, batch, (H, W), dev)
+    if isinstance(ts, torch.Tensor):
+        ts = ts.detach().cpu().numpy()
+    ts = np.ascontiguousarray(np.asarray(ts, dtype=np.float64).reshape(-1), dtype=np.float32)
+    n_ts = int(ts.shape[0])
+    nbytes = L.fk_dopri5_workspace_bytes(H, W, batch, n_stim, int(D.dim() == 3))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    vo, wo, uo = [torch.empty((n_ts,) + tuple(u.shape), dtype=torch.float32, device=dev) for _ in range(3)]
+    P = _params_struct(params)
+    o = _options(None, P, dx)
+    stats = (ctypes.c_longlong * 3)()
+    _lib.check(L.fk_odeint_dopri5(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
+                                  D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
+                                  ts.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n_ts, np.float32(_scalar(dx)),
+                                  np.float32(options.ode_rtol), np.float32(options.ode_atol), float(options.ode_mxstep),
+                                  ctypes.byref(o), ws.data_ptr(), nbytes, _stream(), ctypes.byref(stats)))
+    global last_ode_stats
+    last_ode_stats = dict(attempts=stats[0], accepted=stats[1], rhs_evals=stats[2])
+    return State(vo, wo, uo)
+
+
+last_ode_stats = None
+
+
+def step_rk(state, t, params, diffusivity, stimuli, dt, dx):
+    """cardiax/solve.py:88-89 -- ``ode.odeint(step, state, t, ...)``: ``t`` is the array of output times."""
+    return _forward_dormandprince(state, t, params, diffusivity, stimuli, dt, dx)
 
 
 class TimeIntegrator(Enum):

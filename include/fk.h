@@ -107,6 +107,37 @@ int fk_euler_rows(const float* v_in_dev, const float* w_in_dev, const float* u_i
                   float dx, const FkOptions* opt, int row0, int row1, void* workspace_dev, size_t workspace_bytes,
                   void* stream);
 
+/* solve._forward_dormandprince / solve.step_rk (cardiax/solve.py:88-89, 114-124) ==
+ * jax.experimental.ode.odeint(step, state, ts, params, diffusivity, stimuli, dx): adaptive Dormand-Prince 5(4) with
+ * jax's step-size controller and 4th-order dense output (jax/experimental/ode.py, an un-vendored dependency: algorithm
+ * restated in csrc/fk_ode.h).  The right-hand side is solve.step evaluated at the CONTINUOUS fp32 time t (the reference
+ * passes its step-unit checkpoints as times and never uses dt here).
+ *   ts                HOST array of n_ts fp32 output times, increasing
+ *   v/w/u_out_dev     (n_ts, batch, H, W) each: the state at every ts[i]; entry 0 is the initial state
+ *   rtol, atol, mxstep  odeint's keyword defaults are 1.4e-8, 1.4e-8, +inf
+ *   stats3            optional HOST {attempted steps, accepted steps, right-hand-side evaluations}
+ * The arrays stay on the device; the step-size controller runs on the host and reads ONE reduced scalar per attempted
+ * step, so this entry point synchronises `stream` (the reference's odeint is a device-side while loop).
+ * A batch is integrated as ONE system (one common step size), like a raveled pytree. */
+size_t fk_dopri5_workspace_bytes(int H, int W, int batch, int n_stim, int diffusivity_batched);
+int fk_odeint_dopri5(const float* v0_dev, const float* w0_dev, const float* u0_dev, float* v_out_dev, float* w_out_dev,
+                     float* u_out_dev, const float* diffusivity_dev, int diffusivity_batched, int H, int W, int batch,
+                     const FkParams* params, const FkStimulus* stimuli, int n_stim, const float* ts, int n_ts, float dx,
+                     float rtol, float atol, double mxstep, const FkOptions* opt, void* workspace_dev,
+                     size_t workspace_bytes, void* stream, long long* stats3);
+
+/* io.imresize (cardiax/io.py:118-124) == jax.image.resize(a, a.shape[:-2] + (Ho, Wo), "bilinear"): separable
+ * anti-aliased triangle filter, half-pixel centres, weights renormalised at the edges.  One launch resizes n_planes
+ * (H, W) arrays -- e.g. the v, w, u of a snapshot -- into one packed (n_planes, Ho, Wo) array.
+ *   planes            HOST array of n_planes device pointers */
+size_t fk_resize_workspace_bytes(int H, int W, int Ho, int Wo, int n_planes);
+int fk_resize_bilinear(const float* const* planes, int n_planes, int H, int W, float* out_dev, int Ho, int Wo,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* metrics.electrogram (cardiax/metrics.py:13-22): out[f] = sum_ij x[f][i][j] * sqrt((j - p0)^2 + (i - p1)^2) for every
+ * (H, W) frame of x (the reference multiplies by the distance; its ogrid only broadcasts for H == W). */
+int fk_electrogram(const float* x_dev, int frames, int H, int W, float p0, float p1, float* out_dev, void* stream);
+
 /* Exact numerics divide by the run's constants (time constants, dx) with q = RN(a * RN(1/b)); RN(q + (a - b q) RN(1/b)).
  * This verifies that sequence against __fdiv_rn on the device for every significand x three exponents x both signs x
  * every divisor of (params, dx) and returns the number of mismatches (0 expected; if not, set

@@ -18,7 +18,7 @@ class _Stim(ctypes.Structure):
 
 def build(force=False):
     deps = [os.path.join(_HERE, "fk_emu.cpp")] + [os.path.join(_CSRC, f) for f in
-                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h", "fk_wide.h", "fk_resident.h")]
+                                                    ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h", "fk_wide.h", "fk_resident.h", "fk_aux.h", "fk_ode.h")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
@@ -84,3 +84,50 @@ def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0)
         return None
     return dict(zip(("ntr", "ntc", "th_max", "tw_max", "threads", "smem_bytes", "nc", "xchg_bytes", "edge_rows",
                      "edge_colgroups", "single_phase", "maps_in_l2"), list(out)))
+
+
+def _pack_stims(stimuli):
+    keep, arr = [], (_Stim * max(1, len(stimuli)))()
+    for i, s in enumerate(stimuli):
+        f = np.ascontiguousarray(s.field, dtype=np.float32)
+        keep.append(f)
+        arr[i] = _Stim(f.ctypes.data, *[float(np.asarray(x).reshape(-1)[0]) for x in s.protocol])
+    return arr, keep
+
+
+def dopri5(state, ts, params, D, stimuli, dx, rtol=1.4e-8, atol=1.4e-8, mxstep=float("inf"), exact=True):
+    """The product's Dormand-Prince driver (fk_ode.h) + element bodies (fk_aux.h) on the CPU.  -> (v, w, u) stacked, stats"""
+    v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
+    H, W = u.shape
+    ts = np.ascontiguousarray(ts, dtype=np.float32)
+    D = np.ascontiguousarray(D, dtype=np.float32)
+    par = np.array([float(np.asarray(x).reshape(-1)[0]) for x in params], dtype=np.float32)
+    arr, keep = _pack_stims(stimuli)
+    outs = [np.full((len(ts), H, W), np.nan, np.float32) for _ in range(3)]
+    stats = (ctypes.c_longlong * 3)()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib().fk_emu_dopri5(p(v), p(w), p(u), p(outs[0]), p(outs[1]), p(outs[2]), p(D), H, W, p(par), arr, len(stimuli),
+                             p(ts), len(ts), ctypes.c_float(dx), ctypes.c_float(rtol), ctypes.c_float(atol),
+                             ctypes.c_double(mxstep), int(exact), stats)
+    if rc != 0:
+        raise RuntimeError("fk_emu_dopri5 rc=%d" % rc)
+    return tuple(outs), dict(attempts=stats[0], accepted=stats[1], rhs_evals=stats[2])
+
+
+def resize(a, size):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    H, W = a.shape[-2:]
+    planes = int(np.prod(a.shape[:-2], dtype=np.int64)) if a.ndim > 2 else 1
+    out = np.empty(a.shape[:-2] + tuple(size), np.float32)
+    lib().fk_emu_resize(a.ctypes.data_as(ctypes.c_void_p), planes, H, W, out.ctypes.data_as(ctypes.c_void_p), int(size[0]), int(size[1]))
+    return out
+
+
+def electrogram(x, point):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    H, W = x.shape[-2:]
+    frames = int(np.prod(x.shape[:-2], dtype=np.int64)) if x.ndim > 2 else 1
+    out = np.empty(x.shape[:-2], np.float32)
+    lib().fk_emu_electrogram(x.ctypes.data_as(ctypes.c_void_p), frames, H, W, ctypes.c_float(point[0]), ctypes.c_float(point[1]),
+                             out.ctypes.data_as(ctypes.c_void_p))
+    return out

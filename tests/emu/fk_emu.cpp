@@ -13,6 +13,7 @@
 #include "../../cardiax_b200/csrc/fk_tile.h"
 #include "../../cardiax_b200/csrc/fk_stream.h"
 #include "../../cardiax_b200/csrc/fk_driver.h"
+#include "../../cardiax_b200/csrc/fk_ode.h"
 
 namespace {
 
@@ -159,5 +160,143 @@ extern "C" int fk_emu_dgrad(const float* D, float* DX, float* DY, int H, int W, 
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c)
             fk::dgrad_cell(D, H, W, dx, phys_top, phys_bot, r, c, DX[(long long)r * W + c], DY[(long long)r * W + c]);
+    return 0;
+}
+
+// ---- Dormand-Prince: the product's fk::drive_dopri5 on a CPU backend (element bodies of fk_aux.h, sums in fp64)
+namespace {
+struct EmuOde {
+    EmuBackend be;
+    fk::DriveOptions o;
+    fk::Consts K;
+    fk::Dopri T;
+    const float *D, *DX, *DY;
+    const fk::StimDev* stims;
+    int d_batched, H, W, batch, n_stim, exact;
+    long long n;
+    int rhs(const fk::P3& y, const fk::P3& k, float t) {
+        fk::DriveBuffers B;
+        memset(&B, 0, sizeof(B));
+        B.v_in = y.a[0]; B.w_in = y.a[1]; B.u_in = y.a[2]; B.v_out = k.a[0]; B.w_out = k.a[1]; B.u_out = k.a[2];
+        B.D = D; B.DX = DX; B.DY = DY; B.stims = stims;
+        const char* why = "";
+        return fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, (double)t, 1, o, 1, &why);
+    }
+    int copy(const fk::P3& dst, long long off, const fk::P3& src) {
+        for (int a = 0; a < 3; ++a) memcpy(dst.a[a] + off, src.a[a], sizeof(float) * (size_t)n);
+        return 0;
+    }
+    template <bool E> void init_norms_t(const fk::P3& y, const fk::P3& f, float rtol, float atol, double* s2) {
+        s2[0] = s2[1] = 0.0;
+        for (int a = 0; a < 3; ++a)
+            for (long long e = 0; e < n; ++e) {
+                float qy, qf;
+                fk::ode_scaled<E>(y.a[a][e], f.a[a][e], rtol, atol, qy, qf);
+                s2[0] += (double)(qy * qy); s2[1] += (double)(qf * qf);
+            }
+    }
+    int init_norms(const fk::P3& y, const fk::P3& f, float rtol, float atol, double* s2) {
+        if (exact) init_norms_t<true>(y, f, rtol, atol, s2); else init_norms_t<false>(y, f, rtol, atol, s2);
+        return 0;
+    }
+    int axpy(const fk::P3& y, float h, const fk::P3& f, const fk::P3& out) {
+        for (int a = 0; a < 3; ++a)
+            for (long long e = 0; e < n; ++e) out.a[a][e] = y.a[a][e] + h * f.a[a][e];
+        return 0;
+    }
+    int diff_norm(const fk::P3& f1, const fk::P3& f0, const fk::P3& y, float rtol, float atol, double* s) {
+        *s = 0.0;
+        for (int a = 0; a < 3; ++a)
+            for (long long e = 0; e < n; ++e) {
+                const float scale = atol + fabsf(y.a[a][e]) * rtol;
+                const float q = (f1.a[a][e] - f0.a[a][e]) / scale;
+                *s += (double)(q * q);
+            }
+        return 0;
+    }
+    int stage(int i, const fk::P3& y, const fk::P3* k, float dt, const fk::P3& ys) {
+        for (int a = 0; a < 3; ++a)
+            for (long long e = 0; e < n; ++e) {
+                float kk[6];
+                for (int s = 0; s < 6; ++s) kk[s] = s < i ? k[s].a[a][e] : 0.0f;
+                ys.a[a][e] = exact ? fk::ode_stage<true>(y.a[a][e], T.beta[i - 1], kk, i, dt)
+                                   : fk::ode_stage<false>(y.a[a][e], T.beta[i - 1], kk, i, dt);
+            }
+        return 0;
+    }
+    int finish(const fk::P3& y, const fk::P3* k, float dt, float rtol, float atol, const fk::P3& yn, const fk::P3* c, double* s) {
+        *s = 0.0;
+        for (int a = 0; a < 3; ++a)
+            for (long long e = 0; e < n; ++e) {
+                float kk[7], y1, r2, coef[5];
+                for (int j = 0; j < 7; ++j) kk[j] = k[j].a[a][e];
+                if (exact) fk::ode_finish<true>(T, y.a[a][e], kk, dt, rtol, atol, y1, r2, coef);
+                else fk::ode_finish<false>(T, y.a[a][e], kk, dt, rtol, atol, y1, r2, coef);
+                yn.a[a][e] = y1;
+                for (int j = 0; j < 5; ++j) c[j].a[a][e] = coef[j];
+                *s += (double)r2;
+            }
+        return 0;
+    }
+    int interp(const fk::P3* c, float r, const fk::P3& out, long long off) {
+        for (int a = 0; a < 3; ++a)
+            for (long long e = 0; e < n; ++e) {
+                float coef[5];
+                for (int j = 0; j < 5; ++j) coef[j] = c[j].a[a][e];
+                out.a[a][off + e] = exact ? fk::ode_interp<true>(coef, r) : fk::ode_interp<false>(coef, r);
+            }
+        return 0;
+    }
+};
+}  // namespace
+
+// stats3: {attempts, accepted, rhs evaluations}
+extern "C" int fk_emu_dopri5(const float* v0, const float* w0, const float* u0, float* v_out, float* w_out, float* u_out,
+                             const float* D, int H, int W, const float* params14, const EmuStim* stims, int n_stim,
+                             const float* ts, int n_ts, float dx, float rtol, float atol, double mxstep, int exact,
+                             long long* stats3) {
+    const size_t n = (size_t)H * W;
+    std::vector<float> DX(n), DY(n), store(60 * n);
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) fk::dgrad_cell(D, H, W, dx, 1, 1, r, c, DX[(size_t)r * W + c], DY[(size_t)r * W + c]);
+    float* p = store.data();
+    auto next3 = [&]() { fk::P3 r; for (int a = 0; a < 3; ++a) { r.a[a] = p; p += n; } return r; };
+    fk::OdeBuffers B;
+    B.n = (long long)n;
+    B.y = next3(); B.ys = next3(); B.yn = next3();
+    for (int s = 0; s < 7; ++s) B.k[s] = next3();
+    for (int c = 0; c < 2; ++c) for (int j = 0; j < 5; ++j) B.c[c][j] = next3();
+    B.out.a[0] = v_out; B.out.a[1] = w_out; B.out.a[2] = u_out;
+    memcpy(B.y.a[0], v0, n * 4); memcpy(B.y.a[1], w0, n * 4); memcpy(B.y.a[2], u0, n * 4);
+    EmuOde be;
+    memset(&be.o, 0, sizeof(be.o));
+    be.o.exact = exact; be.o.phys_top = 1; be.o.phys_bottom = 1; be.o.kernel = 1;
+    be.K = fk::make_consts(params14, 0.0f, dx);
+    be.T = fk::make_dopri();
+    be.D = D; be.DX = DX.data(); be.DY = DY.data(); be.stims = (const fk::StimDev*)stims;
+    be.d_batched = 0; be.H = H; be.W = W; be.batch = 1; be.n_stim = n_stim; be.exact = exact; be.n = (long long)n;
+    fk::OdeStats S = {0, 0, 0};
+    const int rc = fk::drive_dopri5(be, B, n_ts, ts, rtol, atol, mxstep, &S);
+    if (stats3) { stats3[0] = S.attempts; stats3[1] = S.accepted; stats3[2] = S.rhs_evals; }
+    return rc;
+}
+
+extern "C" int fk_emu_resize(const float* in, int planes, int H, int W, float* out, int Ho, int Wo) {
+    const fk::ResizeAxis ah = fk::make_resize_axis(H, Ho), aw = fk::make_resize_axis(W, Wo);
+    for (int p = 0; p < planes; ++p)
+        for (int i = 0; i < Ho; ++i)
+            for (int j = 0; j < Wo; ++j)
+                out[((size_t)p * Ho + i) * Wo + j] = fk::resize_pixel(in + (size_t)p * H * W, W, ah.lo[i], ah.wt.data() + (size_t)i * ah.K,
+                                                                      ah.K, aw.lo[j], aw.wt.data() + (size_t)j * aw.K, aw.K);
+    return 0;
+}
+
+extern "C" int fk_emu_electrogram(const float* x, int frames, int H, int W, float p0, float p1, float* out) {
+    for (int f = 0; f < frames; ++f) {
+        double acc = 0.0;
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) acc += (double)(x[((size_t)f * H + i) * W + j] * fk::egm_weight(i, j, p0, p1));
+        out[f] = (float)acc;
+    }
     return 0;
 }

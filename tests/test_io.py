@@ -6,6 +6,7 @@ import pytest
 import torch
 
 import oracle as O
+from oracle import fk_oracle_ext as X
 
 
 def _jax_resize_bilinear_numpy(a, size):
@@ -26,23 +27,59 @@ def _jax_resize_bilinear_numpy(a, size):
     return np.einsum("...hw,hi,wj->...ij", np.asarray(a, np.float64), mat(a.shape[-2], size[0]), mat(a.shape[-1], size[1]))
 
 
-def test_imresize_matches_the_jax_algorithm():
-    from cardiax_b200 import io
+RESIZE_CASES = (((3, 24, 36), (8, 9)), ((20, 20), (7, 13)), ((12, 12), (24, 30)), ((3, 10, 10), (10, 10)),
+                ((2, 3, 75, 61), (16, 13)), ((5, 5), (1, 1)), ((1, 7), (3, 2)), ((3, 150, 150), (32, 32)))
+
+
+def _check_resize(fn):
     rng = np.random.default_rng(0)
-    for shape, size in (((3, 24, 36), (8, 9)), ((20, 20), (7, 13)), ((12, 12), (24, 30)), ((3, 10, 10), (10, 10))):
+    for shape, size in RESIZE_CASES:
         a = rng.random(shape).astype(np.float32)
-        got = io.imresize(torch.as_tensor(a), size).numpy()
+        got = fn(a, size)
         assert got.shape == shape[:-2] + size
-        assert np.abs(got - _jax_resize_bilinear_numpy(a, size)).max() < 1e-5
+        # fp32 accumulation of O(1) values: tolerance 1e-5 absolute (observed < 5e-7)
+        assert np.abs(got - _jax_resize_bilinear_numpy(a, size)).max() < 1e-5, (shape, size)
+        assert np.abs(got - X.resize_bilinear(a, size)).max() < 1e-5, (shape, size)
     # constant stays constant; exact 2x box average of a ramp
-    assert np.allclose(io.imresize(torch.full((16, 16), 3.0), (5, 7)).numpy(), 3.0, atol=1e-6)
-    ramp = torch.arange(16, dtype=torch.float32).repeat(16, 1)
-    assert np.allclose(io.imresize(ramp, (16, 4)).numpy()[0][1:3], [5.5, 9.5], atol=1e-5)
+    assert np.allclose(fn(np.full((16, 16), 3.0, np.float32), (5, 7)), 3.0, atol=1e-6)
+    ramp = np.tile(np.arange(16, dtype=np.float32), (16, 1))
+    assert np.allclose(fn(ramp, (16, 4))[0][1:3], [5.5, 9.5], atol=1e-5)
+
+
+def test_resize_oracle_is_the_jax_algorithm():
+    rng = np.random.default_rng(1)
+    for shape, size in RESIZE_CASES:
+        a = rng.random(shape).astype(np.float32)
+        assert np.abs(X.resize_bilinear(a, size) - _jax_resize_bilinear_numpy(a, size)).max() < 1e-12
+
+
+def test_resize_kernel_body_on_the_cpu_matches_the_oracle():
+    from tests.emu import emu
+    _check_resize(emu.resize)
+
+
+@pytest.mark.gpu
+def test_imresize_matches_the_jax_algorithm():
+    from cardiax_b200 import _lib, io
+    before = _lib.lib().fk_launch_count()
+    _check_resize(lambda a, size: io.imresize(torch.as_tensor(a), size).cpu().numpy())
+    assert _lib.lib().fk_launch_count() > before          # the library's kernel ran, not a torch op
+    big = torch.rand((3, 1200, 1200), device="cuda")       # the reference's standard snapshot: 1200^2 -> 256^2
+    got = io.imresize(big, (256, 256)).cpu().numpy()
+    assert np.abs(got - X.resize_bilinear(big.cpu().numpy(), (256, 256))).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_storage_layout_round_trip_resized(tmp_path):
+    _storage_round_trip(tmp_path, (20, 30), (10, 15))
 
 
 def test_storage_layout_round_trip(tmp_path):
+    _storage_round_trip(tmp_path, (20, 30), (20, 30))      # resizing runs on the GPU only: same shape on the CPU
+
+
+def _storage_round_trip(tmp_path, shape, out):
     from cardiax_b200 import io, params, stimulus
-    shape, out = (20, 30), (10, 15)
     path = os.path.join(tmp_path, "run", "seq.hdf5")
     D = torch.full(shape, 1e-3)
     stim = [stimulus.Stimulus(stimulus.Protocol(0, 2, 1e9), torch.ones(shape)),
