@@ -147,7 +147,7 @@ def lib():
     L.fk_odeint_dopri5.restype = ci
     L.fk_resize_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
     L.fk_resize_workspace_bytes.restype = sz
-    L.fk_resize_bilinear.argtypes = [ctypes.POINTER(vp), ci, ci, ci, vp, ci, ci, vp, sz, vp]
+    L.fk_resize_bilinear.argtypes = [ctypes.POINTER(vp), ci, ci, ci, vp, ci, ci, vp, sz, ci, vp]
     L.fk_resize_bilinear.restype = ci
     L.fk_electrogram.argtypes = [vp, ci, ci, ci, cf, cf, vp, vp]
     L.fk_electrogram.restype = ci

@@ -3,6 +3,8 @@
 // metrics.electrogram (cardiax/metrics.py:13-22).  All HBM-bound elementwise / reduction work, no tensor cores.
 #include <cuda_runtime.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -19,12 +21,33 @@ namespace {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ resize
-__global__ void __launch_bounds__(256) fk_resize_kernel(const ResizeArgs A) {
-    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y, p = blockIdx.z;
+// One thread per output pixel, 32 x 8 pixels per CTA.  The CTA's weights (Kw taps of its 32 columns, Kh taps of its 8
+// rows) are staged in shared memory tap-major: the inner loop is one global load (L1-resident: neighbouring pixels'
+// windows overlap) + one conflict-free shared load + one FMA per tap.
+template <bool SMEM>
+__global__ void __launch_bounds__(256) fk_resize_kernel(const __grid_constant__ ResizeArgs A) {
+    extern __shared__ float sw[];   // [Kw][32] then [Kh][8]
+    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 8, p = blockIdx.z;
+    const int j = j0 + threadIdx.x, i = i0 + threadIdx.y;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (SMEM) {
+        for (int e = tid; e < A.Kw * 32; e += 256) {
+            const int q = e >> 5, c = j0 + (e & 31);
+            sw[e] = c < A.Wo ? __ldg(A.wt_w + (size_t)q * A.Wo + c) : 0.0f;
+        }
+        float* sh = sw + A.Kw * 32;
+        for (int e = tid; e < A.Kh * 8; e += 256) {
+            const int r = e >> 3, c = i0 + (e & 7);
+            sh[e] = c < A.Ho ? __ldg(A.wt_h + (size_t)r * A.Ho + c) : 0.0f;
+        }
+        __syncthreads();
+    }
     if (i >= A.Ho || j >= A.Wo) return;
-    const float* in = A.planes[p];
-    A.out[((size_t)p * A.Ho + i) * A.Wo + j] =
-        resize_pixel(in, A.W, __ldg(A.lo_h + i), A.wt_h + (size_t)i * A.Kh, A.Kh, __ldg(A.lo_w + j), A.wt_w + (size_t)j * A.Kw, A.Kw);
+    const float* in = A.n_planes <= RESIZE_BY_VALUE ? A.plane[p] : A.planes[p];
+    float v;
+    if (SMEM) v = resize_pixel(in, A.W, __ldg(A.lo_h + i), sw + A.Kw * 32 + threadIdx.y, 8, A.Kh, __ldg(A.lo_w + j), sw + threadIdx.x, 32, A.Kw);
+    else v = resize_pixel(in, A.W, __ldg(A.lo_h + i), A.wt_h + i, A.Ho, A.Kh, __ldg(A.lo_w + j), A.wt_w + j, A.Wo, A.Kw);
+    A.out[((size_t)p * A.Ho + i) * A.Wo + j] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
@@ -288,12 +311,12 @@ static size_t aux_align(size_t x) { return (x + 255) / 256 * 256; }
 size_t fk_resize_workspace_bytes(int H, int W, int Ho, int Wo, int n_planes) {
     if (H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || n_planes <= 0) return 0;
     const fk::ResizeAxis ah = fk::make_resize_axis(H, Ho), aw = fk::make_resize_axis(W, Wo);
-    return aux_align(sizeof(void*) * (size_t)n_planes) + aux_align(4 * (size_t)Ho) + aux_align(4 * (size_t)Ho * ah.K) +
-           aux_align(4 * (size_t)Wo) + aux_align(4 * (size_t)Wo * aw.K);
+    return aux_align(4 * (size_t)Ho) + aux_align(4 * (size_t)Ho * ah.K) + aux_align(4 * (size_t)Wo) +
+           aux_align(4 * (size_t)Wo * aw.K) + aux_align(sizeof(void*) * (size_t)n_planes);
 }
 
 int fk_resize_bilinear(const float* const* planes, int n_planes, int H, int W, float* out, int Ho, int Wo, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, int workspace_ready, void* stream) {
     using namespace fk;
     if (!planes || !out || !workspace) return api_fail(-1, "NULL pointer");
     if (H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || n_planes <= 0 || n_planes > 65535) return api_fail(-1, "bad resize shape");
@@ -302,24 +325,32 @@ int fk_resize_bilinear(const float* const* planes, int n_planes, int H, int W, f
     const ResizeAxis ah = make_resize_axis(H, Ho), aw = make_resize_axis(W, Wo);
     char* p = (char*)workspace;
     ResizeArgs A;
+    memset(&A, 0, sizeof(A));
     A.n_planes = n_planes; A.H = H; A.W = W; A.Ho = Ho; A.Wo = Wo; A.Kh = ah.K; A.Kw = aw.K; A.out = out;
     // pageable sources: the runtime stages them before returning
-    A.planes = (const float* const*)p;
-    AUX_CUDA(cudaMemcpyAsync(p, planes, sizeof(void*) * (size_t)n_planes, cudaMemcpyHostToDevice, st));
-    p += aux_align(sizeof(void*) * (size_t)n_planes);
     A.lo_h = (const int*)p;
-    AUX_CUDA(cudaMemcpyAsync(p, ah.lo.data(), 4 * (size_t)Ho, cudaMemcpyHostToDevice, st));
+    if (!workspace_ready) AUX_CUDA(cudaMemcpyAsync(p, ah.lo.data(), 4 * (size_t)Ho, cudaMemcpyHostToDevice, st));
     p += aux_align(4 * (size_t)Ho);
     A.wt_h = (const float*)p;
-    AUX_CUDA(cudaMemcpyAsync(p, ah.wt.data(), 4 * (size_t)Ho * ah.K, cudaMemcpyHostToDevice, st));
+    if (!workspace_ready) AUX_CUDA(cudaMemcpyAsync(p, resize_tap_major(ah).data(), 4 * (size_t)Ho * ah.K, cudaMemcpyHostToDevice, st));
     p += aux_align(4 * (size_t)Ho * ah.K);
     A.lo_w = (const int*)p;
-    AUX_CUDA(cudaMemcpyAsync(p, aw.lo.data(), 4 * (size_t)Wo, cudaMemcpyHostToDevice, st));
+    if (!workspace_ready) AUX_CUDA(cudaMemcpyAsync(p, aw.lo.data(), 4 * (size_t)Wo, cudaMemcpyHostToDevice, st));
     p += aux_align(4 * (size_t)Wo);
     A.wt_w = (const float*)p;
-    AUX_CUDA(cudaMemcpyAsync(p, aw.wt.data(), 4 * (size_t)Wo * aw.K, cudaMemcpyHostToDevice, st));
+    if (!workspace_ready) AUX_CUDA(cudaMemcpyAsync(p, resize_tap_major(aw).data(), 4 * (size_t)Wo * aw.K, cudaMemcpyHostToDevice, st));
+    p += aux_align(4 * (size_t)Wo * aw.K);
+    if (n_planes <= RESIZE_BY_VALUE) {
+        for (int i = 0; i < n_planes; ++i) A.plane[i] = planes[i];
+    } else {
+        A.planes = (const float* const*)p;
+        AUX_CUDA(cudaMemcpyAsync(p, planes, sizeof(void*) * (size_t)n_planes, cudaMemcpyHostToDevice, st));
+    }
     api_count_launch(1);
-    fk_resize_kernel<<<dim3((Wo + 31) / 32, (Ho + 7) / 8, n_planes), dim3(32, 8), 0, st>>>(A);
+    const dim3 grid((Wo + 31) / 32, (Ho + 7) / 8, n_planes);
+    const size_t smem = sizeof(float) * ((size_t)A.Kw * 32 + (size_t)A.Kh * 8);
+    if (smem <= 40 * 1024) fk_resize_kernel<true><<<grid, dim3(32, 8), smem, st>>>(A);
+    else fk_resize_kernel<false><<<grid, dim3(32, 8), 0, st>>>(A);   // extreme reductions: weights straight from L1/L2
     AUX_CUDA(cudaGetLastError());
     return 0;
 }

@@ -52,23 +52,33 @@ inline ResizeAxis make_resize_axis(int n_in, int n_out) {
     return A;
 }
 
+enum { RESIZE_BY_VALUE = 8 };
 struct ResizeArgs {
-    const float* const* planes;   // n_planes pointers to (H, W) arrays
-    float* out;                   // (n_planes, Ho, Wo)
+    const float* plane[RESIZE_BY_VALUE];   // n_planes <= 8: the pointers themselves (a snapshot has three)
+    const float* const* planes;            // otherwise: device table of n_planes pointers to (H, W) arrays
+    float* out;                            // (n_planes, Ho, Wo)
     int n_planes, H, W, Ho, Wo, Kh, Kw;
-    const int* lo_h; const float* wt_h;   // Ho, Ho * Kh
-    const int* lo_w; const float* wt_w;   // Wo, Wo * Kw
+    const int* lo_h; const float* wt_h;    // Ho ints; Kh x Ho weights, TAP-major (coalesced across output indices)
+    const int* lo_w; const float* wt_w;    // Wo ints; Kw x Wo weights
 };
 
-// one output pixel: rows outer, columns inner, fused multiply-adds in tap order
-FK_HD float resize_pixel(const float* __restrict__ in, int W, int r0, const float* __restrict__ wh, int Kh, int c0,
-                         const float* __restrict__ ww, int Kw) {
+// tap-major copy of an axis' weights: t[k * n_out + o]
+inline std::vector<float> resize_tap_major(const ResizeAxis& A) {
+    std::vector<float> t((size_t)A.K * A.n_out);
+    for (int o = 0; o < A.n_out; ++o)
+        for (int k = 0; k < A.K; ++k) t[(size_t)k * A.n_out + o] = A.wt[(size_t)o * A.K + k];
+    return t;
+}
+
+// one output pixel: rows outer, columns inner, fused multiply-adds in tap order; wh[r * sh], ww[q * sw]
+FK_HD float resize_pixel(const float* __restrict__ in, int W, int r0, const float* __restrict__ wh, int sh, int Kh, int c0,
+                         const float* __restrict__ ww, int sw, int Kw) {
     float acc = 0.0f;
     for (int r = 0; r < Kh; ++r) {
         const float* row = in + (size_t)(r0 + r) * W + c0;
         float racc = 0.0f;
-        for (int q = 0; q < Kw; ++q) racc = fmaf(row[q], ww[q], racc);
-        acc = fmaf(wh[r], racc, acc);
+        for (int q = 0; q < Kw; ++q) racc = fmaf(row[q], ww[q * sw], racc);
+        acc = fmaf(wh[r * sh], racc, acc);
     }
     return acc;
 }

@@ -217,9 +217,13 @@ def load_diffusivity(filepath):
 
 
 # --------------------------------------------------------------------------- jax.image.resize(..., "bilinear")
+_resize_ws = {}   # (device, stream, H, W, Ho, Wo, n) -> workspace holding the uploaded filter tables
+
+
 def _resize_planes(planes, H, W, size, out=None):
     """``planes``: list of contiguous fp32 CUDA (H, W) tensors -> packed (len(planes), H', W') tensor, ONE launch of
-    ``fk_resize_kernel`` on the current stream (weights built by the library: csrc/fk_aux.h)."""
+    ``fk_resize_kernel`` on the current stream (filter tables built by the library -- csrc/fk_aux.h -- and kept in a
+    per-geometry workspace, so a repeated snapshot shape costs the kernel launch only)."""
     import ctypes
     from . import _lib
     L = _lib.lib()
@@ -228,11 +232,18 @@ def _resize_planes(planes, H, W, size, out=None):
     n = len(planes)
     if out is None:
         out = torch.empty((n, Ho, Wo), dtype=torch.float32, device=dev)
-    nbytes = L.fk_resize_workspace_bytes(H, W, Ho, Wo, n)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    key = (str(dev), stream.cuda_stream, H, W, Ho, Wo, n)   # per stream: the tables are uploaded in stream order
+    ws = _resize_ws.get(key)
+    ready = ws is not None
+    if not ready:
+        if len(_resize_ws) > 32:
+            _resize_ws.clear()
+        ws = torch.empty(L.fk_resize_workspace_bytes(H, W, Ho, Wo, n), dtype=torch.uint8, device=dev)
+        _resize_ws[key] = ws
     ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in planes])
-    _lib.check(L.fk_resize_bilinear(ptrs, n, H, W, out.data_ptr(), Ho, Wo, ws.data_ptr(), nbytes,
-                                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    _lib.check(L.fk_resize_bilinear(ptrs, n, H, W, out.data_ptr(), Ho, Wo, ws.data_ptr(), ws.numel(), int(ready),
+                                    ctypes.c_void_p(stream.cuda_stream)))
     return out
 
 

@@ -129,10 +129,13 @@ int fk_odeint_dopri5(const float* v0_dev, const float* w0_dev, const float* u0_d
 /* io.imresize (cardiax/io.py:118-124) == jax.image.resize(a, a.shape[:-2] + (Ho, Wo), "bilinear"): separable
  * anti-aliased triangle filter, half-pixel centres, weights renormalised at the edges.  One launch resizes n_planes
  * (H, W) arrays -- e.g. the v, w, u of a snapshot -- into one packed (n_planes, Ho, Wo) array.
- *   planes            HOST array of n_planes device pointers */
+ *   planes            HOST array of n_planes device pointers
+ *   workspace_ready   0: the filter tables of this (H, W, Ho, Wo) are built and uploaded into the workspace first;
+ *                     1: the caller kept the workspace of an earlier call with the same shapes (nothing is uploaded
+ *                        for n_planes <= 8: a snapshot costs one kernel launch) */
 size_t fk_resize_workspace_bytes(int H, int W, int Ho, int Wo, int n_planes);
 int fk_resize_bilinear(const float* const* planes, int n_planes, int H, int W, float* out_dev, int Ho, int Wo,
-                       void* workspace_dev, size_t workspace_bytes, void* stream);
+                       void* workspace_dev, size_t workspace_bytes, int workspace_ready, void* stream);
 
 /* metrics.electrogram (cardiax/metrics.py:13-22): out[f] = sum_ij x[f][i][j] * sqrt((j - p0)^2 + (i - p1)^2) for every
  * (H, W) frame of x (the reference multiplies by the distance; its ogrid only broadcasts for H == W). */

@@ -286,8 +286,8 @@ extern "C" int fk_emu_resize(const float* in, int planes, int H, int W, float* o
     for (int p = 0; p < planes; ++p)
         for (int i = 0; i < Ho; ++i)
             for (int j = 0; j < Wo; ++j)
-                out[((size_t)p * Ho + i) * Wo + j] = fk::resize_pixel(in + (size_t)p * H * W, W, ah.lo[i], ah.wt.data() + (size_t)i * ah.K,
-                                                                      ah.K, aw.lo[j], aw.wt.data() + (size_t)j * aw.K, aw.K);
+                out[((size_t)p * Ho + i) * Wo + j] = fk::resize_pixel(in + (size_t)p * H * W, W, ah.lo[i], ah.wt.data() + (size_t)i * ah.K, 1,
+                                                                      ah.K, aw.lo[j], aw.wt.data() + (size_t)j * aw.K, 1, aw.K);
     return 0;
 }
 
