@@ -77,6 +77,7 @@ FK_HD float resize_pixel(const float* __restrict__ in, int W, int r0, const floa
     for (int r = 0; r < Kh; ++r) {
         const float* row = in + (size_t)(r0 + r) * W + c0;
         float racc = 0.0f;
+#pragma unroll 4
         for (int q = 0; q < Kw; ++q) racc = fmaf(row[q], ww[q * sw], racc);
         acc = fmaf(wh[r * sh], racc, acc);
     }

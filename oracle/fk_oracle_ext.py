@@ -157,7 +157,8 @@ def resize_weights(n_in, n_out):
 def resize_bilinear(a, size):
     """cardiax/io.py:118-124 -- resize the last two axes of ``a`` to ``size`` (fp64 evaluation)."""
     a = np.asarray(a, np.float64)
-    return np.einsum("...hw,hi,wj->...ij", a, resize_weights(a.shape[-2], size[0]), resize_weights(a.shape[-1], size[1]))
+    wh, ww = resize_weights(a.shape[-2], size[0]), resize_weights(a.shape[-1], size[1])
+    return np.swapaxes(np.swapaxes(a @ ww, -1, -2) @ wh, -1, -2)
 
 
 # --------------------------------------------------------------------------- metrics.electrogram
