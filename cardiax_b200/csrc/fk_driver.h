@@ -58,7 +58,7 @@ inline int finish_regions(TileArgs& A, long long* smem_floats) {
         R.ntc = tile_count(R.C1 - R.C0, R.tw);
         R.first = total;
         total += R.ntr * R.ntc;
-        const long long f = tile_smem_floats(R.th + 1, R.tw + 1, A.T);
+        const long long f = tile_smem_floats(R.th + 1, R.tw + 1, A.T, A.heun);
         if (f > maxfloats) maxfloats = f;
     }
     if (smem_floats) *smem_floats = maxfloats;
@@ -215,6 +215,40 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         su = A.u_out; sv = A.v_out; sw = A.w_out;
         t += T;
         remaining -= T;
+    }
+    return 0;
+}
+
+// solve._forward_heun (solve.py:73-85, 103-111): ONE launch of the general tile kernel per Heun step -- its two levels
+// are the predictor and the corrector, both at the same counter; y and k1 of a tile's own cells wait in shared memory.
+template <class Backend>
+int drive_heun(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, int batch, const Consts& K, int n_stim,
+               double t0, long long nsteps, int exact, float h_half) {
+    TileArgs A;
+    A = TileArgs();
+    A.D = B.D; A.DX = B.DX; A.DY = B.DY;
+    A.plane = (long long)H * W;
+    A.plane_D = d_batched ? A.plane : 0;
+    A.H = H; A.W = W;
+    A.phys_top = A.phys_bot = A.phys_left = A.phys_right = 1;
+    A.K = K;
+    A.stims = n_stim ? B.stims : nullptr;
+    A.n_stim = n_stim;
+    A.T = 2; A.heun = 1; A.h_half = h_half;
+    int th = 16, tw = 64;   // 88 KB: two CTAs per SM; measured best of {32x64, 16x64, 24x96, 16x128} on 256^2 ... 4096^2
+    const float *sv = B.v_in, *sw = B.w_in, *su = B.u_in;
+    for (long long l = 0; l < nsteps; ++l) {
+        const bool to_out = ((nsteps - 1 - l) % 2 == 0);
+        A.u_in = su; A.v_in = sv; A.w_in = sw;
+        A.u_out = to_out ? B.u_out : B.pu;
+        A.v_out = to_out ? B.v_out : B.pv;
+        A.w_out = to_out ? B.w_out : B.pw;
+        A.t0 = t0 + (double)l;
+        A.nreg = 0;
+        add_region(A, 0, H, 0, W, th, tw);
+        const int rc = be.tiles(A, exact, batch, false);
+        if (rc) return rc;
+        su = A.u_out; sv = A.v_out; sw = A.w_out;
     }
     return 0;
 }

@@ -33,6 +33,10 @@ struct TileArgs {
     int phys_top, phys_bot, phys_left, phys_right;  // which buffer edges are physical tissue edges
     int T;                             // Euler steps in this launch (levels)
     int rhs_mode;                      // 1: write (d_v, d_w, d_u) of a single step instead of the new state
+    int heun;                          // 1: the launch's two levels are the two stages of ONE Heun step (solve.py:73-85):
+                                       //    level 1 = predictor y1 = y + k1 dt, level 2 evaluates k2 = f(y1) at the SAME
+                                       //    counter and writes y + (k1 + k2) * h_half
+    float h_half;                      // dt * 0.5 (solve.py:83)
     Consts K;
     const StimDev* stims;              // (batch, n_stim)
     int n_stim;
@@ -46,6 +50,8 @@ struct TileCtx {  // per-tile geometry, identical for every thread of the block
     int ra, rb, ca, cb;      // level-0 (input) rectangle
     int nr, nc, SG;
     float *U0, *U1, *V, *Wd, *GX, *GY;  // shared memory
+    float* HS;               // Heun: y.v, y.w, k1.v, k1.w, k1.u of the output cells (5 planes of how cells)
+    int how;                 // cells of the output rectangle
     unsigned mask[8];        // active stimuli per level (bit i = stimulus i)
     long long boff, boffD;   // batch offsets
     const StimDev* stims;
@@ -57,9 +63,9 @@ FK_HD int tile_count(int len, int t) {
     return (n > 1 && len % t == 1) ? n - 1 : n;
 }
 
-FK_HD long long tile_smem_floats(int th, int tw, int T) {
+FK_HD long long tile_smem_floats(int th, int tw, int T, int heun = 0) {
     long long nr = th + 8LL * T, nc = tw + 8LL * T;
-    return 4 * nr * nc + (nr + 3) * nc + nr * (nc + 3);
+    return 4 * nr * nc + (nr + 3) * nc + nr * (nc + 3) + (heun ? 5LL * th * tw : 0);
 }
 
 FK_HD void level_rect(const TileArgs& A, const TileCtx& X, int s, int& a, int& b, int& c, int& d) {
@@ -93,6 +99,8 @@ FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx
     X.Wd = X.V + n;
     X.GX = X.Wd + n;
     X.GY = X.GX + (long long)(X.nr + 3) * X.nc;
+    X.HS = X.GY + (long long)X.nr * X.SG;
+    X.how = (X.r1 - X.r0) * (X.c1 - X.c0);
     X.boff = (long long)sim * A.plane;
     X.boffD = (long long)sim * A.plane_D;
     X.stims = A.stims ? A.stims + (long long)sim * A.n_stim : nullptr;
@@ -106,6 +114,7 @@ FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx
         }
         X.mask[s] = m;
     }
+    if (A.heun) X.mask[1] = X.mask[0];   // both stages see the same counter (solve.py:78, 80)
 }
 
 // phase 0: level-0 state -> shared memory
@@ -234,6 +243,24 @@ FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* 
                     A.w_out[X.boff + g] = d_w;
                     A.u_out[X.boff + g] = d_u;
                     continue;
+                }
+                if (A.heun) {
+                    const bool mine = row >= X.r0 && row < X.r1 && col >= X.c0 && col < X.c1;
+                    const int o = (row - X.r0) * (X.c1 - X.c0) + (col - X.c0);
+                    if (!last) {   // predictor: keep y and k1 of the cells this tile will write
+                        if (mine) {
+                            X.HS[o] = v; X.HS[X.how + o] = w;
+                            X.HS[2 * X.how + o] = d_v; X.HS[3 * X.how + o] = d_w; X.HS[4 * X.how + o] = d_u;
+                        }
+                    } else {       // corrector: y + (k1 + k2) * (dt * 0.5)
+                        if (mine) {
+                            typedef Num<EXACT> N;
+                            A.v_out[X.boff + g] = euler<EXACT>(X.HS[o], N::add(X.HS[2 * X.how + o], d_v), A.h_half);
+                            A.w_out[X.boff + g] = euler<EXACT>(X.HS[X.how + o], N::add(X.HS[3 * X.how + o], d_w), A.h_half);
+                            A.u_out[X.boff + g] = euler<EXACT>(X.U0[i], N::add(X.HS[4 * X.how + o], d_u), A.h_half);
+                        }
+                        continue;
+                    }
                 }
                 const float vn = euler<EXACT>(v, d_v, A.K.dt), wn = euler<EXACT>(w, d_w, A.K.dt),
                             un = euler<EXACT>(u, d_u, A.K.dt);

@@ -215,7 +215,7 @@ def _forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     vo, wo, uo = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
     P = _params_struct(params)
-    o = _options(None, P, dx)
+    o = _options(D, P, dx)
     _lib.check(L.fk_forward_heun(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
                                  D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
                                  _scalar(t), _scalar(t_end), np.float32(_scalar(dt)), np.float32(_scalar(dx)),

@@ -131,3 +131,22 @@ def electrogram(x, point):
     lib().fk_emu_electrogram(x.ctypes.data_as(ctypes.c_void_p), frames, H, W, ctypes.c_float(point[0]), ctypes.c_float(point[1]),
                              out.ctypes.data_as(ctypes.c_void_p))
     return out
+
+
+def heun(state, t0, t1, params, D, stimuli, dt, dx, exact=True):
+    """The fused Heun driver (fk_driver.h: drive_heun, one tile launch per step) on the CPU.  -> (v, w, u), launches"""
+    v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
+    batch = u.shape[0] if u.ndim == 3 else 1
+    H, W = u.shape[-2:]
+    D = np.ascontiguousarray(D, dtype=np.float32)
+    par = np.array([float(np.asarray(x).reshape(-1)[0]) for x in params], dtype=np.float32)
+    arr, keep = _pack_stims(stimuli)
+    vo, wo, uo = np.full_like(v, np.nan), np.full_like(w, np.nan), np.full_like(u, np.nan)
+    n = ctypes.c_int(0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib().fk_emu_heun(p(v), p(w), p(u), p(vo), p(wo), p(uo), p(D), H, W, batch, p(par), arr, len(stimuli),
+                           ctypes.c_double(t0), ctypes.c_double(t1), ctypes.c_float(dt), ctypes.c_float(dx), int(exact),
+                           ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError("fk_emu_heun rc=%d" % rc)
+    return (vo, wo, uo), n.value

@@ -300,3 +300,28 @@ extern "C" int fk_emu_electrogram(const float* x, int frames, int H, int W, floa
     }
     return 0;
 }
+
+// ---- fused Heun: the product's fk::drive_heun (one tile-kernel launch per step) on the CPU backend
+extern "C" int fk_emu_heun(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                           const float* D, int H, int W, int batch, const float* params14, const EmuStim* stims, int n_stim,
+                           double t0, double t1, float dt, float dx, int exact, int* launches) {
+    const size_t plane = (size_t)H * W;
+    std::vector<float> DX(plane), DY(plane), pv(plane * batch), pw(plane * batch), pu(plane * batch);
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) fk::dgrad_cell(D, H, W, dx, 1, 1, r, c, DX[(size_t)r * W + c], DY[(size_t)r * W + c]);
+    fk::DriveBuffers B;
+    memset(&B, 0, sizeof(B));
+    B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
+    B.pv = pv.data(); B.pw = pw.data(); B.pu = pu.data(); B.D = D; B.DX = DX.data(); B.DY = DY.data();
+    B.stims = (const fk::StimDev*)stims;
+    EmuBackend be;
+    const long long nsteps = fk::count_steps(t0, t1);
+    if (nsteps <= 0) {
+        memcpy(v_out, v_in, plane * batch * 4); memcpy(w_out, w_in, plane * batch * 4); memcpy(u_out, u_in, plane * batch * 4);
+        return 0;
+    }
+    const int rc = fk::drive_heun(be, B, 0, H, W, batch, fk::make_consts(params14, dt, dx), n_stim, t0, nsteps, exact,
+                                  (float)((double)dt * 0.5));
+    if (launches) *launches = be.launches_tile;
+    return rc;
+}

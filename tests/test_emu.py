@@ -278,3 +278,16 @@ def test_device_schedule_function_equals_oracle():
         start, dur, per = int(rng.integers(0, 50)), int(rng.integers(1, 6)), float(rng.choice([7, 50, 400, 1e6, 1e9]))
         for t in range(0, 100):
             assert emu.stim_active(t, start, dur, per) == O.stimulus_active(t, O.Protocol(start, dur, per))
+
+
+@pytest.mark.parametrize("shape,n", [((40, 72), 3), ((33, 65), 2), ((97, 130), 2), ((9, 12), 4)])
+def test_fused_heun_exact(shape, n):
+    """fk_driver.h: drive_heun -- ONE tile launch per Heun step (predictor and corrector are the launch's two levels),
+    bit-identical to the oracle's literal step_heun loop (cardiax/solve.py:73-85, 103-111); several tiles per tissue,
+    remainder tiles, stimuli switching on and off between steps (both stages of a step see the same counter)."""
+    st, D, stim = common.random_case(shape, seed=5, n_stim=3)
+    ref = O.forward_heun(st, 2, 2 + n, O.PARAMSETS["3"], D, stim, 0.01, 0.01)
+    got, launches = emu.heun(st, 2, 2 + n, O.PARAMSETS["3"], D, stim, 0.01, 0.01)
+    assert launches == n
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)

@@ -156,6 +156,28 @@ def test_heun_exact_bitwise_vs_oracle(shape, n):
         assert float(np.abs(a.cpu().numpy() - b).max()) <= TOL_FAST * max(1.0, float(np.abs(b).max()))
 
 
+def test_heun_fast_through_the_euler_kernels_matches_exact_heun():
+    """Fast numerics run a Heun step as y + (E(E(y)) - y) / 2 with E = one Euler step of the streaming (large tissue)
+    or wide (small tissue) kernel, both stages at the same counter; exact numerics run the reference's literal formula
+    in one tile-kernel launch per step (bit-identical to the oracle, test above).  Same tolerance as fast Euler."""
+    from cardiax_b200 import _lib, options, solve, stimulus
+    for shape, kernel in (((1024, 1056), "fk_stream_kernel"), ((96, 128), "fk_wide_kernel")):
+        st, D = common.smooth_case(shape, seed=3)
+        stim = [O.linear(shape, 0, 0.2, 20.0, O.Protocol(2, 2, 50))]
+        gst = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in stim]
+        gstate = solve.State(*[torch.as_tensor(x).cuda() for x in st])
+        Dg = torch.as_tensor(D).cuda()
+        options.numerics = "exact"
+        ref = solve._forward_heun(gstate, 0, 6, P3, Dg, gst, 0.01, 0.01)
+        assert _lib.last_kernel() == "fk_tile_kernel"
+        options.numerics = "fast"
+        fast = solve._forward_heun(gstate, 0, 6, P3, Dg, gst, 0.01, 0.01)
+        assert _lib.last_kernel() == kernel
+        for a, b in zip(fast, ref):
+            assert float((a - b).abs().max()) <= TOL_FAST * max(1.0, float(b.abs().max()))
+        assert float((fast.u - gstate.u).abs().max()) > 1e-3      # the stimulus at t = 2, 3 acted
+
+
 @pytest.mark.parametrize("pset", sorted(O.PARAMSETS))
 def test_exact_all_paramsets(pset):
     st, D, stim = common.random_case((64, 96), seed=5)
