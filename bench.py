@@ -385,6 +385,13 @@ def main():
                 x.record_stream(s_out)
             ev_out[b].record(s_out)
 
+    # the host link as this box gives it (diagnostic next to e2e: a box with a busy or degraded PCIe link shows here)
+    link = {}
+    for name, dst, src in (("h2d_gbs", dev_in[0][0], host_in[0]), ("d2h_gbs", host_out[0][0], dev_in[0][0])):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(); dst.copy_(src, non_blocking=True); l1.record(); torch.cuda.synchronize()
+        link[name] = src.numel() * 4 / (l0.elapsed_time(l1) * 1e-3) / 1e9
     for b in range(NB):
         ev_free[b].record(s_run); ev_out[b].record(s_out)
     e2e_step(0, 0)
@@ -440,6 +447,42 @@ def main():
             other[name] = {"value": cs / (tot * 1e-3) / 1e9, "unit": "Gcell-steps/s", "us_per_euler_step": tot * 1e3 / (seg * n_seg),
                            "kernel": _lib.last_kernel(), "launch_geometry": _lib.last_plan(), "segments": n_seg,
                            "euler_steps_per_segment": seg}
+        # the Heun integrator (solve.py:73-85, 103-111; deepx/DataGeneration.ipynb selects it) on the headline tissue
+        wk = work
+        sk = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
+        Dk, pk, hs = torch.as_tensor(wk["D"]).to(dev), O.PARAMSETS[wk["params"]], 40
+        sk = solve._forward_heun(sk, 0, 4, pk, Dk, [], 0.01, 0.01)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fl.fill_(1.0)
+        a0.record()
+        sk = solve._forward_heun(sk, 4, 4 + hs, pk, Dk, [], 0.01, 0.01)
+        a1.record(); torch.cuda.synchronize()
+        other["heun_fk4096"] = {"value": sk.u.numel() * hs / (a0.elapsed_time(a1) * 1e-3) / 1e9, "unit": "Gcell-steps/s (Heun steps)",
+                                "kernel": _lib.last_kernel(), "heun_steps": hs}
+        # the snapshot path of deepx.generate.sequence on the reference's 1200^2 tissue: 500 Euler steps, resize kernel to
+        # 256^2, pinned D2H on a side stream, writer thread -- per-segment time with and without snapshots
+        from cardiax_b200 import io as fio
+        wk = make_fk1200()
+        Dk, pk = torch.as_tensor(wk["D"]).to(dev), O.PARAMSETS["3"]
+        sk = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
+        n_seg = 8
+        snaps = np.zeros((n_seg + 2, 3, 256, 256), np.float32)
+        res = {}
+        for mode in ("solver_only", "with_snapshots"):
+            writer = fio.AsyncSnapshotWriter(snaps, (3, 256, 256)) if mode == "with_snapshots" else None
+            for i in range(2):
+                sk = solve._forward_euler(sk, i * seg, (i + 1) * seg, pk, Dk, [], 0.01, 0.01)
+                if writer: writer.submit(sk, i)
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for i in range(2, n_seg + 2):
+                sk = solve._forward_euler(sk, i * seg, (i + 1) * seg, pk, Dk, [], 0.01, 0.01)
+                if writer: writer.submit(sk, i)
+            if writer: writer.close()
+            torch.cuda.synchronize()
+            res[mode] = (time.perf_counter() - w0) / n_seg * 1e3
+        other["snapshots_fk1200"] = {"ms_per_500_step_segment": res, "snapshot": "3 x 1200^2 -> 3 x 256^2 fp32, async"}
         del fl
         # the reference's README table (README.md:25-31): wall seconds of forward() over 1e3 steps, field size varied,
         # two stimuli (cardiax's fenton_karma notebooks); host wall clock, call + synchronize, best of 3
@@ -499,7 +542,8 @@ def main():
         "metric": "Gcell-steps/s fp32 FK", "value": value, "unit": "Gcell-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "Gcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e, "unit": "Gcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "host_link_gbs": link},
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "other_configs": other,
         "hbm_roofline_frac_whole_step": ALG_BYTES * value / world / peak,
     }
