@@ -477,7 +477,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
         rc = launch_dgrad(D, ws.DX, ws.DY, H, W, d_batched ? batch : 1, dx, opt.phys_top, opt.phys_bottom, st);
         if (rc) return rc;
     }
-    fk::DriveBuffers B;
+    fk::DriveBuffers B = fk::DriveBuffers();
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu; B.D = D; B.stims = ws.stims;
     B.xchg = rows_mode ? nullptr : ws.xchg;
@@ -562,7 +562,7 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
     const float *yv = v_in, *yw = w_in, *yu = u_in;
     const char* why = "";
     auto rhs = [&](const float* sv, const float* sw, const float* su, float** k, double t) {
-        fk::DriveBuffers B;
+        fk::DriveBuffers B = fk::DriveBuffers();
         memset(&B, 0, sizeof(B));
         B.v_in = sv; B.w_in = sw; B.u_in = su; B.v_out = k[0]; B.w_out = k[1]; B.u_out = k[2];
         B.D = D; B.DX = ws.DX; B.DY = ws.DY; B.stims = ws.stims;
@@ -575,60 +575,36 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
         // instead of the general tile kernel: 4x the throughput on large tissues at one extra rounding per step.
         // When no stimulus is active at t or t + 1, E at counter t + 1 equals E at counter t, so E(E(y)) is ONE
         // temporally blocked two-step call (streaming kernel T = 2, or the resident kernel on small tissues).
-        fk::DriveOptions oe;
-        memset(&oe, 0, sizeof(oe));
-        oe.phys_top = 1; oe.phys_bottom = 1;
-        oe.uniform_diffusivity = opt.uniform_diffusivity; oe.cta_threads = opt.cta_threads; oe.rows_per_cta = opt.rows_per_cta;
-        fk::DriveOptions o1 = oe, o2 = oe;
-        const bool small = (long long)H * W * batch < (1LL << 20) && W % 4 == 0 && H >= 3;
-        if (small) o1.kernel = 3;            // one wide launch per stage
-        else o1.steps_per_launch = 1;        // streaming kernel, T = 1
-        bool try_resident = opt.kernel == 4;   // measured slower than two wide launches for a two-step call: opt-in
-        auto quiet = [&](double t) {
-            for (int i = 0; i < batch * n_stim; ++i)
-                if (stimuli[i].field && (fk::stim_active((float)t, stimuli[i].start, stimuli[i].duration, stimuli[i].period) ||
-                                         fk::stim_active((float)(t + 1.0), stimuli[i].start, stimuli[i].duration, stimuli[i].period)))
-                    return false;
-            return true;
-        };
-        for (long long l = 0; l < nsteps; ++l) {
-            const double t = t0 + (double)l;
-            const bool to_out = ((nsteps - 1 - l) % 2 == 0);
-            float *nv = to_out ? v_out : ws.pv, *nw = to_out ? w_out : ws.pw, *nu = to_out ? u_out : ws.pu;
-            fk::DriveBuffers B;
-            memset(&B, 0, sizeof(B));
-            B.D = D; B.DX = ws.DX; B.DY = ws.DY; B.stims = ws.stims;
-            B.pv = k2[0]; B.pw = k2[1]; B.pu = k2[2];   // ping-pong scratch of a two-launch call
-            B.xchg = ws.xchg; B.xchg_bytes = (long long)ws.xchg_bytes;
-            if (quiet(t)) {
-                B.v_in = yv; B.w_in = yw; B.u_in = yu; B.v_out = y1[0]; B.w_out = y1[1]; B.u_out = y1[2];
-                rc = -5;
-                if (try_resident) {
-                    o2.kernel = 4;
-                    rc = fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 2, o2, 0, &why);
-                    if (rc == -5 || rc == -3) { try_resident = false; o2.kernel = 0; }
-                }
-                if (rc == -5 || rc == -3) rc = fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 2, o2, 0, &why);
-                if (rc) return why[0] ? fail(rc, "%s", why) : rc;
-            } else {
-                B.v_in = yv; B.w_in = yw; B.u_in = yu; B.v_out = k1[0]; B.w_out = k1[1]; B.u_out = k1[2];
-                rc = fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 1, o1, 0, &why);
-                if (rc) return why[0] ? fail(rc, "%s", why) : rc;
-                B.v_in = k1[0]; B.w_in = k1[1]; B.u_in = k1[2]; B.v_out = y1[0]; B.w_out = y1[1]; B.u_out = y1[2];
-                rc = fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 1, o1, 0, &why);
-                if (rc) return why[0] ? fail(rc, "%s", why) : rc;
+        // The closing pass is folded into the store of the launch that produces E(E(y)) (fk::drive_heun_fast).
+        fk::HeunFastBuffers HB;
+        HB.v_in = v_in; HB.w_in = w_in; HB.u_in = u_in; HB.v_out = v_out; HB.w_out = w_out; HB.u_out = u_out;
+        HB.pv = ws.pv; HB.pw = ws.pw; HB.pu = ws.pu;
+        for (int a = 0; a < 3; ++a) { HB.s1[a] = k1[a]; HB.s2[a] = y1[a]; HB.s3[a] = k2[a]; }
+        HB.D = D; HB.DX = ws.DX; HB.DY = ws.DY; HB.stims = ws.stims; HB.xchg = ws.xchg; HB.xchg_bytes = (long long)ws.xchg_bytes;
+        struct HeunBackend : CudaBackend {
+            int blocks;
+            int combine(const float* yv, const float* yw, const float* yu, const float* ev, const float* ew, const float* eu,
+                        float* ov, float* ow, float* ou, long long n) {
+                ++g_launches;
+                fk_heun_combine_kernel<<<blocks, 256, 0, st>>>(yv, yw, yu, ev, ew, eu, ov, ow, ou, n);
+                FK_CUDA(cudaGetLastError());
+                return 0;
             }
-            ++g_launches;
-            fk_heun_combine_kernel<<<blocks, 256, 0, st>>>(yv, yw, yu, y1[0], y1[1], y1[2], nv, nw, nu, n);
-            FK_CUDA(cudaGetLastError());
-            yv = nv; yw = nw; yu = nu;
-        }
-        return 0;
+            int copy(float* dst, const float* src, long long n) {
+                FK_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                return 0;
+            }
+        } hb;
+        hb.st = st; hb.blocks = blocks;
+        rc = fk::drive_heun_fast(hb, HB, d_batched, H, W, batch, K, (const fk::StimDev*)stimuli, n_stim, t0, nsteps,
+                                 opt.uniform_diffusivity, opt.cta_threads, opt.rows_per_cta, /*fold=*/opt.kernel != 1,
+                                 /*try_resident=*/opt.kernel == 4, &why);
+        return rc ? (why[0] ? fail(rc, "%s", why) : rc) : 0;
     }
     if (opt.steps_per_launch == 2 || (opt.steps_per_launch == 0 && (long long)H * W * batch < (1LL << 20))) {
         // exact numerics, tissues that do not fill the machine (measured: 1.4 - 1.7x the unfused sequence below 2^20 cells,
         // 0.7 - 0.8x above -- the tile's 8-cell apron is recomputed): ONE launch per Heun step (fk::drive_heun: predictor and corrector are the tile kernel's two levels)
-        fk::DriveBuffers B;
+        fk::DriveBuffers B = fk::DriveBuffers();
         memset(&B, 0, sizeof(B));
         B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
         B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu;
@@ -711,7 +687,7 @@ int fk_odeint_dopri5(const float* v0, const float* w0, const float* u0, float* v
         long long n;
         const char* why;
         int rhs(const fk::P3& y, const fk::P3& k, float t) {
-            fk::DriveBuffers Bf;
+            fk::DriveBuffers Bf = fk::DriveBuffers();
             memset(&Bf, 0, sizeof(Bf));
             Bf.v_in = y.a[0]; Bf.w_in = y.a[1]; Bf.u_in = y.a[2]; Bf.v_out = k.a[0]; Bf.w_out = k.a[1]; Bf.u_out = k.a[2];
             Bf.D = D; Bf.DX = DX; Bf.DY = DY; Bf.stims = stims;

@@ -32,6 +32,8 @@ struct DriveBuffers {
     const StimDev* stims;           // device/emulated copy of the stimulus table, or null
     u64* xchg;                      // resident kernel: mailboxes (zeroed by the backend), xchg_bytes long, or null
     long long xchg_bytes;
+    const float *hy_v, *hy_w, *hy_u;   // fast Heun: y of the step whose E(E(y)) this call computes, or null; applied by
+    bool* hy_folded;                   // the call's last launch if it is a streaming / wide one (*hy_folded says so)
 };
 
 enum { FK_DEFAULT_T = 2, FK_RES_MAX_CTAS = 1024 };
@@ -194,6 +196,11 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         A.v_out = to_out ? B.v_out : B.pv;
         A.w_out = to_out ? B.w_out : B.pw;
         A.T = T; A.t0 = t;
+        A.hy_u = A.hy_v = A.hy_w = nullptr;
+        if (B.hy_u && l == nl - 1 && !rhs_mode && (use_wide || (use_stream && T == plan.T))) {
+            A.hy_u = B.hy_u; A.hy_v = B.hy_v; A.hy_w = B.hy_w;
+            if (B.hy_folded) *B.hy_folded = true;
+        }
         int rc;
         if (use_wide) {
             rc = be.wide(A, opt.exact, batch);
@@ -249,6 +256,90 @@ int drive_heun(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, 
         const int rc = be.tiles(A, exact, batch, false);
         if (rc) return rc;
         su = A.u_out; sv = A.v_out; sw = A.w_out;
+    }
+    return 0;
+}
+
+// solve._forward_heun in FAST numerics: a Heun step through the fast Euler kernels.  With E = one Euler step at counter
+// t, y + (k1 + k2) dt / 2 = y + (E(E(y)) - y) / 2.  E(E(y)) is one temporally blocked two-step call whenever no stimulus is
+// active at t or t + 1 (E at t + 1 then equals E at t), two single-step calls at counter t otherwise; the closing pass is
+// folded into the store of the launch that produces E(E(y)) when that is a streaming / wide launch (TileArgs::hy_*),
+// else a combine pass follows.  Backend: drive_euler's + combine(y.., e.., out.., n) + copy(dst, src, n).
+struct HeunFastBuffers {
+    const float *v_in, *w_in, *u_in;
+    float *v_out, *w_out, *u_out;
+    float *pv, *pw, *pu;            // ping-pong of the step loop
+    float *s1[3], *s2[3], *s3[3];   // three scratch States
+    const float *D, *DX, *DY;
+    const StimDev* stims;           // device table
+    u64* xchg;
+    long long xchg_bytes;
+};
+
+template <class Backend>
+int drive_heun_fast(Backend& be, const HeunFastBuffers& HB, int d_batched, int H, int W, int batch, const Consts& K,
+                    const StimDev* host_stims, int n_stim, double t0, long long nsteps, int uniform, int cta_threads,
+                    int rows_per_cta, bool fold, bool try_resident, const char** why) {
+    *why = "";
+    DriveOptions oe = DriveOptions();
+    oe.phys_top = 1; oe.phys_bottom = 1;
+    oe.uniform_diffusivity = uniform; oe.cta_threads = cta_threads; oe.rows_per_cta = rows_per_cta;
+    DriveOptions o1 = oe, o2 = oe;
+    const bool small = cta_threads == 0 && (long long)H * W * batch < (1LL << 20) && W % 4 == 0 && H >= 3;
+    if (small) o1.kernel = 3;            // one wide launch per stage
+    else o1.steps_per_launch = 1;        // streaming kernel, T = 1
+    if (cta_threads) { o1.kernel = 2; o2.kernel = 2; o2.steps_per_launch = 2; }   // a caller who sizes the CTAs wants streaming
+    const long long n = (long long)H * W * batch;
+    auto quiet = [&](double t) {
+        for (int i = 0; i < batch * n_stim; ++i)
+            if (host_stims[i].field && (stim_active((float)t, host_stims[i].start, host_stims[i].duration, host_stims[i].period) ||
+                                        stim_active((float)(t + 1.0), host_stims[i].start, host_stims[i].duration, host_stims[i].period)))
+                return false;
+        return true;
+    };
+    const float *yv = HB.v_in, *yw = HB.w_in, *yu = HB.u_in;
+    int rc;
+    for (long long l = 0; l < nsteps; ++l) {
+        const double t = t0 + (double)l;
+        const bool to_out = ((nsteps - 1 - l) % 2 == 0);
+        float *nv = to_out ? HB.v_out : HB.pv, *nw = to_out ? HB.w_out : HB.pw, *nu = to_out ? HB.u_out : HB.pu;
+        DriveBuffers B = DriveBuffers();
+        B.D = HB.D; B.DX = HB.DX; B.DY = HB.DY; B.stims = HB.stims;
+        B.pv = HB.s3[0]; B.pw = HB.s3[1]; B.pu = HB.s3[2];   // ping-pong scratch of a two-launch call
+        B.xchg = HB.xchg; B.xchg_bytes = HB.xchg_bytes;
+        bool folded = false;
+        float* e2[3] = {HB.s2[0], HB.s2[1], HB.s2[2]};
+        if (fold) { e2[0] = nv; e2[1] = nw; e2[2] = nu; }
+        auto arm_fold = [&]() {   // for the call that produces E(E(y)) only
+            if (fold) { B.hy_v = yv; B.hy_w = yw; B.hy_u = yu; B.hy_folded = &folded; }
+        };
+        if (quiet(t)) {
+            arm_fold();
+            B.v_in = yv; B.w_in = yw; B.u_in = yu; B.v_out = e2[0]; B.w_out = e2[1]; B.u_out = e2[2];
+            rc = -5;
+            if (try_resident) {
+                o2.kernel = 4;
+                rc = drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 2, o2, 0, why);
+                if (rc == -5 || rc == -3) { try_resident = false; o2.kernel = 0; folded = false; }
+            }
+            if (rc == -5 || rc == -3) rc = drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 2, o2, 0, why);
+            if (rc) return rc;
+        } else {
+            B.v_in = yv; B.w_in = yw; B.u_in = yu; B.v_out = HB.s1[0]; B.w_out = HB.s1[1]; B.u_out = HB.s1[2];
+            rc = drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 1, o1, 0, why);
+            if (rc) return rc;
+            arm_fold();
+            B.v_in = HB.s1[0]; B.w_in = HB.s1[1]; B.u_in = HB.s1[2]; B.v_out = e2[0]; B.w_out = e2[1]; B.u_out = e2[2];
+            rc = drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t, 1, o1, 0, why);
+            if (rc) return rc;
+        }
+        if (!folded) {
+            if (fold) {   // a tile-kernel / resident launch: E(E(y)) sits where the new state belongs
+                if ((rc = be.copy(HB.s2[0], nv, n)) || (rc = be.copy(HB.s2[1], nw, n)) || (rc = be.copy(HB.s2[2], nu, n))) return rc;
+            }
+            if ((rc = be.combine(yv, yw, yu, HB.s2[0], HB.s2[1], HB.s2[2], nv, nw, nu, n))) return rc;
+        }
+        yv = nv; yw = nw; yu = nu;
     }
     return 0;
 }

@@ -695,6 +695,12 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
             }
             if (s == T - 1) {
                 if (c >= C.out_c0 && c < C.out_c1 && rho >= C.r0) {   // (rho < r0: the unrolled body while it fills)
+                    if (A.hy_u) {   // fast Heun: this launch computed E(E(y)); store y + (E(E(y)) - y) / 2 (y: an L2 hit)
+                        float y4[4];
+                        unpack4(ldg4(A.hy_u + grow), y4); heun_fold4(y4, un);
+                        unpack4(ldg4(A.hy_v + grow), y4); heun_fold4(y4, vn);
+                        unpack4(ldg4(A.hy_w + grow), y4); heun_fold4(y4, wn);
+                    }
                     if (ST || !defer_u) st4(A.u_out + grow, un);   // (a deferred first row's u follows below)
                     st4(A.v_out + grow, vn);
                     st4(A.w_out + grow, wn);
@@ -729,6 +735,10 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                 un0[k] = euler<EXACT>(R.sv[s][0][k], Num<EXACT>::add(del_u, R.sv[s][3][k]), A.K.dt);
             }
             if (s == T - 1) {
+                if (A.hy_u) {
+                    float y4[4];
+                    unpack4(ldg4(A.hy_u + grow0), y4); heun_fold4(y4, un0);
+                }
                 if (c >= C.out_c0 && c < C.out_c1) st4(A.u_out + grow0, un0);
             } else {
                 // the next stage should have received this row one iteration ago: its ring slot and its "previous row"

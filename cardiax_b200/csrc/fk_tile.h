@@ -37,6 +37,8 @@ struct TileArgs {
                                        //    level 1 = predictor y1 = y + k1 dt, level 2 evaluates k2 = f(y1) at the SAME
                                        //    counter and writes y + (k1 + k2) * h_half
     float h_half;                      // dt * 0.5 (solve.py:83)
+    const float *hy_v, *hy_w, *hy_u;   // fast Heun (streaming / wide kernels, last level only): when set, the launch stores
+                                       // y + (E - y) / 2 instead of its Euler result E, y = these arrays (fk_forward_heun)
     Consts K;
     const StimDev* stims;              // (batch, n_stim)
     int n_stim;

@@ -134,6 +134,12 @@ FK_HD void wide_thread(const TileArgs& A, int sim, int row, int c, unsigned mask
         wn[k] = euler<EXACT>(w[k], d_w, A.K.dt);
         un[k] = euler<EXACT>(uc[k], d_u, A.K.dt);
     }
+    if (A.hy_u) {   // fast Heun (see fk_stream.h)
+        float y4[4];
+        unpack4(ldg4(A.hy_u + boff + g), y4); heun_fold4(y4, un);
+        unpack4(ldg4(A.hy_v + boff + g), y4); heun_fold4(y4, vn);
+        unpack4(ldg4(A.hy_w + boff + g), y4); heun_fold4(y4, wn);
+    }
     st4(A.u_out + boff + g, un);
     st4(A.v_out + boff + g, vn);
     st4(A.w_out + boff + g, wn);

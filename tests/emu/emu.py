@@ -150,3 +150,22 @@ def heun(state, t0, t1, params, D, stimuli, dt, dx, exact=True):
     if rc != 0:
         raise RuntimeError("fk_emu_heun rc=%d" % rc)
     return (vo, wo, uo), n.value
+
+
+def heun_fast(state, t0, t1, params, D, stimuli, dt, dx, fold=True, force_stream=False):
+    """The fast-numerics Heun driver (fk_driver.h: drive_heun_fast) on the CPU.  -> (v, w, u), dict of launch counts"""
+    v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
+    batch = u.shape[0] if u.ndim == 3 else 1
+    H, W = u.shape[-2:]
+    D = np.ascontiguousarray(D, dtype=np.float32)
+    par = np.array([float(np.asarray(x).reshape(-1)[0]) for x in params], dtype=np.float32)
+    arr, keep = _pack_stims(stimuli)
+    vo, wo, uo = np.full_like(v, np.nan), np.full_like(w, np.nan), np.full_like(u, np.nan)
+    info = (ctypes.c_int * 4)()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib().fk_emu_heun_fast(p(v), p(w), p(u), p(vo), p(wo), p(uo), p(D), H, W, batch, p(par), arr, len(stimuli),
+                                ctypes.c_double(t0), ctypes.c_double(t1), ctypes.c_float(dt), ctypes.c_float(dx), int(fold),
+                                int(force_stream), info)
+    if rc != 0:
+        raise RuntimeError("fk_emu_heun_fast rc=%d" % rc)
+    return (vo, wo, uo), dict(zip(("tile", "stream", "wide", "combine"), list(info)))

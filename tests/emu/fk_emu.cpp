@@ -100,7 +100,7 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
             for (int c = 0; c < W; ++c)
                 fk::dgrad_cell(D + b * plane, H, W, dx, options[3], options[4], r, c, DX[b * plane + (size_t)r * W + c],
                                DY[b * plane + (size_t)r * W + c]);
-    fk::DriveBuffers B;
+    fk::DriveBuffers B = fk::DriveBuffers();
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = pv.data(); B.pw = pw.data(); B.pu = pu.data(); B.D = D; B.DX = DX.data(); B.DY = DY.data();
     B.stims = (const fk::StimDev*)stims;
@@ -175,7 +175,7 @@ struct EmuOde {
     int d_batched, H, W, batch, n_stim, exact;
     long long n;
     int rhs(const fk::P3& y, const fk::P3& k, float t) {
-        fk::DriveBuffers B;
+        fk::DriveBuffers B = fk::DriveBuffers();
         memset(&B, 0, sizeof(B));
         B.v_in = y.a[0]; B.w_in = y.a[1]; B.u_in = y.a[2]; B.v_out = k.a[0]; B.w_out = k.a[1]; B.u_out = k.a[2];
         B.D = D; B.DX = DX; B.DY = DY; B.stims = stims;
@@ -309,7 +309,7 @@ extern "C" int fk_emu_heun(const float* v_in, const float* w_in, const float* u_
     std::vector<float> DX(plane), DY(plane), pv(plane * batch), pw(plane * batch), pu(plane * batch);
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c) fk::dgrad_cell(D, H, W, dx, 1, 1, r, c, DX[(size_t)r * W + c], DY[(size_t)r * W + c]);
-    fk::DriveBuffers B;
+    fk::DriveBuffers B = fk::DriveBuffers();
     memset(&B, 0, sizeof(B));
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = pv.data(); B.pw = pw.data(); B.pu = pu.data(); B.D = D; B.DX = DX.data(); B.DY = DY.data();
@@ -323,5 +323,48 @@ extern "C" int fk_emu_heun(const float* v_in, const float* w_in, const float* u_
     const int rc = fk::drive_heun(be, B, 0, H, W, batch, fk::make_consts(params14, dt, dx), n_stim, t0, nsteps, exact,
                                   (float)((double)dt * 0.5));
     if (launches) *launches = be.launches_tile;
+    return rc;
+}
+
+// ---- fast Heun: the product's fk::drive_heun_fast (Euler kernels + folded closing pass) on the CPU backend
+namespace {
+struct EmuHeunBackend : EmuBackend {
+    int combines = 0;
+    int combine(const float* yv, const float* yw, const float* yu, const float* ev, const float* ew, const float* eu,
+                float* ov, float* ow, float* ou, long long n) {
+        ++combines;
+        for (long long i = 0; i < n; ++i) {
+            ov[i] = fmaf(0.5f, ev[i] - yv[i], yv[i]); ow[i] = fmaf(0.5f, ew[i] - yw[i], yw[i]); ou[i] = fmaf(0.5f, eu[i] - yu[i], yu[i]);
+        }
+        return 0;
+    }
+    int copy(float* dst, const float* src, long long n) { memcpy(dst, src, sizeof(float) * (size_t)n); return 0; }
+};
+}  // namespace
+
+// info (4 ints): tile launches, stream launches, wide launches, combine passes
+extern "C" int fk_emu_heun_fast(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                                const float* D, int H, int W, int batch, const float* params14, const EmuStim* stims, int n_stim,
+                                double t0, double t1, float dt, float dx, int fold, int force_stream, int* info) {
+    const size_t plane = (size_t)H * W, all = plane * batch;
+    std::vector<float> DX(plane), DY(plane), store(12 * all);
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) fk::dgrad_cell(D, H, W, dx, 1, 1, r, c, DX[(size_t)r * W + c], DY[(size_t)r * W + c]);
+    fk::HeunFastBuffers HB;
+    memset(&HB, 0, sizeof(HB));
+    HB.v_in = v_in; HB.w_in = w_in; HB.u_in = u_in; HB.v_out = v_out; HB.w_out = w_out; HB.u_out = u_out;
+    float* p = store.data();
+    HB.pv = p; HB.pw = p + all; HB.pu = p + 2 * all; p += 3 * all;
+    for (int a = 0; a < 3; ++a) { HB.s1[a] = p; p += all; }
+    for (int a = 0; a < 3; ++a) { HB.s2[a] = p; p += all; }
+    for (int a = 0; a < 3; ++a) { HB.s3[a] = p; p += all; }
+    HB.D = D; HB.DX = DX.data(); HB.DY = DY.data(); HB.stims = (const fk::StimDev*)stims;
+    EmuHeunBackend be;
+    const long long nsteps = fk::count_steps(t0, t1);
+    const char* why = "";
+    // force_stream: pretend the tissue is large (cta_threads / rows_per_cta chosen by the test make it streamable)
+    const int rc = fk::drive_heun_fast(be, HB, 0, H, W, batch, fk::make_consts(params14, dt, dx), (const fk::StimDev*)stims, n_stim,
+                                       t0, nsteps, 0, force_stream ? 32 : 0, force_stream ? 24 : 0, fold != 0, false, &why);
+    if (info) { info[0] = be.launches_tile; info[1] = be.launches_stream; info[2] = be.launches_wide; info[3] = be.combines; }
     return rc;
 }

@@ -291,3 +291,28 @@ def test_fused_heun_exact(shape, n):
     assert launches == n
     for a, b in zip(got, ref):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("shape,force_stream", [((64, 96), False), ((80, 128), True), ((37, 50), False)])
+def test_fast_heun_through_the_euler_kernels(shape, force_stream):
+    """fk_driver.h: drive_heun_fast -- y + (E(E(y)) - y) / 2 with E the wide / streaming Euler kernels: one two-step call
+    when no stimulus is active at t or t + 1, two single-step calls at the same counter otherwise; the closing pass folded
+    into the last launch's store gives the same bits as the separate combine pass; within the fast tolerance of the
+    oracle's literal Heun loop (cardiax/solve.py:73-85).  (37, 50): W % 4 != 0 -> general tiles + combine pass.)"""
+    st, D = common.smooth_case(shape, seed=4)
+    stim = [O.linear(shape, 0, 0.3, 20.0, O.Protocol(2, 2, 50))]
+    n = 7
+    ref = O.forward_heun(st, 0, n, O.PARAMSETS["3"], D, stim, 0.01, 0.01)
+    a, ia = emu.heun_fast(st, 0, n, O.PARAMSETS["3"], D, stim, 0.01, 0.01, fold=True, force_stream=force_stream)
+    b, ib = emu.heun_fast(st, 0, n, O.PARAMSETS["3"], D, stim, 0.01, 0.01, fold=False, force_stream=force_stream)
+    for x, y, r in zip(a, b, ref):
+        assert np.array_equal(x, y)
+        assert np.abs(x - r).max() <= 2e-5 * max(1.0, np.abs(r).max())
+    assert np.abs(a[2] - st.u).max() > 1e-3
+    assert ib["combine"] == n
+    if shape[1] % 4 == 0:
+        assert ia["combine"] == 0 and ia["tile"] == 0
+        # quiet steps t = 0, 4, 5, 6 -> one two-step call; t = 1, 2, 3 (stimulus active at t or t + 1) -> two one-step calls
+        assert (ia["stream"] if force_stream else ia["wide"]) == (4 * 1 + 3 * 2 if force_stream else 4 * 2 + 3 * 2)
+    else:
+        assert ia["combine"] == n and ia["tile"] > 0

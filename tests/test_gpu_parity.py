@@ -176,6 +176,16 @@ def test_heun_fast_through_the_euler_kernels_matches_exact_heun():
         for a, b in zip(fast, ref):
             assert float((a - b).abs().max()) <= TOL_FAST * max(1.0, float(b.abs().max()))
         assert float((fast.u - gstate.u).abs().max()) > 1e-3      # the stimulus at t = 2, 3 acted
+        # the closing pass folded into the last launch's store (default) == the separate combine pass (kernel = 1)
+        before = _lib.lib().fk_launch_count()
+        solve._forward_heun(gstate, 0, 6, P3, Dg, gst, 0.01, 0.01)
+        folded_launches = _lib.lib().fk_launch_count() - before
+        options.kernel = 1
+        before = _lib.lib().fk_launch_count()
+        unfolded = solve._forward_heun(gstate, 0, 6, P3, Dg, gst, 0.01, 0.01)
+        assert _lib.lib().fk_launch_count() - before == folded_launches + 6
+        options.kernel = 0
+        assert all(torch.equal(a, b) for a, b in zip(fast, unfolded))
 
 
 @pytest.mark.parametrize("pset", sorted(O.PARAMSETS))
