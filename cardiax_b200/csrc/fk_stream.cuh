@@ -6,7 +6,7 @@
 
 namespace fk {
 
-template <bool EXACT, int T, bool UNI>
+template <bool EXACT, int T, bool UNI, bool HEUN = false>
 __global__ void __launch_bounds__(T == 2 ? 192 : 256, T <= 2 ? 2 : 1)
 fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ StreamGeom G) {
     extern __shared__ __align__(16) float fk_stream_smem[];
@@ -36,7 +36,7 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         i = FK_WARM;
     }
     for (; i < nfill; ++i) {   // pipeline fill (and launches with an active stimulus): fully conditional body
-        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+        stream_iter<EXACT, T, -1, UNI, true, 4, HEUN>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
         __syncthreads();
     }
     // steady state: every stage consumes and emits one row per iteration; unrolled U-fold so that every ring slot is a
@@ -50,12 +50,12 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
 #define FK_STEADY_LOOP(EDGE)                                                                                           \
     for (; i < i_end; i += U) {                                                                                        \
         const StreamBody<T> Y = stream_body_at<T>(tb, i);                                                              \
-        stream_iter<EXACT, T, 0, UNI, EDGE, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
-        stream_iter<EXACT, T, 1, UNI, EDGE, U>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
+        stream_iter<EXACT, T, 0, UNI, EDGE, U, HEUN>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
+        stream_iter<EXACT, T, 1, UNI, EDGE, U, HEUN>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
         if (U == 4) {                                                                                                  \
-            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U>(A, C, R, tb, i + 2, tid,                               \
+            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U, HEUN>(A, C, R, tb, i + 2, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 2 : 0>(Y), bar);      \
-            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U>(A, C, R, tb, i + 3, tid,                               \
+            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U, HEUN>(A, C, R, tb, i + 3, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 3 : 1>(Y), bar);      \
         }                                                                                                              \
     }
@@ -70,7 +70,7 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         StreamCta Ct;
         stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, Ct);
         for (; i < Ct.niter; ++i) {
-            stream_iter<EXACT, T, -1, UNI, true>(A, Ct, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+            stream_iter<EXACT, T, -1, UNI, true, 4, HEUN>(A, Ct, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
             __syncthreads();
         }
     }
@@ -86,6 +86,21 @@ inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cu
         attr_set = P.smem_bytes;
     }
     dim3 grid(P.G.nstrips * P.G.nchunks, batch);
+    if (A.hy_u) {   // fast Heun: the instantiation whose last level stores y + (E - y) / 2 (fast numerics, T <= 2 only)
+        if constexpr (!EXACT && T <= 2) {
+            static long long attr_set_h = 0;
+            if (P.smem_bytes > attr_set_h && attr_set_h < 227 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI, true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes);
+                if (e != cudaSuccess) return (int)e;
+                attr_set_h = P.smem_bytes;
+            }
+            fk_stream_kernel<EXACT, T, UNI, true><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
+            return (int)cudaGetLastError();
+        } else {
+            return -2;   // not built
+        }
+    }
     fk_stream_kernel<EXACT, T, UNI><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
     return (int)cudaGetLastError();
 }

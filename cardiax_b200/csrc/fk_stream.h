@@ -511,11 +511,18 @@ static_assert(FK_PF == 3, "stream_ptrs_phase<U = 2> spells the prefetch slots ou
 //            read, arrive after the last shared-memory write.
 //   UNI      one constant diffusivity (C.Dc, C.DXc, C.DYc) instead of three maps
 //   EDGE     this CTA's strip may contain the tissue's first / last column
-template <bool EXACT, int T, int PH, bool UNI, bool EDGE, int U = 4>
+template <bool EXACT, int T, int PH, bool UNI, bool EDGE, int U = 4, bool HEUN = false>
 FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid,
                        const StreamPtrs& P, float* bar) {
     typedef StreamLay<T> L;
     constexpr bool ST = PH >= 0;
+    // fast Heun's closing pass in the last level's store (TileArgs::hy_*): its own kernel instantiation on the device --
+    // even a uniform run-time branch here cost the plain Euler kernel 7 % -- a run-time flag in the CPU emulation
+#if defined(__CUDA_ARCH__)
+    constexpr bool heun = HEUN;
+#else
+    const bool heun = A.hy_u != nullptr;
+#endif
     // positions of the u_x window rows (rho-2, rho-1, rho, rho+1) in R.GX[s]: U = 4 rotates by one per phase; U = 2
     // keeps the rows of each parity in a pair of register sets and moves one set per phase
     constexpr int W0 = !ST ? 0 : PH;
@@ -695,7 +702,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
             }
             if (s == T - 1) {
                 if (c >= C.out_c0 && c < C.out_c1 && rho >= C.r0) {   // (rho < r0: the unrolled body while it fills)
-                    if (A.hy_u) {   // fast Heun: this launch computed E(E(y)); store y + (E(E(y)) - y) / 2 (y: an L2 hit)
+                    if (heun) {   // fast Heun: this launch computed E(E(y)); store y + (E(E(y)) - y) / 2 (y: an L2 hit)
                         float y4[4];
                         unpack4(ldg4(A.hy_u + grow), y4); heun_fold4(y4, un);
                         unpack4(ldg4(A.hy_v + grow), y4); heun_fold4(y4, vn);
@@ -735,7 +742,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                 un0[k] = euler<EXACT>(R.sv[s][0][k], Num<EXACT>::add(del_u, R.sv[s][3][k]), A.K.dt);
             }
             if (s == T - 1) {
-                if (A.hy_u) {
+                if (heun) {
                     float y4[4];
                     unpack4(ldg4(A.hy_u + grow0), y4); heun_fold4(y4, un0);
                 }

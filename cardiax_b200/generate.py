@@ -140,6 +140,13 @@ def sequence(start, stop, step, dt, dx, params, diffusivity, stimuli, filename, 
                        use_memory=use_memory, plot_while=False)
 
 
+def shard(seeds, rank, world_size):
+    """Contiguous share of ``seeds`` for ``rank``: ceil(n / world_size) each, the last ranks may get fewer (or none)."""
+    seeds = list(seeds)
+    per = (len(seeds) + world_size - 1) // world_size
+    return seeds[rank * per:(rank + 1) * per]
+
+
 class _Scatter:
     """``dset[t] = (3, batch, H', W')`` -> ``states`` dataset of every member file."""
 
@@ -156,9 +163,7 @@ def ensemble(seeds, params, filepattern, shape=(256, 256), n_stimuli=3, start=0,
     """BASELINE config 4: ``random_sequence`` for every seed in ``seeds`` -- this rank's contiguous share of them --
     stepped ``chunk`` tissues at a time as one batch (no communication between ranks).  ``filepattern % seed`` names
     each member's file.  Returns the seeds this rank generated."""
-    seeds = list(seeds)
-    per = (len(seeds) + world_size - 1) // world_size
-    mine = seeds[rank * per:(rank + 1) * per]
+    mine = shard(seeds, rank, world_size)
     dev = solve._device()
     out_shape = tuple(reshape) if reshape is not None else tuple(shape)
     cps = np.arange(convert.ms_to_units(start, dt), convert.ms_to_units(stop, dt), convert.ms_to_units(step, dt))

@@ -156,8 +156,14 @@ def add_stimuli(hdf5, stimuli, shape=None):
 def add_state(dset, state, t, shape=None):
     """io.py:67-72 -- synchronous (resize +) store of one snapshot; see AsyncSnapshotWriter for the overlapped path."""
     if shape is not None:
-        array = torch.stack(tuple(state))
-        state = imresize(array, tuple(shape[-2:]))
+        parts = tuple(state)
+        if all(isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 for x in parts) and \
+                tuple(parts[0].shape) != tuple(shape[-2:]):
+            H, W = parts[0].shape      # v, w, u resized into one packed (3, H', W') array by ONE launch, no stack
+            state = _resize_planes([x.to(torch.float32).contiguous() for x in parts], H, W, tuple(shape[-2:]))
+        else:
+            state = imresize(torch.stack([torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+                                          for x in parts]), tuple(shape[-2:]))
     dset[t] = _to_numpy(state)
     return True
 

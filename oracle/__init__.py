@@ -11,6 +11,7 @@ vectors for u/v/w.  The oracle is pinned on the only known-answer vector the
 reference has (the stimulus schedule of ``tests/macro/stimulate_test.py:16-19``)
 and on the ``tests/unittests/stimulus_test.py:23`` expectation; see DESIGN.md.
 """
+from . import fk_oracle_ext  # noqa: F401  (odeint / resize / electrogram restatements, SURVEY 8f rows)
 from .fk_oracle import (  # noqa: F401
     Params, State, Protocol, Stimulus,
     init, gradient, stimulate, stimulus_active, step, step_euler, forward_euler, step_heun, forward_heun,

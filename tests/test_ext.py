@@ -107,6 +107,15 @@ def test_random_generators_follow_the_reference_ranges():
     assert 0 <= int(p.start[0]) < 1000 and p.start.shape == (1,)
 
 
+def test_ensemble_sharding_covers_every_seed_once():
+    from cardiax_b200 import generate
+    for n, world in ((1024, 8), (1024, 1), (5, 2), (3, 8), (0, 4), (17, 4)):
+        parts = [generate.shard(range(n), r, world) for r in range(world)]
+        assert sum(parts, []) == list(range(n))                 # contiguous, in order, nothing twice
+        assert max(len(p) for p in parts) == -(-n // world)     # ceil(n / world) per rank, the tail gets the rest
+    assert [len(generate.shard(range(1024), r, 8)) for r in range(8)] == [128] * 8     # BASELINE config 4
+
+
 # --------------------------------------------------------------------------- GPU
 def _gpu_stimuli(stim):
     from cardiax_b200 import stimulus
