@@ -50,20 +50,38 @@ class _Dataset:
 
 
 class NpzStore:
-    """Minimal stand-in for the part of ``h5py.File`` the reference uses; saved as ``<path>.npz`` on close."""
+    """Minimal stand-in for the part of ``h5py.File`` the reference uses; saved as ``<path>.npz`` on close.  Datasets
+    created by shape above ``MEMMAP_BYTES`` (the ``states`` of a long run: 1000 snapshots of 3 x 256^2 are 786 MB, and
+    an ensemble holds one per member) live in disk-backed ``<path>.<name>.npy`` memory maps next to the ``.npz``, which
+    then only lists them -- like HDF5, the run's snapshots never have to fit in host memory."""
+    MEMMAP_BYTES = 64 << 20
 
     def __init__(self, path, mode="w"):
         self.path = path if path.endswith(".npz") else path + ".npz"
         self.data = {}
+        self.external = {}
         if mode == "r":
             with np.load(self.path, allow_pickle=False) as f:
-                self.data = {k: _Dataset(f[k]) for k in f.files}
+                for k in f.files:
+                    if k == "__external__":
+                        for item in f[k]:
+                            name, fname = str(item).split("=", 1)
+                            self.data[name] = _Dataset(np.load(os.path.join(os.path.dirname(self.path), fname), mmap_mode="r"))
+                    else:
+                        self.data[k] = _Dataset(f[k])
 
     def create_dataset(self, name, shape=None, dtype=None, data=None):
         if data is not None:
             arr = np.array(_to_numpy(data), dtype=dtype)
         else:
-            arr = np.zeros(shape, dtype=dtype or "float32")
+            dt = np.dtype(dtype or "float32")
+            if int(np.prod(shape, dtype=np.int64)) * dt.itemsize > self.MEMMAP_BYTES:
+                fname = os.path.basename(self.path)[:-4] + "." + name.replace("/", "_") + ".npy"
+                arr = np.lib.format.open_memmap(os.path.join(os.path.dirname(self.path), fname), mode="w+", dtype=dt,
+                                                shape=tuple(int(x) for x in shape))
+                self.external[name] = fname
+            else:
+                arr = np.zeros(shape, dtype=dt)
         self.data[name] = _Dataset(arr)
         return self.data[name]
 
@@ -82,7 +100,12 @@ class NpzStore:
         return iter(self.data)
 
     def close(self):
-        np.savez(self.path, **{k: v.array for k, v in self.data.items()})
+        small = {k: v.array for k, v in self.data.items() if k not in self.external}
+        for k in self.external:
+            self.data[k].array.flush()
+        if self.external:
+            small["__external__"] = np.array(["%s=%s" % kv for kv in sorted(self.external.items())])
+        np.savez(self.path, **small)
 
     def __enter__(self):
         return self

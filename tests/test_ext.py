@@ -85,6 +85,19 @@ def test_electrogram_body_matches_the_oracle():
     assert emu.electrogram(one, (3, 0)) == 10.0 and X.electrogram(one, (3, 0)) == 10.0
 
 
+def test_plot_calls_degrade_gracefully_without_matplotlib():
+    """solve.forward(plot_while=True) / generate.sequence(plot_while=True) call cardiax.plot (solve.py:179-186, 218-220):
+    visualisation is out of scope, but the calls must not break a run on a box without matplotlib."""
+    import warnings
+    import cardiax
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        st = O.init((8, 8))
+        for out in (cardiax.plot.plot_state(st), cardiax.plot.plot_diffusivity(np.ones((8, 8))),
+                    cardiax.plot.plot_stimuli([O.linear((8, 8), 0, 0.5, 1.0, O.Protocol(0, 2, 10))]), cardiax.plot.plot_stimuli([])):
+            assert out is None or len(out) == 2
+
+
 # --------------------------------------------------------------------------- generate (host logic)
 def test_random_generators_follow_the_reference_ranges():
     from cardiax_b200 import generate
@@ -174,7 +187,8 @@ def test_forward_with_the_dormandprince_integrator():
     try:
         options.numerics, options.ode_rtol, options.ode_atol, options.verbose = "exact", 1e-5, 1e-5, False
         cps = np.arange(0, 4, 1)
-        out = solve.forward(state, cps, O.PARAMSETS["5"], Dg, [], 0.01, 0.01, integrator=solve.TimeIntegrator.DORMANDPRINCE)
+        out = solve.forward(state, cps, O.PARAMSETS["5"], Dg, [], 0.01, 0.01, integrator=solve.TimeIntegrator.DORMANDPRINCE,
+                            plot_while=True)
         assert isinstance(out, solve.State) and tuple(out.u.shape) == (4,) + shape
         ref = X.odeint_dopri5(st, cps, O.PARAMSETS["5"], D, [], 0.01, rtol=1e-5, atol=1e-5)
         for a, b in zip(out, ref):

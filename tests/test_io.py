@@ -125,3 +125,21 @@ def test_async_writer_equals_synchronous_snapshots(tmp_path):
     ref = solve._forward_euler(solve.init(shape), 0, 30, O.PARAMSETS["3"], D, [], 0.01, 0.01)
     assert all(torch.equal(a, b) for a, b in zip(final, ref))
     assert np.allclose(g["states"][2], io.imresize(torch.stack(tuple(ref)), out).cpu().numpy())
+
+
+def test_npz_store_keeps_large_datasets_on_disk(tmp_path, monkeypatch):
+    """Without h5py the snapshot store must not hold a long run (or an ensemble's worth of them) in host memory: datasets
+    above the threshold are disk-backed memory maps next to the .npz and read back lazily."""
+    from cardiax_b200 import io
+    monkeypatch.setattr(io, "_HAVE_H5", False)
+    monkeypatch.setattr(io.NpzStore, "MEMMAP_BYTES", 1024)
+    path = os.path.join(tmp_path, "run", "big.hdf5")
+    f = io.init(path, (16, 16), n_iter=5, n_stimuli=1)          # states: 5 * 3 * 256 * 4 B > 1 KiB -> memory map
+    assert isinstance(f["states"].array, np.memmap) and not isinstance(f["stimuli"].array, np.memmap)
+    io.add_state(f["states"], [np.full((16, 16), float(i + 1), np.float32) for i in range(3)], 2)
+    io.add_diffusivity(f, np.full((16, 16), 1e-3, np.float32))
+    f.close()
+    assert os.path.exists(os.path.join(tmp_path, "run", "big.hdf5.states.npy"))
+    g = io._open(path, "r")
+    assert g["states"].shape == (5, 3, 16, 16) and np.all(g["states"][2][1] == 2.0) and np.all(g["states"][0] == 0.0)
+    assert np.allclose(io.load_diffusivity(path), 1e-3)
