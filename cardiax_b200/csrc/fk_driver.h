@@ -75,13 +75,21 @@ inline void add_region(TileArgs& A, int R0, int R1, int C0, int C1, int th, int 
     R.tw = tw < C1 - C0 ? tw : C1 - C0;
 }
 
-inline void pick_tile(int rows, int W, int T, int& th, int& tw) {
+inline void pick_tile(int rows, int W, int T, int batch, int sms, int& th, int& tw) {
     // whole-tissue coverage by general tiles: 32 x 64 output cells (+ 4T apron) keeps two CTAs per SM at T <= 2
     th = 32; tw = 64;
     while (tile_smem_floats(th + 1, tw + 1, T) * 4 > 110 * 1024 && th > 8) th -= 8;
     while (tile_smem_floats(th + 1, tw + 1, T) * 4 > 220 * 1024 && tw > 16) tw -= 16;
     if (th > rows) th = rows;
     if (tw > W) tw = W;
+    // a tissue that 32 x 64 tiles cannot spread over the machine (256^2: 32 tiles for 148 SMs) gets smaller ones: a tile
+    // launch there is latency bound (solve.step, the Dormand-Prince stages, exact Heun), not apron bound
+    auto count = [&]() { return (long long)tile_count(rows, th) * tile_count(W, tw) * batch; };
+    while (count() < sms && (th > 8 || tw > 32)) {
+        if (th >= tw / 2 && th > 8) th = (th + 1) / 2 < 8 ? 8 : (th + 1) / 2;
+        else if (tw > 32) tw = tw / 2 < 32 ? 32 : tw / 2;
+        else th = (th + 1) / 2 < 8 ? 8 : (th + 1) / 2;
+    }
 }
 
 // Backend: int tiles(TileArgs&, int exact, int batch, bool side);
@@ -213,7 +221,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             bool ok;
             rows(T, R0, R1, ok);
             int th, tw;
-            pick_tile(R1 - R0, W, T, th, tw);
+            pick_tile(R1 - R0, W, T, batch, be.num_sms(), th, tw);
             A.nreg = 0;
             add_region(A, R0, R1, 0, W, th, tw);
             rc = be.tiles(A, opt.exact, batch, false);

@@ -43,7 +43,8 @@ for shp, numerics, kernel in (((40, 72), "exact", "fk_tile_kernel"), ((64, 96), 
     if shp[0] < 1000:
         ref = O.forward_heun(st, 0, n, P3, D, stim, 0.01, 0.01)
         for a, b in zip(out, ref):
-            assert np.array_equal(a.cpu().numpy(), b) if numerics == "exact" else np.abs(a.cpu().numpy() - b).max() < 2e-5
+            assert np.array_equal(a.cpu().numpy(), b) if numerics == "exact" else \
+                np.abs(a.cpu().numpy() - b).max() <= 2e-5 * max(1.0, float(np.abs(b).max()))
     else:
         assert bool(torch.isfinite(out.u).all())
     print("ok heun", shp, numerics, kernel, flush=True)
