@@ -71,6 +71,7 @@ def build(force=False, verbose=False):
             jobs.append((os.path.join(objdir, "fk_stream_T%d_E%d.o" % (t, e)),
                          ["-DFK_TU_T=%d" % t, "-DFK_TU_EXACT=%d" % e, "-c", os.path.join(CSRC, "fk_stream_tu.cu")]))
     ptxas = ["-Xptxas", "-v"] if verbose else []
+    ptxas += os.environ.get("FK_EXTRA_NVCC", "").split()   # development: e.g. FK_EXTRA_NVCC="-DFK_MAP_LATE=1" for an A/B build
     aux_deps = ["fk_aux.cu", "fk_aux.cuh", "fk_aux.h", "fk_ode.h", "fk_core.h"]
     res_deps = [d for d in _SOURCES if d not in ("fk_aux.cu", "fk_aux.cuh", "fk_aux.h", "fk_ode.h")]
     stream_deps = ["fk_stream_tu.cu", "fk_stream.cuh", "fk_stream.h", "fk_tile.h", "fk_core.h"]

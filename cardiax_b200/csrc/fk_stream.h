@@ -30,6 +30,30 @@ struct alignas(16) F4 { float x, y, z, w; };
 FK_HD F2 ld2(const float* p) { return *reinterpret_cast<const F2*>(p); }
 FK_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
 // read-only global data (diffusivity maps, stimulus fields): non-coherent path on the device
+#ifndef FK_MAP_PF
+#define FK_MAP_PF 3
+#endif
+#ifndef FK_MAP_LATE
+#define FK_MAP_LATE 1
+#endif
+#ifndef FK_MAP_PF1
+#define FK_MAP_PF1 0
+#endif
+FK_HD void pf_l1(const float* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+FK_HD void pf_l2(const float* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 FK_HD F4 ldg4(const float* p) {
 #if defined(__CUDA_ARCH__)
     const float4 t = __ldg(reinterpret_cast<const float4*>(p));
@@ -570,6 +594,9 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
     }
     // heterogeneous diffusivity: the three maps at the rows the stages emit, requested before the wait as well
     float Dm[UNI ? 1 : T][4], DXm[UNI ? 1 : T][4], DYm[UNI ? 1 : T][4];
+    bool need_map[T];
+#pragma unroll
+    for (int s = 0; s < T; ++s) need_map[s] = false;
     if (!UNI) {
 #pragma unroll
         for (int s = 0; s < T; ++s) {
@@ -580,11 +607,28 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                                                        rho < (C.bot ? A.H : C.r1 + 4 * (T - 1 - s))));
 #pragma unroll
             for (int k = 0; k < 4; ++k) Dm[s][k] = DXm[s][k] = DYm[s][k] = 0.0f;
+            need_map[s] = need;
             if (need) {
                 const long long back = 4LL * (s + 1) * A.W;
+#if !FK_MAP_LATE
                 unpack4(ldg4(A.D + gd - back), Dm[s]);
                 unpack4(ldg4(A.DX + gd - back), DXm[s]);
                 unpack4(ldg4(A.DY + gd - back), DYm[s]);
+#endif
+#if FK_MAP_PF
+                // the maps come from DRAM once (the later stages re-read them from L2): ask L2 for the rows the first
+                // stage emits FK_MAP_PF iterations from now -- no register is held, unlike a load issued that early
+                if (s == 0 && rho + FK_MAP_PF < A.H) {
+                    const long long ahead = (long long)FK_MAP_PF * A.W - back;
+                    pf_l2(A.D + gd + ahead); pf_l2(A.DX + gd + ahead); pf_l2(A.DY + gd + ahead);
+                }
+#endif
+#if FK_MAP_PF1
+                if (rho + FK_MAP_PF1 < A.H) {
+                    const long long ahead1 = (long long)FK_MAP_PF1 * A.W - back;
+                    pf_l1(A.D + gd + ahead1); pf_l1(A.DX + gd + ahead1); pf_l1(A.DY + gd + ahead1);
+                }
+#endif
             }
         }
     }
@@ -672,6 +716,15 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                     for (int k = 0; k < 4; ++k) DXv[k] = C.DXcB;
                 }
             } else {
+#if FK_MAP_LATE
+                // loaded here, stage by stage (L2 hits thanks to the prefetch above), so that only one stage's maps are
+                // live at a time
+                if (need_map[s]) {
+                    unpack4(ldg4(A.D + gd - back), Dm[s]);
+                    unpack4(ldg4(A.DX + gd - back), DXm[s]);
+                    unpack4(ldg4(A.DY + gd - back), DYm[s]);
+                }
+#endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { Dv[k] = Dm[UNI ? 0 : s][k]; DXv[k] = DXm[UNI ? 0 : s][k]; DYv[k] = DYm[UNI ? 0 : s][k]; }
             }
