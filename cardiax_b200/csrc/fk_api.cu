@@ -598,7 +598,8 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
         hb.st = st; hb.blocks = blocks;
         rc = fk::drive_heun_fast(hb, HB, d_batched, H, W, batch, K, (const fk::StimDev*)stimuli, n_stim, t0, nsteps,
                                  opt.uniform_diffusivity, opt.cta_threads, opt.rows_per_cta, /*fold=*/opt.kernel != 1,
-                                 /*try_resident=*/opt.kernel == 4, &why);
+                                 /*try_resident=*/opt.kernel == 4,   // opt-in: 24-32 us per step vs 16.5 with two wide launches
+                                 &why);
         return rc ? (why[0] ? fail(rc, "%s", why) : rc) : 0;
     }
     if (opt.steps_per_launch == 2 || (opt.steps_per_launch == 0 && (long long)H * W * batch < (1LL << 20))) {
