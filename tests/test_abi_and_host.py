@@ -45,7 +45,7 @@ def test_solver_refuses_to_run_without_cuda():
 
 
 def test_product_never_imports_the_oracle():
-    for base in ("cardiax_b200", "cardiax"):
+    for base in ("cardiax_b200", "cardiax", "deepx"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
             for f in files:
                 if f.endswith((".py", ".cu", ".h", ".cuh")):
