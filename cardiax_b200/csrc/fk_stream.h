@@ -36,6 +36,8 @@ FK_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
 #ifndef FK_MAP_LATE
 #define FK_MAP_LATE 1
 #endif
+// which stages load their maps at the point of use: 0 none (all up front), 1 all, 2 all but the first, 3 the first only
+#define FK_MAP_IS_LATE(s) (FK_MAP_LATE == 1 || (FK_MAP_LATE == 2 && (s) > 0) || (FK_MAP_LATE == 3 && (s) == 0))
 #ifndef FK_MAP_PF1
 #define FK_MAP_PF1 0
 #endif
@@ -610,11 +612,11 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
             need_map[s] = need;
             if (need) {
                 const long long back = 4LL * (s + 1) * A.W;
-#if !FK_MAP_LATE
-                unpack4(ldg4(A.D + gd - back), Dm[s]);
-                unpack4(ldg4(A.DX + gd - back), DXm[s]);
-                unpack4(ldg4(A.DY + gd - back), DYm[s]);
-#endif
+                if (!FK_MAP_IS_LATE(s)) {
+                    unpack4(ldg4(A.D + gd - back), Dm[s]);
+                    unpack4(ldg4(A.DX + gd - back), DXm[s]);
+                    unpack4(ldg4(A.DY + gd - back), DYm[s]);
+                }
 #if FK_MAP_PF
                 // the maps come from DRAM once (the later stages re-read them from L2): ask L2 for the rows the first
                 // stage emits FK_MAP_PF iterations from now -- no register is held, unlike a load issued that early
@@ -716,15 +718,13 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                     for (int k = 0; k < 4; ++k) DXv[k] = C.DXcB;
                 }
             } else {
-#if FK_MAP_LATE
                 // loaded here, stage by stage (L2 hits thanks to the prefetch above), so that only one stage's maps are
                 // live at a time
-                if (need_map[s]) {
+                if (FK_MAP_IS_LATE(s) && need_map[s]) {
                     unpack4(ldg4(A.D + gd - back), Dm[s]);
                     unpack4(ldg4(A.DX + gd - back), DXm[s]);
                     unpack4(ldg4(A.DY + gd - back), DYm[s]);
                 }
-#endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { Dv[k] = Dm[UNI ? 0 : s][k]; DXv[k] = DXm[UNI ? 0 : s][k]; DYv[k] = DYm[UNI ? 0 : s][k]; }
             }
