@@ -33,6 +33,35 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().fk_workspace_bytes(4096, 4096, 1, 0, 0) >= 5 * 4096 * 4096 * 4
 
 
+def test_new_entry_points_validate_their_arguments_before_touching_the_device():
+    """fk_odeint_dopri5 / fk_resize_bilinear / fk_electrogram (the SURVEY 8f rows): argument errors come back as negative
+    codes with a message, like the rest of the ABI; the workspace queries are pure host arithmetic."""
+    from cardiax_b200 import _lib
+    L = _lib.lib()
+    P = _lib.FkParams(*([1.0] * 14))
+    ts = (ctypes.c_float * 2)(0.0, 1.0)
+    rc = L.fk_odeint_dopri5(None, None, None, None, None, None, None, 0, 16, 16, 1, ctypes.byref(P), None, 0, ts, 2, 0.01, 1e-5,
+                            1e-5, float("inf"), None, None, 0, None, None)
+    assert rc < 0 and b"NULL" in L.fk_last_error()
+    rc = L.fk_odeint_dopri5(None, None, None, None, None, None, None, 0, 2, 2, 1, ctypes.byref(P), None, 0, ts, 2, 0.01, 1e-5,
+                            1e-5, float("inf"), None, None, 0, None, None)
+    assert rc < 0 and b"3 x 3" in L.fk_last_error()
+    base = L.fk_workspace_bytes(64, 96, 1, 2, 0)
+    assert L.fk_dopri5_workspace_bytes(64, 96, 1, 2, 0) >= base + 60 * 64 * 96 * 4      # 20 States of scratch
+    assert L.fk_heun_workspace_bytes(64, 96, 1, 2, 0) >= base + 9 * 64 * 96 * 4
+    assert L.fk_resize_bilinear(None, 3, 8, 8, None, 4, 4, None, 0, 0, None) < 0 and b"NULL" in L.fk_last_error()
+    one = (ctypes.c_void_p * 1)(8)
+    assert L.fk_resize_bilinear(one, 1, 0, 8, ctypes.c_void_p(8), 4, 4, ctypes.c_void_p(8), 1 << 20, 0, None) < 0
+    assert b"shape" in L.fk_last_error()
+    assert L.fk_resize_bilinear(one, 1, 8, 8, ctypes.c_void_p(8), 4, 4, ctypes.c_void_p(8), 16, 0, None) == -4   # workspace too small
+    need = L.fk_resize_workspace_bytes(1200, 1200, 256, 256, 3)
+    # two index tables + tap-major weights: K = floor(2 * 1200 / 256) + 2 = 11 taps per output index and axis
+    assert 2 * (256 * 4 + 256 * 11 * 4) <= need <= 2 * (256 * 4 + 256 * 11 * 4) + 5 * 256
+    assert L.fk_resize_workspace_bytes(0, 8, 4, 4, 1) == 0
+    assert L.fk_electrogram(None, 1, 8, 8, 0.0, 0.0, None, None) < 0
+    assert L.fk_electrogram(ctypes.c_void_p(8), 0, 8, 8, 0.0, 0.0, ctypes.c_void_p(8), None) < 0
+
+
 def test_solver_refuses_to_run_without_cuda():
     import torch
     if torch.cuda.is_available():
