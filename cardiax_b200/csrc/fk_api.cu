@@ -695,17 +695,6 @@ int fk_odeint_dopri5(const float* v0, const float* w0, const float* u0, float* v
             const int rc = fk::drive_euler(be, Bf, d_batched, H, W, batch, K, n_stim, (double)t, 1, o, 1, &why);
             return rc ? (why[0] ? fail(rc, "%s", why) : rc) : 0;
         }
-        int rhs_stage(int i, const fk::P3& y, const fk::P3* k, const float* beta_row, float dt, const fk::P3& out, float t) {
-            fk::TileOde O;
-            memset(&O, 0, sizeof(O));
-            O.n = i; O.exact = exact; O.dt = dt;
-            for (int s = 0; s < 6; ++s) { O.c[s] = beta_row[s]; O.kv[s] = k[s].a[0]; O.kw[s] = k[s].a[1]; O.ku[s] = k[s].a[2]; }
-            fk::DriveBuffers Bf = fk::DriveBuffers();
-            Bf.v_in = y.a[0]; Bf.w_in = y.a[1]; Bf.u_in = y.a[2]; Bf.v_out = out.a[0]; Bf.w_out = out.a[1]; Bf.u_out = out.a[2];
-            Bf.D = D; Bf.DX = DX; Bf.DY = DY; Bf.stims = stims; Bf.ode = &O;
-            const int rc = fk::drive_euler(be, Bf, d_batched, H, W, batch, K, n_stim, (double)t, 1, o, 1, &why);
-            return rc ? (why[0] ? fail(rc, "%s", why) : rc) : 0;
-        }
         int copy(const fk::P3& dst, long long off, const fk::P3& src) { return fk::launch_ode_copy(dst, off, src, n, be.st); }
         int init_norms(const fk::P3& y, const fk::P3& f, float rtol, float atol, double* s2) {
             return fk::launch_ode_init_norms(exact, y, f, rtol, atol, n, S, s2, be.st);
@@ -733,10 +722,7 @@ int fk_odeint_dopri5(const float* v0, const float* w0, const float* u0, float* v
     be.d_batched = d_batched; be.H = H; be.W = W; be.batch = batch; be.n_stim = n_stim; be.exact = opt.exact;
     be.n = B.n; be.why = "";
     fk::OdeStats S = {0, 0, 0};
-    // stage fused into the right-hand-side launch's load: opt-in (steps_per_launch = 2).  Measured against the separate
-    // stage pass: 263 vs 307 us per attempt at 512^2, but 260 vs 239 at 256^2 and 2695 vs 684 at 1024^2 -- every tile
-    // re-reads up to seven arrays for its apron cells, which costs more than the six launches it saves
-    rc = fk::drive_dopri5(be, B, n_ts, ts, rtol, atol, mxstep, &S, /*fuse=*/opt.steps_per_launch == 2);
+    rc = fk::drive_dopri5(be, B, n_ts, ts, rtol, atol, mxstep, &S);
     if (rc) return rc;
     if (stats3) { stats3[0] = S.attempts; stats3[1] = S.accepted; stats3[2] = S.rhs_evals; }
     return 0;

@@ -32,7 +32,6 @@ struct DriveBuffers {
     const StimDev* stims;           // device/emulated copy of the stimulus table, or null
     u64* xchg;                      // resident kernel: mailboxes (zeroed by the backend), xchg_bytes long, or null
     long long xchg_bytes;
-    const TileOde* ode;                // rhs_mode: Dormand-Prince stage fused into the launch's load (or null)
     const float *hy_v, *hy_w, *hy_u;   // fast Heun: y of the step whose E(E(y)) this call computes, or null; applied by
     bool* hy_folded;                   // the call's last launch if it is a streaming / wide one (*hy_folded says so)
 };
@@ -178,7 +177,6 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     A.H = H; A.W = W;
     A.phys_top = opt.phys_top; A.phys_bot = opt.phys_bottom; A.phys_left = 1; A.phys_right = 1;
     A.rhs_mode = rhs_mode;
-    if (rhs_mode && B.ode) A.ode = *B.ode;
     A.K = K;
     A.stims = n_stim ? B.stims : nullptr;
     A.n_stim = n_stim;

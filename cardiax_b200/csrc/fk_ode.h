@@ -49,6 +49,7 @@ inline float optimal_step_size(float last_step, float mean_error_ratio) {
     const float hi = div(1.0f, dfactor);
     if (hi < factor) factor = hi;                       // jnp.minimum(.., 1 / dfactor)
     if (f32(1.0 / 10.0) > factor) factor = f32(1.0 / 10.0);   // jnp.maximum(1 / ifactor, ..)
+    if (factor != factor) factor = NAN;
     return mean_error_ratio == 0.0f ? mul(last_step, ifactor) : div(last_step, factor);
 }
 }  // namespace ode
@@ -59,14 +60,11 @@ inline float optimal_step_size(float last_step, float mean_error_ratio) {
 //   int init_norms(const P3& y, const P3& f, float rtol, float atol, double* sumsq2)   sum (y/scale)^2, sum (f/scale)^2
 //   int axpy(const P3& y, float h, const P3& f, const P3& out)      out = y + h f
 //   int diff_norm(const P3& f1, const P3& f0, const P3& y, float rtol, float atol, double* sumsq)
-//   int stage(int i, const P3& y, const P3* k, float dt, const P3& ys)          ys = y + dt * dot(beta[i-1], k)
-//   int rhs_stage(int i, const P3& y, const P3* k, const float* beta_row, float dt, const P3& out, float t)
-//                                                                   out = step(y + dt * dot(beta_row, k), t) in ONE launch
+//   int stage(int i, const P3& y, const P3* k, float dt, const P3& ys)
 //   int finish(const P3& y, const P3* k, float dt, float rtol, float atol, const P3& yn, const P3* c, double* sum)
 //   int interp(const P3* c, float r, const P3& out, long long off)
 template <class BE>
-int drive_dopri5(BE& be, OdeBuffers& B, int n_ts, const float* ts, float rtol, float atol, double mxstep, OdeStats* stats,
-                 bool fuse = true) {
+int drive_dopri5(BE& be, OdeBuffers& B, int n_ts, const float* ts, float rtol, float atol, double mxstep, OdeStats* stats) {
     using namespace ode;
     const Dopri T = make_dopri();
     OdeStats S = {0, 0, 0};
@@ -107,12 +105,8 @@ int drive_dopri5(BE& be, OdeBuffers& B, int n_ts, const float* ts, float rtol, f
             // runge_kutta_step
             for (int s = 1; s < 7; ++s) {
                 const float ti = add(t, mul(dt, T.alpha[s - 1]));
-                if (fuse) {   // the right-hand-side launch builds y + dt * dot(beta[s-1], k) while it loads its tile
-                    if ((rc = be.rhs_stage(s, B.y, B.k, T.beta[s - 1], dt, B.k[s], ti))) return rc;
-                } else {
-                    if ((rc = be.stage(s, B.y, B.k, dt, B.ys))) return rc;
-                    if ((rc = be.rhs(B.ys, B.k[s], ti))) return rc;
-                }
+                if ((rc = be.stage(s, B.y, B.k, dt, B.ys))) return rc;
+                if ((rc = be.rhs(B.ys, B.k[s], ti))) return rc;
                 ++S.rhs_evals;
             }
             double sum;

@@ -13,7 +13,6 @@
 // tests/emu calls the same phases with one emulated thread.
 #pragma once
 #include "fk_core.h"
-#include "fk_aux.h"
 
 namespace fk {
 
@@ -22,16 +21,6 @@ struct TileRegion {  // a rectangle of output cells cut into th x tw tiles
     int th, tw;
     int ntr, ntc;    // tile counts
     int first;       // index of this region's first tile in the launch
-};
-
-// Dormand-Prince stage fused into the right-hand-side launch (fk_ode.h): the tile reads y and the earlier stage
-// derivatives and builds its input y + dt * sum_j c[j] k_j on the fly (ode_stage of fk_aux.h) instead of a separate pass
-struct TileOde {
-    int n;                  // number of stage derivatives entering (0 = off)
-    int exact;
-    float dt;
-    float c[6];
-    const float *kv[6], *kw[6], *ku[6];
 };
 
 struct TileArgs {
@@ -48,7 +37,6 @@ struct TileArgs {
                                        //    level 1 = predictor y1 = y + k1 dt, level 2 evaluates k2 = f(y1) at the SAME
                                        //    counter and writes y + (k1 + k2) * h_half
     float h_half;                      // dt * 0.5 (solve.py:83)
-    TileOde ode;                       // rhs_mode only: the input state is y + dt * sum c_j k_j (Dormand-Prince stage)
     const float *hy_v, *hy_w, *hy_u;   // fast Heun (streaming / wide kernels, last level only): when set, the launch stores
                                        // y + (E - y) / 2 instead of its Euler result E, y = these arrays (fk_forward_heun)
     Consts K;
@@ -131,13 +119,6 @@ FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx
     if (A.heun) X.mask[1] = X.mask[0];   // both stages see the same counter (solve.py:78, 80)
 }
 
-FK_HD float tile_ode_input(const TileOde& O, const float* const* karr, long long g, float y) {
-    float k[6];
-#pragma unroll
-    for (int s = 0; s < 6; ++s) k[s] = (s < O.n && O.c[s] != 0.0f) ? ldg1(karr[s] + g) : 0.0f;
-    return O.exact ? ode_stage<true>(y, O.c, k, O.n, O.dt) : ode_stage<false>(y, O.c, k, O.n, O.dt);
-}
-
 // phase 0: level-0 state -> shared memory
 FK_HD void tile_load(const TileArgs& A, const TileCtx& X, int tx, int ty, int ntx, int nty) {
     for (int r = X.ra + ty; r < X.rb; r += nty)
@@ -149,11 +130,6 @@ FK_HD void tile_load(const TileArgs& A, const TileCtx& X, int tx, int ty, int nt
                 if (c < X.cb) {
                     const long long g = X.boff + (long long)r * A.W + c;
                     uu[q] = ldg1(A.u_in + g); vv[q] = ldg1(A.v_in + g); ww[q] = ldg1(A.w_in + g);
-                    if (A.ode.n) {
-                        uu[q] = tile_ode_input(A.ode, A.ode.ku, g, uu[q]);
-                        vv[q] = tile_ode_input(A.ode, A.ode.kv, g, vv[q]);
-                        ww[q] = tile_ode_input(A.ode, A.ode.kw, g, ww[q]);
-                    }
                 }
             }
 #pragma unroll

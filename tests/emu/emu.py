@@ -95,7 +95,7 @@ def _pack_stims(stimuli):
     return arr, keep
 
 
-def dopri5(state, ts, params, D, stimuli, dx, rtol=1.4e-8, atol=1.4e-8, mxstep=float("inf"), exact=True, fuse=True):
+def dopri5(state, ts, params, D, stimuli, dx, rtol=1.4e-8, atol=1.4e-8, mxstep=float("inf"), exact=True):
     """The product's Dormand-Prince driver (fk_ode.h) + element bodies (fk_aux.h) on the CPU.  -> (v, w, u) stacked, stats"""
     v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
     H, W = u.shape
@@ -108,7 +108,7 @@ def dopri5(state, ts, params, D, stimuli, dx, rtol=1.4e-8, atol=1.4e-8, mxstep=f
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib().fk_emu_dopri5(p(v), p(w), p(u), p(outs[0]), p(outs[1]), p(outs[2]), p(D), H, W, p(par), arr, len(stimuli),
                              p(ts), len(ts), ctypes.c_float(dx), ctypes.c_float(rtol), ctypes.c_float(atol),
-                             ctypes.c_double(mxstep), int(exact), stats, int(fuse))
+                             ctypes.c_double(mxstep), int(exact), stats)
     if rc != 0:
         raise RuntimeError("fk_emu_dopri5 rc=%d" % rc)
     return tuple(outs), dict(attempts=stats[0], accepted=stats[1], rhs_evals=stats[2])

@@ -182,17 +182,6 @@ struct EmuOde {
         const char* why = "";
         return fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, (double)t, 1, o, 1, &why);
     }
-    int rhs_stage(int i, const fk::P3& y, const fk::P3* k, const float* beta_row, float dt, const fk::P3& out, float t) {
-        fk::TileOde O;
-        memset(&O, 0, sizeof(O));
-        O.n = i; O.exact = exact; O.dt = dt;
-        for (int s = 0; s < 6; ++s) { O.c[s] = beta_row[s]; O.kv[s] = k[s].a[0]; O.kw[s] = k[s].a[1]; O.ku[s] = k[s].a[2]; }
-        fk::DriveBuffers B = fk::DriveBuffers();
-        B.v_in = y.a[0]; B.w_in = y.a[1]; B.u_in = y.a[2]; B.v_out = out.a[0]; B.w_out = out.a[1]; B.u_out = out.a[2];
-        B.D = D; B.DX = DX; B.DY = DY; B.stims = stims; B.ode = &O;
-        const char* why = "";
-        return fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, (double)t, 1, o, 1, &why);
-    }
     int copy(const fk::P3& dst, long long off, const fk::P3& src) {
         for (int a = 0; a < 3; ++a) memcpy(dst.a[a] + off, src.a[a], sizeof(float) * (size_t)n);
         return 0;
@@ -265,7 +254,7 @@ struct EmuOde {
 extern "C" int fk_emu_dopri5(const float* v0, const float* w0, const float* u0, float* v_out, float* w_out, float* u_out,
                              const float* D, int H, int W, const float* params14, const EmuStim* stims, int n_stim,
                              const float* ts, int n_ts, float dx, float rtol, float atol, double mxstep, int exact,
-                             long long* stats3, int fuse) {
+                             long long* stats3) {
     const size_t n = (size_t)H * W;
     std::vector<float> DX(n), DY(n), store(60 * n);
     for (int r = 0; r < H; ++r)
@@ -287,7 +276,7 @@ extern "C" int fk_emu_dopri5(const float* v0, const float* w0, const float* u0, 
     be.D = D; be.DX = DX.data(); be.DY = DY.data(); be.stims = (const fk::StimDev*)stims;
     be.d_batched = 0; be.H = H; be.W = W; be.batch = 1; be.n_stim = n_stim; be.exact = exact; be.n = (long long)n;
     fk::OdeStats S = {0, 0, 0};
-    const int rc = fk::drive_dopri5(be, B, n_ts, ts, rtol, atol, mxstep, &S, fuse != 0);
+    const int rc = fk::drive_dopri5(be, B, n_ts, ts, rtol, atol, mxstep, &S);
     if (stats3) { stats3[0] = S.attempts; stats3[1] = S.accepted; stats3[2] = S.rhs_evals; }
     return rc;
 }

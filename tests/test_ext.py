@@ -37,9 +37,6 @@ def test_dopri_driver_and_bodies_bit_identical_to_the_oracle():
         (v, w, u), stats = emu.dopri5(st, g["ts"], O.PARAMSETS["3"], D, stim, 0.01, rtol=tol, atol=tol)
         assert np.array_equal(v, g["v_" + name]) and np.array_equal(w, g["w_" + name]) and np.array_equal(u, g["u_" + name])
         assert [stats["attempts"], stats["accepted"], stats["rhs_evals"]] == list(g["stats_" + name])
-    # the separate stage pass (fuse=False) and the stage fused into the right-hand-side launch's load give the same bits
-    (v2, w2, u2), stats2 = emu.dopri5(st, g["ts"], O.PARAMSETS["3"], D, stim, 0.01, rtol=tol, atol=tol, fuse=False)
-    assert np.array_equal(v, v2) and np.array_equal(w, w2) and np.array_equal(u, u2) and stats == stats2
     # rejected attempts exist in this run (the controller's reject branch is exercised) and 6 evaluations per attempt + 2
     assert g["stats_tight"][0] > g["stats_tight"][1] and g["stats_tight"][2] == 6 * g["stats_tight"][0] + 2
 
@@ -153,7 +150,7 @@ def test_dopri_gpu_exact_bitwise_vs_oracle_fixture():
             options.ode_rtol = options.ode_atol = float(g["tol_" + name])
             before = _lib.lib().fk_launch_count()
             out = solve._forward_dormandprince(state, g["ts"], O.PARAMSETS["3"], Dg, gst, 0.01, 0.01)
-            assert _lib.lib().fk_launch_count() - before >= 8 * int(g["stats_" + name][0])   # at least 6 rhs, finish, reduce
+            assert _lib.lib().fk_launch_count() - before > 8 * int(g["stats_" + name][0])
             assert out.u.shape == (4, 24, 28)
             for nm, a in zip("vwu", out):
                 assert np.array_equal(a.cpu().numpy(), g[nm + "_" + name]), (name, nm)
