@@ -49,7 +49,6 @@ inline float optimal_step_size(float last_step, float mean_error_ratio) {
     const float hi = div(1.0f, dfactor);
     if (hi < factor) factor = hi;                       // jnp.minimum(.., 1 / dfactor)
     if (f32(1.0 / 10.0) > factor) factor = f32(1.0 / 10.0);   // jnp.maximum(1 / ifactor, ..)
-    if (factor != factor) factor = NAN;
     return mean_error_ratio == 0.0f ? mul(last_step, ifactor) : div(last_step, factor);
 }
 }  // namespace ode
