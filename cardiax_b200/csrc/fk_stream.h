@@ -634,6 +634,20 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
             }
         }
     }
+    // fast Heun: y at the row the last stage stores, requested before the wait as well -- L2 hits (this CTA read those rows
+    // 4T iterations ago), but loaded at the store they were 40 % of the warp samples (ncu: long scoreboard)
+    float hyu[4], hyv[4], hyw[4];
+    bool hy_ok = false;
+    if (heun && UNI) {   // (with diffusivity maps the twelve extra live registers spill: -9 % at 1200^2; uniform D: +6 %)
+        const int rho_l = n0 - 4 * T;
+        hy_ok = act && c >= C.out_c0 && c < C.out_c1 && rho_l >= C.r0 && rho_l < A.H;
+        if (hy_ok) {
+            const long long gl = g0 - 4LL * T * A.W;
+            unpack4(ldg4(A.hy_u + gl), hyu);
+            unpack4(ldg4(A.hy_v + gl), hyv);
+            unpack4(ldg4(A.hy_w + gl), hyw);
+        }
+    }
     if (ST && !bar_done) sb_wait(bar, PH & 1);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
@@ -755,11 +769,13 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
             }
             if (s == T - 1) {
                 if (c >= C.out_c0 && c < C.out_c1 && rho >= C.r0) {   // (rho < r0: the unrolled body while it fills)
-                    if (heun) {   // fast Heun: this launch computed E(E(y)); store y + (E(E(y)) - y) / 2 (y: an L2 hit)
-                        float y4[4];
-                        unpack4(ldg4(A.hy_u + grow), y4); heun_fold4(y4, un);
-                        unpack4(ldg4(A.hy_v + grow), y4); heun_fold4(y4, vn);
-                        unpack4(ldg4(A.hy_w + grow), y4); heun_fold4(y4, wn);
+                    if (heun) {   // fast Heun: this launch computed E(E(y)); store y + (E(E(y)) - y) / 2
+                        if (!hy_ok) {
+                            unpack4(ldg4(A.hy_u + grow), hyu);
+                            unpack4(ldg4(A.hy_v + grow), hyv);
+                            unpack4(ldg4(A.hy_w + grow), hyw);
+                        }
+                        heun_fold4(hyu, un); heun_fold4(hyv, vn); heun_fold4(hyw, wn);
                     }
                     if (ST || !defer_u) st4(A.u_out + grow, un);   // (a deferred first row's u follows below)
                     st4(A.v_out + grow, vn);
