@@ -14,7 +14,7 @@ and on the ``tests/unittests/stimulus_test.py:23`` expectation; see DESIGN.md.
 from . import fk_oracle_ext  # noqa: F401  (odeint / resize / electrogram restatements)
 from .fk_oracle import (  # noqa: F401
     Params, State, Protocol, Stimulus,
-    init, gradient, stimulate, stimulus_active, step, step_euler, forward_euler, step_heun, forward_heun,
+    init, gradient, stimulate, stimulus_active, stimulus_active_typed, step, step_euler, forward_euler, step_heun, forward_heun,
     tanh_xla_f32, PARAMSETS,
     rectangular, linear, triangular,
 )

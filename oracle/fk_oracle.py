@@ -148,18 +148,47 @@ def stimulus_active(t, protocol, dtype=np.float32):
     return bool(active)
 
 
-def stimulate(t, X, stimuli: Sequence[Stimulus], dtype=np.float32):
-    """cardiax/solve.py:257-271 -- later stimuli override earlier; zero cells never stimulate."""
+def stimulus_active_typed(t, protocol):
+    """cardiax/solve.py:262-267 with jax's typing (x64 disabled): the counter and each protocol entry is an int32 or a
+    float32 according to what the caller passed -- Python int / integer array -> int32 (``deepx/generate.py:24-27``
+    draws ``start`` and ``period`` as shape-(1,) int32 arrays and ``generate.sequence`` :187-196 runs an int32 counter),
+    Python float / float array -> float32 (``solve.forward`` :210-211 passes ``float(checkpoint)``) -- and every binary
+    operation runs in float32 as soon as one side is a float, in int32 otherwise."""
+    def canon(x):
+        a = np.asarray(x).reshape(-1)[0]
+        return np.int32(a) if a.dtype.kind in "iub" else np.float32(a)
+
+    def both(a, b):
+        if isinstance(a, np.float32) or isinstance(b, np.float32):
+            return np.float32(a), np.float32(b)
+        return a, b
+
+    t, start, duration, period = canon(t), canon(protocol.start), canon(protocol.duration), canon(protocol.period)
+    a, b = both(t, start)
+    active = bool(a >= b)
+    a, b = both(start, t)
+    with np.errstate(all="ignore"):
+        x = a - b
+        x = x + type(x)(1)
+        a, b = both(x, period)
+        m = np.mod(a, b)                      # jnp.mod: sign of the divisor, for ints and floats alike
+    a, b = both(m, duration)
+    return active and bool(a < b)
+
+
+def stimulate(t, X, stimuli: Sequence[Stimulus], dtype=np.float32, typed=False):
+    """cardiax/solve.py:257-271 -- later stimuli override earlier; zero cells never stimulate.  ``typed``: evaluate the
+    schedule with the callers' own int / float types (`stimulus_active_typed`) instead of casting everything to ``dtype``."""
     X = np.asarray(X)
     stimulated = np.zeros_like(X)
     for s in stimuli:
-        active = stimulus_active(t, s.protocol, dtype)
+        active = stimulus_active_typed(t, s.protocol) if typed else stimulus_active(t, s.protocol, dtype)
         field = np.asarray(s.field, dtype=X.dtype)
         stimulated = np.where((field * X.dtype.type(active)) != 0, field, stimulated)
     return np.where(stimulated != 0, stimulated, X)
 
 
-def step(state: State, t, params: Params, diffusivity, stimuli, dx, dtype=np.float32, tanh="xla"):
+def step(state: State, t, params: Params, diffusivity, stimuli, dx, dtype=np.float32, tanh="xla", typed=False):
     """cardiax/solve.py:26-65 -- RHS (d_v, d_w, d_u) at step index t."""
     f = dtype
     P = Params(*[f(x) for x in params])
@@ -189,7 +218,7 @@ def step(state: State, t, params: Params, diffusivity, stimuli, dx, dtype=np.flo
 
     # :45-46 stimulus REPLACES j_ion
     stimuli = [Stimulus(s.protocol, np.pad(np.asarray(s.field, f), 1, mode="edge")) for s in stimuli]
-    j_ion = stimulate(t, j_ion, stimuli, dtype=f)
+    j_ion = stimulate(t, j_ion, stimuli, dtype=f, typed=typed)
 
     # :49-55 diffusion term
     u_x = gradient(u, 0) / dx
@@ -208,39 +237,55 @@ def step(state: State, t, params: Params, diffusivity, stimuli, dx, dtype=np.flo
     return State(d_v[1:-1, 1:-1], d_w[1:-1, 1:-1], d_u[1:-1, 1:-1])
 
 
-def step_euler(state, t, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla"):
+def step_euler(state, t, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla", typed=False):
     """cardiax/solve.py:68-70 -- x + d_x*dt."""
-    g = step(state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh)
+    g = step(state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh, typed=typed)
     dt = dtype(dt)
     return State(*[np.add(np.asarray(x, dtype), dx_ * dt) for x, dx_ in zip(state, g)])
 
 
-def forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla"):
-    """cardiax/solve.py:92-100 -- fori_loop over [t, t_end) with a counter of t's dtype."""
-    i = float(t)
-    while i < float(t_end):
-        state = step_euler(state, i, params, diffusivity, stimuli, dt, dx, dtype=dtype, tanh=tanh)
-        i += 1.0
+def _counter(t, t_end, counter):
+    """The values ``lax.fori_loop(t, t_end, ...)`` hands to the body: ``i = t; while i < t_end: yield i; i = i + 1`` in
+    the bounds' dtype.  "f32": the float32 counter of ``solve.forward``; "i32": the int32 counter of
+    ``deepx.generate.sequence``; None: a Python float (exact below 2^53; identical to "f32" below 2^24)."""
+    if counter == "f32":
+        i, end, one = np.float32(t), np.float32(t_end), np.float32(1)
+    elif counter == "i32":
+        i, end, one = np.int32(t), np.int32(t_end), np.int32(1)
+    else:
+        i, end, one = float(t), float(t_end), 1.0
+    while i < end:
+        yield i
+        nxt = i + one
+        if nxt == i:
+            raise OverflowError("the reference's float32 loop counter stops advancing at 2^24")
+        i = nxt
+
+
+def forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla", counter=None):
+    """cardiax/solve.py:92-100 -- fori_loop over [t, t_end) with a counter of t's dtype (see `_counter`)."""
+    for i in _counter(t, t_end, counter):
+        state = step_euler(state, i, params, diffusivity, stimuli, dt, dx, dtype=dtype, tanh=tanh,
+                           typed=counter is not None)
     return state
 
 
-def step_heun(state, t, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla"):
+def step_heun(state, t, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla", typed=False):
     """cardiax/solve.py:73-85 -- Heun: k1 at y, k2 at y + k1*dt (SAME counter t), y + (k1 + k2) * (dt * 0.5)."""
     def euler(y, dy, h):  # :74-75  jnp.add(v, dv * h)
         return State(*[np.add(np.asarray(a, dtype), b * h) for a, b in zip(y, dy)])
-    d_state = step(state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh)
+    d_state = step(state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh, typed=typed)
     new_state = euler(state, d_state, dtype(dt))
-    d_new_state = step(new_state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh)
+    d_new_state = step(new_state, t, params, diffusivity, stimuli, dx, dtype=dtype, tanh=tanh, typed=typed)
     summed = State(*[np.add(a, b) for a, b in zip(d_state, d_new_state)])
-    return euler(state, summed, dtype(float(dt) * 0.5))   # `dt * 0.5` is a Python-float product, then weak-typed
+    return euler(state, summed, dtype(dt) * dtype(0.5))   # `dt * 0.5`: dt is a 32-bit scalar inside the jitted loop
 
 
-def forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla"):
+def forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx, dtype=np.float32, tanh="xla", counter=None):
     """cardiax/solve.py:103-111."""
-    i = float(t)
-    while i < float(t_end):
-        state = step_heun(state, i, params, diffusivity, stimuli, dt, dx, dtype=dtype, tanh=tanh)
-        i += 1.0
+    for i in _counter(t, t_end, counter):
+        state = step_heun(state, i, params, diffusivity, stimuli, dt, dx, dtype=dtype, tanh=tanh,
+                          typed=counter is not None)
     return state
 
 

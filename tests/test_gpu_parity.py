@@ -391,3 +391,66 @@ def test_large_field_properties_4096():
     ref = C.forward_euler(crop, 0, n, P5, Dc, [], 0.01, 0.01)
     for x, r in zip(e, ref):
         assert np.array_equal(x[:sub, :sub].cpu().numpy(), r[:sub, :sub])
+
+
+# --------------------------------------------------------------------------- vectors frozen from the reference's own source
+def _ref_fixture(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+
+
+def _gpu_stimuli(g):
+    from cardiax_b200 import stimulus
+    out, i = [], 0
+    while "field%d" % i in g.files:
+        out.append(stimulus.Stimulus(stimulus.Protocol(*[float(x) for x in g["proto%d" % i]]), torch.as_tensor(g["field%d" % i]).cuda()))
+        i += 1
+    return out
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4])
+def test_cuda_equals_reference_vectors_forward(kernel):
+    """tests/golden/ref_fk_48x40.npz was produced by the UNMODIFIED reference source (cardiax/solve.py on the NumPy
+    stand-in for jax, XLA's tanh): `solve.forward` with EULER and HEUN and the int-counter `_forward_euler` of
+    deepx.generate.sequence.  Exact numerics reproduce it bit for bit through every kernel; fast numerics within TOL."""
+    from cardiax_b200 import options, solve
+    g = _ref_fixture("ref_fk_48x40.npz")
+    P, stim, cps = O.Params(*g["params"]), _gpu_stimuli(g), g["checkpoints"]
+    st0 = solve.State(*[torch.as_tensor(g[k + "0"]).cuda() for k in "vwu"])
+    D = torch.as_tensor(g["D"]).cuda()
+    options.kernel = kernel
+    for name, integ in (("euler", solve.TimeIntegrator.EULER), ("heun", solve.TimeIntegrator.HEUN)):
+        options.numerics = "exact"
+        states = solve.forward(st0, cps, P, D, stim, float(g["dt"]), float(g["dx"]), integ)
+        assert len(states) == len(cps) - 1
+        for i, s in enumerate(states):
+            assert_exact([x.cpu().numpy() for x in s], [g["%s_xla_%s%d" % (name, f, i + 1)] for f in "vwu"],
+                         "%s checkpoint %d kernel %d" % (name, i, kernel))
+        options.numerics = "fast"
+        states = solve.forward(st0, cps, P, D, stim, float(g["dt"]), float(g["dx"]), integ)
+        for i, s in enumerate(states):
+            for f, x in zip("vwu", s):
+                for tanh in ("xla", "numpy"):     # two legitimate tanh functions: fast numerics sit within TOL of both
+                    assert float(np.abs(x.cpu().numpy() - g["%s_%s_%s%d" % (name, tanh, f, i + 1)]).max()) <= TOL_FAST, (name, f, i)
+    options.numerics = "exact"
+    s = solve._forward_euler(st0, 0, 60, P, D, stim, 0.01, 0.01)       # Python-int bounds: the int32 counter
+    assert_exact([x.cpu().numpy() for x in s], [g["euler_int_xla_" + f] for f in "vwu"], "int counter")
+
+
+def test_cuda_equals_reference_vectors_step_gradient_stimulate():
+    """tests/golden/ref_fk_steps.npz (reference source): `solve.step` for all 16 parameter sets, `gradient`, `stimulate`."""
+    from cardiax_b200 import options, solve
+    g = _ref_fixture("ref_fk_steps.npz")
+    stim = _gpu_stimuli(g)
+    st = solve.State(*[torch.as_tensor(g[k + "0"]).cuda() for k in "vwu"])
+    D = torch.as_tensor(g["D"]).cuda()
+    for key, P in O.PARAMSETS.items():
+        options.numerics = "exact"
+        d = solve.step(st, float(g["t"]), P, D, stim, float(g["dx"]))
+        assert_exact([x.cpu().numpy() for x in d], [g["d%s_xla_%s" % (f, key)] for f in "vwu"], "step paramset " + key)
+    a = torch.as_tensor(g["grad_in"]).cuda()
+    for axis in range(4):
+        assert np.array_equal(solve.gradient(a, axis).cpu().numpy(), g["grad_axis%d" % axis])
+    X = torch.as_tensor(g["stimulate_in"]).cuda()
+    for t in range(24):
+        assert np.array_equal(solve.stimulate(float(t), X, stim).cpu().numpy(), g["stimulate_out"][t]), t

@@ -204,3 +204,55 @@ def test_heun_restatement_is_second_order_and_matches_its_definition():
     e_h = [np.abs(run(O.forward_heun, dt, n) - exact).max() for dt, n in ((0.01, 8), (0.005, 16))]
     e_e = [np.abs(run(O.forward_euler, dt, n) - exact).max() for dt, n in ((0.01, 8), (0.005, 16))]
     assert e_h[0] / e_h[1] > 3.0 and 1.6 < e_e[0] / e_e[1] < 2.6 and e_h[0] < e_e[0]
+
+
+# --------------------------------------------------------------------------- vectors frozen from the reference's own source
+def _ref_fixture(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+
+
+def _fixture_stimuli(g):
+    stim, i = [], 0
+    while "field%d" % i in g.files:
+        stim.append(O.Stimulus(O.Protocol(*[float(x) for x in g["proto%d" % i]]), g["field%d" % i]))
+        i += 1
+    return stim
+
+
+@pytest.mark.parametrize("tanh,oracle_tanh", [("xla", "xla"), ("numpy", "libm")])
+def test_oracle_equals_reference_vectors_integrators(tanh, oracle_tanh):
+    """tests/golden/ref_fk_48x40.npz: `solve.forward` (Euler, Heun) and the int32-counter `_forward_euler` as computed by
+    the UNMODIFIED reference source (make_reference_golden.py); needs no reference tree."""
+    g = _ref_fixture("ref_fk_48x40.npz")
+    P, stim, cps = O.Params(*g["params"]), _fixture_stimuli(g), g["checkpoints"]
+    for name, fwd in (("euler", O.forward_euler), ("heun", O.forward_heun)):
+        s = O.State(g["v0"], g["w0"], g["u0"])
+        for i in range(len(cps) - 1):
+            s = fwd(s, float(cps[i]), float(cps[i + 1]), P, g["D"], stim, float(g["dt"]), float(g["dx"]), tanh=oracle_tanh)
+            for f, a in zip("vwu", s):
+                assert np.array_equal(a, g["%s_%s_%s%d" % (name, tanh, f, i + 1)]), (name, f, i)
+    s = O.forward_euler(O.State(g["v0"], g["w0"], g["u0"]), 0, 60, P, g["D"], stim, 0.01, 0.01, tanh=oracle_tanh, counter="i32")
+    for f, a in zip("vwu", s):
+        assert np.array_equal(a, g["euler_int_%s_%s" % (tanh, f)])
+    if tanh == "xla":   # the C port (CPU baseline, long fixtures) reproduces the reference vectors as well
+        s = O.State(g["v0"], g["w0"], g["u0"])
+        for i in range(len(cps) - 1):
+            s = C.forward_euler(s, float(cps[i]), float(cps[i + 1]), P, g["D"], stim, float(g["dt"]), float(g["dx"]))
+            for f, a in zip("vwu", s):
+                assert np.array_equal(a, g["euler_xla_%s%d" % (f, i + 1)]), ("C", f, i)
+
+
+@pytest.mark.parametrize("tanh,oracle_tanh", [("xla", "xla"), ("numpy", "libm")])
+def test_oracle_equals_reference_vectors_step_gradient_stimulate(tanh, oracle_tanh):
+    """tests/golden/ref_fk_steps.npz: `solve.step` for all 16 parameter sets, N-D `gradient`, `stimulate` schedule."""
+    g = _ref_fixture("ref_fk_steps.npz")
+    st, stim = O.State(g["v0"], g["w0"], g["u0"]), _fixture_stimuli(g)
+    for key, P in O.PARAMSETS.items():
+        d = O.step(st, float(g["t"]), P, g["D"], stim, float(g["dx"]), tanh=oracle_tanh)
+        for f, a in zip("vwu", d):
+            assert np.array_equal(a, g["d%s_%s_%s" % (f, tanh, key)]), (key, f)
+    for axis in range(4):
+        assert np.array_equal(O.gradient(g["grad_in"], axis), g["grad_axis%d" % axis])
+    for t in range(24):
+        assert np.array_equal(O.stimulate(float(t), g["stimulate_in"], stim), g["stimulate_out"][t]), t
