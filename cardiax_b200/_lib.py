@@ -163,6 +163,7 @@ def lib():
     L.fk_profile_collect.argtypes = [ctypes.POINTER(cd), ctypes.POINTER(ll), ctypes.POINTER(cd), ctypes.POINTER(ll),
                                       ctypes.POINTER(cd)]
     L.fk_profile_collect.restype = ci
+    L.fk_profile_dropped.restype = ll
     if L.fk_abi_version() != 1:
         raise RuntimeError("libfk.so ABI version mismatch")
     _lib = L

@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/fk.h"
@@ -33,18 +35,19 @@ int cuda_fail(cudaError_t e, const char* where) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
     } while (0)
 
-long long g_launches = 0;
-int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-const char* g_last_kernel = "";
-int g_num_sms = 0;
+// diagnostics: the launch counter is shared (atomic); "last plan / last kernel" describe the calling thread's last call
+std::atomic<long long> g_launches{0};
+thread_local int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+thread_local const char* g_last_kernel = "";
 int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static int sms[fk::FK_MAX_DEVICES] = {0};   // per device
+    const int dev = fk::cur_device();
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
     }
-    return g_num_sms;
+    return sms[dev];
 }
 
 }  // namespace
@@ -238,8 +241,11 @@ int launch_dgrad(const float* D, float* DX, float* DY, int H, int W, int planes,
 }
 
 // ---- optional per-launch timing (bench.py): CUDA events around every launch, on the launch stream
+enum { FK_PROF_MAX_EVENTS = 1 << 20 };   // 2^19 launches between two fk_profile_collect calls; beyond: counted as dropped
 struct Prof {
+    std::mutex mu;                    // the event lists are shared by every thread that calls into the library
     bool on = false;
+    long long dropped = 0;            // launches not timed because the event lists were full (reported, never silent)
     std::vector<cudaEvent_t> ev[2];   // [0] streaming kernel, [1] tile kernel : begin/end pairs
     std::vector<cudaEvent_t> pool;
     double stream_cs = 0;             // cell-steps the timed streaming launches produced
@@ -252,11 +258,17 @@ struct Prof {
 } g_prof;
 struct ProfScope {
     int kind; cudaStream_t st; bool active;
-    ProfScope(int k, cudaStream_t s) : kind(k), st(s), active(g_prof.on && g_prof.ev[k].size() < 8192) {
-        if (active) { cudaEvent_t e = g_prof.get(); cudaEventRecord(e, st); g_prof.ev[kind].push_back(e); }
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), active(false) {
+        if (!g_prof.on) return;
+        std::lock_guard<std::mutex> lock(g_prof.mu);
+        active = g_prof.ev[k].size() < (size_t)FK_PROF_MAX_EVENTS;
+        if (!active) { ++g_prof.dropped; return; }
+        cudaEvent_t e = g_prof.get(); cudaEventRecord(e, st); g_prof.ev[kind].push_back(e);
     }
     ~ProfScope() {
-        if (active) { cudaEvent_t e = g_prof.get(); cudaEventRecord(e, st); g_prof.ev[kind].push_back(e); }
+        if (!active) return;
+        std::lock_guard<std::mutex> lock(g_prof.mu);
+        cudaEvent_t e = g_prof.get(); cudaEventRecord(e, st); g_prof.ev[kind].push_back(e);
     }
 };
 
@@ -282,7 +294,8 @@ struct CudaBackend {
         ProfScope ps(1, st);
         g_last_kernel = "fk_tile_kernel";
         ++g_launches;
-        static size_t attr_set[2] = {0, 0};   // largest dynamic shared memory already allowed, per instantiation
+        static size_t attr_set_dev[fk::FK_MAX_DEVICES][2] = {{0, 0}};   // largest dynamic shared memory already allowed,
+        size_t* attr_set = attr_set_dev[fk::cur_device()];              // per device and instantiation
         if (smem > attr_set[exact ? 1 : 0]) {
             if (exact) FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else FK_CUDA(cudaFuncSetAttribute(fk_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -369,6 +382,7 @@ void fk_profile_enable(int on) { g_prof.on = on != 0; }
 
 int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches,
                        double* stream_cell_steps) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     if (stream_cell_steps) *stream_cell_steps = g_prof.stream_cs;
     g_prof.stream_cs = 0;
     double ms[2] = {0, 0};
@@ -390,6 +404,13 @@ int fk_profile_collect(double* stream_ms, long long* stream_launches, double* ti
     if (tile_ms) *tile_ms = ms[1];
     if (tile_launches) *tile_launches = n[1];
     return 0;
+}
+
+long long fk_profile_dropped(void) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    const long long d = g_prof.dropped;
+    g_prof.dropped = 0;
+    return d;
 }
 const char* fk_last_error(void) { return g_err; }
 

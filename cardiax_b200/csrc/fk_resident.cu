@@ -60,7 +60,10 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
 
 template <bool EXACT, int NC, bool MG>
 int launch_nc(const ResPlan& P, const TileArgs& A, const ResGeom& G, int batch, cudaStream_t st) {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};   // the opt-in is per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    bool& attr_set = attr_set_dev[dev];
     cudaError_t e;
     if (!attr_set) {
         e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN);

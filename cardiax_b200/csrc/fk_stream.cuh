@@ -6,6 +6,15 @@
 
 namespace fk {
 
+// cudaFuncSetAttribute and occupancy answers are PER DEVICE: every cache of them in this library is indexed by the
+// current device ordinal, so a process that drives several GPUs (or switches device) opts in on each of them
+enum { FK_MAX_DEVICES = 64 };
+inline int cur_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= FK_MAX_DEVICES) d = 0;
+    return d;
+}
+
 template <bool EXACT, int T, bool UNI, bool HEUN = false>
 __global__ void __launch_bounds__(T == 2 ? 192 : 256, T <= 2 ? 2 : 1)
 fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ StreamGeom G) {
@@ -78,7 +87,8 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
 
 template <bool EXACT, int T, bool UNI>
 inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
-    static long long attr_set = 0;   // largest dynamic shared memory already allowed for this instantiation
+    static long long attr_set_dev[FK_MAX_DEVICES] = {0};   // largest dynamic shared memory already allowed, per device
+    long long& attr_set = attr_set_dev[cur_device()];
     if (P.smem_bytes > attr_set && attr_set < 227 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)P.smem_bytes);
@@ -88,7 +98,8 @@ inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cu
     dim3 grid(P.G.nstrips * P.G.nchunks, batch);
     if (A.hy_u) {   // fast Heun: the instantiation whose last level stores y + (E - y) / 2 (fast numerics, T <= 2 only)
         if constexpr (!EXACT && T <= 2) {
-            static long long attr_set_h = 0;
+            static long long attr_set_h_dev[FK_MAX_DEVICES] = {0};
+            long long& attr_set_h = attr_set_h_dev[cur_device()];
             if (P.smem_bytes > attr_set_h && attr_set_h < 227 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI, true>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes);
@@ -108,10 +119,11 @@ inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cu
 template <bool EXACT, int T, bool UNI>
 inline int stream_occupancy_t(int NT, long long smem) {
     // memoised: the planner asks for the same few configurations at every call
-    static int memo_nt[64], memo_n[64], memo_cnt = 0;
+    static int memo_nt[64], memo_n[64], memo_dev[64], memo_cnt = 0;
     static long long memo_smem[64];
+    const int dev = cur_device();
     for (int i = 0; i < memo_cnt; ++i)
-        if (memo_nt[i] == NT && memo_smem[i] == smem) return memo_n[i];
+        if (memo_nt[i] == NT && memo_smem[i] == smem && memo_dev[i] == dev) return memo_n[i];
     if (cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
         cudaSuccess) {
         cudaGetLastError();
@@ -123,7 +135,7 @@ inline int stream_occupancy_t(int NT, long long smem) {
         cudaGetLastError();
         return 0;
     }
-    if (memo_cnt < 64) { memo_nt[memo_cnt] = NT; memo_smem[memo_cnt] = smem; memo_n[memo_cnt] = n; ++memo_cnt; }
+    if (memo_cnt < 64) { memo_nt[memo_cnt] = NT; memo_smem[memo_cnt] = smem; memo_n[memo_cnt] = n; memo_dev[memo_cnt] = dev; ++memo_cnt; }
     return n;
 }
 

@@ -7,7 +7,8 @@ Layout kept (io.py:18-22, 31-35, 43, 53-63): ``states (T, 3, H', W') f32`` in (v
   reference's names and arguments.  ``h5py`` is optional: without it the same calls go to an in-memory store that is
   written as one ``.npz`` on ``close()`` (dataset names with ``/`` kept as keys).
 * ``imresize`` is ``jax.image.resize(a, shape, "bilinear")`` (anti-aliased triangle filter, half-pixel centres, edge
-  weights renormalised) evaluated on the GPU as two small dense products with host-built weight matrices.
+  weights renormalised) evaluated on the GPU by ``fk_resize_kernel`` (one thread per output pixel, the separable filter
+  taps staged in shared memory; all planes of a snapshot in one launch).
 * ``AsyncSnapshotWriter`` is what the north star asks for: snapshots are (optionally resized and) copied into a ring of
   PINNED host buffers on a SIDE stream, ordered after the producing kernels by an event, and written to the dataset by
   a host thread -- the solver stream never waits for the disk or the PCIe copy.
@@ -266,13 +267,14 @@ def _resize_planes(planes, H, W, size, out=None):
     ws = _resize_ws.get(key)
     ready = ws is not None
     if not ready:
-        if len(_resize_ws) > 32:
-            _resize_ws.clear()
         ws = torch.empty(L.fk_resize_workspace_bytes(H, W, Ho, Wo, n), dtype=torch.uint8, device=dev)
-        _resize_ws[key] = ws
     ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in planes])
     _lib.check(L.fk_resize_bilinear(ptrs, n, H, W, out.data_ptr(), Ho, Wo, ws.data_ptr(), ws.numel(), int(ready),
                                     ctypes.c_void_p(stream.cuda_stream)))
+    if not ready:   # remembered only once the call that uploads the filter tables has succeeded
+        if len(_resize_ws) > 32:
+            _resize_ws.clear()
+        _resize_ws[key] = ws
     return out
 
 
@@ -373,12 +375,20 @@ def sequence(start, stop, step, dt, dx, params, diffusivity, stimuli, filename, 
     add_diffusivity(hdf5, diffusivity, shape=out_shape)
     states_dset = hdf5["states"]
     state = solve.init(shape)
-    writer = AsyncSnapshotWriter(states_dset, (3,) + out_shape)
+    # the static inputs go to the device ONCE: every segment then sees the same tensor objects (no re-upload, and the
+    # solver's per-tensor uniform-diffusivity verdict is reused)
+    D_dev = solve._as_f32(diffusivity)
+    stim_dev = [type(s)(s.protocol, solve._as_f32(s.field)) for s in stimuli]
+    writer = None
     try:
+        writer = AsyncSnapshotWriter(states_dset, (3,) + out_shape)
         for i in range(len(checkpoints) - 1):
-            state = solve._forward_euler(state, checkpoints[i], checkpoints[i + 1], params, diffusivity, stimuli, dt, dx)
+            state = solve._forward_euler(state, checkpoints[i], checkpoints[i + 1], params, D_dev, stim_dev, dt, dx)
             writer.submit(state, i)
     finally:
-        writer.close()
-    hdf5.close()
+        try:
+            if writer is not None:
+                writer.close()
+        finally:
+            hdf5.close()
     return state

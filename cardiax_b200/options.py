@@ -2,7 +2,8 @@
 
 numerics           "fast" (default): reciprocal multiplications + FMAs, a few ulp per step from the
                    reference's operation order; "exact": the reference's order, op for op, bit-identical
-                   to the CPU oracle (about half the throughput).
+                   to the CPU oracle and to the reference's own source (tests/test_reference_pin.py); slower -- every
+                   division keeps the reference's rounding (see DESIGN.md section 6 for the measured ratio).
 steps_per_launch   temporal blocking depth T (0 = library default).
 kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel, 3 require the one-step wide kernel,
                    4 require the resident kernel (whole call in one cooperative launch, state in shared memory).

@@ -97,7 +97,7 @@ class SlabRunner:
         self.Hb = self.o1 + (0 if self.bot else self.Hh)
         # static maps with their halos (exchanged once)
         self.D = self._with_halo(_as_f32(diffusivity, self.dev))
-        self.uniform = bool((self.D.min() == self.D.max()).item()) and self._all_equal(float(self.D[0, 0].item()))
+        self.uniform = self._uniform_everywhere(self.D)
         self.DX, self.DY = self.be.dgrad(self.D, self.dx, self.top, self.bot)
         self.stimuli = [type(s)(s.protocol, self._with_halo(_as_f32(s.field, self.dev))) for s in stimuli]
         self.buf = [[torch.zeros((self.Hb, self.W), dtype=torch.float32, device=self.dev) for _ in range(3)]
@@ -105,10 +105,15 @@ class SlabRunner:
         self.cur = 0
 
     # ---- communication
-    def _all_equal(self, x):
-        t = torch.tensor([x, -x], dtype=torch.float64, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
-        return float(t[0].item()) == -float(t[1].item())
+    def _uniform_everywhere(self, D):
+        """Is the diffusivity ONE constant over the whole tissue?  Every rank enters the same collective exactly once
+        (a rank-local shortcut would leave the ranks whose slab holds a scar out of the all_reduce and hang the job):
+        global max of [max(D), -min(D)], uniform iff the global max equals the global min."""
+        t = torch.stack([D.max(), -D.min()]).to(torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        t = t.cpu()
+        return float(t[0]) == -float(t[1])
 
     def _exchange_ops(self, arrays, rows=None):
         """P2P ops moving `rows` (default: the whole halo depth) own edge rows of each array into the neighbours' halos."""

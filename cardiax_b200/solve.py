@@ -7,6 +7,9 @@ enqueued on the current torch CUDA stream without synchronising.
 Extension (not in the reference): every function that takes a ``State`` also accepts a batch of
 independent tissues, ``(batch, H, W)`` tensors, with ``diffusivity`` either ``(H, W)`` or
 ``(batch, H, W)`` and ``stimuli`` either one list shared by all tissues or one list per tissue.
+
+Limit (not in the reference): at most 32 stimuli per tissue (the kernels carry the set of active stimuli of a level as
+a 32-bit mask); a longer list raises ``ValueError``.  The reference's own drivers use 1-3.
 """
 import ctypes
 from enum import Enum
@@ -81,19 +84,29 @@ def _pack_stimuli(stimuli, batch, shape, device):
     return arr, n_stim, keep
 
 
-_uniform_cache = {}
+_uniform_cache = {}   # id(tensor) -> (weakref to that tensor, its _version, verdict)
 
 
 def _is_uniform(D):
-    """Is the diffusivity map one constant?  Checked once per tensor version (one host sync)."""
-    key = (D.data_ptr(), tuple(D.shape), D._version)
-    hit = _uniform_cache.get(key)
-    if hit is None:
+    """Is the diffusivity map one constant?  One device reduction + host read.
+
+    The verdict is remembered only for the caller's OWN tensor object: the entry holds a weak reference and is valid
+    while ``ref() is D`` and ``D._version`` is unchanged.  A device address does not identify a tensor -- the caching
+    allocator hands a freed block straight back, so a scar map uploaded where a constant map just lived would have
+    inherited its verdict -- and tensors this module had to create itself (NumPy / CPU / non-fp32 inputs) are new
+    objects on every call, hence always re-examined."""
+    import weakref
+    hit = _uniform_cache.get(id(D))
+    if hit is not None and hit[0]() is D and hit[1] == D._version:
+        return hit[2]
+    verdict = bool((D.min() == D.max()).item())
+    if len(_uniform_cache) > 64:
+        for k in [k for k, v in _uniform_cache.items() if v[0]() is None]:
+            del _uniform_cache[k]
         if len(_uniform_cache) > 64:
             _uniform_cache.clear()
-        hit = bool((D.min() == D.max()).item())
-        _uniform_cache[key] = hit
-    return hit
+    _uniform_cache[id(D)] = (weakref.ref(D), D._version, verdict)
+    return verdict
 
 
 _division_checked = {}

@@ -192,6 +192,9 @@ int fk_resident_timing(unsigned long long* out8);
 void fk_profile_enable(int on);
 int fk_profile_collect(double* stream_ms, long long* stream_launches, double* tile_ms, long long* tile_launches,
                        double* stream_cell_steps);
+/* launches that were NOT timed since the last call because 2^19 event pairs were already pending (0 in any sane
+ * collection interval); resets the counter.  A non-zero value means the collected sums are a sample, not the total. */
+long long fk_profile_dropped(void);
 
 #ifdef __cplusplus
 }

@@ -133,3 +133,26 @@ def test_api_surface_matches_reference_names():
     assert sig(solve.gradient) == ["a", "axis"] and sig(solve.stimulate) == ["t", "X", "stimuli"]
     assert solve.TimeIntegrator.EULER == solve._forward_euler and callable(solve.TimeIntegrator.HEUN)
     assert inspect.signature(solve.forward).parameters["integrator"].default == solve.TimeIntegrator.EULER
+
+
+def test_uniform_diffusivity_verdict_is_tied_to_the_tensor_object():
+    """The verdict is cached for the caller's own tensor only (weak reference + version counter): an entry left behind
+    under a recycled id / address must not be believed, and an in-place edit must be seen."""
+    import weakref
+    import torch
+    from cardiax_b200 import solve
+    solve._uniform_cache.clear()
+    a = torch.full((8, 8), 1e-3)
+    assert solve._is_uniform(a) is True
+    assert solve._uniform_cache[id(a)][0]() is a
+    a[3, 3] = 5e-4                       # in place: same object, new version
+    assert solve._is_uniform(a) is False
+    b = torch.full((8, 8), 1e-3)
+    b[0, 0] = 2e-3
+    other = torch.full((8, 8), 1e-3)
+    solve._uniform_cache[id(b)] = (weakref.ref(other), b._version, True)    # a stale entry under b's id
+    assert solve._is_uniform(b) is False
+    dead = torch.full((8, 8), 1e-3)
+    solve._uniform_cache[id(b)] = (weakref.ref(dead), b._version, True)
+    del dead                              # ... and one whose tensor is gone
+    assert solve._is_uniform(b) is False
