@@ -40,7 +40,7 @@ SEG = 500         # Euler steps per checkpoint segment (experiments/generate_fd_
 def ncu_traffic(workload):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
             return float(json.load(f)[workload]["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -95,7 +95,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ workloads (host side, NumPy)
-def make_fk4096(H=4096, W=4096, seed=0):
+# Stimulus masks come from `S`: the product's own cardiax_b200.stimulus on the GPU arm, the oracle's builders on the
+# reference (CPU) arm -- the same fields (tests/test_reference_pin.py::test_mask_builders).  Scar maps come from the
+# product's generator (cardiax_b200.generate.random_diffusivity: NumPy / SciPy, seeded) on both arms.
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
+def _stim(S, proto, field):
+    return (tuple(float(np.asarray(_np(p)).reshape(-1)[0]) for p in proto), np.ascontiguousarray(_np(field), dtype=np.float32))
+
+
+def scar_map(shape, seed):
+    from cardiax_b200 import generate
+    return np.ascontiguousarray(generate.random_diffusivity(np.random.default_rng(seed), shape), dtype=np.float32)
+
+
+def make_fk4096(S=None, H=4096, W=4096, seed=0):
     rng = np.random.default_rng(seed)
     u = np.zeros((H, W), np.float32)
     for _ in range(max(4, H * W // 400000)):
@@ -105,51 +121,77 @@ def make_fk4096(H=4096, W=4096, seed=0):
                 D=np.full((H, W), 1e-3, np.float32), stimuli=[], params="5")
 
 
-def make_fk128():
+def make_fk128(S):
     """BASELINE config 1 (the README benchmark): 128 x 128, PARAMSET_3, D = 1e-3, NORTH stripe, one stimulus."""
-    import oracle as O
     shape = (128, 128)
+    s = S.linear(shape, 0, 0.2, 20.0, S.Protocol(0, 2, 1e9))
     return dict(v=np.ones(shape, np.float32), w=np.ones(shape, np.float32), u=np.zeros(shape, np.float32),
-                D=np.full(shape, 1e-3, np.float32), stimuli=[O.linear(shape, 0, 0.2, 20.0, O.Protocol(0, 2, 1e9))],
-                params="3")
+                D=np.full(shape, 1e-3, np.float32), stimuli=[_stim(S, s.protocol, s.field)], params="3")
 
 
-def make_fk512(seed=0):
-    import oracle as O
-    from tests import common
+def make_fk512(S, seed=0):
+    """BASELINE config 2: 512 x 512 scar map, S1 at step 0, S2 (rotated by 90 degrees) at step 40 000
+    (experiments/generate_fd_data_256.py:22-40)."""
     shape = (512, 512)
-    _, D = common.smooth_case(shape, seed)
     ang = float(np.random.default_rng(seed).uniform(0, 180))
-    s1 = O.triangular(shape, 0, ang, 0.2, 20.0, O.Protocol(0, 2, 1e9))
-    s2 = O.triangular(shape, 0, ang + 90, 0.5, 20.0, O.Protocol(40000, 2, 1e9))
-    return dict(v=np.ones(shape, np.float32), w=np.ones(shape, np.float32), u=np.zeros(shape, np.float32), D=D,
-                stimuli=[s1, s2], params="3")
+    s1 = S.triangular(shape, 0, ang, 0.2, 20.0, S.Protocol(0, 2, 1e9))
+    s2 = S.triangular(shape, 0, ang + 90, 0.5, 20.0, S.Protocol(40000, 2, 1e9))
+    return dict(v=np.ones(shape, np.float32), w=np.ones(shape, np.float32), u=np.zeros(shape, np.float32),
+                D=scar_map(shape, seed), stimuli=[_stim(S, s.protocol, s.field) for s in (s1, s2)], params="3")
 
 
-def make_ens256(nsims, seed=0):
-    import oracle as O
-    from tests import common
+def make_fk1200(S=None):
+    """the reference's data-generation tissue: 1200 x 1200, scar-map D (deepx/generate.py:92)"""
+    wq = make_fk4096(None, 1200, 1200)
+    wq.update(D=scar_map((1200, 1200), 0), params="3")
+    return wq
+
+
+def make_ens256(S, nsims, seed=0):
+    """BASELINE config 4, one GPU's share: `nsims` independent 256 x 256 tissues, scar D, three stimuli each drawn like
+    deepx/generate.py:59-76 (type in {rectangular, triangular, linear}, amplitude 20, duration 2)."""
     shape = (256, 256)
     rng = np.random.default_rng(seed)
     D = np.empty((nsims,) + shape, np.float32)
     stim = []
     for b in range(nsims):
-        _, D[b] = common.smooth_case(shape, seed * 100003 + b)
+        D[b] = scar_map(shape, seed * 100003 + b)
         ss = []
         for k in range(3):
             kind = rng.integers(0, 3)
-            proto = O.Protocol(int(1 + k * 25000 + rng.integers(0, 2)), 2, int(rng.integers(400, 10 ** 9)))
+            proto = S.Protocol(int(1 + k * 25000 + rng.integers(0, 2)), 2, int(rng.integers(400, 10 ** 9)))
             if kind == 0:
                 size = rng.integers(10, 85, 2)
-                ss.append(O.rectangular(shape, rng.integers(int(size.min()), 256, 2), size, 20.0, proto))
+                s = S.rectangular(shape, rng.integers(int(size.min()), 256, 2), size, 20.0, proto)
             elif kind == 1:
-                ss.append(O.triangular(shape, int(rng.integers(0, 3)), float(abs(rng.normal()) * 45),
-                                       float(abs(rng.normal()) * 0.2), 20.0, proto))
+                s = S.triangular(shape, int(rng.integers(0, 3)), float(abs(rng.normal()) * 45),
+                                 float(abs(rng.normal()) * 0.2), 20.0, proto)
             else:
-                ss.append(O.linear(shape, int(rng.integers(0, 3)), float(abs(rng.normal()) * 0.2), 20.0, proto))
+                s = S.linear(shape, int(rng.integers(0, 3)), float(abs(rng.normal()) * 0.2), 20.0, proto)
+            ss.append(_stim(S, s.protocol, s.field))
         stim.append(ss)
     return dict(v=np.ones((nsims,) + shape, np.float32), w=np.ones((nsims,) + shape, np.float32),
                 u=np.zeros((nsims,) + shape, np.float32), D=D, stimuli=stim, params="3")
+
+
+def build_work(workload, S, rank, world):
+    if workload == "fk4096":
+        return make_fk4096(), {"workload": "fk4096: 4096x4096 homogeneous D=1e-3, PARAMSET_5, random rectangular excitations",
+                               "grid": [4096, 4096]}
+    if workload == "slab":
+        return make_fk4096(None, 2048, 16384, seed=rank), {
+            "workload": "slab: (2048*N)x16384 tissue (16384^2 at N=8), row slabs of 2048 rows per GPU; halo rows stored into "
+                        "the neighbouring GPUs' memory by the step kernel itself (peer-mapped buffers over NVLink, flags)",
+            "grid": [2048 * world, 16384]}
+    if workload == "fk512":
+        return make_fk512(S), {"workload": "fk512: 512x512 scar-map D, S1-S2 cross-field stimuli, PARAMSET_3", "grid": [512, 512]}
+    if workload == "fk128":
+        return make_fk128(S), {"workload": "fk128: 128x128 plane wave, PARAMSET_3, D=1e-3 (README benchmark shape)", "grid": [128, 128]}
+    if workload == "ens256":
+        return make_ens256(S, 128, seed=rank), {
+            "workload": "ens256: 128 independent 256x256 tissues per GPU, scar D, 3 random stimuli each, no communication",
+            "grid": [128 * world, 256, 256]}
+    raise SystemExit("unknown workload " + workload)
 
 
 # ------------------------------------------------------------------ reference arm / cpu baseline
@@ -164,6 +206,7 @@ def cpu_run(work, euler_steps, repeats=1):
         D, stim = work["D"][0], work["stimuli"][0]
     else:
         D, stim = work["D"], work["stimuli"]
+    stim = [O.Stimulus(O.Protocol(*p), f) for p, f in stim]
     cells = st.u.size
     t0 = time.perf_counter()
     for _ in range(repeats):
@@ -173,9 +216,6 @@ def cpu_run(work, euler_steps, repeats=1):
 
 
 def reference_arm(args, workload, work, config):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     cells = work["u"].shape[-1] * work["u"].shape[-2]
     n_euler = max(1, int(2.0e8 // cells))  # ~2e8 cell-steps (about a second of CPU work) per bench step
     for _ in range(args.warmup):
@@ -199,6 +239,28 @@ def reference_arm(args, workload, work, config):
 
 
 # ------------------------------------------------------------------ main
+def numa_bind(local_rank):
+    """Pin this process (and so the first-touch placement of its pinned buffers) to the CPUs of the NUMA node its GPU
+    hangs off: at 8 ranks the host copies of the e2e leg otherwise cross the socket interconnect."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,8 +276,9 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--halo-launches", type=int, default=8)
+    ap.add_argument("--comm", default=None, choices=["peer", "dist"], help="slab halo exchange: fused peer stores (default) or NCCL")
     ap.add_argument("--no-extra", action="store_true",
-                    help="skip the quick fk512 / fk128 / fk1200 lines (BASELINE configs 2, 1; the reference's data-generation tissue)")
+                    help="skip the lines beside the headline (other BASELINE configs, ensemble, single-GPU slab shape, checks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -223,42 +286,27 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = args.workload or ("fk4096" if args.gpus == 1 else "slab")
-
-    if workload == "fk4096":
-        work = make_fk4096()
-        config = {"workload": "fk4096: 4096x4096 homogeneous D=1e-3, PARAMSET_5, random rectangular excitations",
-                  "grid": [4096, 4096]}
-    elif workload == "slab":
-        work = make_fk4096(2048, 16384, seed=rank)
-        config = {"workload": "slab: (2048*N)x16384 tissue (16384^2 at N=8), row slabs of 2048 rows per GPU, "
-                              "halo rows exchanged over NCCL/NVLink and overlapped with the interior",
-                  "grid": [2048 * world, 16384]}
-    elif workload == "fk512":
-        work = make_fk512()
-        config = {"workload": "fk512: 512x512 scar-map D, S1-S2 cross-field stimuli, PARAMSET_3", "grid": [512, 512]}
-    elif workload == "fk128":
-        work = make_fk128()
-        config = {"workload": "fk128: 128x128 plane wave, PARAMSET_3, D=1e-3 (README benchmark shape)", "grid": [128, 128]}
-    elif workload == "ens256":
-        work = make_ens256(128, seed=rank)
-        config = {"workload": "ens256: 128 independent 256x256 tissues per GPU, scar D, 3 random stimuli each",
-                  "grid": [128 * world, 256, 256]}
-    else:
-        raise SystemExit("unknown workload " + workload)
-    config.update({"euler_steps_per_step": args.seg, "dt": 0.01, "dx": 0.01, "numerics": args.numerics,
-                   "l2": "state (3 arrays of >= 64 MiB per GPU) larger than the 126 MB L2" if workload in ("fk4096", "slab")
-                   else "working set is L2 resident by nature of the config; an L2 flush buffer is written between steps"})
+    l2_note = {"euler_steps_per_step": args.seg, "dt": 0.01, "dx": 0.01, "numerics": args.numerics,
+               "l2": "state (3 arrays of >= 64 MiB per GPU) larger than the 126 MB L2" if workload in ("fk4096", "slab")
+               else "working set is L2 resident by nature of the config; an L2 flush buffer is written between steps"}
 
     if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle as O   # the reference arm is the one place bench.py executes oracle/
+        work, config = build_work(workload, O, rank, world)
+        config.update(l2_note)
         return reference_arm(args, workload, work, config)
 
+    import ctypes
     import torch
-    import oracle as O
     from cardiax_b200 import _lib, options, solve, stimulus
+    from cardiax_b200 import params as fkparams
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = numa_bind(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -270,35 +318,64 @@ def main():
     options.numerics = args.numerics
     options.steps_per_launch = args.T
     options.cta_threads, options.rows_per_cta, options.kernel = args.cta_threads, args.rows_per_cta, args.kernel
-    params = O.PARAMSETS[work["params"]]
+    work, config = build_work(workload, stimulus, rank, world)
+    config.update(l2_note)
+    pset = lambda name: getattr(fkparams, "PARAMSET_" + name)  # noqa: E731
+    params = pset(work["params"])
     seg = args.seg
 
     def dev_stim(stimuli):
         if len(stimuli) and isinstance(stimuli[0], list):
             return [dev_stim(s) for s in stimuli]
-        return [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).to(dev)) for s in stimuli]
+        return [stimulus.Stimulus(stimulus.Protocol(*p), torch.as_tensor(f).to(dev)) for p, f in stimuli]
 
-    gstim = dev_stim(work["stimuli"])
-    D = torch.as_tensor(work["D"]).to(dev)
-    state0 = solve.State(*[torch.as_tensor(work[k]).to(dev) for k in "vwu"])
-    cells = state0.u.numel()
-    flush = None
-    if workload in ("fk512", "ens256", "fk128"):
-        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-
-    if workload == "slab" and world > 1:
-        from cardiax_b200 import slab
-        runner = slab.SlabRunner(state0, D, params, gstim, 0.01, 0.01, rank, world, steps_per_launch=args.T or 0,
-                                 halo_launches=args.halo_launches)
-        step_fn = lambda st, t: runner.advance(st, t, t + seg)  # noqa: E731
-        state0 = runner.scatter_local(state0)
-    else:
-        step_fn = lambda st, t: solve._forward_euler(st, t, t + seg, params, D, gstim, 0.01, 0.01)  # noqa: E731
+    def dev_state(wk):
+        return solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_segments(step, n_warm, n_timed, flush_buf=None):
+        """Device time (ms, CUDA events on the launch stream) of n_timed calls of step(i); L2 flushed outside the timing."""
+        for i in range(n_warm):
+            step(i)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for i in range(n_timed):
+            if flush_buf is not None:
+                flush_buf.fill_(1.0)
+            a0.record()
+            step(n_warm + i)
+            a1.record(); torch.cuda.synchronize()
+            tot += a0.elapsed_time(a1)
+        return tot
+
+    gstim = dev_stim(work["stimuli"])
+    D = torch.as_tensor(work["D"]).to(dev)
+    state0 = dev_state(work)
+    cells = state0.u.numel()
+    flush = None
+    if workload in ("fk512", "ens256", "fk128"):
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    runner = None
+    if workload == "slab" and world > 1:
+        from cardiax_b200 import slab
+        runner = slab.SlabRunner(state0, D, params, gstim, 0.01, 0.01, rank, world, steps_per_launch=args.T or 0,
+                                 halo_launches=args.halo_launches, comm=args.comm)
+        step_fn = lambda st, t: runner.advance(None, t, t + seg, copy=False)  # noqa: E731  (the state stays resident)
+    else:
+        step_fn = lambda st, t: solve._forward_euler(st, t, t + seg, params, D, gstim, 0.01, 0.01)  # noqa: E731
 
     # ---- device-resident measurement
     st, t = state0, 0
@@ -311,6 +388,7 @@ def main():
     launches0 = L.fk_launch_count()
     L.fk_profile_enable(0 if os.environ.get("FK_BENCH_NOPROF") else 1)
     L.fk_profile_collect(None, None, None, None, None)
+    L.fk_profile_dropped()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -321,9 +399,9 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    import ctypes
     sm_ms, sm_n, tl_ms, tl_n, sm_cs = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     L.fk_profile_collect(ctypes.byref(sm_ms), ctypes.byref(sm_n), ctypes.byref(tl_ms), ctypes.byref(tl_n), ctypes.byref(sm_cs))
+    prof_dropped = int(L.fk_profile_dropped())
     plan = _lib.last_plan()
     main_kernel_name = _lib.last_kernel()
     L.fk_profile_enable(0)
@@ -337,12 +415,10 @@ def main():
         f1.record(); torch.cuda.synchronize()
         ms -= f0.elapsed_time(f1)
     assert all(bool(torch.isfinite(x).all()) for x in st)
-    if dist is not None:
-        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms = max_over_ranks(ms)
     total_cells = cells * world
     value = total_cells * seg * args.steps / (ms * 1e-3) / 1e9
+    t_end_main = t
 
     # ---- end to end through the public API from pinned host buffers: every step copies its input state host->device
     # and its result device->host inside the timed region.  The copies run on their own streams (double-buffered device
@@ -370,8 +446,8 @@ def main():
             ev_in[b].record(s_in)
         s_run.wait_event(ev_in[b])
         s = solve.State(*dev_in[b])
-        if workload == "slab" and world > 1:
-            s = runner.gather_local(step_fn(runner.scatter_local(s), t))
+        if runner is not None:
+            s = runner.advance(s, t, t + seg, copy=True)    # loads the uploaded rows, refreshes the neighbours' halos
         else:
             s = step_fn(s, t)
         ev_free[b].record(s_run)
@@ -405,52 +481,146 @@ def main():
     barrier()
     ems = g0.elapsed_time(g1)
     assert all(bool(torch.isfinite(x).all()) for x in host_out[(args.steps - 1) % NB])
-    if dist is not None:
-        tms = torch.tensor([ems], device=dev, dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ems = float(tms.item())
+    ems = max_over_ranks(ems)
     e2e = total_cells * seg * args.steps / (ems * 1e-3) / 1e9
+    del host_in, host_out, dev_in, results
+
+    other = {} if not args.no_extra else None
+    exit_code = 0
+
+    # ---- slab: the exchange's exposed time, and the result checked against a single-GPU recomputation
+    if runner is not None and other is not None:
+        n_grp = 6
+        grp_steps = runner.M * runner.T
+        def slab_ms(comm_on):
+            runner.comm_enabled = comm_on
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            runner.advance(None, 0, n_grp * grp_steps, copy=False)
+            a1.record()
+            barrier()
+            runner.comm_enabled = True
+            return max_over_ranks(a0.elapsed_time(a1))
+        slab_ms(True)
+        with_comm = min(slab_ms(True) for _ in range(3))
+        runner.load(state0)          # (the runs without communication leave wrong halos behind)
+        slab_ms(False)
+        without = min(slab_ms(False) for _ in range(3))
+        other["exposed_us_per_exchange"] = {"value": (with_comm - without) * 1e3 / n_grp, "groups": n_grp,
+                                            "steps_per_group": grp_steps, "ms_with_exchange": with_comm, "ms_without": without,
+                                            "comm": runner.comm.kind, "fused_mirror_launches": getattr(runner.be, "fused_mirrors", None)}
+        # check: a band around every rank boundary recomputed by ONE GPU as a tissue of its own.  With K = 4 n + 8 rows
+        # on each side the recomputation's artificial top / bottom edges cannot reach the compared rows in n steps.
+        n_chk, band = 40, 64
+        K = 4 * n_chk + 8 + band
+        runner.load(state0)
+        out = runner.advance(None, 0, n_chk, copy=True)
+        ok = True
+        if rank + 1 < world:      # this rank checks the boundary below it: the neighbour sends its first K rows
+            top_in = [torch.empty((K, state0.u.shape[1]), device=dev) for _ in range(3)]
+            top_out = [torch.empty((band, state0.u.shape[1]), device=dev) for _ in range(3)]
+        ops = []
+        if rank > 0:
+            ops += [dist.P2POp(dist.isend, x[:K].contiguous(), rank - 1) for x in state0]
+            ops += [dist.P2POp(dist.isend, x[:band].contiguous(), rank - 1) for x in out]
+        if rank + 1 < world:
+            ops += [dist.P2POp(dist.irecv, x, rank + 1) for x in top_in]
+            ops += [dist.P2POp(dist.irecv, x, rank + 1) for x in top_out]
+        for w_ in dist.batch_isend_irecv(ops):
+            w_.wait()
+        if rank + 1 < world:
+            win = solve.State(*[torch.cat([mine[-K:], theirs]) for mine, theirs in zip(state0, top_in)])
+            ref = solve._forward_euler(win, 0, n_chk, params, torch.full(win.u.shape, 1e-3, device=dev), [], 0.01, 0.01)
+            ok = all(torch.equal(r_[K - band:K], o[-band:]) and torch.equal(r_[K:K + band], t_)
+                     for r_, o, t_ in zip(ref, out, top_out))
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        other["slab_check"] = ("bit-equal" if int(flag.item()) else "MISMATCH") + \
+            ": %d rows around each of the %d rank boundaries after %d steps vs a single-GPU recomputation" % (2 * band, world - 1, n_chk)
+        if not int(flag.item()):
+            exit_code = 1
+        runner.close()
+        runner = None
+
+    # ---- beside the headline, at EVERY N: BASELINE config 4 (ensemble, 128 tissues per GPU, no communication) and the
+    # slab shape on one GPU (the denominator of SURVEY 8e's weak-scaling efficiency)
+    if other is not None:
+        del st, state0, D
+        fl = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        wk = make_ens256(stimulus, 128, seed=rank)
+        gs, Dk, pk = dev_stim(wk["stimuli"]), torch.as_tensor(wk["D"]).to(dev), pset(wk["params"])
+        box = [dev_state(wk)]
+        def ens_step(i):
+            box[0] = solve._forward_euler(box[0], i * seg, (i + 1) * seg, pk, Dk, gs, 0.01, 0.01)
+        barrier()
+        n_seg = 6
+        tot = max_over_ranks(timed_segments(ens_step, 3, n_seg, fl))
+        other["ens256"] = {"value": world * box[0].u.numel() * seg * n_seg / (tot * 1e-3) / 1e9, "unit": "Gcell-steps/s",
+                           "tissues": 128 * world, "tissues_per_gpu": 128, "grid": [256, 256], "segments": n_seg,
+                           "euler_steps_per_segment": seg, "kernel": _lib.last_kernel(), "launch_geometry": _lib.last_plan(),
+                           "note": "BASELINE config 4 sharded over the ranks with no communication; time = max over ranks"}
+        other["ens256"]["frac_of_28B_roofline_per_gpu"] = ALG_BYTES * other["ens256"]["value"] / world / peaks()[0]
+        del box, gs, Dk
+        wk = make_fk4096(None, 2048, 16384, seed=rank)
+        Dk, pk = torch.as_tensor(wk["D"]).to(dev), pset(wk["params"])
+        box = [dev_state(wk)]
+        def slab1_step(i):
+            box[0] = solve._forward_euler(box[0], i * seg, (i + 1) * seg, pk, Dk, [], 0.01, 0.01)
+        barrier()
+        n_seg = 4
+        tot = max_over_ranks(timed_segments(slab1_step, 2, n_seg))
+        slab_n1 = box[0].u.numel() * seg * n_seg / (tot * 1e-3) / 1e9
+        other["slab_n1"] = {"value": slab_n1, "unit": "Gcell-steps/s", "grid": [2048, 16384],
+                            "note": "ONE GPU running a 2048x16384 tissue standalone (every rank measures it at the same time; slowest rank)"}
+        if workload == "slab" and world > 1:
+            other["efficiency_vs_slab_n1"] = value / (world * slab_n1)
+        del box, Dk, fl
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return
+        sys.exit(exit_code)
 
     # ---- BASELINE configs 2 and 1 beside the headline (N = 1 default run only): a few segments each, device resident
-    other = None
-    if world == 1 and workload == "fk4096" and not args.no_extra:
-        other = {}
+    if world == 1 and workload == "fk4096" and other is not None:
         fl = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-        def make_fk1200():   # the reference's data-generation tissue: 1200 x 1200, scar-map D (deepx/generate.py:92)
-            from tests import common
-            _, Dm = common.smooth_case((1200, 1200), 0)
-            wq = make_fk4096(1200, 1200)
-            wq.update(D=Dm, params="3")
-            return wq
         for name, mk in (("fk512", make_fk512), ("fk128", make_fk128), ("fk1200", make_fk1200)):
-            wk = mk()
+            wk = mk(stimulus)
             gs, Dk = dev_stim(wk["stimuli"]), torch.as_tensor(wk["D"]).to(dev)
-            pk = O.PARAMSETS[wk["params"]]
-            sk, tk = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"]), 0
-            for _ in range(3):
-                sk = solve._forward_euler(sk, tk, tk + seg, pk, Dk, gs, 0.01, 0.01); tk += seg
-            torch.cuda.synchronize()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_seg, tot = 8, 0.0
-            for _ in range(n_seg):   # L2 flushed between segments, outside the timed region
-                fl.fill_(1.0)
-                a0.record()
-                sk = solve._forward_euler(sk, tk, tk + seg, pk, Dk, gs, 0.01, 0.01); tk += seg
-                a1.record(); torch.cuda.synchronize()
-                tot += a0.elapsed_time(a1)
-            cs = sk.u.numel() * seg * n_seg
+            pk = pset(wk["params"])
+            box = [dev_state(wk)]
+            def seg_step(i):
+                box[0] = solve._forward_euler(box[0], i * seg, (i + 1) * seg, pk, Dk, gs, 0.01, 0.01)
+            n_seg = 8
+            tot = timed_segments(seg_step, 3, n_seg, fl)
+            cs = box[0].u.numel() * seg * n_seg
             other[name] = {"value": cs / (tot * 1e-3) / 1e9, "unit": "Gcell-steps/s", "us_per_euler_step": tot * 1e3 / (seg * n_seg),
                            "kernel": _lib.last_kernel(), "launch_geometry": _lib.last_plan(), "segments": n_seg,
                            "euler_steps_per_segment": seg}
+        # BASELINE config 2 at its REAL protocol: S2 fires at step 40 000 of 1e5 (generate_fd_data_256.py:22-40) -- the
+        # whole run, 200 segments of 500 steps, timed end to end on the device
+        wk = make_fk512(stimulus)
+        gs, Dk, pk = dev_stim(wk["stimuli"]), torch.as_tensor(wk["D"]).to(dev), pset("3")
+        sk = dev_state(wk)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        u_before = None
+        for i in range(200):
+            if i == 80:
+                u_before = sk.u
+            sk = solve._forward_euler(sk, i * 500, (i + 1) * 500, pk, Dk, gs, 0.01, 0.01)
+            if i == 80:
+                s2_jump = float((sk.u - u_before).abs().max().item())    # S2 fired inside this segment (host read: one sync)
+        a1.record(); torch.cuda.synchronize()
+        other["fk512_full_protocol"] = {"value": sk.u.numel() * 1e5 / (a0.elapsed_time(a1) * 1e-3) / 1e9, "unit": "Gcell-steps/s",
+                                        "euler_steps": 100000, "seconds": a0.elapsed_time(a1) * 1e-3, "s2_fired_at_step_40000": s2_jump > 0.05,
+                                        "max_u_change_in_the_s2_segment": s2_jump, "finite": bool(torch.isfinite(sk.u).all())}
         # the Heun integrator (solve.py:73-85, 103-111; deepx/DataGeneration.ipynb selects it) on the headline tissue
         wk = work
-        sk = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
-        Dk, pk, hs = torch.as_tensor(wk["D"]).to(dev), O.PARAMSETS[wk["params"]], 40
+        sk = dev_state(wk)
+        Dk, pk, hs = torch.as_tensor(wk["D"]).to(dev), pset(wk["params"]), 40
         sk = solve._forward_heun(sk, 0, 4, pk, Dk, [], 0.01, 0.01)
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -460,12 +630,23 @@ def main():
         a1.record(); torch.cuda.synchronize()
         other["heun_fk4096"] = {"value": sk.u.numel() * hs / (a0.elapsed_time(a1) * 1e-3) / 1e9, "unit": "Gcell-steps/s (Heun steps)",
                                 "kernel": _lib.last_kernel(), "heun_steps": hs}
+        # exact numerics (bit-identical to the reference's source, tests/test_reference_pin.py) on the headline tissue
+        options.numerics = "exact"
+        sk = dev_state(wk)
+        sk = solve._forward_euler(sk, 0, 20, pk, Dk, [], 0.01, 0.01)
+        torch.cuda.synchronize()
+        a0.record()
+        sk = solve._forward_euler(sk, 20, 120, pk, Dk, [], 0.01, 0.01)
+        a1.record(); torch.cuda.synchronize()
+        other["exact_fk4096"] = {"value": sk.u.numel() * 100 / (a0.elapsed_time(a1) * 1e-3) / 1e9, "unit": "Gcell-steps/s",
+                                 "kernel": _lib.last_kernel()}
+        options.numerics = args.numerics
         # the snapshot path of deepx.generate.sequence on the reference's 1200^2 tissue: 500 Euler steps, resize kernel to
         # 256^2, pinned D2H on a side stream, writer thread -- per-segment time with and without snapshots
         from cardiax_b200 import io as fio
         wk = make_fk1200()
-        Dk, pk = torch.as_tensor(wk["D"]).to(dev), O.PARAMSETS["3"]
-        sk = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
+        Dk, pk = torch.as_tensor(wk["D"]).to(dev), pset("3")
+        sk = dev_state(wk)
         n_seg = 8
         snaps = np.zeros((n_seg + 2, 3, 256, 256), np.float32)
         res = {}
@@ -486,21 +667,20 @@ def main():
         del fl
         # the reference's README table (README.md:25-31): wall seconds of forward() over 1e3 steps, field size varied,
         # two stimuli (cardiax's fenton_karma notebooks); host wall clock, call + synchronize, best of 3
-        import time as _t
         table = {}
         for n in (64, 128, 256, 512, 1024):
             shp = (n, n)
-            s1 = stimulus.Stimulus(stimulus.Protocol(0, 2, 1e9), torch.as_tensor(O.linear(shp, 0, 0.2, 20.0, O.Protocol(0, 2, 1e9)).field).to(dev))
-            s2 = stimulus.Stimulus(stimulus.Protocol(200, 2, 1e9), torch.as_tensor(O.linear(shp, 1, 0.2, 20.0, O.Protocol(200, 2, 1e9)).field).to(dev))
+            s1 = stimulus.linear(shp, stimulus.Direction.NORTH, 0.2, 20.0, stimulus.Protocol(0, 2, 1e9))
+            s2 = stimulus.linear(shp, stimulus.Direction.EAST, 0.2, 20.0, stimulus.Protocol(200, 2, 1e9))
             Dn = torch.full(shp, 1e-3, device=dev)
             best = 1e30
             for _ in range(4):
                 s0 = solve.init(shp)
                 torch.cuda.synchronize()
-                w0 = _t.perf_counter()
-                out_states = solve.forward(s0, [0, 1000], O.PARAMSETS["3"], Dn, [s1, s2], 0.01, 0.01)
+                w0 = time.perf_counter()
+                out_states = solve.forward(s0, [0, 1000], pset("3"), Dn, [s1, s2], 0.01, 0.01)
                 torch.cuda.synchronize()
-                best = min(best, _t.perf_counter() - w0)
+                best = min(best, time.perf_counter() - w0)
             assert bool(torch.isfinite(out_states[-1].u).all())
             table[str(n)] = best
         other["readme_table_seconds_1e3_steps"] = {
@@ -513,16 +693,21 @@ def main():
     peak, peak_kind = peaks()
     roof = None
     main_kernel = main_kernel_name
+    traffic = ncu_traffic(workload)
     if sm_n.value > 0:
         # streaming kernel: T steps over the rows/columns it owns per launch (counted by the library per launch)
         cs_per_launch = sm_cs.value / sm_n.value
-        achieved = ALG_BYTES * cs_per_launch / (sm_ms.value / sm_n.value * 1e-3) / 1e9
+        avg_ms = sm_ms.value / sm_n.value
+        achieved = ALG_BYTES * cs_per_launch / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(workload), "peak_kind": peak_kind, "kernel": main_kernel,
-                "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": sm_ms.value / sm_n.value,
+                "traffic": traffic, "peak_kind": peak_kind, "kernel": main_kernel,
+                "dram_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": avg_ms,
                 "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms,
+                "launches_timed": int(sm_n.value), "launches_not_timed": prof_dropped,
                 "note": ("the streaming kernel covers the whole tissue, physical edges included; the rest of the step is "
-                         "fk_dgrad_kernel (once per call) and launch gaps") if main_kernel == "fk_stream_kernel" else
+                         "fk_dgrad_kernel (once per call) and launch gaps; dram_frac = the ncu-measured DRAM bytes of one "
+                         "launch / its event-timed duration / peak") if main_kernel == "fk_stream_kernel" else
                         ("one resident launch per segment: the state lives in shared memory for all of its Euler steps and "
                          "halos travel through L2, so HBM sees only the segment's first load and last store; the fraction "
                          "compares the ALGORITHMIC 28 B per cell-step with the HBM peak like every other line"),
@@ -543,13 +728,14 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "Gcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "host_link_gbs": link},
+                "host_link_gbs": link, "numa_node": numa},
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "other_configs": other,
         "hbm_roofline_frac_whole_step": ALG_BYTES * value / world / peak,
     }
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+    sys.exit(exit_code)
 
 
 if __name__ == "__main__":

@@ -39,6 +39,12 @@ class FkOptions(ctypes.Structure):
                 ("reserved", ctypes.c_int * 1)]
 
 
+class FkPeerMirror(ctypes.Structure):
+    """include/fk.h: rows of a slab launch that are also stored into the neighbouring GPUs' (peer-mapped) arrays."""
+    _fields_ = [("v", ctypes.c_void_p * 2), ("w", ctypes.c_void_p * 2), ("u", ctypes.c_void_p * 2),
+                ("row0", ctypes.c_int * 2), ("row1", ctypes.c_int * 2), ("dst_row0", ctypes.c_int * 2)]
+
+
 def needs_build():
     if not os.path.exists(SO_PATH):
         return True
@@ -57,7 +63,7 @@ def build(force=False, verbose=False):
     env = dict(os.environ)
     env.pop("CC", None)   # the image's CC/CXX point at a gcc without its support files
     env.pop("CXX", None)
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.environ.get("FK_OBJDIR") or os.path.join(CSRC, "build")   # FK_OBJDIR + FK_SO: a second build next to the first
     os.makedirs(objdir, exist_ok=True)
     depths = STREAM_DEPTHS
     if os.environ.get("FK_DEPTHS"):   # development: e.g. FK_DEPTHS=2 links only the T = 2 kernels (others: "unsupported")
@@ -129,6 +135,17 @@ def lib():
     L.fk_euler_rows.argtypes = [vp] * 6 + [vp, vp, vp, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd,
                                            ci, cf, cf, ctypes.POINTER(FkOptions), ci, ci, vp, sz, vp]
     L.fk_euler_rows.restype = ci
+    L.fk_euler_rows_peer.argtypes = L.fk_euler_rows.argtypes + [ctypes.POINTER(FkPeerMirror), ctypes.POINTER(ci)]
+    L.fk_euler_rows_peer.restype = ci
+    L.fk_peer_alloc.argtypes = [sz, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_ubyte * 64)]
+    L.fk_peer_open.argtypes = [ctypes.POINTER(ctypes.c_ubyte * 64), ctypes.POINTER(vp)]
+    L.fk_peer_close.argtypes = [vp]
+    L.fk_peer_free.argtypes = [vp]
+    L.fk_peer_signal.argtypes = [vp, ctypes.c_uint, vp]
+    L.fk_peer_wait.argtypes = [vp, ctypes.c_uint, vp]
+    L.fk_peer_copy.argtypes = [vp, vp, sz, vp]
+    for f in (L.fk_peer_alloc, L.fk_peer_open, L.fk_peer_close, L.fk_peer_free, L.fk_peer_signal, L.fk_peer_wait, L.fk_peer_copy):
+        f.restype = ci
     L.fk_check_exact_division.argtypes = [ctypes.POINTER(FkParams), cf, ctypes.POINTER(ll), vp]
     L.fk_check_exact_division.restype = ci
     L.fk_rhs.argtypes = [vp] * 6 + [vp, ci, ci, ci, ci, ctypes.POINTER(FkParams), ctypes.POINTER(FkStimulus), ci, cd, cf,

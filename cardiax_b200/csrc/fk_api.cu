@@ -465,7 +465,8 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
                      const float* D, int d_batched, int H, int W, int batch, const FkParams* params,
                      const FkStimulus* stimuli, int n_stim, double t0, long long nsteps, float dt, float dx,
                      const FkOptions* opt_in, int rhs_mode, void* workspace, size_t workspace_bytes, void* stream,
-                     const float* DXext = nullptr, const float* DYext = nullptr, int row0 = 0, int row1 = 0) {
+                     const float* DXext = nullptr, const float* DYext = nullptr, int row0 = 0, int row1 = 0,
+                     const fk::SlabMirror* mirror = nullptr, bool* mirrored = nullptr) {
     int rc = check_common(H, W, batch, params, n_stim, stimuli);
     if (rc) return rc;
     if (!v_in || !w_in || !u_in || !v_out || !w_out || !u_out || !D) return fail(-1, "NULL pointer%s");
@@ -505,6 +506,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     B.xchg_bytes = rows_mode ? 0 : (long long)ws.xchg_bytes;
     B.DX = DXext ? DXext : ws.DX;
     B.DY = DYext ? DYext : ws.DY;
+    B.mirror = mirror; B.mirrored = mirrored;
     fk::DriveOptions o;
     o.exact = opt.exact; o.steps_per_launch = opt.steps_per_launch; o.kernel = opt.kernel;
     o.phys_top = opt.phys_top; o.phys_bottom = opt.phys_bottom; o.cta_threads = opt.cta_threads;
@@ -776,6 +778,145 @@ int fk_euler_rows(const float* v_in, const float* w_in, const float* u_in, float
     o.steps_per_launch = nsteps;
     return run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, 0, H, W, 1, params, stimuli, n_stim, t0, nsteps, dt, dx, &o,
                      0, workspace, workspace_bytes, stream, DX, DY, row0, row1);
+}
+
+// ---- peer memory for the slab decomposition
+namespace {
+__global__ void fk_flag_signal_kernel(unsigned int* flag, unsigned int value) {
+    __threadfence_system();   // everything this stream wrote before (kernel boundary) is ordered before the flag
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// fallback when the driver offers no stream memory operations: one thread polls (and gives up after ~20 s rather than hang)
+__global__ void fk_flag_wait_kernel(const unsigned int* flag, unsigned int value) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - value) >= 0) return;
+        if (clock64() - t0 > 40000000000LL) __trap();
+        __nanosleep(256);
+    }
+}
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        if (!getenv("FK_PEER_WAIT_KERNEL")) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                fn = (StreamWaitValue32Fn)p;
+            else
+                cudaGetLastError();
+        }
+    }
+    return fn;
+}
+}  // namespace
+
+int fk_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle64_out) {
+    if (!dev_ptr_out || !handle64_out || bytes == 0) return fail(-1, "fk_peer_alloc: bad arguments%s");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    FK_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "fk_peer_alloc"); }
+    memcpy(handle64_out, &h, 64);
+    *dev_ptr_out = p;
+    return 0;
+}
+
+int fk_peer_open(const unsigned char* handle64, void** dev_ptr_out) {
+    if (!handle64 || !dev_ptr_out) return fail(-1, "fk_peer_open: bad arguments%s");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    FK_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int fk_peer_close(void* mapped_dev_ptr) {
+    if (mapped_dev_ptr) FK_CUDA(cudaIpcCloseMemHandle(mapped_dev_ptr));
+    return 0;
+}
+
+int fk_peer_free(void* dev_ptr) {
+    if (dev_ptr) FK_CUDA(cudaFree(dev_ptr));
+    return 0;
+}
+
+int fk_peer_signal(unsigned int* flag_peer_dev, unsigned int value, void* stream) {
+    if (!flag_peer_dev) return fail(-1, "fk_peer_signal: NULL flag%s");
+    ++g_launches;
+    fk_flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag_peer_dev, value);
+    FK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fk_peer_wait(const unsigned int* flag_local_dev, unsigned int value, void* stream) {
+    if (!flag_local_dev) return fail(-1, "fk_peer_wait: NULL flag%s");
+    if (StreamWaitValue32Fn fn = stream_wait_value32()) {
+        const int rc = fn((cudaStream_t)stream, (unsigned long long)(uintptr_t)flag_local_dev, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+        if (rc == 0) return 0;
+        // (a driver that refuses the operation: fall through to the polling kernel)
+    }
+    ++g_launches;
+    fk_flag_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag_local_dev, value);
+    FK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fk_peer_copy(void* dst_dev, const void* src_dev, size_t bytes, void* stream) {
+    if (!dst_dev || !src_dev) return fail(-1, "fk_peer_copy: NULL pointer%s");
+    if (bytes) FK_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
+int fk_euler_rows_peer(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
+                       const float* D, const float* DX, const float* DY, int H, int W, const FkParams* params,
+                       const FkStimulus* stimuli, int n_stim, double t0, int nsteps, float dt, float dx, const FkOptions* opt,
+                       int row0, int row1, void* workspace, size_t workspace_bytes, void* stream, const FkPeerMirror* mirror,
+                       int* fused_out) {
+    if (fused_out) *fused_out = 0;
+    if (nsteps < 1 || nsteps > 4) return fail(-1, "fk_euler_rows advances 1..4 steps per call%s");
+    if (row1 <= row0 || row0 < 0 || row1 > H) return fail(-1, "bad row window%s");
+    fk::SlabMirror M;
+    memset(&M, 0, sizeof(M));
+    bool any = false;
+    if (mirror)
+        for (int nb = 0; nb < 2; ++nb) {
+            if (!mirror->u[nb]) continue;
+            if (!mirror->v[nb] || !mirror->w[nb]) return fail(-1, "mirror: NULL array%s");
+            if (mirror->row0[nb] < row0 || mirror->row1[nb] > row1 || mirror->row1[nb] < mirror->row0[nb] || mirror->dst_row0[nb] < 0)
+                return fail(-1, "mirror rows must lie inside the rows this call writes%s");
+            M.u[nb] = mirror->u[nb]; M.v[nb] = mirror->v[nb]; M.w[nb] = mirror->w[nb];
+            M.row0[nb] = mirror->row0[nb]; M.row1[nb] = mirror->row1[nb]; M.dst_row0[nb] = mirror->dst_row0[nb];
+            any = any || M.row1[nb] > M.row0[nb];
+        }
+    FkOptions o;
+    if (opt) o = *opt; else fk_default_options(&o);
+    o.steps_per_launch = nsteps;
+    bool mirrored = false;
+    int rc = run_euler(v_in, w_in, u_in, v_out, w_out, u_out, D, 0, H, W, 1, params, stimuli, n_stim, t0, nsteps, dt, dx, &o,
+                       0, workspace, workspace_bytes, stream, DX, DY, row0, row1, any ? &M : nullptr, &mirrored);
+    if (rc) return rc;
+    if (any && !mirrored) {   // not a streaming launch: the band rows follow as copies on the same stream
+        cudaStream_t st = (cudaStream_t)stream;
+        for (int nb = 0; nb < 2; ++nb) {
+            if (!M.u[nb] || M.row1[nb] <= M.row0[nb]) continue;
+            const size_t bytes = (size_t)(M.row1[nb] - M.row0[nb]) * W * sizeof(float);
+            const size_t so = (size_t)M.row0[nb] * W, dof = (size_t)M.dst_row0[nb] * W;
+            FK_CUDA(cudaMemcpyAsync(M.v[nb] + dof, v_out + so, bytes, cudaMemcpyDefault, st));
+            FK_CUDA(cudaMemcpyAsync(M.w[nb] + dof, w_out + so, bytes, cudaMemcpyDefault, st));
+            FK_CUDA(cudaMemcpyAsync(M.u[nb] + dof, u_out + so, bytes, cudaMemcpyDefault, st));
+        }
+    }
+    if (fused_out) *fused_out = mirrored ? 1 : 0;
+    return 0;
 }
 
 int fk_rhs(const float* v, const float* w, const float* u, float* dv, float* dw, float* du, const float* D, int d_batched,

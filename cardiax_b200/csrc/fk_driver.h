@@ -24,6 +24,13 @@ struct DriveOptions {
     int maps_global;        // resident kernel: 1 = diffusivity maps read from global memory (L2), 0 = planner's choice
 };
 
+// row-slab decomposition: rows [row0[n], row1[n]) of a call's result are also wanted in the memory of the neighbouring
+// GPU n (0 = the slab above, 1 = the slab below) -- peer-mapped (Hb', W) arrays -- starting at its row dst_row0[n]
+struct SlabMirror {
+    float *v[2], *w[2], *u[2];   // null: no neighbour on that side
+    int row0[2], row1[2], dst_row0[2];
+};
+
 struct DriveBuffers {
     const float *v_in, *w_in, *u_in;
     float *v_out, *w_out, *u_out;
@@ -34,6 +41,8 @@ struct DriveBuffers {
     long long xchg_bytes;
     const float *hy_v, *hy_w, *hy_u;   // fast Heun: y of the step whose E(E(y)) this call computes, or null; applied by
     bool* hy_folded;                   // the call's last launch if it is a streaming / wide one (*hy_folded says so)
+    const SlabMirror* mirror;          // slab halo mirror of the call's last launch, or null; done by the launch itself when
+    bool* mirrored;                    // it is a streaming one (*mirrored says so), else left to the caller (plain copies)
 };
 
 enum { FK_DEFAULT_T = 2, FK_RES_MAX_CTAS = 1024 };
@@ -208,6 +217,16 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
         if (B.hy_u && l == nl - 1 && !rhs_mode && (use_wide || (use_stream && T == plan.T))) {
             A.hy_u = B.hy_u; A.hy_v = B.hy_v; A.hy_w = B.hy_w;
             if (B.hy_folded) *B.hy_folded = true;
+        }
+        for (int nb = 0; nb < 2; ++nb) { A.mir_u[nb] = A.mir_v[nb] = A.mir_w[nb] = nullptr; A.mir_r0[nb] = A.mir_r1[nb] = 0; A.mir_off[nb] = 0; }
+        if (B.mirror && l == nl - 1 && !rhs_mode && batch == 1 && use_stream && T == plan.T && T <= 2) {
+            for (int nb = 0; nb < 2; ++nb)
+                if (B.mirror->u[nb] && B.mirror->row1[nb] > B.mirror->row0[nb]) {
+                    A.mir_u[nb] = B.mirror->u[nb]; A.mir_v[nb] = B.mirror->v[nb]; A.mir_w[nb] = B.mirror->w[nb];
+                    A.mir_r0[nb] = B.mirror->row0[nb]; A.mir_r1[nb] = B.mirror->row1[nb];
+                    A.mir_off[nb] = (long long)(B.mirror->dst_row0[nb] - B.mirror->row0[nb]) * W;
+                }
+            if (B.mirrored) *B.mirrored = true;
         }
         int rc;
         if (use_wide) {

@@ -497,12 +497,8 @@ FK_HD void res_block2(const TileArgs& A, const ResGeom& G, const ResCta& X, cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float u_yy = dcen<EXACT>(A.K, gy[k], gy[k + 1], gy[k + 3], gy[k + 4]);
-            const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], u_x[r][k], gy[k + 2], u_xx[r][k], u_yy);
-            float d_v, d_w, d_u;
-            cell_rhs<EXACT>(A.K, uc[r][k], v[k], w[k], del_u, stim[k], d_v, d_w, d_u);
-            vn[k] = euler<EXACT>(v[k], d_v, A.K.dt);
-            wn[k] = euler<EXACT>(w[k], d_w, A.K.dt);
-            un[k] = euler<EXACT>(uc[r][k], d_u, A.K.dt);
+            cell_step<EXACT>(A.K, uc[r][k], v[k], w[k], Dv[k], DXv[k], DYv[k], u_x[r][k], gy[k + 2], u_xx[r][k], u_yy, stim[k],
+                             un[k], vn[k], wn[k]);
         }
         if (last) {
             st4(A.u_out + X.boff + g, un);
@@ -620,12 +616,8 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     float un[NC], vn[NC], wn[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], u_x[k], u_y[k], u_xx[k], u_yy[k]);
-        float d_v, d_w, d_u;
-        cell_rhs<EXACT>(A.K, uc[k], v[k], w[k], del_u, stim[k], d_v, d_w, d_u);
-        vn[k] = euler<EXACT>(v[k], d_v, A.K.dt);
-        wn[k] = euler<EXACT>(w[k], d_w, A.K.dt);
-        un[k] = euler<EXACT>(uc[k], d_u, A.K.dt);
+        cell_step<EXACT>(A.K, uc[k], v[k], w[k], Dv[k], DXv[k], DYv[k], u_x[k], u_y[k], u_xx[k], u_yy[k], stim[k], un[k], vn[k],
+                         wn[k]);
     }
     if (last) {
         stn<NC>(A.u_out + X.boff + g, un);

@@ -15,7 +15,7 @@ inline int cur_device() {
     return d;
 }
 
-template <bool EXACT, int T, bool UNI, bool HEUN = false>
+template <bool EXACT, int T, bool UNI, int MODE = FK_STORE_PLAIN>
 __global__ void __launch_bounds__(T == 2 ? 192 : 256, T <= 2 ? 2 : 1)
 fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ StreamGeom G) {
     extern __shared__ __align__(16) float fk_stream_smem[];
@@ -45,7 +45,7 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         i = FK_WARM;
     }
     for (; i < nfill; ++i) {   // pipeline fill (and launches with an active stimulus): fully conditional body
-        stream_iter<EXACT, T, -1, UNI, true, 4, HEUN>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+        stream_iter<EXACT, T, -1, UNI, true, 4, MODE>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
         __syncthreads();
     }
     // steady state: every stage consumes and emits one row per iteration; unrolled U-fold so that every ring slot is a
@@ -59,12 +59,12 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
 #define FK_STEADY_LOOP(EDGE)                                                                                           \
     for (; i < i_end; i += U) {                                                                                        \
         const StreamBody<T> Y = stream_body_at<T>(tb, i);                                                              \
-        stream_iter<EXACT, T, 0, UNI, EDGE, U, HEUN>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
-        stream_iter<EXACT, T, 1, UNI, EDGE, U, HEUN>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
+        stream_iter<EXACT, T, 0, UNI, EDGE, U, MODE>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
+        stream_iter<EXACT, T, 1, UNI, EDGE, U, MODE>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
         if (U == 4) {                                                                                                  \
-            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U, HEUN>(A, C, R, tb, i + 2, tid,                               \
+            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U, MODE>(A, C, R, tb, i + 2, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 2 : 0>(Y), bar);      \
-            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U, HEUN>(A, C, R, tb, i + 3, tid,                               \
+            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U, MODE>(A, C, R, tb, i + 3, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 3 : 1>(Y), bar);      \
         }                                                                                                              \
     }
@@ -79,10 +79,13 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         StreamCta Ct;
         stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, Ct);
         for (; i < Ct.niter; ++i) {
-            stream_iter<EXACT, T, -1, UNI, true, 4, HEUN>(A, Ct, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+            stream_iter<EXACT, T, -1, UNI, true, 4, MODE>(A, Ct, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
             __syncthreads();
         }
     }
+    // halo mirror: this thread's stores into the neighbouring GPUs' memory are performed, system wide, before the kernel
+    // ends -- the flag the neighbour waits for is written by a later operation of the same stream
+    if (MODE == FK_STORE_MIRROR) __threadfence_system();
 }
 
 template <bool EXACT, int T, bool UNI>
@@ -101,15 +104,31 @@ inline int launch_stream_t(const StreamPlan& P, const TileArgs& A, int batch, cu
             static long long attr_set_h_dev[FK_MAX_DEVICES] = {0};
             long long& attr_set_h = attr_set_h_dev[cur_device()];
             if (P.smem_bytes > attr_set_h && attr_set_h < 227 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI, true>,
+                cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI, FK_STORE_HEUN>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes);
                 if (e != cudaSuccess) return (int)e;
                 attr_set_h = P.smem_bytes;
             }
-            fk_stream_kernel<EXACT, T, UNI, true><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
+            fk_stream_kernel<EXACT, T, UNI, FK_STORE_HEUN><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
             return (int)cudaGetLastError();
         } else {
             return -2;   // not built
+        }
+    }
+    if (A.mir_u[0] || A.mir_u[1]) {   // row-slab decomposition: the instantiation that mirrors the band rows to the neighbours
+        if constexpr (T <= 2) {
+            static long long attr_set_m_dev[FK_MAX_DEVICES] = {0};
+            long long& attr_set_m = attr_set_m_dev[cur_device()];
+            if (P.smem_bytes > attr_set_m && attr_set_m < 227 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(fk_stream_kernel<EXACT, T, UNI, FK_STORE_MIRROR>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes);
+                if (e != cudaSuccess) return (int)e;
+                attr_set_m = P.smem_bytes;
+            }
+            fk_stream_kernel<EXACT, T, UNI, FK_STORE_MIRROR><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);
+            return (int)cudaGetLastError();
+        } else {
+            return -2;   // not built: the caller copies the bands instead
         }
     }
     fk_stream_kernel<EXACT, T, UNI><<<grid, P.G.NT, P.smem_bytes, st>>>(A, P.G);

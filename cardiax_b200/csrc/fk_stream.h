@@ -13,8 +13,8 @@
 // its last 2 u_y rows in shared-memory rings; v and w (pointwise) wait 4 rows in a private ring.
 // One block barrier per row iteration orders all ring traffic.
 //
-// Only cells whose whole dependency cone is the 4th-order central formula are produced here:
-// rows/cols [4T, N-4T).  The frame of 4T cells is done by the general tile kernel (fk_tile.h).
+// The kernel owns all four physical edges (one launch per T steps, nothing else on the hot path): the edge thread of a
+// strip applies the reference's one-sided formulas on the padded columns, the first / last row chunk on the padded rows.
 // Strip edges: columns within 4s of a strip edge are garbage at level s and are never stored.
 //
 // Written as FK_HD code over an explicit per-thread state so tests/emu can run it on the CPU
@@ -367,8 +367,7 @@ FK_HD void stream_make_gy(const Consts& K, const float* r1p, const float* u1, bo
     const F2 Lh = ld2(r1p - CH + 2), Rh = ld2(r1p + CH);
     // edge-pad (solve.py:31): the column outside the tissue repeats the edge column
     const float e[8] = {Lh.x, edgeL ? u1[0] : Lh.y, u1[0], u1[1], u1[2], u1[3], edgeR ? u1[3] : Rh.x, Rh.y};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) gy[k] = dcen<EXACT>(K, e[k], e[k + 1], e[k + 3], e[k + 4]);
+    dcen_span4<EXACT>(K, e, gy);
     if (edgeL) {  // padded columns 0 (the pad) and 1 (tissue column 0) use the forward formula
         gypad = edge_deriv<EXACT>(K, FWD, e[1], e[2], e[3], e[4]);
         gy[0] = edge_deriv<EXACT>(K, FWD, e[2], e[3], e[4], e[5]);
@@ -433,7 +432,34 @@ FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const f
                        bool edgeL, bool edgeR, float* un, float* vn, float* wn, int mode = 0,
                        float (*sv)[4] = nullptr) {
     // mode 0: the ordinary row.  mode 2: u_xx supplied in sv[3] (the tissue's last row).  mode 1: the caller finishes u
-    // itself one iteration later (the tissue's first row): u_yy and j_ion go to sv[2], sv[3], un is not meaningful.
+    // itself one iteration later (the tissue's first row): u_yy and j_ion (fast numerics: the reaction term g of
+    // cell_react_fast) go to sv[2], sv[3], un is not meaningful.
+    if (!EXACT) {
+        // fast numerics: two cells per instruction (fk_core.h, f2): the same operations, lane for lane, as the scalar
+        // loop below runs with Num<false>
+        float uxx[4], uyy[4];
+        dcen_rows4<false>(K, gxm2, gxm1, gxp1, gxp2, uxx);                       // solve.py:51
+        if (mode == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) uxx[k] = sv[3][k];
+        }
+        dcen_span4<false>(K, g, uyy);                                            // solve.py:52
+        // the tissue's first / last column: forward / backward formula on u_y of padded columns 1..4 / W-3..W
+        if (EDGE && edgeL) uyy[0] = edge_deriv<false>(K, FWD, g[2], g[3], g[4], g[5]);
+        if (EDGE && edgeR) uyy[3] = edge_deriv<false>(K, BWD, g[2], g[3], g[4], g[5]);
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+            const f2 uu = f2_at(u0 + k), vv = f2_at(v + k), ww = f2_at(w + k);
+            f2 gg, v2, w2;
+            cell_react_fast2<HAS_STIM>(K, uu, vv, ww, HAS_STIM ? f2_at(stim + k) : f2_all(0.0f), gg, v2, w2);
+            if (mode == 1) { f2_to(sv[2] + k, f2_at(uyy + k)); f2_to(sv[3] + k, gg); }
+            f2_to(vn + k, v2);
+            f2_to(wn + k, w2);
+            f2_to(un + k, cell_u_fast2(K, uu, gg, f2_at(Dv + k), f2_at(DXv + k), f2_at(DYv + k), f2_at(gx0 + k),
+                                        f2_at(gy0 + k), f2_at(uxx + k), f2_at(uyy + k)));   // solve.py:55, 59, 70
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
@@ -537,7 +563,11 @@ static_assert(FK_PF == 3, "stream_ptrs_phase<U = 2> spells the prefetch slots ou
 //            read, arrive after the last shared-memory write.
 //   UNI      one constant diffusivity (C.Dc, C.DXc, C.DYc) instead of three maps
 //   EDGE     this CTA's strip may contain the tissue's first / last column
-template <bool EXACT, int T, int PH, bool UNI, bool EDGE, int U = 4, bool HEUN = false>
+//   MODE     what the last level's store does besides storing: 0 nothing, FK_STORE_HEUN the closing pass of a fast Heun
+//            step, FK_STORE_MIRROR the halo mirror of the row-slab decomposition (rows of TileArgs::mir_* go to the
+//            neighbouring GPU's memory as well) -- separate kernel instantiations on the device, run-time flags on the CPU
+enum { FK_STORE_PLAIN = 0, FK_STORE_HEUN = 1, FK_STORE_MIRROR = 2 };
+template <bool EXACT, int T, int PH, bool UNI, bool EDGE, int U = 4, int MODE = 0>
 FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid,
                        const StreamPtrs& P, float* bar) {
     typedef StreamLay<T> L;
@@ -545,9 +575,11 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
     // fast Heun's closing pass in the last level's store (TileArgs::hy_*): its own kernel instantiation on the device --
     // even a uniform run-time branch here cost the plain Euler kernel 7 % -- a run-time flag in the CPU emulation
 #if defined(__CUDA_ARCH__)
-    constexpr bool heun = HEUN;
+    constexpr bool heun = MODE == FK_STORE_HEUN;
+    constexpr bool mirror = MODE == FK_STORE_MIRROR;
 #else
     const bool heun = A.hy_u != nullptr;
+    const bool mirror = A.mir_u[0] != nullptr || A.mir_u[1] != nullptr;
 #endif
     // positions of the u_x window rows (rho-2, rho-1, rho, rho+1) in R.GX[s]: U = 4 rotates by one per phase; U = 2
     // keeps the rows of each parity in a pair of register sets and moves one set per phase
@@ -656,8 +688,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         if (s > 0 && have_in) st4(r0p[s], in_u);  // row rho+4 takes the slot of row rho
         // u_x of row rho+2 (solve.py:49)
         float ngx[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ngx[k] = dcen<EXACT>(A.K, u0[s][k], u1[s][k], R.prev[s][k], in_u[k]);
+        dcen_rows4<EXACT>(A.K, u0[s], u1[s], R.prev[s], in_u, ngx);
         // ---- physical top / bottom edge (general body, chunks that touch it).  m = the newest input row of this stage.
         // Along the rows the reference differentiates the edge-PADDED array twice (solve.py:29-32, 49, 51) with one-sided
         // formulas in padded rows 0, 1 and H, H+1.  In terms of tissue rows, with gx[r] = u_x of row r:
@@ -780,6 +811,16 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
                     if (ST || !defer_u) st4(A.u_out + grow, un);   // (a deferred first row's u follows below)
                     st4(A.v_out + grow, vn);
                     st4(A.w_out + grow, wn);
+                    if (mirror) {   // the rows a neighbouring slab needs as its halo: stored into its memory as well
+#pragma unroll
+                        for (int nb = 0; nb < 2; ++nb)
+                            if (rho >= A.mir_r0[nb] && rho < A.mir_r1[nb]) {   // (never the tissue's first row: no deferral)
+                                const long long gm = grow + A.mir_off[nb];
+                                st4(A.mir_u[nb] + gm, un);
+                                st4(A.mir_v[nb] + gm, vn);
+                                st4(A.mir_w[nb] + gm, wn);
+                            }
+                    }
                 }
             } else {
 #pragma unroll
@@ -807,8 +848,13 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float u_xx = edge_deriv<EXACT>(A.K, FWD, R.GX[s][1][k], R.GX[s][2][k], R.GX[s][3][k], ngx[k]);
-                const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], R.GX[s][1][k], R.sv[s][1][k], u_xx, R.sv[s][2][k]);
-                un0[k] = euler<EXACT>(R.sv[s][0][k], Num<EXACT>::add(del_u, R.sv[s][3][k]), A.K.dt);
+                if (EXACT) {
+                    const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], R.GX[s][1][k], R.sv[s][1][k], u_xx, R.sv[s][2][k]);
+                    un0[k] = euler<EXACT>(R.sv[s][0][k], Num<EXACT>::add(del_u, R.sv[s][3][k]), A.K.dt);
+                } else {
+                    un0[k] = cell_u_fast(A.K, R.sv[s][0][k], R.sv[s][3][k], Dv[k], DXv[k], DYv[k], R.GX[s][1][k], R.sv[s][1][k],
+                                         u_xx, R.sv[s][2][k]);
+                }
             }
             if (s == T - 1) {
                 if (heun) {

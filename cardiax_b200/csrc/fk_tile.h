@@ -39,6 +39,12 @@ struct TileArgs {
     float h_half;                      // dt * 0.5 (solve.py:83)
     const float *hy_v, *hy_w, *hy_u;   // fast Heun (streaming / wide kernels, last level only): when set, the launch stores
                                        // y + (E - y) / 2 instead of its Euler result E, y = these arrays (fk_forward_heun)
+    // row-slab decomposition (streaming kernel, last level only): rows [mir_r0[n], mir_r1[n]) of the result are ALSO
+    // stored into the neighbour's halo, a peer-mapped array of GPU n (0 = the slab above, 1 = the slab below), at element
+    // index (this launch's index) + mir_off[n] -- the halo exchange travels over NVLink as the rows are produced
+    float *mir_u[2], *mir_v[2], *mir_w[2];
+    long long mir_off[2];
+    int mir_r0[2], mir_r1[2];
     Consts K;
     const StimDev* stims;              // (batch, n_stim)
     int n_stim;
@@ -234,12 +240,17 @@ FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* 
                 const float u_yy =
                     deriv<EXACT>(A.K, kindc, q0, q1, q2, q3, GYr[Q + p0], GYr[Q + p1], GYr[Q + p2], GYr[Q + p3]);
                 const float u_x = GC[col], u_y = GYr[Q];
-                const float del_u = diffusion<EXACT>(Dq[q], DXq[q], DYq[q], u_x, u_y, u_xx, u_yy);
                 const long long g = (long long)row * A.W + col;
                 const int i = (row - X.ra) * X.nc + (col - X.ca);
                 const float u = Uc[i], v = X.V[i], w = X.Wd[i];
-                float d_v, d_w, d_u;
-                cell_rhs<EXACT>(A.K, u, v, w, del_u, stq[q], d_v, d_w, d_u);
+                float d_v = 0.0f, d_w = 0.0f, d_u = 0.0f, vn, wn, un;
+                if (A.rhs_mode || A.heun) {   // the derivatives themselves are wanted (solve.step, the Heun stages)
+                    const float del_u = diffusion<EXACT>(Dq[q], DXq[q], DYq[q], u_x, u_y, u_xx, u_yy);
+                    cell_rhs<EXACT>(A.K, u, v, w, del_u, stq[q], d_v, d_w, d_u);
+                    vn = euler<EXACT>(v, d_v, A.K.dt); wn = euler<EXACT>(w, d_w, A.K.dt); un = euler<EXACT>(u, d_u, A.K.dt);
+                } else {                      // the ordinary Euler update: the same cell function as every other kernel
+                    cell_step<EXACT>(A.K, u, v, w, Dq[q], DXq[q], DYq[q], u_x, u_y, u_xx, u_yy, stq[q], un, vn, wn);
+                }
                 if (A.rhs_mode) {
                     A.v_out[X.boff + g] = d_v;
                     A.w_out[X.boff + g] = d_w;
@@ -264,8 +275,6 @@ FK_HD void tile_update(const TileArgs& A, const TileCtx& X, int s, const float* 
                         continue;
                     }
                 }
-                const float vn = euler<EXACT>(v, d_v, A.K.dt), wn = euler<EXACT>(w, d_w, A.K.dt),
-                            un = euler<EXACT>(u, d_u, A.K.dt);
                 if (last) {
                     if (row >= X.r0 && row < X.r1 && col >= X.c0 && col < X.c1) {
                         A.v_out[X.boff + g] = vn;

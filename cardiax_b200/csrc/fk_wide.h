@@ -127,12 +127,8 @@ FK_HD void wide_thread(const TileArgs& A, int sim, int row, int c, unsigned mask
     float un[4], vn[4], wn[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], u_x[k], u_y[k], u_xx[k], u_yy[k]);
-        float d_v, d_w, d_u;
-        cell_rhs<EXACT>(A.K, uc[k], v[k], w[k], del_u, stim[k], d_v, d_w, d_u);
-        vn[k] = euler<EXACT>(v[k], d_v, A.K.dt);
-        wn[k] = euler<EXACT>(w[k], d_w, A.K.dt);
-        un[k] = euler<EXACT>(uc[k], d_u, A.K.dt);
+        cell_step<EXACT>(A.K, uc[k], v[k], w[k], Dv[k], DXv[k], DYv[k], u_x[k], u_y[k], u_xx[k], u_yy[k], stim[k], un[k], vn[k],
+                         wn[k]);
     }
     if (A.hy_u) {   // fast Heun (see fk_stream.h)
         float y4[4];

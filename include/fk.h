@@ -112,6 +112,40 @@ int fk_euler_rows(const float* v_in_dev, const float* w_in_dev, const float* u_i
                   float dx, const FkOptions* opt, int row0, int row1, void* workspace_dev, size_t workspace_bytes,
                   void* stream);
 
+/* ---- halo exchange of the row-slab decomposition over peer memory (NVLink / NVSwitch); no reference counterpart.
+ * One process per GPU.  Each rank allocates its exchange buffers with fk_peer_alloc (cudaMalloc + a CUDA IPC handle),
+ * hands the 64-byte handle to its neighbours (any host channel: torch.distributed.all_gather_object) and maps theirs with
+ * fk_peer_open.  fk_euler_rows_peer is fk_euler_rows whose result rows [mirror->row0[n], row1[n]) are ALSO stored into
+ * the mapped arrays of neighbour n (0 = the slab above, 1 = below) starting at its row dst_row0[n]: by the streaming
+ * kernel itself, as it produces them (peer stores that overlap the interior's arithmetic row by row; *fused_out = 1), or,
+ * when the call is not a streaming launch, by copies the library enqueues after it (*fused_out = 0).  Either way the
+ * rows are in the neighbours' memory once the stream reaches the next operation: fk_peer_signal then writes a sequence
+ * number into a flag in the neighbour's memory (system-scope release), and the neighbour orders its next launch after
+ * fk_peer_wait(own flag, sequence number) -- a stream memory operation (cuStreamWaitValue32, >=), no SM is held while
+ * waiting and no host thread is involved. */
+typedef struct FkPeerMirror {
+    float* v[2];          /* peer-mapped (H', W) arrays of the neighbour above [0] / below [1]; u[n] NULL = no neighbour */
+    float* w[2];
+    float* u[2];
+    int row0[2], row1[2]; /* local rows to mirror */
+    int dst_row0[2];      /* first destination row in the neighbour's arrays */
+} FkPeerMirror;
+
+int fk_peer_alloc(size_t bytes, void** dev_ptr_out, unsigned char* handle64_out);
+int fk_peer_open(const unsigned char* handle64, void** dev_ptr_out);
+int fk_peer_close(void* mapped_dev_ptr);
+int fk_peer_free(void* dev_ptr);
+int fk_peer_signal(unsigned int* flag_peer_dev, unsigned int value, void* stream);
+int fk_peer_wait(const unsigned int* flag_local_dev, unsigned int value, void* stream);
+/* plain asynchronous copy between any two device pointers this process can address (own or peer-mapped) */
+int fk_peer_copy(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+int fk_euler_rows_peer(const float* v_in_dev, const float* w_in_dev, const float* u_in_dev, float* v_out_dev,
+                       float* w_out_dev, float* u_out_dev, const float* diffusivity_dev, const float* dx_map_dev,
+                       const float* dy_map_dev, int H, int W, const FkParams* params, const FkStimulus* stimuli,
+                       int n_stim, double t0, int nsteps, float dt, float dx, const FkOptions* opt, int row0, int row1,
+                       void* workspace_dev, size_t workspace_bytes, void* stream, const FkPeerMirror* mirror,
+                       int* fused_out);
+
 /* solve._forward_dormandprince / solve.step_rk (cardiax/solve.py:88-89, 114-124) ==
  * jax.experimental.ode.odeint(step, state, ts, params, diffusivity, stimuli, dx): adaptive Dormand-Prince 5(4) with
  * jax's step-size controller and 4th-order dense output (jax/experimental/ode.py, an un-vendored dependency: algorithm

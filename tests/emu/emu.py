@@ -76,6 +76,20 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
     return (vo, wo, uo), (info[0], info[1])
 
 
+def set_mirror(up, down, row0, row1, dst_row0):
+    """Halo mirror of the next `euler` call: up / down = (v, w, u) host arrays of the neighbouring slab (or None)."""
+    def ptrs(arrs):
+        if arrs is None:
+            return None
+        return (ctypes.c_void_p * 3)(*[a.ctypes.data for a in arrs])
+    i2 = lambda x: (ctypes.c_int * 2)(*x)  # noqa: E731
+    lib().fk_emu_set_mirror(ptrs(up), ptrs(down), i2(row0), i2(row1), i2(dst_row0))
+
+
+def mirror_was_fused():
+    return bool(lib().fk_emu_mirror_was_fused())
+
+
 def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0), maps_global=0):
     """The resident kernel's geometry for a problem: dict or None."""
     out = (ctypes.c_int * 12)()

@@ -88,6 +88,22 @@ struct EmuStim {
 // options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse,
 //           row0, row1, tiles_r, tiles_c, cells_per_thread, edge_rows, edge_colgroups, maps_global}
 // info (optional, 2 ints): tile launches, stream launches + 1000 * wide launches + 1000000 * resident launches
+// slab halo mirror of the NEXT fk_emu_euler call (fk::SlabMirror; consumed by that call): the emulated streaming kernel
+// stores rows [row0[n], row1[n]) of its result into these host arrays as well, like the device kernel does into peer memory
+static fk::SlabMirror g_mirror;
+static bool g_mirror_set = false, g_mirror_done = false;
+int fk_emu_set_mirror(float* const* vwu_up, float* const* vwu_down, const int* row0, const int* row1, const int* dst_row0) {
+    memset(&g_mirror, 0, sizeof(g_mirror));
+    float* const* nb[2] = {vwu_up, vwu_down};
+    for (int n = 0; n < 2; ++n) {
+        if (nb[n]) { g_mirror.v[n] = nb[n][0]; g_mirror.w[n] = nb[n][1]; g_mirror.u[n] = nb[n][2]; }
+        g_mirror.row0[n] = row0[n]; g_mirror.row1[n] = row1[n]; g_mirror.dst_row0[n] = dst_row0[n];
+    }
+    g_mirror_set = true;
+    return 0;
+}
+int fk_emu_mirror_was_fused(void) { return g_mirror_done ? 1 : 0; }
+
 int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float* v_out, float* w_out, float* u_out,
                  const float* D, int d_batched, int H, int W, int batch, const float* params14, const EmuStim* stims,
                  int n_stim, double t0, double t1, float dt, float dx, const int* options, int rhs_mode, int* info) {
@@ -104,6 +120,8 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
     B.pv = pv.data(); B.pw = pw.data(); B.pu = pu.data(); B.D = D; B.DX = DX.data(); B.DY = DY.data();
     B.stims = (const fk::StimDev*)stims;
+    g_mirror_done = false;
+    if (g_mirror_set) { B.mirror = &g_mirror; B.mirrored = &g_mirror_done; g_mirror_set = false; }
     fk::u64 dummy[1] = {0};
     B.xchg = dummy;          // the emulation allocates its own mailboxes
     B.xchg_bytes = fk::res_xchg_bytes(H, W, batch);

@@ -316,3 +316,26 @@ def test_fast_heun_through_the_euler_kernels(shape, force_stream):
         assert (ia["stream"] if force_stream else ia["wide"]) == (4 * 1 + 3 * 2 if force_stream else 4 * 2 + 3 * 2)
     else:
         assert ia["combine"] == n and ia["tile"] > 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_stream_kernel_mirrors_the_slab_edge_rows(exact):
+    """Row-slab halo exchange fused into the step kernel (FK_STORE_MIRROR): a row-window launch also stores its first /
+    last `band` result rows into the neighbours' arrays at the requested rows -- and nothing else there."""
+    H, W, T, band = 120, 160, 2, 16
+    st, D, stim = common.random_case((H, W), seed=21, n_stim=2)
+    row0, row1 = 8, 112                       # a middle slab: halos of 4T rows on both sides are inputs only
+    up = [np.full((90, W), -7.0, np.float32) for _ in range(3)]
+    down = [np.full((70, W), -9.0, np.float32) for _ in range(3)]
+    emu.set_mirror(up, down, (row0, row1 - band), (row0 + band, row1), (90 - band, 3))
+    got, _ = emu.euler(st, 5, 5 + T, P3, D, stim, 0.01, 0.01, exact=exact, T=T, kernel=2, cta_threads=32, phys_top=0,
+                       phys_bottom=0, row0=row0, row1=row1)
+    assert emu.mirror_was_fused()
+    ref, _ = emu.euler(st, 5, 5 + T, P3, D, stim, 0.01, 0.01, exact=exact, T=T, kernel=2, cta_threads=32, phys_top=0,
+                       phys_bottom=0, row0=row0, row1=row1)
+    assert not emu.mirror_was_fused()
+    for k in range(3):
+        assert np.array_equal(got[k][row0:row1], ref[k][row0:row1])
+        assert np.array_equal(up[k][90 - band:], ref[k][row0:row0 + band]) and np.all(up[k][:90 - band] == -7.0)
+        assert np.array_equal(down[k][3:3 + band], ref[k][row1 - band:row1])
+        assert np.all(down[k][:3] == -9.0) and np.all(down[k][3 + band:] == -9.0)

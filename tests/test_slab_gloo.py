@@ -26,7 +26,9 @@ class EmuBackend:
         emu.lib().fk_emu_dgrad(p(Dn), p(DX), p(DY), Dn.shape[0], Dn.shape[1], ctypes.c_float(dx), int(phys_top), int(phys_bottom))
         return torch.from_numpy(DX), torch.from_numpy(DY)
 
-    def euler_rows(self, src, dst, D, DX, DY, params, stimuli, t0, nsteps, dt, dx, phys_top, phys_bottom, row0, row1, uniform):
+    def euler_rows(self, src, dst, D, DX, DY, params, stimuli, t0, nsteps, dt, dx, phys_top, phys_bottom, row0, row1, uniform,
+                   mirror=None):
+        assert mirror is None     # the CPU runs exchange with torch.distributed (comm="dist")
         import oracle as O
         from tests.emu import emu
         st = [x.numpy() for x in src]
@@ -53,8 +55,11 @@ def _worker(rank, world, port, nsteps, M, overlap, q):
         lstim = [Stimulus(Protocol(*s.protocol), torch.from_numpy(np.ascontiguousarray(s.field[lo:hi]))) for s in stim]
         r = slab.SlabRunner(local, torch.from_numpy(np.ascontiguousarray(D[lo:hi])), O.PARAMSETS["3"], lstim, 0.01, 0.01, rank,
                             world, steps_per_launch=1, halo_launches=M, backend=EmuBackend(), overlap=overlap)
-        out = r.advance(local, 0, nsteps)
-        out = r.advance(out, nsteps, nsteps + 3)          # a second segment continues from the first
+        out = r.advance(None, 0, nsteps)                  # the constructor loaded `local`
+        if overlap:
+            out = r.advance(None, nsteps, nsteps + 3)     # a second segment continues from the resident state
+        else:
+            out = r.advance(out, nsteps, nsteps + 3)      # ... or from a state handed back in
         gathered = [None] * world
         dist.all_gather_object(gathered, [x.numpy() for x in out])
         if rank == 0:
