@@ -26,8 +26,9 @@ class FkParams(ctypes.Structure):
 
 
 class FkStimulus(ctypes.Structure):
-    _fields_ = [("field", ctypes.c_void_p), ("start", ctypes.c_float), ("duration", ctypes.c_float),
-                ("period", ctypes.c_float)]
+    """include/fk.h: protocol values as doubles + which of them the caller held as integers (bits 1, 2, 4)."""
+    _fields_ = [("field", ctypes.c_void_p), ("start", ctypes.c_double), ("duration", ctypes.c_double),
+                ("period", ctypes.c_double), ("int_mask", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class FkOptions(ctypes.Structure):
@@ -36,7 +37,7 @@ class FkOptions(ctypes.Structure):
                 ("rows_per_cta", ctypes.c_int), ("uniform_diffusivity", ctypes.c_int), ("safe_division", ctypes.c_int),
                 ("tiles_r", ctypes.c_int), ("tiles_c", ctypes.c_int), ("cells_per_thread", ctypes.c_int),
                 ("edge_rows", ctypes.c_int), ("edge_colgroups", ctypes.c_int), ("maps_global", ctypes.c_int),
-                ("reserved", ctypes.c_int * 1)]
+                ("counter_is_int", ctypes.c_int)]
 
 
 class FkPeerMirror(ctypes.Structure):
@@ -153,7 +154,7 @@ def lib():
     L.fk_rhs.restype = ci
     L.fk_gradient.argtypes = [vp, vp, ll, ll, ll, vp]
     L.fk_gradient.restype = ci
-    L.fk_stimulate.argtypes = [cd, vp, vp, ci, ci, ctypes.POINTER(FkStimulus), ci, vp, sz, vp]
+    L.fk_stimulate.argtypes = [cd, ci, vp, vp, ci, ci, ctypes.POINTER(FkStimulus), ci, vp, sz, vp]
     L.fk_stimulate.restype = ci
     L.fk_diffusivity_gradients.argtypes = [vp, vp, vp, ci, ci, ci, cf, ci, ci, vp]
     L.fk_diffusivity_gradients.restype = ci
@@ -181,7 +182,7 @@ def lib():
                                       ctypes.POINTER(cd)]
     L.fk_profile_collect.restype = ci
     L.fk_profile_dropped.restype = ll
-    if L.fk_abi_version() != 1:
+    if L.fk_abi_version() != 2:
         raise RuntimeError("libfk.so ABI version mismatch")
     _lib = L
     return L

@@ -126,13 +126,13 @@ __global__ void fk_dgrad_kernel(const float* __restrict__ D, float* __restrict__
 
 // solve.stimulate on one array
 __global__ void fk_stimulate_kernel(const float* __restrict__ x, float* __restrict__ out, long long n,
-                                    const fk::StimDev* __restrict__ stims, int n_stim, float t) {
+                                    const fk::StimDev* __restrict__ stims, int n_stim, double t, int t_is_int) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
         float st = 0.0f;
         for (int i = 0; i < n_stim; ++i) {
             const fk::StimDev s = stims[i];
-            if (s.field && fk::stim_active(t, s.start, s.duration, s.period)) {
+            if (s.field && fk::stim_on(s, t, t_is_int)) {
                 const float f = s.field[idx];
                 if (f != 0.0f) st = f;
             }
@@ -445,8 +445,8 @@ int fk_gradient(const float* a, float* out, long long outer, long long n, long l
     return 0;
 }
 
-int fk_stimulate(double t, const float* x, float* out, int H, int W, const FkStimulus* stimuli, int n_stim, void* workspace,
-                 size_t workspace_bytes, void* stream) {
+int fk_stimulate(double t, int t_is_int, const float* x, float* out, int H, int W, const FkStimulus* stimuli, int n_stim,
+                 void* workspace, size_t workspace_bytes, void* stream) {
     if (!x || !out) return fail(-1, "NULL pointer%s");
     if (H < 1 || W < 1 || n_stim < 0) return fail(-1, "bad shape%s");
     if (n_stim > 0 && (!workspace || workspace_bytes < sizeof(fk::StimDev) * (size_t)n_stim))
@@ -456,7 +456,7 @@ int fk_stimulate(double t, const float* x, float* out, int H, int W, const FkSti
     if (rc) return rc;
     const long long n = (long long)H * W;
     int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 32);
-    fk_stimulate_kernel<<<blocks, 256, 0, st>>>(x, out, n, (const fk::StimDev*)workspace, n_stim, (float)t);
+    fk_stimulate_kernel<<<blocks, 256, 0, st>>>(x, out, n, (const fk::StimDev*)workspace, n_stim, t, t_is_int);
     FK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -514,6 +514,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     o.row0 = row0; o.row1 = row1;
     o.tiles_r = opt.tiles_r; o.tiles_c = opt.tiles_c; o.cells_per_thread = opt.cells_per_thread;
     o.edge_rows = opt.edge_rows; o.edge_colgroups = opt.edge_colgroups; o.maps_global = opt.maps_global;
+    o.t_is_int = opt.counter_is_int;
     CudaBackend be;
     be.st = st;
     const char* why = "";
@@ -574,7 +575,7 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
     if (rc) return rc;
     fk::DriveOptions o;
     memset(&o, 0, sizeof(o));
-    o.exact = opt.exact; o.phys_top = 1; o.phys_bottom = 1; o.kernel = 1;
+    o.exact = opt.exact; o.phys_top = 1; o.phys_bottom = 1; o.kernel = 1; o.t_is_int = opt.counter_is_int;
     CudaBackend be;
     be.st = st;
     fk::Consts K = make_consts(*params, dt, dx);
@@ -622,7 +623,7 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
         rc = fk::drive_heun_fast(hb, HB, d_batched, H, W, batch, K, (const fk::StimDev*)stimuli, n_stim, t0, nsteps,
                                  opt.uniform_diffusivity, opt.cta_threads, opt.rows_per_cta, /*fold=*/opt.kernel != 1,
                                  /*try_resident=*/opt.kernel == 4,   // opt-in: 24-32 us per step vs 16.5 with two wide launches
-                                 &why);
+                                 &why, opt.counter_is_int);
         return rc ? (why[0] ? fail(rc, "%s", why) : rc) : 0;
     }
     if (opt.steps_per_launch == 2 || (opt.steps_per_launch == 0 && (long long)H * W * batch < (1LL << 20))) {
@@ -633,7 +634,7 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
         B.v_in = v_in; B.w_in = w_in; B.u_in = u_in; B.v_out = v_out; B.w_out = w_out; B.u_out = u_out;
         B.pv = ws.pv; B.pw = ws.pw; B.pu = ws.pu;
         B.D = D; B.DX = ws.DX; B.DY = ws.DY; B.stims = ws.stims;
-        rc = fk::drive_heun(be, B, d_batched, H, W, batch, K, n_stim, t0, nsteps, opt.exact, h_half);
+        rc = fk::drive_heun(be, B, d_batched, H, W, batch, K, n_stim, t0, nsteps, opt.exact, h_half, opt.counter_is_int);
         return rc;
     }
     // the unfused sequence (two right-hand-side launches + two stage kernels per step); steps_per_launch = 1 forces it

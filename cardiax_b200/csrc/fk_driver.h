@@ -22,6 +22,7 @@ struct DriveOptions {
     int cells_per_thread;   // resident kernel: 1, 2 or 4 adjacent cells per thread (0 = planner's choice)
     int edge_rows, edge_colgroups;   // resident kernel: size of the tiles at the tissue's edges (0 auto, < 0 even split)
     int maps_global;        // resident kernel: 1 = diffusivity maps read from global memory (L2), 0 = planner's choice
+    int t_is_int;           // the loop counter is an int32 (stimulus schedule typing, fk_core.h: stim_active_typed)
 };
 
 // row-slab decomposition: rows [row0[n], row1[n]) of a call's result are also wanted in the memory of the neighbouring
@@ -189,6 +190,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     A.K = K;
     A.stims = n_stim ? B.stims : nullptr;
     A.n_stim = n_stim;
+    A.t_is_int = opt.t_is_int;
 
     if (use_res) {
         A.u_in = B.u_in; A.v_in = B.v_in; A.w_in = B.w_in;
@@ -257,7 +259,7 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
 // are the predictor and the corrector, both at the same counter; y and k1 of a tile's own cells wait in shared memory.
 template <class Backend>
 int drive_heun(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, int batch, const Consts& K, int n_stim,
-               double t0, long long nsteps, int exact, float h_half) {
+               double t0, long long nsteps, int exact, float h_half, int t_is_int = 0) {
     TileArgs A;
     A = TileArgs();
     A.D = B.D; A.DX = B.DX; A.DY = B.DY;
@@ -268,6 +270,7 @@ int drive_heun(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, 
     A.K = K;
     A.stims = n_stim ? B.stims : nullptr;
     A.n_stim = n_stim;
+    A.t_is_int = t_is_int;
     A.T = 2; A.heun = 1; A.h_half = h_half;
     int th = 16, tw = 64;   // 88 KB: two CTAs per SM; measured best of {32x64, 16x64, 24x96, 16x128} on 256^2 ... 4096^2
     const float *sv = B.v_in, *sw = B.w_in, *su = B.u_in;
@@ -306,10 +309,10 @@ struct HeunFastBuffers {
 template <class Backend>
 int drive_heun_fast(Backend& be, const HeunFastBuffers& HB, int d_batched, int H, int W, int batch, const Consts& K,
                     const StimDev* host_stims, int n_stim, double t0, long long nsteps, int uniform, int cta_threads,
-                    int rows_per_cta, bool fold, bool try_resident, const char** why) {
+                    int rows_per_cta, bool fold, bool try_resident, const char** why, int t_is_int = 0) {
     *why = "";
     DriveOptions oe = DriveOptions();
-    oe.phys_top = 1; oe.phys_bottom = 1;
+    oe.phys_top = 1; oe.phys_bottom = 1; oe.t_is_int = t_is_int;
     oe.uniform_diffusivity = uniform; oe.cta_threads = cta_threads; oe.rows_per_cta = rows_per_cta;
     DriveOptions o1 = oe, o2 = oe;
     const bool small = cta_threads == 0 && (long long)H * W * batch < (1LL << 20) && W % 4 == 0 && H >= 3;
@@ -319,8 +322,7 @@ int drive_heun_fast(Backend& be, const HeunFastBuffers& HB, int d_batched, int H
     const long long n = (long long)H * W * batch;
     auto quiet = [&](double t) {
         for (int i = 0; i < batch * n_stim; ++i)
-            if (host_stims[i].field && (stim_active((float)t, host_stims[i].start, host_stims[i].duration, host_stims[i].period) ||
-                                        stim_active((float)(t + 1.0), host_stims[i].start, host_stims[i].duration, host_stims[i].period)))
+            if (host_stims[i].field && (stim_on(host_stims[i], t, t_is_int) || stim_on(host_stims[i], t + 1.0, t_is_int)))
                 return false;
         return true;
     };

@@ -369,13 +369,13 @@ FK_HD void res_load(const TileArgs& A, const ResGeom& G, const ResCta& X, int ti
     }
 }
 
-// stimuli of this CTA's tissue that are active at step s of the launch (solve.py:262-267, fp32 counter)
+// stimuli of this CTA's tissue that are active at step s of the launch (solve.py:262-267, the caller's typing)
 FK_HD unsigned res_mask(const TileArgs& A, const ResCta& X, int s) {
     unsigned m = 0;
-    const float t = (float)(A.t0 + (double)s);
+    const double t = A.t0 + (double)s;
     for (int i = 0; i < A.n_stim; ++i) {
         const StimDev sd = X.stims[i];
-        if (sd.field && stim_active(t, sd.start, sd.duration, sd.period)) m |= 1u << i;
+        if (sd.field && stim_on(sd, t, A.t_is_int)) m |= 1u << i;
     }
     return m;
 }

@@ -34,7 +34,7 @@ FK_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
 #define FK_MAP_PF 3
 #endif
 #ifndef FK_MAP_LATE
-#define FK_MAP_LATE 1
+#define FK_MAP_LATE 2
 #endif
 // which stages load their maps at the point of use: 0 none (all up front), 1 all, 2 all but the first, 3 the first only
 #define FK_MAP_IS_LATE(s) (FK_MAP_LATE == 1 || (FK_MAP_LATE == 2 && (s) > 0) || (FK_MAP_LATE == 3 && (s) == 0))
@@ -248,11 +248,11 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     C.niter = C.r1 + 4 * T - C.rin0;   // the last stage emits row r1 - 1 when (virtual) row r1 - 1 + 4T is the newest
     for (int s = 0; s < 8; ++s) C.mask[s] = 0;
     for (int s = 0; s < T; ++s) {
-        const float t = (float)(A.t0 + (double)s);
+        const double t = A.t0 + (double)s;
         unsigned m = 0;
         for (int i = 0; i < A.n_stim; ++i) {
             const StimDev sd = C.stims[i];
-            if (sd.field && stim_active(t, sd.start, sd.duration, sd.period)) m |= 1u << i;
+            if (sd.field && stim_on(sd, t, A.t_is_int)) m |= 1u << i;
         }
         C.mask[s] = m;
     }
@@ -323,7 +323,10 @@ enum { FK_WARM = 8 };   // iterations the warm start stands for
 
 // steady-state unroll factor: 4 (a phase knows i & 3, only the halves of the 8-slot ring alternate) while the loop body
 // fits the instruction cache, 2 from T = 2 on (32 KB of code per loop otherwise: every instruction line would miss)
-FK_HD constexpr int stream_unroll(int T) { return T >= 2 ? 2 : 4; }
+#ifndef FK_UNROLL_T2
+#define FK_UNROLL_T2 2   // development: 4 = the 4-way loop at T = 2 as well (25 KB of code with the packed arithmetic)
+#endif
+FK_HD constexpr int stream_unroll(int T) { return T == 2 ? FK_UNROLL_T2 : (T >= 2 ? 2 : 4); }
 
 // may iterations i >= 8T use the condition-free body?  (no stimulus active in any level of this launch)
 template <int T>

@@ -49,6 +49,7 @@ struct TileArgs {
     const StimDev* stims;              // (batch, n_stim)
     int n_stim;
     double t0;                         // counter value of the first level
+    int t_is_int;                      // the counter is an int32 (deepx.generate.sequence) rather than a float32 (solve.forward)
     TileRegion reg[4];
     int nreg;
 };
@@ -114,11 +115,11 @@ FK_HD void tile_setup(const TileArgs& A, int tile, int sim, float* smem, TileCtx
     X.stims = A.stims ? A.stims + (long long)sim * A.n_stim : nullptr;
     for (int s = 0; s < 8; ++s) X.mask[s] = 0;
     for (int s = 0; s < A.T; ++s) {
-        const float t = (float)(A.t0 + (double)s);
+        const double t = A.t0 + (double)s;
         unsigned m = 0;
         for (int i = 0; i < A.n_stim; ++i) {
             const StimDev sd = X.stims[i];
-            if (sd.field && stim_active(t, sd.start, sd.duration, sd.period)) m |= 1u << i;
+            if (sd.field && stim_on(sd, t, A.t_is_int)) m |= 1u << i;
         }
         X.mask[s] = m;
     }

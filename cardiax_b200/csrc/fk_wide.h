@@ -146,10 +146,9 @@ FK_HD unsigned wide_mask(const TileArgs& A, int sim) {
     unsigned m = 0;
     if (A.n_stim) {
         const StimDev* st = A.stims + (long long)sim * A.n_stim;
-        const float t = (float)A.t0;
         for (int i = 0; i < A.n_stim; ++i) {
             const StimDev sd = st[i];
-            if (sd.field && stim_active(t, sd.start, sd.duration, sd.period)) m |= 1u << i;
+            if (sd.field && stim_on(sd, A.t0, A.t_is_int)) m |= 1u << i;
         }
     }
     return m;

@@ -34,7 +34,7 @@ import numpy as np
 import torch
 
 from . import _lib, options
-from .solve import State, _as_f32, _params_struct, _scalar
+from .solve import State, _as_f32, _is_int, _params_struct, _scalar, _stimulus_struct
 
 
 class CudaBackend:
@@ -63,8 +63,7 @@ class CudaBackend:
         P = _params_struct(params)
         arr = (_lib.FkStimulus * max(1, len(stimuli)))()
         for i, s in enumerate(stimuli):
-            arr[i] = _lib.FkStimulus(s.field.data_ptr(), _scalar(s.protocol.start), _scalar(s.protocol.duration),
-                                     _scalar(s.protocol.period))
+            arr[i] = _stimulus_struct(s.field.data_ptr(), s.protocol)
         o = _lib.FkOptions()
         self.L.fk_default_options(ctypes.byref(o))
         o.exact = int(options.numerics == "exact")
@@ -73,11 +72,12 @@ class CudaBackend:
         o.phys_top, o.phys_bottom = int(phys_top), int(phys_bottom)
         o.uniform_diffusivity = int(uniform)
         o.safe_division = int(options.safe_division)
+        o.counter_is_int = int(_is_int(t0))
         fused = ctypes.c_int(0)
         _lib.check(self.L.fk_euler_rows_peer(
             src[0].data_ptr(), src[1].data_ptr(), src[2].data_ptr(), dst[0].data_ptr(), dst[1].data_ptr(),
             dst[2].data_ptr(), D.data_ptr(), DX.data_ptr(), DY.data_ptr(), H, W, ctypes.byref(P), arr, len(stimuli),
-            float(t0), int(nsteps), np.float32(dt), np.float32(dx), ctypes.byref(o), int(row0), int(row1),
+            float(_scalar(t0)), int(nsteps), np.float32(dt), np.float32(dx), ctypes.byref(o), int(row0), int(row1),
             self._ws.data_ptr(), self._ws.numel(), self._stream(), ctypes.byref(mirror) if mirror is not None else None,
             ctypes.byref(fused)))
         self.fused_mirrors += fused.value
@@ -338,9 +338,10 @@ class SlabRunner:
         ``copy`` False returns views into the exchange buffers, valid until the next call that advances."""
         if state is not None:
             self.load(state)
+        ints = _is_int(t0) and _is_int(t1)           # the counter's type follows the bounds (stimulus schedule typing)
         t0, t1 = _scalar(t0), _scalar(t1)
         left = int(max(0, np.ceil(t1 - t0)))
-        t = t0
+        t = int(t0) if ints else t0
         while left > 0:
             steps = []                                   # one group: up to M launches between two halo exchanges
             while left > 0 and len(steps) < self.M:

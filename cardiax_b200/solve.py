@@ -49,6 +49,24 @@ def _scalar(x):
     return float(np.asarray(x).reshape(-1)[0])
 
 
+def _is_int(x):
+    """Does jax (x64 disabled) see this scalar / shape-(1,) array as an int32 rather than a float32?  Python ints, NumPy
+    and torch integers and booleans do; everything else is a float.  Decides the typing of the stimulus schedule
+    (cardiax/solve.py:262-267): see include/fk.h, FkStimulus::int_mask and FkOptions::counter_is_int."""
+    if isinstance(x, torch.Tensor):
+        return not (x.dtype.is_floating_point or x.dtype.is_complex)
+    if isinstance(x, (bool, int, np.integer, np.bool_)):
+        return True
+    if isinstance(x, (float, np.floating)):
+        return False
+    return np.asarray(x).dtype.kind in "iub"
+
+
+def _stimulus_struct(field_ptr, protocol):
+    mask = (1 if _is_int(protocol.start) else 0) | (2 if _is_int(protocol.duration) else 0) | (4 if _is_int(protocol.period) else 0)
+    return _lib.FkStimulus(field_ptr, _scalar(protocol.start), _scalar(protocol.duration), _scalar(protocol.period), mask, 0)
+
+
 def _params_struct(params):
     return _lib.FkParams(*[np.float32(_scalar(p)) for p in params])
 
@@ -77,10 +95,9 @@ def _pack_stimuli(stimuli, batch, shape, device):
                 if tuple(f.shape) != tuple(shape):
                     raise ValueError("stimulus field shape %s != tissue shape %s" % (tuple(f.shape), tuple(shape)))
                 keep.append(f)
-                arr[b * n_stim + i] = _lib.FkStimulus(f.data_ptr(), _scalar(s.protocol.start),
-                                                      _scalar(s.protocol.duration), _scalar(s.protocol.period))
+                arr[b * n_stim + i] = _stimulus_struct(f.data_ptr(), s.protocol)
             else:
-                arr[b * n_stim + i] = _lib.FkStimulus(None, 0.0, 0.0, 1.0)
+                arr[b * n_stim + i] = _lib.FkStimulus(None, 0.0, 0.0, 1.0, 0, 0)
     return arr, n_stim, keep
 
 
@@ -184,7 +201,7 @@ def step(state, t, params, diffusivity, stimuli, dx):
     ws, nbytes = _workspace(L, H, W, batch, n_stim, int(D.dim() == 3), dev)
     dv, dw, du = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
     P = _params_struct(params)
-    o = _options(None, P, dx)
+    o = _options(None, P, dx, counter_is_int=_is_int(t))
     _lib.check(L.fk_rhs(v.data_ptr(), w.data_ptr(), u.data_ptr(), dv.data_ptr(), dw.data_ptr(), du.data_ptr(),
                         D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim, _scalar(t),
                         np.float32(_scalar(dx)), ctypes.byref(o), ws.data_ptr(), nbytes, _stream()))
@@ -199,7 +216,7 @@ def _forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx):
     ws, nbytes = _workspace(L, H, W, batch, n_stim, int(D.dim() == 3), dev)
     vo, wo, uo = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
     P = _params_struct(params)
-    o = _options(D, P, dx)
+    o = _options(D, P, dx, counter_is_int=_is_int(t) and _is_int(t_end))   # the fori_loop counter takes the bounds' dtype
     _lib.check(L.fk_forward_euler(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
                                   D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
                                   _scalar(t), _scalar(t_end), np.float32(_scalar(dt)), np.float32(_scalar(dx)),
@@ -209,14 +226,14 @@ def _forward_euler(state, t, t_end, params, diffusivity, stimuli, dt, dx):
 
 def step_euler(state, t, params, diffusivity, stimuli, dt, dx):
     """cardiax/solve.py:68-70 -- one Euler step ``x + d_x * dt``."""
-    t = _scalar(t)
-    return _forward_euler(state, t, t + 1.0, params, diffusivity, stimuli, dt, dx)
+    t1 = (int(_scalar(t)) + 1) if _is_int(t) else (_scalar(t) + 1.0)
+    return _forward_euler(state, t, t1, params, diffusivity, stimuli, dt, dx)
 
 
 def step_heun(state, t, params, diffusivity, stimuli, dt, dx):
     """cardiax/solve.py:73-85 -- Heun: both stages evaluated at the same counter ``t``."""
-    t = _scalar(t)
-    return _forward_heun(state, t, t + 1.0, params, diffusivity, stimuli, dt, dx)
+    t1 = (int(_scalar(t)) + 1) if _is_int(t) else (_scalar(t) + 1.0)
+    return _forward_heun(state, t, t1, params, diffusivity, stimuli, dt, dx)
 
 
 def _forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx):
@@ -228,7 +245,7 @@ def _forward_heun(state, t, t_end, params, diffusivity, stimuli, dt, dx):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     vo, wo, uo = torch.empty_like(v), torch.empty_like(w), torch.empty_like(u)
     P = _params_struct(params)
-    o = _options(D, P, dx)
+    o = _options(D, P, dx, counter_is_int=_is_int(t) and _is_int(t_end))
     _lib.check(L.fk_forward_heun(v.data_ptr(), w.data_ptr(), u.data_ptr(), vo.data_ptr(), wo.data_ptr(), uo.data_ptr(),
                                  D.data_ptr(), int(D.dim() == 3), H, W, batch, ctypes.byref(P), arr, n_stim,
                                  _scalar(t), _scalar(t_end), np.float32(_scalar(dt)), np.float32(_scalar(dx)),
@@ -347,8 +364,8 @@ def stimulate(t, X, stimuli):
         raise ValueError("stimulate expects a 2-D array")
     H, W = X.shape
     arr, n_stim, keep = _pack_stimuli(stimuli, 1, (H, W), X.device)
-    ws = torch.empty(max(64, 32 * n_stim), dtype=torch.uint8, device=X.device)
+    ws = torch.empty(max(64, 64 * n_stim), dtype=torch.uint8, device=X.device)
     out = torch.empty_like(X)
-    _lib.check(L.fk_stimulate(_scalar(t), X.data_ptr(), out.data_ptr(), H, W, arr, n_stim, ws.data_ptr(), ws.numel(),
+    _lib.check(L.fk_stimulate(_scalar(t), int(_is_int(t)), X.data_ptr(), out.data_ptr(), H, W, arr, n_stim, ws.data_ptr(), ws.numel(),
                               _stream()))
     return out

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FK_ABI_VERSION 1
+#define FK_ABI_VERSION 2
 
 /* cardiax/params.py:4-18 -- same 14 fields, same order, already converted to fp32. */
 typedef struct FkParams {
@@ -35,15 +35,24 @@ typedef struct FkParams {
 /* cardiax/stimulus.py:13-21 -- Protocol (start, duration, period in STEP units, fp32 like the
  * reference's loop counter) + field.  `field` is a device pointer to an (H, W) fp32 array (NULL =
  * unused slot). */
+/* cardiax/stimulus.py:13-21.  The protocol is in STEP units and keeps the caller's typing, because the reference's
+ * schedule (solve.py:262-267) is evaluated by jax in the operands' own types: `deepx.generate.random_protocol`
+ * (generate.py:24-27) draws start and period as int32 arrays, `solve.forward` callers pass Python ints or 1e9 floats.
+ * Values are doubles (exact for int32 and float32 alike); `int_mask` says which of them the caller held as integers. */
+#define FK_STIM_INT_START 1
+#define FK_STIM_INT_DURATION 2
+#define FK_STIM_INT_PERIOD 4
 typedef struct FkStimulus {
-    const float* field;
-    float start, duration, period;
+    const float* field;   /* (H, W) fp32 on the device; NULL = unused slot */
+    double start, duration, period;
+    int int_mask;         /* FK_STIM_INT_* bits */
+    int reserved;
 } FkStimulus;
 
 typedef struct FkOptions {
     int exact;            /* 1: reference operation order, bit-identical to the CPU oracle; 0: fast numerics */
     int steps_per_launch; /* temporal blocking depth T (1..8); 0 = library default */
-    int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = streaming kernel + frame tiles,
+    int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = require the streaming kernel,
                              3 = low-latency one-step kernel for small tissues, 4 = resident kernel (whole call in one
                              cooperative launch, state in shared memory) */
     int phys_top;         /* is buffer row 0 the physical tissue edge? (0 only for slab decomposition) */
@@ -60,7 +69,9 @@ typedef struct FkOptions {
                                       (0 = auto, < 0 = even split) */
     int maps_global;      /* resident kernel: 1 = read the diffusivity maps from global memory (L2) instead of keeping
                              them in shared memory (0 = only when the tissue would not fit otherwise) */
-    int reserved[1];
+    int counter_is_int;   /* the loop counter t0, t0 + 1, ... is an int32 (`deepx.generate.sequence` passes integer
+                             checkpoints) rather than the float32 of `solve.forward`: decides, with FkStimulus::int_mask,
+                             in which type each operation of the stimulus schedule is done (exact above 2^24) */
 } FkOptions;
 
 /* Fills *opt with the defaults (exact = 0, auto everything, both edges physical). */
@@ -77,7 +88,7 @@ size_t fk_workspace_bytes(int H, int W, int batch, int n_stim, int diffusivity_b
  *   diffusivity_dev      (H, W) shared by all tissues, or (batch, H, W) when diffusivity_batched
  *   stimuli              HOST array of batch * n_stim entries (tissue-major); the schedule
  *                        `t >= start && mod(start - t + 1, period) < duration` (solve.py:262-267)
- *                        is evaluated on the device, per step, in fp32
+ *                        is evaluated on the device, per step, in the caller's typing (FkStimulus, FkOptions::counter_is_int)
  * Outputs must not alias inputs. */
 int fk_forward_euler(const float* v_in_dev, const float* w_in_dev, const float* u_in_dev, float* v_out_dev,
                      float* w_out_dev, float* u_out_dev, const float* diffusivity_dev, int diffusivity_batched, int H,
@@ -197,8 +208,8 @@ int fk_rhs(const float* v_dev, const float* w_dev, const float* u_dev, float* dv
 int fk_gradient(const float* a_dev, float* out_dev, long long outer, long long n, long long inner, void* stream);
 
 /* solve.stimulate (cardiax/solve.py:257-271) on one (H, W) array. */
-int fk_stimulate(double t, const float* x_dev, float* out_dev, int H, int W, const FkStimulus* stimuli, int n_stim,
-                 void* workspace_dev, size_t workspace_bytes, void* stream);
+int fk_stimulate(double t, int t_is_int, const float* x_dev, float* out_dev, int H, int W, const FkStimulus* stimuli,
+                 int n_stim, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* D_x, D_y of solve.py:53-54 (gradient of the edge-padded map / dx, cropped), the two static
  * maps the step kernels read next to D. */

@@ -12,8 +12,12 @@ _lib = None
 
 
 class _Stim(ctypes.Structure):
-    _fields_ = [("field", ctypes.c_void_p), ("start", ctypes.c_float), ("duration", ctypes.c_float),
-                ("period", ctypes.c_float)]
+    _fields_ = [("field", ctypes.c_void_p), ("start", ctypes.c_double), ("duration", ctypes.c_double),
+                ("period", ctypes.c_double), ("int_mask", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
+def _is_int(x):
+    return np.asarray(x).dtype.kind in "iub" and not isinstance(x, float)
 
 
 def build(force=False):
@@ -41,9 +45,22 @@ def stim_active(t, start, duration, period):
     return bool(lib().fk_emu_stim_active(t, start, duration, period))
 
 
+def stim_active_typed(t, protocol):
+    """fk::stim_active_typed with the typing of the Python objects handed in (the oracle's stimulus_active_typed)."""
+    L = lib()
+    L.fk_emu_stim_active_typed.restype = ctypes.c_int
+    L.fk_emu_stim_active_typed.argtypes = [ctypes.c_double, ctypes.c_int] + [ctypes.c_double] * 3 + [ctypes.c_int]
+    mask = sum(bit for bit, x in zip((1, 2, 4), protocol) if _is_int(x))
+    return bool(L.fk_emu_stim_active_typed(float(np.asarray(t).reshape(-1)[0]), int(_is_int(t)),
+                                           *[float(np.asarray(x).reshape(-1)[0]) for x in protocol], mask))
+
+
 def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, cta_threads=0, rows_per_cta=0,
-          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0, tiles=(0, 0), nc=0, edge_tile=(0, 0), maps_global=0):
-    """state: (v, w, u) arrays of shape (H, W) or (batch, H, W).  Returns (v, w, u) and launch counts."""
+          uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0, tiles=(0, 0), nc=0, edge_tile=(0, 0), maps_global=0,
+          typed=False):
+    """state: (v, w, u) arrays of shape (H, W) or (batch, H, W).  Returns (v, w, u) and launch counts.
+    typed: keep the int / float typing of t0, t1 and the protocol entries (the reference's int32-counter path) instead
+    of the all-float typing of `solve.forward`."""
     v, w, u = [np.ascontiguousarray(x, dtype=np.float32) for x in state]
     batched = u.ndim == 3
     batch = u.shape[0] if batched else 1
@@ -62,10 +79,11 @@ def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, 
         for i, s in enumerate(per[b]):
             f = np.ascontiguousarray(s.field, dtype=np.float32)
             keep.append(f)
-            arr[b * n_stim + i] = _Stim(f.ctypes.data, *[float(np.asarray(x).reshape(-1)[0]) for x in s.protocol])
-    opts = (ctypes.c_int * 17)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse,
+            mask = sum(bit for bit, x in zip((1, 2, 4), s.protocol) if typed and _is_int(x))
+            arr[b * n_stim + i] = _Stim(f.ctypes.data, *[float(np.asarray(x).reshape(-1)[0]) for x in s.protocol], mask, 0)
+    opts = (ctypes.c_int * 18)(int(exact), T, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform, reverse,
                                row0, row1, int(tiles[0]), int(tiles[1]), int(nc), int(edge_tile[0]), int(edge_tile[1]),
-                               int(maps_global))
+                               int(maps_global), int(typed and _is_int(t0) and _is_int(t1)))
     info = (ctypes.c_int * 2)()
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib().fk_emu_euler(p(v), p(w), p(u), p(vo), p(wo), p(uo), p(D), d_batched, H, W, batch, p(par), arr, n_stim,

@@ -82,11 +82,12 @@ extern "C" {
 
 struct EmuStim {
     const float* field;
-    float start, duration, period;
+    double start, duration, period;
+    int int_mask, reserved;
 };
 
 // options: {exact, steps_per_launch, kernel, phys_top, phys_bottom, cta_threads, rows_per_cta, uniform_diffusivity, reverse,
-//           row0, row1, tiles_r, tiles_c, cells_per_thread, edge_rows, edge_colgroups, maps_global}
+//           row0, row1, tiles_r, tiles_c, cells_per_thread, edge_rows, edge_colgroups, maps_global, counter_is_int}
 // info (optional, 2 ints): tile launches, stream launches + 1000 * wide launches + 1000000 * resident launches
 // slab halo mirror of the NEXT fk_emu_euler call (fk::SlabMirror; consumed by that call): the emulated streaming kernel
 // stores rows [row0[n], row1[n]) of its result into these host arrays as well, like the device kernel does into peer memory
@@ -129,6 +130,7 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
     o.exact = options[0]; o.steps_per_launch = options[1]; o.kernel = options[2]; o.phys_top = options[3];
     o.phys_bottom = options[4]; o.cta_threads = options[5]; o.rows_per_cta = options[6]; o.uniform_diffusivity = options[7];
     o.row0 = options[9]; o.row1 = options[10]; o.tiles_r = options[11]; o.tiles_c = options[12]; o.cells_per_thread = options[13]; o.edge_rows = options[14]; o.edge_colgroups = options[15]; o.maps_global = options[16];
+    o.t_is_int = options[17];
     EmuBackend be;
     be.reverse = options[8];
     const long long nsteps = rhs_mode ? 1 : fk::count_steps(t0, t1);
@@ -145,6 +147,9 @@ int fk_emu_euler(const float* v_in, const float* w_in, const float* u_in, float*
 
 int fk_emu_stim_active(float t, float start, float duration, float period) {
     return fk::stim_active(t, start, duration, period) ? 1 : 0;
+}
+int fk_emu_stim_active_typed(double t, int t_is_int, double start, double duration, double period, int kinds) {
+    return fk::stim_active_typed(t, t_is_int, start, duration, period, kinds) ? 1 : 0;
 }
 
 }  // extern "C"

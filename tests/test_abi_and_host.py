@@ -23,8 +23,11 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.SO_PATH)
     for n in sorted(names):
         assert hasattr(L, n), n
-    assert _lib.lib().fk_abi_version() == 1
-    assert ctypes.sizeof(_lib.FkParams) == 56 and ctypes.sizeof(_lib.FkStimulus) == 24 and ctypes.sizeof(_lib.FkOptions) == 64
+    assert _lib.lib().fk_abi_version() == 2
+    # ABI v2: the protocol travels as doubles + an integer-typing mask ("f64 or i64 + flag")
+    assert ctypes.sizeof(_lib.FkParams) == 56 and ctypes.sizeof(_lib.FkStimulus) == 40 and ctypes.sizeof(_lib.FkOptions) == 64
+    assert ctypes.sizeof(_lib.FkPeerMirror) == 72
+    assert {"fk_euler_rows_peer", "fk_peer_alloc", "fk_peer_open", "fk_peer_signal", "fk_peer_wait", "fk_peer_copy"} <= names
     # argument errors are reported, not crashed on (no GPU needed: validation comes first)
     P = _lib.FkParams(*([1.0] * 14))
     rc = _lib.lib().fk_forward_euler(None, None, None, None, None, None, None, 0, 2, 2, 1, ctypes.byref(P), None, 0, 0.0, 1.0,

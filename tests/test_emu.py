@@ -339,3 +339,53 @@ def test_stream_kernel_mirrors_the_slab_edge_rows(exact):
         assert np.array_equal(up[k][90 - band:], ref[k][row0:row0 + band]) and np.all(up[k][:90 - band] == -7.0)
         assert np.array_equal(down[k][3:3 + band], ref[k][row1 - band:row1])
         assert np.all(down[k][:3] == -9.0) and np.all(down[k][3 + band:] == -9.0)
+
+
+def _typed_cases():
+    protos = [O.Protocol(np.array([3], np.int32), 2, np.array([16777259], np.int32)), O.Protocol(0, 2, 33554467),
+              O.Protocol(5, 4, np.array([123456789], np.int32)), O.Protocol(7, 2, 1e9), O.Protocol(7.0, 2, 400), O.Protocol(0, 2, 50),
+              O.Protocol(3.0, 2.0, 16777259.0), O.Protocol(2, 3.0, 9), O.Protocol(np.array([1], np.int32), 2.0, 6)]
+    for proto in protos:
+        s0, p0 = int(np.asarray(proto.start).reshape(-1)[0]), int(float(np.asarray(proto.period).reshape(-1)[0]))
+        ts = sorted(set(list(range(0, 14)) + [s0 + k * p0 + d for k in (1, 2) for d in range(-5, 6)]))
+        for t in ts:
+            if 0 <= t < 2 ** 31 - 8:
+                yield proto, t
+
+
+def test_typed_stimulus_schedule_equals_the_oracle_above_2_pow_24():
+    """fk::stim_active_typed (every kernel's schedule predicate, ABI v2) == the oracle's typed restatement -- which
+    tests/test_reference_pin.py holds to the reference's own `stimulate` -- for int32 and float32 counters, int / float /
+    shape-(1,) int32 protocol entries, periods and counters above 2^24 where the two typings part."""
+    n = 0
+    for proto, t in _typed_cases():
+        for tt in (int(t), np.int32(t), float(t), np.float32(t)):
+            assert emu.stim_active_typed(tt, proto) == O.stimulus_active_typed(tt, proto), (proto, tt)
+            n += 1
+    assert n > 1000
+    # the all-float typing is the fp32 predicate the kernels used before ABI v2
+    for proto, t in _typed_cases():
+        fl = [float(np.asarray(x).reshape(-1)[0]) for x in proto]
+        assert emu.stim_active_typed(float(t), O.Protocol(*fl)) == emu.stim_active(float(t), *fl)
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+def test_int_counter_run_matches_the_typed_oracle(kernel):
+    """`deepx.generate.sequence`'s typing end to end: int bounds, int32-array protocols, a period above 2^24 whose
+    second pulse the float32 typing would misplace; every kernel, exact numerics, bit for bit."""
+    shape = (24, 64) if kernel != 2 else (40, 96)
+    st, D, _ = common.random_case(shape, seed=31, n_stim=0)
+    f = np.zeros(shape, np.float32); f[:6] = 20.0
+    g = np.zeros(shape, np.float32); g[:, -9:] = -3.0
+    t0 = 3 + 16777259 - 3
+    stim = [O.Stimulus(O.Protocol(np.array([3], np.int32), 2, np.array([16777259], np.int32)), f),
+            O.Stimulus(O.Protocol(t0 + 1, 3, 1e9), g)]
+    ref = O.forward_euler(st, t0, t0 + 8, P3, D, stim, 0.01, 0.01, counter="i32")
+    got, _ = emu.euler(st, t0, t0 + 8, P3, D, stim, 0.01, 0.01, exact=True, kernel=kernel, T=2 if kernel in (1, 2) else 0,
+                       cta_threads=32 if kernel == 2 else 0, typed=True)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    # (the reference's float32 counter cannot even run here: above 2^24 `i + 1 == i` and its fori_loop never ends)
+    with pytest.raises(OverflowError):
+        O.forward_euler(st, float(t0), float(t0 + 8), P3, D, stim, 0.01, 0.01, counter="f32")
+    assert any(float(np.abs(a - b).max()) > 1e-3 for a, b in zip(ref, O.forward_euler(st, t0, t0 + 8, P3, D, [], 0.01, 0.01, counter="i32")))

@@ -484,3 +484,121 @@ def test_uniform_then_scar_map_of_the_same_shape_from_numpy_inputs():
         out = solve._forward_euler(gstate, 0, 8, P3, Dg, gst, 0.01, 0.01)
         assert_exact([x.cpu().numpy() for x in out], ref, "device tensors")
         del Dg, out
+
+
+def test_int_counter_and_typed_protocols_above_2_pow_24():
+    """The reference's int32-counter path (deepx/generate.py:24-27, 187-196) keeps exact integer semantics where the
+    float32 path rounds: counters and periods above 2^24 (VERDICT r1 missing 6; ABI v2 carries the typing)."""
+    from cardiax_b200 import options, solve, stimulus
+    options.numerics = "exact"
+    shape = (40, 96)
+    st, D, _ = common.random_case(shape, seed=31, n_stim=0)
+    f = np.zeros(shape, np.float32); f[:6] = 20.0
+    g = np.zeros(shape, np.float32); g[:, -9:] = -3.0
+    t0 = 3 + 16777259 - 3
+    protos = [O.Protocol(np.array([3], np.int32), 2, np.array([16777259], np.int32)), O.Protocol(t0 + 1, 3, 1e9)]
+    stim = [O.Stimulus(p, x) for p, x in zip(protos, (f, g))]
+    gst = [stimulus.Stimulus(stimulus.Protocol(*p), torch.as_tensor(x).cuda()) for p, x in zip(protos, (f, g))]
+    gs = solve.State(*[torch.as_tensor(x).cuda() for x in st])
+    Dg = torch.as_tensor(D).cuda()
+    ref = O.forward_euler(st, t0, t0 + 8, P3, D, stim, 0.01, 0.01, counter="i32")
+    for kernel in (0, 1, 2, 3, 4):
+        options.kernel, options.cta_threads = kernel, (32 if kernel == 2 else 0)
+        got = solve._forward_euler(gs, t0, t0 + 8, P3, Dg, gst, 0.01, 0.01)                    # Python-int bounds
+        assert_exact([x.cpu().numpy() for x in got], ref, "int counter, kernel %d" % kernel)
+    options.kernel, options.cta_threads = 0, 0
+    X = np.zeros(shape, np.float32)
+    for t in range(t0 - 2, t0 + 9):
+        for tt in (int(t), float(t)):
+            out = solve.stimulate(tt, torch.as_tensor(X).cuda(), gst).cpu().numpy()
+            assert np.array_equal(out, O.stimulate(tt, X, stim, typed=True)), tt
+    d = solve.step(gs, t0 + 3, P3, Dg, gst, 0.01)
+    assert_exact([x.cpu().numpy() for x in d], O.step(st, t0 + 3, P3, D, stim, 0.01, typed=True), "step, int t")
+
+
+def test_forward_dimensional_is_executed():
+    """solve.forward_dimensional (cardiax/solve.py:133-165): AssertionError on a diffusivity / stimulus shape mismatch,
+    checkpoints = arange(0, stop, step) in step units, init state; equals the reference-source run frozen in the oracle."""
+    from cardiax_b200 import options, solve, stimulus
+    options.numerics = "exact"
+    D = torch.full((12, 16), 1e-3, device="cuda")
+    stim = [stimulus.linear((12, 16), stimulus.Direction.NORTH, 0.3, 20.0, stimulus.Protocol(0, 2, 1e9))]
+    with pytest.raises(AssertionError):
+        solve.forward_dimensional((0.12, 0.17), 0.4, 0.1, P3, D, stim, 0.01, 0.01)
+    with pytest.raises(AssertionError):
+        solve.forward_dimensional((0.121, 0.161), 0.4, 0.1, P3, D, [stimulus.linear((12, 20), 0, 0.3, 20.0, stimulus.Protocol(0, 2, 1e9))], 0.01, 0.01)
+    got = solve.forward_dimensional((0.121, 0.161), 0.401, 0.101, P3, D, stim, 0.01, 0.01)
+    cps = np.arange(0, int(0.401 / 0.01), int(0.101 / 0.01))
+    assert len(got) == len(cps) - 1
+    ost = [O.Stimulus(O.Protocol(0, 2, 1e9), stim[0].field.cpu().numpy())]
+    s = O.init((12, 16))
+    for i in range(len(cps) - 1):
+        s = O.forward_euler(s, float(cps[i]), float(cps[i + 1]), P3, np.full((12, 16), 1e-3, np.float32), ost, 0.01, 0.01)
+        assert_exact([x.cpu().numpy() for x in got[i]], s, "forward_dimensional checkpoint %d" % i)
+
+
+@pytest.mark.parametrize("uniform", [False, True])
+@pytest.mark.parametrize("pset", sorted(O.PARAMSETS))
+def test_fast_all_paramsets_on_the_streaming_kernel(pset, uniform):
+    """Fast numerics against the oracle for ALL 16 parameter sets -- incl. sets 2 and 7, whose k = 1e5 / 1e6 and
+    V_csi = 1e6 drive ex2.approx to +inf and rcp.approx(inf) to 0 (j_si == 0, as in the reference where tanh == -1) -- on
+    the streaming kernel's heterogeneous-D and uniform-D instantiations."""
+    from cardiax_b200 import _lib
+    shape = (96, 640)
+    st, D = common.smooth_case(shape, seed=12)
+    if uniform:
+        D = np.full(shape, 1e-3, np.float32)
+    _, _, stim = common.random_case(shape, seed=12, n_stim=2)
+    P = O.PARAMSETS[pset]
+    ref = C.forward_euler(st, 0, 60, P, D, stim, 0.01, 0.01)
+    ref64 = C.forward_euler(st, 0, 60, P, D, stim, 0.01, 0.01, dtype=np.float64)
+    got = run_gpu(st, 0, 60, P, D, stim, numerics="fast", kernel=2, steps_per_launch=2)
+    assert _lib.last_kernel() == "fk_stream_kernel"
+    for name, g, a, b in zip("vwu", got, ref, ref64):
+        assert np.isfinite(g).all(), name
+        assert np.abs(g - a).max() <= TOL_FAST, (pset, name, float(np.abs(g - a).max()))
+        # the float32 oracle itself sits 9e-7 ... 1e-5 from the float64 twin over the 16 sets of this case (its gap is a
+        # draw, not a bound: tools measured on the CPU emulation), so the envelope has that floor
+        assert np.abs(g - b).max() <= max(2 * np.abs(a - b).max() + 2e-6, 1e-5), (pset, name)
+
+
+def test_config2_real_protocol_across_the_second_stimulus():
+    """BASELINE config 2 as the reference runs it (experiments/generate_fd_data_256.py:11-12, 22-40): 512 x 512 scar map,
+    S2 at step 40 000, segments of 500 steps -- up to step 40 500, ACROSS S2.  Exact numerics: SHA-256 of v, w, u equal the
+    C oracle's at steps 39 500, 40 000, 40 002 and 40 500.  Fast numerics: as close to the float64 run as the float32
+    oracle is (the fixture holds both), and S2 has visibly fired.  Fixture + generator: tests/golden/make_config2.py."""
+    import hashlib
+    import os
+    from cardiax_b200 import _lib, options, solve, stimulus
+    from tests.golden import make_config2 as M
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fk_512_config2_s2.npz"))
+    D, stim = M.inputs()
+    assert (M.sha(D), M.sha(stim[0].field), M.sha(stim[1].field)) == (str(g["D_sha"]), str(g["s1_sha"]), str(g["s2_sha"])), \
+        "the regenerated inputs differ from the ones the fixture was made from (scipy / numpy version?)"
+    gst = [stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in stim]
+    Dg = torch.as_tensor(D).cuda()
+    marks = [int(m) for m in g["marks"]]
+    for numerics in ("exact", "fast"):
+        options.numerics = numerics
+        s, t = solve.init(M.SHAPE), 0
+        for m in marks:
+            while t < m:                                   # the reference's 500-step segments, float counters
+                nxt = min(m, t + 500)
+                s = solve._forward_euler(s, float(t), float(nxt), P3, Dg, gst, 0.01, 0.01)
+                t = nxt
+            host = [x.cpu().numpy() for x in s]
+            if numerics == "exact":
+                got = [hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() for x in host]
+                assert got == [str(x) for x in g["sha_%d" % m]], "step %d" % m
+            elif m >= 40002:
+                for name, x in zip("vwu", host):
+                    f32, f64 = g["%s_f32_%d" % (name, m)], g["%s_f64_%d" % (name, m)]
+                    sub = x[::4, ::4]
+                    gap, ours = np.abs(f32 - f64), np.abs(sub - f64)
+                    print("config 2 step %d %s: |f32 - f64| max %.3g p99 %.3g, |fast - f64| max %.3g p99 %.3g" % (
+                        m, name, gap.max(), np.percentile(gap, 99), ours.max(), np.percentile(ours, 99)))
+                    assert np.percentile(ours, 99) <= 3 * np.percentile(gap, 99) + 1e-5, (m, name)
+                    assert ours.max() <= 3 * gap.max() + 1e-4, (m, name)
+        assert _lib.last_kernel() == "fk_resident_kernel"
+    # S2 did fire: the state just after it differs from the state just before by a stimulus-sized jump
+    assert float(np.abs(g["u_f32_40002"] - g["u_f32_40500"]).max()) > 0.05
