@@ -732,6 +732,16 @@ def main():
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "other_configs": other,
         "hbm_roofline_frac_whole_step": ALG_BYTES * value / world / peak,
     }
+    if other:   # the multi-GPU evidence also at the top level of the line
+        for k in ("slab_check", "efficiency_vs_slab_n1"):
+            if k in other:
+                out[k] = other[k]
+        if "exposed_us_per_exchange" in other:
+            out["exposed_us_per_exchange"] = other["exposed_us_per_exchange"]["value"]
+        if "ens256" in other:
+            out["ensemble"] = {k: other["ens256"][k] for k in ("value", "unit", "tissues", "frac_of_28B_roofline_per_gpu")}
+        if "slab_n1" in other:
+            out["slab_n1"] = other["slab_n1"]["value"]
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
