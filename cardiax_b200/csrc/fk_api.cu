@@ -169,23 +169,39 @@ __global__ void fk_heun_combine_kernel(const float* __restrict__ yv, const float
     }
 }
 
-// exhaustive check of Num<true>::divc against __fdiv_rn: every significand, three exponents, every divisor of a run
+// exhaustive check of the exact-mode divisions against __fdiv_rn: every significand (both signs), every exponent at which
+// a quotient can be a denormal number plus a few ordinary and extreme ones, every divisor of a run -- each through the
+// sequence the cell update uses for it (fk_core.h: divd for dx and Cm, divd / divd_tie for tau_d and tau_0, divd above
+// div_lo for the others)
 __global__ void fk_divcheck_kernel(fk::Consts K, unsigned long long* bad) {
-    const float divisors[10] = {K.tau_d, K.tau_0, K.two_tau_si, K.Cm, K.tau_v_plus, K.tau_v1_minus, K.tau_v2_minus,
-                                K.tau_w_plus, K.tau_w_minus, K.dx};
-    const float recips[10] = {K.y_tau_d, K.y_tau_0, K.y_two_tau_si, K.y_Cm, K.y_tvp, K.y_tvm1, K.y_tvm2, K.y_twp, K.y_twm,
-                              K.y_dx};
+    const float divisors[10] = {K.dx, K.Cm, K.tau_d, K.tau_0, K.two_tau_si, K.tau_v_plus, K.tau_v1_minus, K.tau_v2_minus,
+                                K.tau_w_plus, K.tau_w_minus};
+    const double recips[10] = {K.yd_dx, K.yd_Cm, K.yd_tau_d, K.yd_tau_0, K.yd_two_tau_si, K.yd_tvp, K.yd_tvm1, K.yd_tvm2,
+                               K.yd_twp, K.yd_twm};
     unsigned long long local = 0;
     for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < (1u << 23); m += gridDim.x * blockDim.x)
-        for (int e = 0; e < 7; ++e) {
-            // exponents 2^-40, 2^0, 2^40 (direct path), 2^-104, 2^-120 (scaled path), 2^-126 and denormals (fp64 path)
-            const unsigned ex[7] = {87u, 127u, 167u, 23u, 7u, 1u, 0u};
-            const float a = __uint_as_float((ex[e] << 23) | m);
+        for (int e = 0; e < 40; ++e) {
+            // exponent fields 0 (denormals, +-0) .. 31, then 2^-40, 2^0, 2^40, 2^100 and the largest finite binade, inf / NaN
+            const unsigned ex = e < 32 ? (unsigned)e : (e == 32 ? 87u : e == 33 ? 127u : e == 34 ? 167u : e == 35 ? 227u : e == 36 ? 254u : e == 37 ? 255u : 64u + e);
+            const float a = __uint_as_float((ex << 23) | m);
             for (int i = 0; i < 10; ++i) {
                 const float x = (i & 1) ? -a : a;
-                if (fk::Num<true>::divc(x, divisors[i], recips[i], K.div_lo, K.div_hi) != __fdiv_rn(x, divisors[i])) ++local;
+                float q;
+                if (i < 2) q = fk::Num<true>::divd(x, divisors[i], recips[i]);
+                else if (i < 4) q = K.tie_num ? fk::Num<true>::divd_tie(x, divisors[i], recips[i], i == 2 ? K.hb_tau_d : K.hb_tau_0)
+                                              : fk::Num<true>::divd(x, divisors[i], recips[i]);
+                else if (fabsf(x) > K.div_lo || x == 0.0f) q = fk::Num<true>::divd(x, divisors[i], recips[i]);
+                else continue;   // below div_lo the cell is redone with IEEE divisions
+                const float ref = __fdiv_rn(x, divisors[i]);
+                if (__float_as_uint(q) != __float_as_uint(ref) && !(q != q && ref != ref)) ++local;
             }
         }
+    // ... and the quotient inside tanh (Num<true>::div_nr) for every one of the 2^32 arguments
+    for (unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; x < (1ull << 32);
+         x += (unsigned long long)gridDim.x * blockDim.x) {
+        const float f = __uint_as_float((unsigned)x);
+        if (__float_as_uint(fk::tanh_xla<true>(f, false)) != __float_as_uint(fk::tanh_xla<true>(f, true))) ++local;
+    }
     if (local) atomicAdd(bad, local);
 }
 
@@ -519,7 +535,7 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     be.st = st;
     const char* why = "";
     fk::Consts K = make_consts(*params, dt, dx);
-    if (opt.safe_division) K.div_lo = INFINITY;   // every exact-mode division through __fdiv_rn
+    if (opt.safe_division) fk::set_safe_division(K);   // every exact-mode division the IEEE way
     rc = fk::drive_euler(be, B, d_batched, H, W, batch, K, n_stim, t0, nsteps, o, rhs_mode, &why);
     if (rc && why[0]) return fail(rc, "%s", why);
     return rc;
@@ -579,7 +595,7 @@ int fk_forward_heun(const float* v_in, const float* w_in, const float* u_in, flo
     CudaBackend be;
     be.st = st;
     fk::Consts K = make_consts(*params, dt, dx);
-    if (opt.safe_division) K.div_lo = INFINITY;
+    if (opt.safe_division) fk::set_safe_division(K);
     const long long n = (long long)H * W * batch;
     const int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 16);
     const float h_half = (float)((double)dt * 0.5);   // `dt * 0.5` of solve.py:83: exact halving of fl32(dt)
@@ -739,7 +755,7 @@ int fk_odeint_dopri5(const float* v0, const float* w0, const float* u0, float* v
     memset(&be.o, 0, sizeof(be.o));
     be.o.exact = opt.exact; be.o.phys_top = 1; be.o.phys_bottom = 1; be.o.kernel = 1;
     be.K = make_consts(*params, 0.0f, dx);
-    if (opt.safe_division) be.K.div_lo = INFINITY;
+    if (opt.safe_division) fk::set_safe_division(be.K);
     be.T = fk::make_dopri();
     be.S = scratch;
     be.D = D; be.DX = ws.DX; be.DY = ws.DY; be.stims = ws.stims;

@@ -426,7 +426,7 @@ FK_HD float res_deriv(const Consts& K, int kind, const float* a) {
     const float k2 = f ? -(float)(3.0 / 2.0) : -3.0f, k3 = f ? (float)(1.0 / 3.0) : (float)(11.0 / 6.0);
     const float t = tap4<EXACT>(k0, k1, k2, k3, f ? a[3] : a[0], f ? a[4] : a[1], f ? a[5] : a[2], f ? a[6] : a[3]);
     float one;
-    if (EXACT) one = Num<true>::divc(t, K.dx, K.y_dx, K.div_lo, K.div_hi);
+    if (EXACT) one = div_dx(K, t);
     else one = Num<false>::mul(t, K.r_dx);
     return kind == CEN ? cen : one;
 }

@@ -463,18 +463,23 @@ FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const f
         }
         return;
     }
+    // exact numerics: the four u_xx and the four u_yy each share one range test of their divisions (fk_core.h, DivTrack)
+    float uxx[4], uyy[4];
+    dcen_rows4<EXACT>(K, gxm2, gxm1, gxp1, gxp2, uxx);                           // solve.py:51
+    if (mode == 2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) uxx[k] = sv[3][k];
+    }
+    dcen_span4<EXACT>(K, g, uyy);                                                // solve.py:52
+    // the tissue's first / last column: forward / backward formula on u_y of padded columns 1..4 / W-3..W
+    if (EDGE && edgeL) uyy[0] = edge_deriv<EXACT>(K, FWD, g[2], g[3], g[4], g[5]);
+    if (EDGE && edgeR) uyy[3] = edge_deriv<EXACT>(K, BWD, g[2], g[3], g[4], g[5]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float u_xx = dcen<EXACT>(K, gxm2[k], gxm1[k], gxp1[k], gxp2[k]);    // solve.py:51
-        if (mode == 2) u_xx = sv[3][k];
-        float u_yy = dcen<EXACT>(K, g[k], g[k + 1], g[k + 3], g[k + 4]);          // solve.py:52
-        // the tissue's first / last column: forward / backward formula on u_y of padded columns 1..4 / W-3..W
-        if (EDGE && k == 0 && edgeL) u_yy = edge_deriv<EXACT>(K, FWD, g[2], g[3], g[4], g[5]);
-        if (EDGE && k == 3 && edgeR) u_yy = edge_deriv<EXACT>(K, BWD, g[2], g[3], g[4], g[5]);
-        const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], gx0[k], gy0[k], u_xx, u_yy);
+        const float del_u = diffusion<EXACT>(Dv[k], DXv[k], DYv[k], gx0[k], gy0[k], uxx[k], uyy[k]);
         float d_v, d_w, j_ion;
         cell_rhs_parts<EXACT, HAS_STIM>(K, u0[k], v[k], w[k], HAS_STIM ? stim[k] : 0.0f, d_v, d_w, j_ion);
-        if (mode == 1) { sv[2][k] = u_yy; sv[3][k] = j_ion; }
+        if (mode == 1) { sv[2][k] = uyy[k]; sv[3][k] = j_ion; }
         vn[k] = euler<EXACT>(v[k], d_v, K.dt);
         wn[k] = euler<EXACT>(w[k], d_w, K.dt);
         un[k] = euler<EXACT>(u0[k], Num<EXACT>::add(del_u, j_ion), K.dt);   // solve.py:59, 70
