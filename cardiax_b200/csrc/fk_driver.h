@@ -112,7 +112,9 @@ template <class Backend>
 int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W, int batch, const Consts& K, int n_stim,
                 double t0, long long nsteps, const DriveOptions& opt, int rhs_mode, const char** why) {
     *why = "";
-    int Tmax = rhs_mode ? 1 : (opt.steps_per_launch ? opt.steps_per_launch : FK_DEFAULT_T);
+    // exact numerics are latency bound (unfused dependent chains, 215 instructions per cell-step): one step per launch
+    // runs at 128 registers with twice the resident warps (68 vs 57 Gcell-steps/s on 4096^2, profiles/probe_exact_r02.md)
+    int Tmax = rhs_mode ? 1 : (opt.steps_per_launch ? opt.steps_per_launch : (opt.exact ? 1 : FK_DEFAULT_T));
     const bool slab = !opt.phys_top || !opt.phys_bottom;
     if (slab) {
         // slab decomposition: halo rows are inputs only and must be re-exchanged after every launch
