@@ -195,7 +195,7 @@ def last_kernel():
 def last_plan():
     out = (ctypes.c_int * 8)()
     lib().fk_last_plan(ctypes.byref(out))
-    if last_kernel() == "fk_resident_kernel":
+    if last_kernel() in ("fk_resident_kernel", "fk_cluster_kernel"):
         d = dict(zip(("steps", "cta_threads", "tile_cols", "tile_w", "tile_h", "tile_rows", "cells_per_thread", "smem_bytes"),
                      list(out)))
         d["maps_in_l2"], d["cells_per_thread"] = d["cells_per_thread"] >> 3, d["cells_per_thread"] & 7

@@ -337,13 +337,18 @@ struct CudaBackend {
         return 0;
     }
     long long resident_smem_limit() { return 227 * 1024 - 256; }
+    bool cluster_ok(const fk::ResPlan& P, int exact) {
+        return fk::cluster_capacity(exact, P.G.nc, P.G.ntr * P.G.ntc, P.threads, P.smem_bytes) >= 1;
+    }
     int resident(const fk::ResPlan& P, const fk::TileArgs& A, int exact, int batch) {
         g_last_plan[0] = P.G.nsteps; g_last_plan[1] = P.threads; g_last_plan[2] = P.G.ntc; g_last_plan[3] = P.G.tw_max;
         g_last_plan[4] = P.G.th_max; g_last_plan[5] = P.G.ntr; g_last_plan[6] = P.G.nc + 8 * P.G.mg; g_last_plan[7] = (int)P.smem_bytes;
-        const int cap = fk::resident_capacity(exact, P.G.nc, P.G.mg, P.threads, P.smem_bytes, num_sms());
-        if ((long long)P.G.ntr * P.G.ntc * batch > cap) return fail(-3, "resident kernel: the tiles are not co-resident on this device%s");
+        if (!P.G.cluster) {
+            const int cap = fk::resident_capacity(exact, P.G.nc, P.G.mg, P.threads, P.smem_bytes, num_sms());
+            if ((long long)P.G.ntr * P.G.ntc * batch > cap) return fail(-3, "resident kernel: the tiles are not co-resident on this device%s");
+        }
         ProfScope ps(0, st);
-        g_last_kernel = "fk_resident_kernel";
+        g_last_kernel = P.G.cluster ? "fk_cluster_kernel" : "fk_resident_kernel";
         if (ps.active) g_prof.stream_cs += (double)A.H * A.W * batch * P.G.nsteps;
         ++g_launches;
         const int rc = fk::launch_resident(P, A, exact, batch, st);

@@ -47,6 +47,10 @@ struct DriveBuffers {
 };
 
 enum { FK_DEFAULT_T = 2, FK_RES_MAX_CTAS = 1024 };
+// tissues up to this many cells go to the cluster transport of the resident kernel by default (fk_resident.h)
+#ifndef FK_CLUSTER_MAX_CELLS
+#define FK_CLUSTER_MAX_CELLS (80 * 80)   // measured (profiles/probe_cluster_r02.md): ahead of the mailbox form only up to ~64^2
+#endif
 // mailbox bytes fk_workspace_bytes provisions for the resident kernel: 32 per cell of problems it may take, else none
 inline long long res_xchg_bytes(int H, int W, int batch) {
     const long long cells = (long long)H * W * batch;
@@ -106,6 +110,7 @@ inline void pick_tile(int rows, int W, int T, int batch, int sms, int& th, int& 
 //          int stream(const StreamPlan&, const TileArgs&, int exact, int batch);
 //          int wide(const TileArgs&, int exact, int batch);
 //          int resident(const ResPlan&, const TileArgs&, int exact, int batch);  long long resident_smem_limit();
+//          bool cluster_ok(const ResPlan&, int exact);   // can this cluster shape be launched?
 //          int num_sms(); int occupancy(int T, int exact, int uniform, int NT, long long smem_bytes);
 // Returns 0 or the backend's error code; *why gets a static message on argument errors.
 template <class Backend>
@@ -143,7 +148,15 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
     // tissues that fit the machine's shared memory: the whole call in one resident launch (fk_resident.h)
     ResPlan rplan;
     bool use_res = false;
-    if (!rhs_mode && !slab && opt.row1 <= 0 && B.xchg && nsteps < (1LL << 30) &&
+    // ... a small tissue as ONE thread-block cluster (halos through distributed shared memory); kernel = 5 forces it
+    if (!rhs_mode && !slab && opt.row1 <= 0 && nsteps < (1LL << 30) &&
+        (opt.kernel == 5 || (opt.kernel == 0 && opt.steps_per_launch == 0 && nsteps >= 4 && batch == 1 &&
+                             (long long)H * W <= FK_CLUSTER_MAX_CELLS))) {
+        use_res = plan_cluster(H, W, be.resident_smem_limit(), opt.tiles_r, opt.tiles_c, opt.cta_threads, opt.cells_per_thread, rplan) &&
+                  be.cluster_ok(rplan, opt.exact);
+    }
+    if (opt.kernel == 5 && !use_res) { *why = "cluster kernel not applicable (needs W % 4 == 0, a tissue of at most 16 tiles that fit shared memory)"; return -5; }
+    if (!use_res && !rhs_mode && !slab && opt.row1 <= 0 && B.xchg && nsteps < (1LL << 30) &&
         (opt.kernel == 4 || (opt.kernel == 0 && opt.steps_per_launch == 0 && nsteps >= 4 &&
                              (long long)H * W * batch <= FK_RES_MAX_CELLS))) {
         const int cap = be.num_sms() < FK_RES_MAX_CTAS ? be.num_sms() : FK_RES_MAX_CTAS;

@@ -11,6 +11,9 @@ int launch_resident(const ResPlan& P, const TileArgs& A, int exact, int batch, c
 // CTAs of this shape the device holds at once (0: does not fit)
 int resident_capacity(int exact, int nc, int mg, int threads, long long smem_bytes, int num_sms);
 
+// cluster transport: clusters of `ntiles` CTAs of this shape the device holds at once (0: cannot be launched)
+int cluster_capacity(int exact, int nc, int ntiles, int threads, long long smem_bytes);
+
 // development (FK_RES_TIMING=1): cycle counters of CTA (0, 0) of the last launch; synchronises the device
 int resident_timing(unsigned long long* out8);
 

@@ -22,6 +22,12 @@
 // Mailboxes alternate by step parity: a CTA can only overwrite the records of step s-1 with those of step s+1 after
 // it received its neighbours' step-s records, which they computed from its step s-1 ones.
 //
+// CLUSTER transport (ResGeom::cluster, fk_cluster_kernel): a tissue of at most 16 tiles is ONE thread-block cluster.  A
+// ring cell's new u is then stored straight into the halo of the neighbouring CTA's next u buffer through distributed
+// shared memory, and one cluster barrier per step (arrive.release / wait.acquire) replaces mailboxes, tags, polling and
+// the halo copy: ~0.2 us per exchange instead of the ~1.1 us a store -> L2 -> polled load round trip costs on B200.
+// Clusters are independent, so a batch of small tissues needs no co-residency (any batch size, scheduled in waves).
+//
 // A thread computes groups of NC = 1, 2 or 4 adjacent cells of one row (the planner takes the smallest NC that keeps
 // the groups of a tile within one round of 512 threads: a small tile is latency bound and wants every lane busy).
 // The vertical and horizontal two-pass derivatives are rebuilt in registers from the shared-memory window like the
@@ -41,6 +47,10 @@
 #ifndef FK_RES_R2
 #define FK_RES_R2 0
 #endif
+// development switches for A/B builds
+#ifndef FK_RES_EDGE_SPECIAL
+#define FK_RES_EDGE_SPECIAL 1   // physical-edge cells through res_axis_edge (specialised by position) instead of res_axis_general
+#endif
 
 namespace fk {
 
@@ -58,6 +68,7 @@ struct ResGeom {
     int mg;              // 1: the diffusivity maps stay in global memory (L2) instead of shared memory (larger tissues)
     int r2;              // 1 (nc = 4 only): interior items are blocks of 2 rows x 4 cells
     int slots;           // mailbox records per tile and parity: 8 * tw_max (4 top + 4 bottom rows) + 8 * th_max (columns)
+    int cluster;         // 1: the tiles of a tissue form one thread-block cluster and exchange through distributed shared memory
     u64* xchg;           // mailboxes [2 parities][batch * ntr * ntc tiles][slots], tags zero at launch
     u64* timing;         // null, or cycle counters CTA (0, 0) fills (development: FK_RES_TIMING=1)
     unsigned spin_limit; // reads of one record after which the kernel traps instead of hanging the device
@@ -74,6 +85,8 @@ struct ResCta {
     int e_nt, e_nb, e_nl, e_nr;      // cells within 4 of a PHYSICAL edge: top/bottom rows, left/right columns of the rest
     int nedge;                       // ... their number
     int nhalo[4];                    // 16-byte units (2 records) of the north, south, west, east halo
+    int th_n, tw_w;                  // rows of the tile above, columns of the tile to the left (cluster transport)
+    float* peer[4];                  // cluster transport: the north, south, west, east neighbour's U0 (its shared memory)
     float *U0, *V, *Wd, *Dm, *DXm, *DYm;   // u buffer of parity p: U0 + p * nu
     int nu;                                // floats per u buffer
     long long boff, boffD;
@@ -131,6 +144,9 @@ FK_HD void res_tile_geom(int H, int W, const ResGeom& G, int tile, ResCta& X) {
         X.ninner = X.npair + (rows & 1) * qi;
     }
     X.nedge = res_edge_counts(H, W, X.r0, X.r1, X.c0, X.c1, X.e_nt, X.e_nb, X.e_nl, X.e_nr);
+    X.th_n = X.has_n ? X.r0 - res_split(H, G.ntr, G.eh, X.ti - 1) : 0;
+    X.tw_w = X.has_w ? X.c0 - 4 * res_split(W >> 2, G.ntc, G.ewq, X.tj - 1) : 0;
+    X.peer[0] = X.peer[1] = X.peer[2] = X.peer[3] = nullptr;
     X.nhalo[0] = X.has_n ? 2 * X.tw : 0; X.nhalo[1] = X.has_s ? 2 * X.tw : 0;
     X.nhalo[2] = X.has_w ? 2 * X.th : 0; X.nhalo[3] = X.has_e ? 2 * X.th : 0;
 }
@@ -414,6 +430,18 @@ FK_HD void stn(float* p, const float* v) {
     else p[0] = v[0];
 }
 
+// cluster transport: the same cells stored straight into the neighbours' halos (of the u buffer at float offset `off`
+// from U0: the one the step writes), through distributed shared memory.  Layouts are identical in every CTA of the
+// cluster (same pitch, same buffer offsets); only the neighbour's own height / width enters the address.
+template <int NC>
+FK_HD void res_publish_cl(const ResGeom& G, const ResCta& X, long long off, int lr, int lc, const float* un) {
+    const int P = G.pitch;
+    if (X.has_n && lr < 4) stn<NC>(X.peer[0] + off + (X.th_n + 4 + lr) * P + 4 + lc, un);
+    if (X.has_s && lr >= X.th - 4) stn<NC>(X.peer[1] + off + (lr - (X.th - 4)) * P + 4 + lc, un);
+    if (X.has_w && lc < 4) stn<NC>(X.peer[2] + off + (lr + 4) * P + X.tw_w + 4 + lc, un);
+    if (X.has_e && lc >= X.tw - 4) stn<NC>(X.peer[3] + off + (lr + 4) * P + (lc - (X.tw - 4)), un);
+}
+
 // first derivative / dx of whichever kind (solve.py:232-249) from a window a[0..6] centred on a[3].  Branch free: the
 // central value and ONE one-sided value (coefficients and operands selected) are both computed and one is kept -- a
 // cell at a physical edge is a lone dependent chain on the step's critical path, and straight-line code lets its
@@ -442,6 +470,71 @@ FK_HD void res_axis_general(const Consts& K, const float* up, int P, int n, floa
     d1 = g[3];
     d2 = res_deriv<EXACT>(K, kind_of(P, n, 1, 1), g);
 }
+
+// The same two derivatives for a cell within 4 of a physical edge of a long axis (n >= 16), SPECIALISED by where the cell
+// sits: side 0 = D cells from the low edge (padded P = D + 1), side 1 = D cells from the high edge (P = n - D), D = 0..3.
+// The kinds of the first-pass derivatives the second pass reads are then compile-time facts, so only those 4-5 of the 7
+// are computed, each by its own formula, without selects -- 5 four-tap sums instead of the 16 of res_axis_general (both
+// variants of all 7 plus 2 for the second pass).  Same operations on the same operands: identical bits.  A thread's edge
+// cell is the same every step, so the switch is perfectly predicted; it is warp-coherent where the tiles are at least a
+// warp wide (the cells of a row sit in consecutive threads), and only there is it used: measured (B200, profiles/
+// probe_cluster_r02.md) 512^2 3.46 -> 3.30 us per step, but 128^2 (tiles 16 wide: 4-8 cases per warp) 1.53 -> 1.84.
+template <bool EXACT>
+FK_HD float res_d_cen(const Consts& K, const float* a) { return dcen<EXACT>(K, a[1], a[2], a[4], a[5]); }
+template <bool EXACT>
+FK_HD float res_d_one(const Consts& K, bool f, const float* a) {   // f: forward (a[3..6]), else backward (a[0..3])
+    const float t = f ? tap4<EXACT>((float)(-11.0 / 6.0), 3.0f, -(float)(3.0 / 2.0), (float)(1.0 / 3.0), a[3], a[4], a[5], a[6])
+                      : tap4<EXACT>((float)(-1.0 / 3.0), (float)(3.0 / 2.0), -3.0f, (float)(11.0 / 6.0), a[0], a[1], a[2], a[3]);
+    if (EXACT) return div_dx(K, t);
+    return Num<false>::mul(t, K.r_dx);
+}
+template <bool EXACT, int SIDE, int D>
+FK_HD void res_axis_edge_t(const Consts& K, const float* up, float& d1, float& d2) {
+    float g[7];   // first derivative at padded P-3 .. P+3: only the entries the second pass reads
+    if (D == 3) {                       // every formula central (the windows reach the pad: clamped loads)
+        g[1] = res_d_cen<EXACT>(K, up + 1); g[2] = res_d_cen<EXACT>(K, up + 2); g[3] = res_d_cen<EXACT>(K, up + 3);
+        g[4] = res_d_cen<EXACT>(K, up + 4); g[5] = res_d_cen<EXACT>(K, up + 5);
+        d2 = res_d_cen<EXACT>(K, g);
+    } else if (SIDE == 0) {
+        if (D == 0) {                   // P = 1: first pass forward at padded 1, second pass forward
+            g[3] = res_d_one<EXACT>(K, true, up + 3); g[4] = res_d_cen<EXACT>(K, up + 4); g[5] = res_d_cen<EXACT>(K, up + 5);
+            g[6] = res_d_cen<EXACT>(K, up + 6);
+            d2 = res_d_one<EXACT>(K, true, g);
+        } else {                        // P = 2, 3: padded 0 and 1 forward
+            g[1] = res_d_one<EXACT>(K, true, up + 1);
+            g[2] = D == 1 ? res_d_one<EXACT>(K, true, up + 2) : res_d_cen<EXACT>(K, up + 2);
+            g[3] = res_d_cen<EXACT>(K, up + 3); g[4] = res_d_cen<EXACT>(K, up + 4); g[5] = res_d_cen<EXACT>(K, up + 5);
+            d2 = res_d_cen<EXACT>(K, g);
+        }
+    } else {
+        if (D == 0) {                   // P = n: first pass backward at padded n, second pass backward
+            g[0] = res_d_cen<EXACT>(K, up + 0); g[1] = res_d_cen<EXACT>(K, up + 1); g[2] = res_d_cen<EXACT>(K, up + 2);
+            g[3] = res_d_one<EXACT>(K, false, up + 3);
+            d2 = res_d_one<EXACT>(K, false, g);
+        } else {                        // P = n - 1, n - 2: padded n and n + 1 backward
+            g[1] = res_d_cen<EXACT>(K, up + 1); g[2] = res_d_cen<EXACT>(K, up + 2); g[3] = res_d_cen<EXACT>(K, up + 3);
+            g[4] = D == 1 ? res_d_one<EXACT>(K, false, up + 4) : res_d_cen<EXACT>(K, up + 4);
+            g[5] = res_d_one<EXACT>(K, false, up + 5);
+            d2 = res_d_cen<EXACT>(K, g);
+        }
+    }
+    d1 = g[3];
+}
+// code = D (low side) or 4 + D (high side)
+template <bool EXACT>
+FK_HD void res_axis_edge(const Consts& K, const float* up, int code, float& d1, float& d2) {
+    switch (code) {
+        case 0: res_axis_edge_t<EXACT, 0, 0>(K, up, d1, d2); break;
+        case 1: res_axis_edge_t<EXACT, 0, 1>(K, up, d1, d2); break;
+        case 2: res_axis_edge_t<EXACT, 0, 2>(K, up, d1, d2); break;
+        case 4: res_axis_edge_t<EXACT, 1, 0>(K, up, d1, d2); break;
+        case 5: res_axis_edge_t<EXACT, 1, 1>(K, up, d1, d2); break;
+        case 6: res_axis_edge_t<EXACT, 1, 2>(K, up, d1, d2); break;
+        default: res_axis_edge_t<EXACT, 0, 3>(K, up, d1, d2); break;
+    }
+}
+// cell `x` of an axis of n >= 16 cells, within 4 of one of its ends -> code
+FK_HD int res_edge_code(int x, int n) { return x < 4 ? x : 4 + (n - 1 - x); }
 
 // one Euler step of an INTERIOR block of 2 rows x 4 cells (rows lr, lr + 1; every formula central, nothing published):
 // the six u_x rows the two cells of a column need are computed once (6 + 2 first-pass/second-pass derivatives per
@@ -517,7 +610,7 @@ FK_HD void res_block2(const TileArgs& A, const ResGeom& G, const ResCta& X, cons
 // GENERAL = false: the caller guarantees that every formula of the group is central (no cell within 4 of a physical
 // edge) and only that path is compiled.
 // MG: the diffusivity maps are read from global memory (L2 resident) instead of shared memory.
-template <bool EXACT, int NC, bool GENERAL, bool MG>
+template <bool EXACT, int NC, bool GENERAL, bool MG, bool CL = false>
 FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const float* cur, float* nxt, int lr, int lc,
                      unsigned mask, bool last, u64* box, unsigned tag) {
     const int H = A.H, W = A.W, P = G.pitch, row = X.r0 + lr, c = X.c0 + lc;
@@ -577,7 +670,8 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
             float col[13];
 #pragma unroll
             for (int j = 0; j < 13; ++j) col[j] = ur[j][k];
-            res_axis_general<EXACT>(A.K, col, row + 1, H, u_x[k], u_xx[k]);
+            if (FK_RES_EDGE_SPECIAL && H >= 16 && G.tw_max >= 32) res_axis_edge<EXACT>(A.K, col, res_edge_code(row, H), u_x[k], u_xx[k]);
+            else res_axis_general<EXACT>(A.K, col, row + 1, H, u_x[k], u_xx[k]);
         }
     }
     // ---- horizontal (axis 1)
@@ -610,7 +704,8 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
             const int lo = -(c + k), hi = W - 1 - (c + k);
 #pragma unroll
             for (int j = 0; j < 13; ++j) win[j] = uc0[k + clampi(j - 6, lo, hi)];
-            res_axis_general<EXACT>(A.K, win, c + k + 1, W, u_y[k], u_yy[k]);
+            if (FK_RES_EDGE_SPECIAL && W >= 16 && G.tw_max >= 32) res_axis_edge<EXACT>(A.K, win, res_edge_code(c + k, W), u_y[k], u_yy[k]);
+            else res_axis_general<EXACT>(A.K, win, c + k + 1, W, u_y[k], u_yy[k]);
         }
     }
     float un[NC], vn[NC], wn[NC];
@@ -624,7 +719,10 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
         stn<NC>(A.v_out + X.boff + g, vn);
         stn<NC>(A.w_out + X.boff + g, wn);
     } else {
-        if (box) res_publish<NC>(G, X, box, lr, lc, un, tag);
+        if (box) {
+            if (CL) { if (!(G.spin_limit & 1u)) res_publish_cl<NC>(G, X, (long long)(nxt - X.U0), lr, lc, un); }
+            else res_publish<NC>(G, X, box, lr, lc, un, tag);
+        }
         stn<NC>(nxt + (lr + 4) * P + (lc + 4), un);
         stn<NC>(X.V + o, vn);
         stn<NC>(X.Wd + o, wn);
@@ -667,20 +765,23 @@ FK_HD void res_thread_setup(const TileArgs& A, const ResGeom& G, const ResCta& X
 }
 
 // one phase of step s, its items strided over the CTA's threads
-template <bool EXACT, int NC, bool MG>
+// CL: the cluster transport (ring cells stored into the neighbours' halos) -- its own instantiation, so that the mailbox
+// kernels carry none of it (as a run-time branch it cost them 7-14 %: profiles/probe_cluster_r02.md)
+template <bool EXACT, int NC, bool MG, bool CL = false>
 FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
                      unsigned mask, int tid, int nthr) {   // (called from ONE site, in a phase loop: a single copy)
     const float* cur = X.U0 + (s & 1) * X.nu;
     float* nxt = X.U0 + ((s + 1) & 1) * X.nu;
     const bool last = s == G.nsteps - 1;
-    u64* box = (last || phase) ? nullptr : G.xchg + ((s + 1) & 1) * X.pstride + X.mbox;
+    u64* box = (last || phase) ? nullptr : (CL ? reinterpret_cast<u64*>(X.U0)   // (non-null: "publish")
+                                               : G.xchg + ((s + 1) & 1) * X.pstride + X.mbox);
     const unsigned tag = (unsigned)(s + 1);
     const int n = phase ? X.ninner : (NC == 1 ? X.nring : X.nring + X.nedge);
     for (int i = tid; i < n; i += nthr) {
         int lr = phase ? T.lr1 : T.lr0, lc = phase ? T.lc1 : T.lc0, ty = phase ? T.ty1 : T.ty0;
         if (i != tid) ty = res_item<NC>(A, G, X, phase, i, lr, lc);
-        if (ty == 2) res_group<EXACT, 1, true, MG>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
-        else if (NC > 1 && ty == 1) res_group<EXACT, NC, false, MG>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        if (ty == 2) res_group<EXACT, 1, true, MG, CL>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        else if (NC > 1 && ty == 1) res_group<EXACT, NC, false, MG, CL>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
         else if (FK_RES_R2 && NC == 4 && ty == 3) res_block2<EXACT, MG>(A, G, X, cur, nxt, lr, lc, mask, last);
     }
 }
@@ -836,6 +937,20 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
     return found;
 }
 
+// Tiles of ONE tissue for the cluster transport: at most FK_CLUSTER_MAX CTAs (the non-portable cluster size of sm_100),
+// maps in shared memory, no mailboxes.  The same planner, told that the machine has 16 SMs.
+enum { FK_CLUSTER_MAX = 16 };
+inline bool plan_cluster(int H, int W, long long smem_limit, int force_ntr, int force_ntc, int force_threads, int force_nc,
+                         ResPlan& P) {
+    if (force_ntr > 0 && force_ntc > 0 && force_ntr * force_ntc > FK_CLUSTER_MAX) return false;
+    if (!plan_resident(H, W, 1, FK_CLUSTER_MAX, smem_limit, 1LL << 40, force_ntr, force_ntc, force_threads, force_nc, -1, -1, 0, P))
+        return false;
+    if (P.G.mg) return false;
+    P.G.cluster = 1;
+    P.xchg_bytes = 0;
+    return true;
+}
+
 // ------------------------------------------------------------------ CPU emulation of one launch (tests/emu)
 #if !defined(__CUDACC__)
 }  // namespace fk
@@ -844,7 +959,11 @@ namespace fk {
 template <bool EXACT>
 inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
                           unsigned mask) {
-    if (G.mg) {
+    if (G.cluster) {
+        if (G.nc == 1) res_phase<EXACT, 1, false, true>(A, G, X, T, s, phase, mask, 0, 1);
+        else if (G.nc == 2) res_phase<EXACT, 2, false, true>(A, G, X, T, s, phase, mask, 0, 1);
+        else res_phase<EXACT, 4, false, true>(A, G, X, T, s, phase, mask, 0, 1);
+    } else if (G.mg) {
         if (G.nc == 1) res_phase<EXACT, 1, true>(A, G, X, T, s, phase, mask, 0, 1);
         else if (G.nc == 2) res_phase<EXACT, 2, true>(A, G, X, T, s, phase, mask, 0, 1);
         else res_phase<EXACT, 4, true>(A, G, X, T, s, phase, mask, 0, 1);
@@ -870,6 +989,12 @@ inline int emu_resident_launch(const ResPlan& P, const TileArgs& A, int batch, i
         for (int t = 0; t < ntiles; ++t) {
             ResCta& x = X[(size_t)sim * ntiles + t];
             res_setup(A, G, t, sim, batch, smem[(size_t)sim * ntiles + t].data(), x);
+            if (G.cluster) {   // the neighbours' shared memory, as cluster.map_shared_rank gives it on the device
+                if (x.has_n) x.peer[0] = smem[(size_t)sim * ntiles + t - G.ntc].data();
+                if (x.has_s) x.peer[1] = smem[(size_t)sim * ntiles + t + G.ntc].data();
+                if (x.has_w) x.peer[2] = smem[(size_t)sim * ntiles + t - 1].data();
+                if (x.has_e) x.peer[3] = smem[(size_t)sim * ntiles + t + 1].data();
+            }
             res_load(A, G, x, 0, 1);
             ResThread& th = T[(size_t)sim * ntiles + t];
             if (G.nc == 1) res_thread_setup<1>(A, G, x, 0, 1, th);
@@ -884,7 +1009,7 @@ inline int emu_resident_launch(const ResPlan& P, const TileArgs& A, int batch, i
                 else emu_res_phase<false>(A, G, X[i], T[i], s, phase, mask);
             }
         }
-        if (s == G.nsteps - 1) break;
+        if (s == G.nsteps - 1 || G.cluster) continue;   // (cluster transport: the halos were stored by their producers)
         for (size_t i = 0; i < X.size(); ++i)
             if (!res_halo(G, X[i], T[i], s, 0, 1)) return -7;
     }

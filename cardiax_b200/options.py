@@ -6,7 +6,8 @@ numerics           "fast" (default): reciprocal multiplications + FMAs, a few ul
                    division keeps the reference's rounding (see DESIGN.md section 6 for the measured ratio).
 steps_per_launch   temporal blocking depth T (0 = library default).
 kernel             0 auto, 1 general tile kernel only, 2 require the streaming kernel, 3 require the one-step wide kernel,
-                   4 require the resident kernel (whole call in one cooperative launch, state in shared memory).
+                   4 require the resident kernel (whole call in one cooperative launch, state in shared memory),
+                   5 require its cluster form (a tissue of <= 16 tiles = one thread-block cluster, halos through DSMEM).
 tiles              resident kernel: (rows, columns) of the tile grid, one CTA per tile ((0, 0) = planner's choice).
 """
 numerics = "fast"

@@ -53,7 +53,9 @@ typedef struct FkOptions {
     int exact;            /* 1: reference operation order, bit-identical to the CPU oracle; 0: fast numerics */
     int steps_per_launch; /* temporal blocking depth T (1..8); 0 = library default */
     int kernel;           /* 0 = auto, 1 = general tile kernel everywhere, 2 = require the streaming kernel,
-                             3 = low-latency one-step kernel for small tissues, 4 = resident kernel (whole call in one
+                             3 = low-latency one-step kernel for small tissues, 5 = resident kernel with the tissue as ONE
+                             thread-block cluster (<= 16 tiles, halos through distributed shared memory: the default for
+                             single tissues up to 256 x 256 cells), 4 = resident kernel (whole call in one
                              cooperative launch, state in shared memory) */
     int phys_top;         /* is buffer row 0 the physical tissue edge? (0 only for slab decomposition) */
     int phys_bottom;      /* is buffer row H-1 the physical tissue edge? */

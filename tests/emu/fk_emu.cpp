@@ -64,6 +64,7 @@ struct EmuBackend {
     }
     int launches_res = 0;
     long long resident_smem_limit() { return 227 * 1024 - 256; }
+    bool cluster_ok(const fk::ResPlan&, int) { return true; }
     int resident(const fk::ResPlan& P, const fk::TileArgs& A, int exact, int batch) {
         ++launches_res;
         last_res = P;

@@ -55,6 +55,36 @@ def test_resident_kernel_exact(shape, nsteps, tiles, nc):
     assert info == (0, 1000000)   # one launch, nothing else
 
 
+@pytest.mark.parametrize("nc", [0, 1, 2, 4])
+@pytest.mark.parametrize("shape,nsteps,tiles", [
+    ((12, 16), 6, (0, 0)), ((64, 96), 7, (0, 0)), ((64, 96), 7, (2, 3)), ((64, 96), 7, (4, 1)), ((64, 96), 7, (1, 5)),
+    ((40, 64), 9, (3, 2)), ((37, 52), 8, (2, 2)), ((130, 20), 6, (0, 0)), ((128, 128), 5, (0, 0)), ((128, 128), 5, (4, 4)),
+    ((96, 160), 6, (3, 5)), ((7, 8), 5, (1, 1)), ((64, 96), 1, (2, 3))])
+def test_cluster_transport_exact(shape, nsteps, tiles, nc):
+    """The resident kernel with the tissue as ONE thread-block cluster: ring cells stored straight into the neighbours'
+    halos (distributed shared memory on the device, the neighbour's buffer here), no mailboxes -- bit-identical to the
+    oracle for any grid of <= 16 tiles, uneven tiles, every cells-per-thread, all physical edges, stimuli."""
+    info = _exact(shape, 1, nsteps=nsteps, kernel=5, tiles=tiles, nc=nc)
+    assert info == (0, 1000000)
+
+
+def test_cluster_transport_batch_and_limits():
+    shape, batch = (40, 48), 3
+    cases = [common.random_case(shape, seed=20 + b, n_stim=2) for b in range(batch)]
+    st = [np.stack([c[0][k] for c in cases]) for k in range(3)]
+    D = np.stack([c[1] for c in cases])
+    stims = [c[2] for c in cases]
+    got, info = emu.euler(st, 0, 6, P3, D, stims, 0.01, 0.01, exact=True, kernel=5, tiles=(2, 2))
+    assert info == (0, 1000000)
+    for b in range(batch):
+        ref = C.forward_euler(cases[b][0], 0, 6, P3, cases[b][1], cases[b][2], 0.01, 0.01)
+        for a, r in zip(got, ref):
+            assert np.array_equal(a[b], r)
+    # more than 16 tiles is not a cluster
+    with pytest.raises(Exception):
+        emu.euler([x[0] for x in st], 0, 6, P3, D[0], stims[0], 0.01, 0.01, exact=True, kernel=5, tiles=(5, 4))
+
+
 @pytest.mark.parametrize("shape,tiles,edge,nc", [((96, 160), (5, 6), (12, 4), 4), ((96, 160), (5, 6), (12, 4), 1),
                                                  ((120, 96), (4, 3), (20, 6), 2), ((120, 96), (6, 1), (10, 0), 4)])
 def test_resident_kernel_uneven_edge_tiles(shape, tiles, edge, nc):

@@ -85,6 +85,52 @@ def test_resident_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads, 
     assert_exact(got, ref, "resident %s tiles %s" % (shape, tiles))
 
 
+@pytest.mark.parametrize("shape,nsteps,tiles,threads,nc", [
+    ((12, 16), 9, (0, 0), 0, 0), ((64, 96), 9, (2, 3), 0, 4), ((64, 96), 9, (4, 1), 256, 2), ((128, 128), 40, (0, 0), 0, 0),
+    ((128, 128), 9, (4, 4), 0, 4), ((128, 128), 9, (2, 8), 128, 1), ((100, 200), 9, (3, 5), 0, 0), ((256, 256), 40, (0, 0), 0, 0),
+    ((64, 64), 33, (0, 0), 0, 0), ((320, 320), 7, (4, 4), 0, 0), ((64, 96), 1, (2, 3), 0, 0), ((200, 120), 25, (3, 3), 96, 1)])
+def test_cluster_kernel_exact_bitwise_vs_oracle(shape, nsteps, tiles, threads, nc):
+    """The resident kernel's cluster form (a tissue of <= 16 tiles = ONE thread-block cluster; ring cells stored into the
+    neighbouring CTAs' halos through distributed shared memory, one cluster barrier per Euler step): bit-identical to the
+    oracle for any tile grid, CTA size and cells per thread."""
+    from cardiax_b200 import _lib
+    st, D, stim = common.random_case(shape, seed=4, n_stim=3)
+    ref = C.forward_euler(st, 0, nsteps, P3, D, stim, 0.01, 0.01)
+    before = _lib.lib().fk_launch_count()
+    got = run_gpu(st, 0, nsteps, P3, D, stim, numerics="exact", kernel=5, tiles=tiles, cta_threads=threads,
+                  cells_per_thread=nc)
+    assert _lib.lib().fk_launch_count() - before == 2   # D_x/D_y maps + ONE launch
+    assert _lib.last_kernel() == "fk_cluster_kernel"
+    assert_exact(got, ref, "cluster %s tiles %s" % (shape, tiles))
+
+
+def test_cluster_kernel_fast_matches_the_other_kernels_and_takes_any_batch():
+    """Fast numerics: cluster == mailbox-resident == streaming bit for bit over 300 steps with stimuli; a batch of 40
+    tissues (more clusters than the device holds at once: they are independent, scheduled in waves) against single runs."""
+    from cardiax_b200 import _lib, options, solve, stimulus
+    st, D = common.smooth_case((64, 64), seed=8)
+    _, _, stim = common.random_case((64, 64), seed=8, n_stim=3)
+    a = run_gpu(st, 0, 300, P3, D, stim, numerics="fast")
+    assert _lib.last_kernel() == "fk_cluster_kernel"        # the default for a single tissue up to 80 x 80
+    b = run_gpu(st, 0, 300, P3, D, stim, numerics="fast", kernel=4)
+    assert _lib.last_kernel() == "fk_resident_kernel"
+    c = run_gpu(st, 0, 300, P3, D, stim, numerics="fast", kernel=3)
+    assert_exact(a, b, "cluster vs resident")
+    assert_exact(a, c, "cluster vs wide")
+    shape, batch = (64, 64), 40
+    cases = [common.random_case(shape, seed=30 + b, n_stim=2) for b in range(batch)]
+    stb = [np.stack([cs[0][k] for cs in cases]) for k in range(3)]
+    Db = np.stack([cs[1] for cs in cases])
+    options.numerics, options.kernel = "exact", 5
+    gst = [[stimulus.Stimulus(stimulus.Protocol(*s.protocol), torch.as_tensor(s.field).cuda()) for s in cs[2]] for cs in cases]
+    out = solve._forward_euler(solve.State(*[torch.as_tensor(x).cuda() for x in stb]), 0, 11, P3, torch.as_tensor(Db).cuda(), gst, 0.01, 0.01)
+    torch.cuda.synchronize()
+    assert _lib.last_kernel() == "fk_cluster_kernel"
+    for b in range(0, batch, 7):
+        ref = C.forward_euler(cases[b][0], 0, 11, P3, cases[b][1], cases[b][2], 0.01, 0.01)
+        assert_exact([x[b].cpu().numpy() for x in out], ref, "tissue %d" % b)
+
+
 @pytest.mark.parametrize("shape,nsteps,tiles,edge,mg", [((1200, 1200), 5, (0, 0), (0, 0), 0), ((96, 160), 9, (5, 6), (12, 4), 1),
                                                         ((200, 120), 12, (3, 3), (0, 0), 1), ((512, 512), 8, (0, 0), (0, 0), 0)])
 def test_resident_kernel_maps_in_l2_and_uneven_edge_tiles(shape, nsteps, tiles, edge, mg):
