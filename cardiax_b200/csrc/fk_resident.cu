@@ -21,7 +21,7 @@ __device__ u64 g_res_timing[8];
         t_ = now_;                       \
     }
 
-template <bool EXACT, int NC, bool MG>
+template <bool EXACT, int NC, bool MG, bool TP = false>
 __global__ void __launch_bounds__(FK_RES_MAX_THREADS, 1)
 fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ ResGeom G) {
     extern __shared__ __align__(16) float fk_res_smem[];
@@ -39,9 +39,9 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
     // left each phase (max over warps, relative to the step's start): what the step really waits for
     const bool tcta = G.timing != nullptr && (int)blockIdx.x == (int)(G.spin_limit >> 25) && blockIdx.y == 0;
     const bool timed = tcta && tid == 0;
-    __shared__ unsigned s_wmax[2];
+    __shared__ unsigned s_wmax[3];
     __shared__ long long s_t0;
-    u64 acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0;
+    u64 acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0, acc7 = 0;
     long long t_ = timed ? clock64() : 0;
     for (int s = 0; s < G.nsteps; ++s) {
         if ((s & 31) == 0) {   // (every thread passed the barrier that ended step s - 1: nobody reads the old masks)
@@ -50,14 +50,19 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
         }
         const unsigned mask = s_mask[s & 31];
         if (tcta) {
-            if (tid == 0) { s_wmax[0] = s_wmax[1] = 0; s_t0 = clock64(); }
+            if (tid == 0) { s_wmax[0] = s_wmax[1] = s_wmax[2] = 0; s_t0 = clock64(); }
+            __syncthreads();
+        }
+        if (TP) {   // two-pass step: first derivatives of the tile (and the cells at a physical edge), then the cells
+            res_phase_a<EXACT, MG>(A, G, X, s, mask, tid, nthr);
+            if (tcta && (tid & 31) == 0) atomicMax(&s_wmax[2], (unsigned)(clock64() - s_t0));
             __syncthreads();
         }
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
             // phase 0: the ring, published to the neighbours' mailboxes as it is computed; phase 1: the interior, while
             // those records travel.  ONE call site: the body exists once and stays inside the instruction cache.
-            res_phase<EXACT, NC, MG>(A, G, X, T, s, phase, mask, tid, nthr);
+            res_phase<EXACT, NC, MG, false, TP>(A, G, X, T, s, phase, mask, tid, nthr);
             if (tcta && (tid & 31) == 0) atomicMax(&s_wmax[phase], (unsigned)(clock64() - s_t0));
             if (phase == 0) { FK_TICK(0) } else { FK_TICK(1) }
         }
@@ -66,10 +71,10 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
         FK_TICK(2)
         __syncthreads();
         FK_TICK(3)
-        if (timed) { acc4 += s_wmax[0]; acc5 += s_wmax[1]; }
+        if (timed) { acc4 += s_wmax[0]; acc5 += s_wmax[1]; acc7 += s_wmax[2]; }
     }
     if (timed) {
-        G.timing[0] = acc0; G.timing[1] = acc1; G.timing[2] = acc2; G.timing[3] = acc3; G.timing[4] = acc4; G.timing[5] = acc5;
+        G.timing[0] = acc0; G.timing[1] = acc1; G.timing[2] = acc2; G.timing[3] = acc3; G.timing[4] = acc4; G.timing[5] = acc5; G.timing[7] = acc7;
         G.timing[6] = (u64)G.nsteps;
     }
 }
@@ -186,7 +191,7 @@ int cluster_capacity_nc(int ntiles, int threads, size_t smem) {
     return n;
 }
 
-template <bool EXACT, int NC, bool MG>
+template <bool EXACT, int NC, bool MG, bool TP = false>
 int launch_nc(const ResPlan& P, const TileArgs& A, const ResGeom& G, int batch, cudaStream_t st) {
     static bool attr_set_dev[64] = {false};   // the opt-in is per device
     int dev = 0;
@@ -194,12 +199,12 @@ int launch_nc(const ResPlan& P, const TileArgs& A, const ResGeom& G, int batch, 
     bool& attr_set = attr_set_dev[dev];
     cudaError_t e;
     if (!attr_set) {
-        e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN);
+        e = cudaFuncSetAttribute(fk_resident_kernel<EXACT, NC, MG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_RES_SMEM_OPTIN);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     void* args[2] = {(void*)&A, (void*)&G};
-    return (int)cudaLaunchCooperativeKernel((const void*)fk_resident_kernel<EXACT, NC, MG>, dim3(G.ntr * G.ntc, batch),
+    return (int)cudaLaunchCooperativeKernel((const void*)fk_resident_kernel<EXACT, NC, MG, TP>, dim3(G.ntr * G.ntc, batch),
                                             dim3(P.threads), args, (size_t)P.smem_bytes, st);
 }
 
@@ -229,6 +234,7 @@ int launch_t(const ResPlan& P, const TileArgs& A, int batch, cudaStream_t st) {
         if (cudaGetSymbolAddress(&sym, g_res_timing) == cudaSuccess) G.timing = (u64*)sym;
         G.spin_limit = (G.spin_limit & ((1u << 25) - 1)) | ((unsigned)atoi(getenv("FK_RES_TIMING")) << 25);   // which CTA
     }
+    if (G.tp) return G.mg ? launch_nc<EXACT, 4, true, true>(P, A, G, batch, st) : launch_nc<EXACT, 4, false, true>(P, A, G, batch, st);
     if (G.mg) {
         if (G.nc == 1) return launch_nc<EXACT, 1, true>(P, A, G, batch, st);
         if (G.nc == 2) return launch_nc<EXACT, 2, true>(P, A, G, batch, st);

@@ -48,6 +48,12 @@
 #define FK_RES_R2 0
 #endif
 // development switches for A/B builds
+#ifndef FK_RES_TWO_PASS
+#define FK_RES_TWO_PASS 0       // 1: the planner may choose the two-pass step (ResGeom::tp).  EXPERIMENT, off: bit-identical
+#endif                          // (CPU emulation and GPU suite green with it on) but slower on B200 -- 512^2 4.03 vs 3.30 us per
+                                // step, 1024^2 8.7 vs 7.6: a phase of this kernel is bound by the latency of ONE item's
+                                // dependent chain at ~3 warps per scheduler (IPC ~0.25), not by its instruction count, so
+                                // three short phases + a barrier lose to two long ones (profiles/probe_cluster_r02.md)
 #ifndef FK_RES_EDGE_SPECIAL
 #define FK_RES_EDGE_SPECIAL 1   // physical-edge cells through res_axis_edge (specialised by position) instead of res_axis_general
 #endif
@@ -69,6 +75,7 @@ struct ResGeom {
     int r2;              // 1 (nc = 4 only): interior items are blocks of 2 rows x 4 cells
     int slots;           // mailbox records per tile and parity: 8 * tw_max (4 top + 4 bottom rows) + 8 * th_max (columns)
     int cluster;         // 1: the tiles of a tissue form one thread-block cluster and exchange through distributed shared memory
+    int tp;              // 1 (nc = 4): TWO-PASS step -- first derivatives of the whole tile into shared memory, then the cells
     u64* xchg;           // mailboxes [2 parities][batch * ntr * ntc tiles][slots], tags zero at launch
     u64* timing;         // null, or cycle counters CTA (0, 0) fills (development: FK_RES_TIMING=1)
     unsigned spin_limit; // reads of one record after which the kernel traps instead of hanging the device
@@ -88,6 +95,7 @@ struct ResCta {
     int th_n, tw_w;                  // rows of the tile above, columns of the tile to the left (cluster transport)
     float* peer[4];                  // cluster transport: the north, south, west, east neighbour's U0 (its shared memory)
     float *U0, *V, *Wd, *Dm, *DXm, *DYm;   // u buffer of parity p: U0 + p * nu
+    float *GX, *GY;                        // two-pass form: u_x of rows -2 .. th+1 (pitch tw_max), u_y of columns -4 .. tw+3 (pitch)
     int nu;                                // floats per u buffer
     long long boff, boffD;
     long long mbox;                  // this tile's mailbox: xchg + mbox (+ parity * pstride)
@@ -95,8 +103,9 @@ struct ResCta {
     const StimDev* stims;
 };
 
-FK_HD long long res_smem_floats(int th_max, int tw_max, int mg) {
-    return 2LL * (th_max + 8) * (tw_max + 8) + (mg ? 2LL : 5LL) * th_max * tw_max;
+FK_HD long long res_smem_floats(int th_max, int tw_max, int mg, int tp = 0) {
+    return 2LL * (th_max + 8) * (tw_max + 8) + (mg ? 2LL : 5LL) * th_max * tw_max +
+           (tp ? (long long)(th_max + 4) * tw_max + (long long)th_max * (tw_max + 8) : 0LL);
 }
 
 // the cells of tile rows [r0, r1) x columns [c0, c1) that lie within 4 cells of a physical edge of the H x W tissue
@@ -157,6 +166,8 @@ FK_HD void res_setup(const TileArgs& A, const ResGeom& G, int tile, int sim, int
     const long long nu = (long long)(G.th_max + 8) * G.pitch, nv = (long long)G.th_max * G.tw_max;
     X.U0 = smem; X.nu = (int)nu;
     X.V = smem + 2 * nu; X.Wd = X.V + nv; X.Dm = X.Wd + nv; X.DXm = X.Dm + nv; X.DYm = X.DXm + nv;   // (maps: only if !G.mg)
+    X.GX = G.mg ? X.Dm : X.DYm + nv;   // (two-pass form only)
+    X.GY = X.GX + (long long)(G.th_max + 4) * G.tw_max;
     X.boff = (long long)sim * A.plane;
     X.boffD = (long long)sim * A.plane_D;
     const long long ntiles = (long long)G.ntr * G.ntc;
@@ -729,6 +740,114 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     }
 }
 
+// ------------------------------------------------------------------ the TWO-PASS step (ResGeom::tp, nc = 4)
+// res_group rebuilds every first derivative a cell needs from the u window: 9 four-tap sums per cell where the reference's
+// two passes need 4, and 16 shared-memory loads per group.  Here the step is done the way the reference does it -- gradient,
+// then gradient of the gradient (solve.py:49-52) -- with the first pass kept in shared memory:
+//   pass A   u_x of tile rows -2 .. th+1 and u_y of tile columns -2 .. tw+1 (what the second pass of the tile's cells
+//            reads; the apron comes from the u halo) -> GX, GY; the cells within 4 of a PHYSICAL edge are done in this
+//            phase too, one per thread through the general formulas (they read u only);
+//   barrier
+//   pass B   per group of 4 cells: u_xx from 5 GX rows, u_yy from GY, then the cell update -- stream_emit, the streaming
+//            kernel's own (two cells per instruction in fast numerics); ring groups first (published), then the interior.
+// Same operations on the same operands as res_group: identical bits.  Per cell ~5 four-tap sums and ~6 16-byte loads.
+FK_HD int res_grad_items(const ResCta& X) { return (X.th + 4) * (X.tw >> 2) + 2 * X.th; }
+
+template <bool EXACT>
+FK_HD void res_grad_item(const TileArgs& A, const ResGeom& G, const ResCta& X, const float* cur, int i) {
+    const int q4 = X.tw >> 2, nmain = (X.th + 4) * q4, P = G.pitch;
+    if (i < nmain) {
+        const int rr = i / q4, lr = rr - 2, lc = 4 * (i - rr * q4);
+        const int R = X.r0 + lr;
+        if (R < 0 || R >= A.H) return;
+        const float* uc = cur + (lr + 4) * P + (lc + 4);
+        if (R >= 2 && R <= A.H - 3) {   // central along the rows: solve.py:49 at a row whose window is inside the tissue
+            float a0[4], a1[4], a3[4], a4[4], gx[4];
+            unpack4(ld4(uc - 2 * P), a0); unpack4(ld4(uc - P), a1); unpack4(ld4(uc + P), a3); unpack4(ld4(uc + 2 * P), a4);
+            dcen_rows4<EXACT>(A.K, a0, a1, a3, a4, gx);
+            st4(X.GX + (lr + 2) * G.tw_max + lc, gx);
+        }
+        if (lr >= 0 && lr < X.th) {     // solve.py:50 (groups at a physical left / right edge: their two outer values are
+            float e[12], gy[4];         //  never read -- the cells that would read them go through the general formulas)
+            unpack4(ld4(uc - 4), e); unpack4(ld4(uc), e + 4); unpack4(ld4(uc + 4), e + 8);
+            dcen_span4<EXACT>(A.K, e + 2, gy);
+            st4(X.GY + lr * P + (lc + 4), gy);
+        }
+        return;
+    }
+    // the two u_y values beyond each side of the tile (only where a neighbour's halo is there)
+    const int j = i - nmain, lr = j >> 1, right = j & 1;
+    if (right ? !X.has_e : !X.has_w) return;
+    const float* uc = cur + (lr + 4) * P + 4 + (right ? X.tw - 2 : -4);   // e[0..5]: columns -4 .. 1, or tw-2 .. tw+3
+    const F2 a = ld2(uc), b = ld2(uc + 2), c = ld2(uc + 4);
+    F2 g;
+    g.x = dcen<EXACT>(A.K, a.x, a.y, b.y, c.x);
+    g.y = dcen<EXACT>(A.K, a.y, b.x, c.x, c.y);
+    *reinterpret_cast<F2*>(X.GY + lr * P + 4 + (right ? X.tw : -2)) = g;
+}
+
+template <bool EXACT, bool MG>
+FK_HD void res_group2p(const TileArgs& A, const ResGeom& G, const ResCta& X, const float* cur, float* nxt, int lr, int lc,
+                       unsigned mask, bool last, u64* box, unsigned tag) {
+    const int P = G.pitch, TW = G.tw_max, W = A.W, row = X.r0 + lr, c = X.c0 + lc;
+    const int o = lr * TW + lc;
+    const long long g = (long long)row * W + c;
+    float Dv[4], DXv[4], DYv[4], v[4], w[4], stim[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MG) {   // requested first: the longest latency of the group
+        unpack4(ldg4(A.D + X.boffD + g), Dv); unpack4(ldg4(A.DX + X.boffD + g), DXv); unpack4(ldg4(A.DY + X.boffD + g), DYv);
+    } else {
+        unpack4(ld4(X.Dm + o), Dv); unpack4(ld4(X.DXm + o), DXv); unpack4(ld4(X.DYm + o), DYv);
+    }
+    const float* gxp = X.GX + (lr + 2) * TW + lc;
+    float gm2[4], gm1[4], g0[4], gp1[4], gp2[4], e[12], u0[4];
+    unpack4(ld4(gxp - 2 * TW), gm2); unpack4(ld4(gxp - TW), gm1); unpack4(ld4(gxp), g0);
+    unpack4(ld4(gxp + TW), gp1); unpack4(ld4(gxp + 2 * TW), gp2);
+    const float* gyp = X.GY + lr * P + (lc + 4);
+    unpack4(ld4(gyp - 4), e); unpack4(ld4(gyp), e + 4); unpack4(ld4(gyp + 4), e + 8);
+    unpack4(ld4(cur + (lr + 4) * P + (lc + 4)), u0);
+    unpack4(ld4(X.V + o), v);
+    unpack4(ld4(X.Wd + o), w);
+    float un[4], vn[4], wn[4];
+    if (mask) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) stim[k] = res_stim(A, X, mask, g + k);
+        stream_emit<EXACT, true, false>(A.K, u0, v, w, gm2, gm1, g0, gp1, gp2, e + 2, e + 4, Dv, DXv, DYv, stim, false, false, un, vn, wn);
+    } else {
+        stream_emit<EXACT, false, false>(A.K, u0, v, w, gm2, gm1, g0, gp1, gp2, e + 2, e + 4, Dv, DXv, DYv, stim, false, false, un, vn, wn);
+    }
+    if (last) {
+        st4(A.u_out + X.boff + g, un);
+        st4(A.v_out + X.boff + g, vn);
+        st4(A.w_out + X.boff + g, wn);
+    } else {
+        if (box) res_publish<4>(G, X, box, lr, lc, un, tag);
+        st4(nxt + (lr + 4) * P + (lc + 4), un);
+        st4(X.V + o, vn);
+        st4(X.Wd + o, wn);
+    }
+}
+
+// pass A of step s: the gradient items, then the cells at a physical edge (general formulas, published like ring cells)
+template <bool EXACT, bool MG>
+FK_HD void res_phase_a(const TileArgs& A, const ResGeom& G, const ResCta& X, int s, unsigned mask, int tid, int nthr) {
+    const float* cur = X.U0 + (s & 1) * X.nu;
+    float* nxt = X.U0 + ((s + 1) & 1) * X.nu;
+    const bool last = s == G.nsteps - 1;
+    u64* box = last ? nullptr : G.xchg + ((s + 1) & 1) * X.pstride + X.mbox;
+    const unsigned tag = (unsigned)(s + 1);
+    const int ng = res_grad_items(X), n = ng + X.nedge;
+    for (int i = tid; i < n; i += nthr) {
+        if (i < ng) res_grad_item<EXACT>(A, G, X, cur, i);
+        else {
+            int lr, lc;
+            res_locate_edge(X, i - ng, lr, lc);
+            res_group<EXACT, 1, true, MG>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        }
+    }
+}
+
 // item i of a phase -> its cell(s) and what to do with them: 1 = a group of NC cells whose formulas are all central,
 // 2 = ONE cell through the general formulas, 0 = nothing.  Phase 0 = the ring (what the neighbours wait for), published
 // as it is computed; phase 1 = the interior, computed while those records travel.  With NC > 1 the groups that touch a
@@ -737,6 +856,7 @@ FK_HD void res_group(const TileArgs& A, const ResGeom& G, const ResCta& X, const
 template <int NC>
 FK_HD int res_item(const TileArgs& A, const ResGeom& G, const ResCta& X, int phase, int i, int& lr, int& lc) {
     const int n = phase ? X.ninner : X.nring;
+    if (G.tp && i >= n) return 0;   // two-pass form: the cells at a physical edge belong to the gradient phase
     if (NC == 1) {
         if (i >= n) return 0;
         res_locate(G, X, phase, i, lr, lc);
@@ -767,7 +887,7 @@ FK_HD void res_thread_setup(const TileArgs& A, const ResGeom& G, const ResCta& X
 // one phase of step s, its items strided over the CTA's threads
 // CL: the cluster transport (ring cells stored into the neighbours' halos) -- its own instantiation, so that the mailbox
 // kernels carry none of it (as a run-time branch it cost them 7-14 %: profiles/probe_cluster_r02.md)
-template <bool EXACT, int NC, bool MG, bool CL = false>
+template <bool EXACT, int NC, bool MG, bool CL = false, bool TP = false>
 FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
                      unsigned mask, int tid, int nthr) {   // (called from ONE site, in a phase loop: a single copy)
     const float* cur = X.U0 + (s & 1) * X.nu;
@@ -776,11 +896,12 @@ FK_HD void res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const
     u64* box = (last || phase) ? nullptr : (CL ? reinterpret_cast<u64*>(X.U0)   // (non-null: "publish")
                                                : G.xchg + ((s + 1) & 1) * X.pstride + X.mbox);
     const unsigned tag = (unsigned)(s + 1);
-    const int n = phase ? X.ninner : (NC == 1 ? X.nring : X.nring + X.nedge);
+    const int n = phase ? X.ninner : ((NC == 1 || TP) ? X.nring : X.nring + X.nedge);
     for (int i = tid; i < n; i += nthr) {
         int lr = phase ? T.lr1 : T.lr0, lc = phase ? T.lc1 : T.lc0, ty = phase ? T.ty1 : T.ty0;
         if (i != tid) ty = res_item<NC>(A, G, X, phase, i, lr, lc);
         if (ty == 2) res_group<EXACT, 1, true, MG, CL>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
+        else if (TP && NC == 4 && ty == 1) res_group2p<EXACT, MG>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
         else if (NC > 1 && ty == 1) res_group<EXACT, NC, false, MG, CL>(A, G, X, cur, nxt, lr, lc, mask, last, box, tag);
         else if (FK_RES_R2 && NC == 4 && ty == 3) res_block2<EXACT, MG>(A, G, X, cur, nxt, lr, lc, mask, last);
     }
@@ -827,13 +948,13 @@ inline double res_tile_work(int H, int W, const ResGeom& G, int tile) {
 // maps_global: 1 = keep the diffusivity maps in global memory (L2), 0 = in shared memory if any plan fits, else global.
 inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_limit, long long xchg_limit, int force_ntr,
                           int force_ntc, int force_threads, int force_nc, int force_eh, int force_ewq, int maps_global,
-                          ResPlan& P) {
+                          ResPlan& P, int one_pass_smem_maps_only = 0) {
     if (W % 4 != 0 || H < 3 || W < 4 || batch < 1) return false;
     // the last plan is kept: a run calls this once per segment with the same problem
     struct Memo { int key[8]; bool ok; ResPlan plan; };
     static Memo memo = {{-1, 0, 0, 0, 0, 0, 0, 0}, false, ResPlan()};
     const int key[8] = {H, W, batch, capacity, force_ntr * 4096 + force_ntc, force_eh * 4096 + force_ewq,
-                        force_threads * 16 + force_nc * 2 + (maps_global ? 1 : 0),
+                        force_threads * 32 + force_nc * 4 + (maps_global ? 2 : 0) + (one_pass_smem_maps_only ? 1 : 0),
                         (int)(smem_limit / 64) + (int)((xchg_limit / 4096) % 1000003)};
     bool same = true;
     for (int i = 0; i < 8; ++i) same = same && memo.key[i] == key[i];
@@ -842,7 +963,11 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
     static const double fs[5] = {1.0, 0.85, 0.7, 0.55, 0.45};
     double best = 1e300;
     bool found = false;
-    for (int mg = maps_global ? 1 : 0; mg < 2 && !found; ++mg)
+    // Plans with the maps in shared memory and plans with the maps in L2 compete on cost (the latter 2 % dearer); nc = 4
+    // tiles take the two-pass step when its first derivatives fit shared memory as well, and pay for it when they do
+    // not (the one-pass body spends ~2.5 x the instructions per cell) -- so 1024^2 moves its maps to L2 to get it.
+    // FK_RES_TWO_PASS=0 (development) switches the two-pass form off.
+    for (int mg = maps_global ? 1 : 0; mg < (one_pass_smem_maps_only ? 1 : 2); ++mg)
     for (int ntr = 1; ntr <= H; ++ntr) {
         if (ntr > 1 && H / ntr < 8) break;
         if (force_ntr > 0 && ntr != force_ntr) continue;
@@ -870,8 +995,10 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
                 int th = 0, tw = 0;
                 for (int t = 0; t < ntr; ++t) { const int h = res_split(H, ntr, G.eh, t + 1) - res_split(H, ntr, G.eh, t); if (h > th) th = h; }
                 for (int t = 0; t < ntc; ++t) { const int w = 4 * (res_split(Q, ntc, G.ewq, t + 1) - res_split(Q, ntc, G.ewq, t)); if (w > tw) tw = w; }
-                const long long smem = res_smem_floats(th, tw, mg) * 4;
+                const int tp = (FK_RES_TWO_PASS && !one_pass_smem_maps_only && nc == 4 && res_smem_floats(th, tw, mg, 1) * 4 <= smem_limit) ? 1 : 0;
+                const long long smem = res_smem_floats(th, tw, mg, tp) * 4;
                 if (smem > smem_limit) continue;
+                G.tp = tp;
                 G.th_max = th; G.tw_max = tw; G.pitch = tw + 8; G.slots = 8 * tw + 8 * th;
                 const long long xbytes = 2LL * batch * ntr * ntc * G.slots * (long long)sizeof(u64);
                 if (xbytes > xchg_limit) continue;
@@ -890,6 +1017,8 @@ inline bool plan_resident(int H, int W, int batch, int capacity, long long smem_
                     cost = (double)th * tw + 6.0 * (th + tw);
                     if (H % ntr != 0 || Q % ntc != 0) cost *= 1.15;
                 }
+                if (nc == 4 && !G.tp && FK_RES_TWO_PASS && !one_pass_smem_maps_only) cost *= 1.8;
+                if (mg) cost *= 1.02;
                 cost += 0.01 * th + 1e-3 * ntr * ntc;
                 if (cost >= best) continue;
                 best = cost;
@@ -943,9 +1072,9 @@ enum { FK_CLUSTER_MAX = 16 };
 inline bool plan_cluster(int H, int W, long long smem_limit, int force_ntr, int force_ntc, int force_threads, int force_nc,
                          ResPlan& P) {
     if (force_ntr > 0 && force_ntc > 0 && force_ntr * force_ntc > FK_CLUSTER_MAX) return false;
-    if (!plan_resident(H, W, 1, FK_CLUSTER_MAX, smem_limit, 1LL << 40, force_ntr, force_ntc, force_threads, force_nc, -1, -1, 0, P))
+    if (!plan_resident(H, W, 1, FK_CLUSTER_MAX, smem_limit, 1LL << 40, force_ntr, force_ntc, force_threads, force_nc, -1, -1, 0, P,
+                       /*one_pass_smem_maps_only=*/1))   // (the cluster kernel has the one-pass body, maps in shared memory)
         return false;
-    if (P.G.mg) return false;
     P.G.cluster = 1;
     P.xchg_bytes = 0;
     return true;
@@ -959,7 +1088,10 @@ namespace fk {
 template <bool EXACT>
 inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, const ResThread& T, int s, int phase,
                           unsigned mask) {
-    if (G.cluster) {
+    if (G.tp) {
+        if (G.mg) res_phase<EXACT, 4, true, false, true>(A, G, X, T, s, phase, mask, 0, 1);
+        else res_phase<EXACT, 4, false, false, true>(A, G, X, T, s, phase, mask, 0, 1);
+    } else if (G.cluster) {
         if (G.nc == 1) res_phase<EXACT, 1, false, true>(A, G, X, T, s, phase, mask, 0, 1);
         else if (G.nc == 2) res_phase<EXACT, 2, false, true>(A, G, X, T, s, phase, mask, 0, 1);
         else res_phase<EXACT, 4, false, true>(A, G, X, T, s, phase, mask, 0, 1);
@@ -979,7 +1111,7 @@ inline void emu_res_phase(const TileArgs& A, const ResGeom& G, const ResCta& X, 
 inline int emu_resident_launch(const ResPlan& P, const TileArgs& A, int batch, int exact) {
     ResGeom G = P.G;
     const int ntiles = G.ntr * G.ntc;
-    const long long floats = res_smem_floats(G.th_max, G.tw_max, G.mg);
+    const long long floats = res_smem_floats(G.th_max, G.tw_max, G.mg, G.tp);
     std::vector<std::vector<float>> smem((size_t)ntiles * batch, std::vector<float>((size_t)floats, __builtin_nanf("")));
     std::vector<u64> xchg((size_t)(P.xchg_bytes / sizeof(u64)), 0ull);
     G.xchg = xchg.data();
@@ -1004,6 +1136,10 @@ inline int emu_resident_launch(const ResPlan& P, const TileArgs& A, int batch, i
     for (int s = 0; s < G.nsteps; ++s) {
         for (size_t i = 0; i < X.size(); ++i) {
             const unsigned mask = res_mask(A, X[i], s);
+            if (G.tp) {
+                if (exact) { if (G.mg) res_phase_a<true, true>(A, G, X[i], s, mask, 0, 1); else res_phase_a<true, false>(A, G, X[i], s, mask, 0, 1); }
+                else { if (G.mg) res_phase_a<false, true>(A, G, X[i], s, mask, 0, 1); else res_phase_a<false, false>(A, G, X[i], s, mask, 0, 1); }
+            }
             for (int phase = 0; phase < 2; ++phase) {
                 if (exact) emu_res_phase<true>(A, G, X[i], T[i], s, phase, mask);
                 else emu_res_phase<false>(A, G, X[i], T[i], s, phase, mask);

@@ -110,12 +110,12 @@ def mirror_was_fused():
 
 def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0), maps_global=0):
     """The resident kernel's geometry for a problem: dict or None."""
-    out = (ctypes.c_int * 12)()
+    out = (ctypes.c_int * 13)()
     force = (ctypes.c_int * 7)(int(tiles[0]), int(tiles[1]), threads, nc, int(edge_tile[0]), int(edge_tile[1]), maps_global)
     if not lib().fk_emu_plan_resident(H, W, batch, out, force):
         return None
     return dict(zip(("ntr", "ntc", "th_max", "tw_max", "threads", "smem_bytes", "nc", "xchg_bytes", "edge_rows",
-                     "edge_colgroups", "single_phase", "maps_in_l2"), list(out)))
+                     "edge_colgroups", "single_phase", "maps_in_l2", "two_pass"), list(out)))
 
 
 def _pack_stims(stimuli):

@@ -176,7 +176,7 @@ extern "C" int fk_emu_plan_resident(int H, int W, int batch, int* out, const int
     if (!fk::plan_resident(H, W, batch, 148, 227 * 1024 - 256, fk::res_xchg_bytes(H, W, batch), force6[0], force6[1], force6[2],
                            force6[3], force6[4], force6[5], force6[6], P)) return 0;
     out[0] = P.G.ntr; out[1] = P.G.ntc; out[2] = P.G.th_max; out[3] = P.G.tw_max; out[4] = P.threads; out[5] = (int)P.smem_bytes;
-    out[6] = P.G.nc; out[7] = (int)P.xchg_bytes; out[8] = P.G.eh; out[9] = P.G.ewq; out[10] = P.G.single; out[11] = P.G.mg;
+    out[6] = P.G.nc; out[7] = (int)P.xchg_bytes; out[8] = P.G.eh; out[9] = P.G.ewq; out[10] = P.G.single; out[11] = P.G.mg; out[12] = P.G.tp;
     return 1;
 }
 

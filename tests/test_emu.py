@@ -117,6 +117,7 @@ def test_resident_kernel_exact_batched_per_tissue_inputs():
 def test_resident_planner():
     p = emu.plan_resident(512, 512)
     assert p and p["ntr"] * p["ntc"] <= 148 and p["smem_bytes"] <= 227 * 1024 and p["threads"] % 32 == 0
+    assert p["nc"] == 4 and p["two_pass"] == 0            # (the two-pass step is a compile-time experiment, off)
     p = emu.plan_resident(1200, 1200)                      # the reference's data-generation tissue: 40 MB of state + maps
     assert p and p["maps_in_l2"] == 1 and p["smem_bytes"] <= 227 * 1024   # do not fit 148 x 227 KB; u, v, w alone do
     assert emu.plan_resident(1600, 1600) is None

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(for c in 0 6 78; do FK_RES_TIMING=$c timeout 300 python tools/probe_res_timing.py 512 2>&1 | grep -A1 fast; done
+echo "== one-pass build"
+for c in 78; do FK_SO=$PWD/cardiax_b200/csrc/build/alt_A/libfk_A.so FK_RES_TIMING=$c timeout 300 python tools/probe_res_timing.py 512 2>&1 | grep -A1 fast; done) > gpurun_out/r02s_res_timing.log 2>&1
+cat gpurun_out/r02s_res_timing.log

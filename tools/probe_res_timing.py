@@ -31,5 +31,5 @@ for n in [int(a) for a in sys.argv[1:]] or [128, 256, 512, 1024]:
         _lib.lib().fk_resident_timing(out)
         ns = max(1, out[6])
         print("%4d^2 %-5s %6.2f us/step %6.1f Gcs/s  plan %s" % (n, numerics, us, n * n / us / 1e3, _lib.last_plan()))
-        print("        cycles/step of CTA %s: ring %.0f | interior %.0f | halo wait+copy %.0f | barrier %.0f | total %.0f ; slowest warp leaves ring at %.0f, interior at %.0f" % tuple(
-            [os.environ.get("FK_RES_TIMING", "0")] + [out[k] / ns for k in range(4)] + [sum(out[:4]) / ns, out[4] / ns, out[5] / ns]), flush=True)
+        print("        cycles/step of CTA %s: ring %.0f | interior %.0f | halo wait+copy %.0f | barrier %.0f | total %.0f ; slowest warp leaves pass A at %.0f, ring at %.0f, interior at %.0f" % tuple(
+            [os.environ.get("FK_RES_TIMING", "0")] + [out[k] / ns for k in range(4)] + [sum(out[:4]) / ns, out[7] / ns, out[4] / ns, out[5] / ns]), flush=True)
