@@ -468,6 +468,23 @@ def main():
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0.record(); dst.copy_(src, non_blocking=True); l1.record(); torch.cuda.synchronize()
         link[name] = src.numel() * 4 / (l0.elapsed_time(l1) * 1e-3) / 1e9
+    # ... and with every rank copying in BOTH directions at once (what the e2e loop does): on a box whose host memory is
+    # the shared resource this, not the kernels, bounds e2e at large N
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    s_in.wait_event(l0); s_out.wait_event(l0)
+    with torch.cuda.stream(s_in):
+        for d, h in zip(dev_in[0], host_in):
+            d.copy_(h, non_blocking=True)
+    with torch.cuda.stream(s_out):
+        for o, x in zip(host_out[1], dev_in[1]):
+            o.copy_(x, non_blocking=True)
+    s_run.wait_stream(s_in); s_run.wait_stream(s_out)
+    l1.record(); torch.cuda.synchronize()
+    both_ms = max_over_ranks(l0.elapsed_time(l1))
+    link["all_ranks_both_directions_ms"] = both_ms
+    link["all_ranks_both_directions_gbs_each_way"] = h2d / (both_ms * 1e-3) / 1e9
     for b in range(NB):
         ev_free[b].record(s_run); ev_out[b].record(s_out)
     e2e_step(0, 0)
