@@ -915,7 +915,10 @@ struct ResPlan {
     long long xchg_bytes;   // mailboxes of the launch (both parities)
 };
 
-enum { FK_RES_MAX_THREADS = 512 };
+#ifndef FK_RES_THREADS_CAP
+#define FK_RES_THREADS_CAP 512   // development: 1024 for an A/B build (64 registers per thread)
+#endif
+enum { FK_RES_MAX_THREADS = FK_RES_THREADS_CAP };
 
 
 // thread slots the busiest phase of a tile walks through
