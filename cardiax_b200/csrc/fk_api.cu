@@ -514,6 +514,9 @@ static int run_euler(const float* v_in, const float* w_in, const float* u_in, fl
     } else {
         ws = carve(workspace, H, W, batch, n_stim, d_batched);
     }
+    // a launch during which no stimulus can fire runs without the stimulus machinery (fk_core.h: stims_quiet)
+    static_assert(sizeof(fk::StimDev) == sizeof(FkStimulus), "layout");
+    if (n_stim > 0 && !rhs_mode && fk::stims_quiet((const fk::StimDev*)stimuli, batch * n_stim, t0, nsteps)) n_stim = 0;
     rc = upload_stims(stimuli, batch * n_stim, ws.stims, st);
     if (rc) return rc;
     if (!DXext || !DYext) {

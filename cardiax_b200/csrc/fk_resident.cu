@@ -37,6 +37,9 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
     __syncthreads();
     // development (FK_RES_TIMING=<cta>): thread 0 of that CTA times the phases; every warp of it also records when it
     // left each phase (max over warps, relative to the step's start): what the step really waits for
+#ifndef FK_RES_WARP_TIMING
+#define FK_RES_WARP_TIMING 0   // 1: development build whose timed CTA also records when its slowest warp leaves each phase
+#endif
     const bool tcta = G.timing != nullptr && (int)blockIdx.x == (int)(G.spin_limit >> 25) && blockIdx.y == 0;
     const bool timed = tcta && tid == 0;
     __shared__ unsigned s_wmax[3];
@@ -49,13 +52,13 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
             __syncthreads();
         }
         const unsigned mask = s_mask[s & 31];
-        if (tcta) {
+        if (FK_RES_WARP_TIMING && tcta) {
             if (tid == 0) { s_wmax[0] = s_wmax[1] = s_wmax[2] = 0; s_t0 = clock64(); }
             __syncthreads();
         }
         if (TP) {   // two-pass step: first derivatives of the tile (and the cells at a physical edge), then the cells
             res_phase_a<EXACT, MG>(A, G, X, s, mask, tid, nthr);
-            if (tcta && (tid & 31) == 0) atomicMax(&s_wmax[2], (unsigned)(clock64() - s_t0));
+            if (FK_RES_WARP_TIMING && tcta && (tid & 31) == 0) atomicMax(&s_wmax[2], (unsigned)(clock64() - s_t0));
             __syncthreads();
         }
 #pragma unroll 1
@@ -63,7 +66,7 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
             // phase 0: the ring, published to the neighbours' mailboxes as it is computed; phase 1: the interior, while
             // those records travel.  ONE call site: the body exists once and stays inside the instruction cache.
             res_phase<EXACT, NC, MG, false, TP>(A, G, X, T, s, phase, mask, tid, nthr);
-            if (tcta && (tid & 31) == 0) atomicMax(&s_wmax[phase], (unsigned)(clock64() - s_t0));
+            if (FK_RES_WARP_TIMING && tcta && (tid & 31) == 0) atomicMax(&s_wmax[phase], (unsigned)(clock64() - s_t0));
             if (phase == 0) { FK_TICK(0) } else { FK_TICK(1) }
         }
         if (s == G.nsteps - 1) break;
@@ -71,7 +74,7 @@ fk_resident_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ R
         FK_TICK(2)
         __syncthreads();
         FK_TICK(3)
-        if (timed) { acc4 += s_wmax[0]; acc5 += s_wmax[1]; acc7 += s_wmax[2]; }
+        if (FK_RES_WARP_TIMING && timed) { acc4 += s_wmax[0]; acc5 += s_wmax[1]; acc7 += s_wmax[2]; }
     }
     if (timed) {
         G.timing[0] = acc0; G.timing[1] = acc1; G.timing[2] = acc2; G.timing[3] = acc3; G.timing[4] = acc4; G.timing[5] = acc5; G.timing[7] = acc7;

@@ -55,6 +55,15 @@ def stim_active_typed(t, protocol):
                                            *[float(np.asarray(x).reshape(-1)[0]) for x in protocol], mask))
 
 
+def stims_quiet(t0, nsteps, protocol):
+    """fk::stims_quiet for one stimulus with the typing of the Python objects handed in."""
+    L = lib()
+    L.fk_emu_stims_quiet.restype = ctypes.c_int
+    L.fk_emu_stims_quiet.argtypes = [ctypes.c_double, ctypes.c_longlong] + [ctypes.c_double] * 3 + [ctypes.c_int]
+    mask = sum(bit for bit, x in zip((1, 2, 4), protocol) if _is_int(x))
+    return bool(L.fk_emu_stims_quiet(float(t0), int(nsteps), *[float(np.asarray(x).reshape(-1)[0]) for x in protocol], mask))
+
+
 def euler(state, t0, t1, params, D, stimuli, dt, dx, exact=True, T=0, kernel=0, cta_threads=0, rows_per_cta=0,
           uniform=0, reverse=0, phys_top=1, phys_bottom=1, rhs=False, row0=0, row1=0, tiles=(0, 0), nc=0, edge_tile=(0, 0), maps_global=0,
           typed=False):

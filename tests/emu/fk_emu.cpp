@@ -152,6 +152,13 @@ int fk_emu_stim_active(float t, float start, float duration, float period) {
 int fk_emu_stim_active_typed(double t, int t_is_int, double start, double duration, double period, int kinds) {
     return fk::stim_active_typed(t, t_is_int, start, duration, period, kinds) ? 1 : 0;
 }
+// fk_core.h: stims_quiet for one stimulus (tests compare it with the schedule evaluated step by step)
+int fk_emu_stims_quiet(double t0, long long nsteps, double start, double duration, double period, int kinds) {
+    static float dummy = 1.0f;
+    fk::StimDev sd;
+    sd.field = &dummy; sd.start = start; sd.duration = duration; sd.period = period; sd.kinds = kinds; sd.reserved = 0;
+    return fk::stims_quiet(&sd, 1, t0, nsteps) ? 1 : 0;
+}
 
 }  // extern "C"
 

@@ -420,3 +420,24 @@ def test_int_counter_run_matches_the_typed_oracle(kernel):
     with pytest.raises(OverflowError):
         O.forward_euler(st, float(t0), float(t0 + 8), P3, D, stim, 0.01, 0.01, counter="f32")
     assert any(float(np.abs(a - b).max()) > 1e-3 for a, b in zip(ref, O.forward_euler(st, t0, t0 + 8, P3, D, [], 0.01, 0.01, counter="i32")))
+
+
+def test_quiet_launches_are_never_wrongly_declared():
+    """fk_core.h: stims_quiet -- a launch is run without the stimulus machinery only if NO step of it can fire: compared
+    with the typed schedule evaluated step by step (float32 and int32 counters, small and huge periods, launches before,
+    across and after the pulses, counters beyond 2^24 where float32 counters stall)."""
+    rng = np.random.default_rng(5)
+    protos = [(0, 2, 1e9), (40000, 2, 1e9), (3, 5, 20), (1, 2, 400), (25001, 2, 123456789), (7, 3, 50.0), (0.0, 2.0, 1e9),
+              (np.int32(1), 2, np.int32(999999999)), (16777210, 2, 1e9), (16777300, 2, 40), (5, 2, 1)]
+    said_quiet = 0
+    for proto in protos:
+        starts = [0, 1, 2, 5, 19, 38, 399, 400, 39990, 40001, 16777200, 16777290, int(rng.integers(0, 100000))]
+        for t0 in starts:
+            for nsteps in (1, 2, 4, 16, 500):
+                for typed_int in (False, True):
+                    ts = [(t0 + k) if typed_int else float(t0 + k) for k in range(nsteps)]
+                    active = any(emu.stim_active_typed(t if typed_int else np.float32(t), proto) for t in ts)
+                    quiet = emu.stims_quiet(t0, nsteps, proto)
+                    assert not (quiet and active), (proto, t0, nsteps, typed_int)
+                    said_quiet += quiet
+    assert said_quiet > 300     # ... and it does recognise the sleeping launches
