@@ -23,29 +23,28 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     StreamCta C;
     stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, C);
     const int tid = threadIdx.x;
-    float* tb = stream_chunk<T>(fk_stream_smem, tid);
+    const StreamMem M = stream_mem<T>(fk_stream_smem, tid, G.NT);
     StreamState<T> R;
     stream_state_init<T>(A, C, tid, R);
     const int nfill = stream_nfill<T>(C);
-    // the split barrier of the steady-state loop lives in the pad granule of the CTA's first (pad) chunk
-    float* bar = fk_stream_smem + StreamLay<T>::CHUNK - 4;
-    if (tid == 0) sb_init(bar, (int)blockDim.x);
+    float* bar = stream_bar<T>(fk_stream_smem, G.NT);
+    if (tid == 0) sb_init(bar, G.NT);
     int i = 0;
     if (!stream_use_warm<T>(C)) {
         // (a chunk at the physical top edge emits from iteration 4 on): plain prologue, general body from iteration 0
 #pragma unroll
-        for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, C, tb, j, tid, C.cs + 4 * tid < C.c_end);
+        for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, C, M, j, tid, C.cs + 4 * tid < C.c_end);
         __syncthreads();
     } else {
-        stream_warm_load<T>(A, C, tb, tid);
+        stream_warm_load<T>(A, C, M, tid);
         async_wait<0>();
         __syncthreads();
-        stream_warm_start<EXACT, T>(A, C, R, tb, tid);   // stands for iterations 0 .. 7
+        stream_warm_start<EXACT, T>(A, C, R, M, tid);   // stands for iterations 0 .. 7
         __syncthreads();
         i = FK_WARM;
     }
     for (; i < nfill; ++i) {   // pipeline fill (and launches with an active stimulus): fully conditional body
-        stream_iter<EXACT, T, -1, UNI, true, 4, MODE>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+        stream_iter<EXACT, T, -1, UNI, true, 4, MODE>(A, C, R, M, i, tid, stream_ptrs_any<T>(M, i), nullptr);
         __syncthreads();
     }
     // steady state: every stage consumes and emits one row per iteration; unrolled U-fold so that every ring slot is a
@@ -58,13 +57,13 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
 #define FK_STEADY_LOOP(EDGE)                                                                                           \
     for (; i < i_end; i += U) {                                                                                        \
-        const StreamBody<T> Y = stream_body_at<T>(tb, i);                                                              \
-        stream_iter<EXACT, T, 0, UNI, EDGE, U, MODE>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
-        stream_iter<EXACT, T, 1, UNI, EDGE, U, MODE>(A, C, R, tb, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
+        const StreamBody<T> Y = stream_body_at<T>(M, i);                                                               \
+        stream_iter<EXACT, T, 0, UNI, EDGE, U, MODE>(A, C, R, M, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
+        stream_iter<EXACT, T, 1, UNI, EDGE, U, MODE>(A, C, R, M, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
         if (U == 4) {                                                                                                  \
-            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U, MODE>(A, C, R, tb, i + 2, tid,                               \
+            stream_iter<EXACT, T, U == 4 ? 2 : 0, UNI, EDGE, U, MODE>(A, C, R, M, i + 2, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 2 : 0>(Y), bar);      \
-            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U, MODE>(A, C, R, tb, i + 3, tid,                               \
+            stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U, MODE>(A, C, R, M, i + 3, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 3 : 1>(Y), bar);      \
         }                                                                                                              \
     }
@@ -79,7 +78,7 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
         StreamCta Ct;
         stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, Ct);
         for (; i < Ct.niter; ++i) {
-            stream_iter<EXACT, T, -1, UNI, true, 4, MODE>(A, Ct, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+            stream_iter<EXACT, T, -1, UNI, true, 4, MODE>(A, Ct, R, M, i, tid, stream_ptrs_any<T>(M, i), nullptr);
             __syncthreads();
         }
     }

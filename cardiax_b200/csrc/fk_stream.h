@@ -144,16 +144,25 @@ FK_HD int sb_test(float* bar, int parity) {
 
 enum { FK_PF = 3 };      // level-0 rows are fetched this many iterations ahead
 
-// Shared memory is THREAD-major: every thread owns one chunk of StreamLay<T>::CHUNK floats that holds its 4 columns
-// (one 16-byte granule) of every ring row, so that each access is `chunk base + compile-time offset` -- the
-// neighbours' halo values sit at +-CHUNK.  CHUNK is an odd number of granules, which keeps the 16-byte accesses of
-// consecutive threads on distinct banks.  One pad chunk on each side of the CTA absorbs the halo reads of its first and
-// last thread (garbage that only reaches columns which are never stored).
+// Shared memory has two regions.
+//
+// ROW-major rows for what cp.async brings in from global memory (level 0): 16 rows of (NT + 2) 16-byte granules, granule
+// tid + 1 of a row being thread tid's 4 columns -- rows 0..7 the U(0) ring, 8..11 V(0), 12..15 W(0).  Consecutive threads
+// copy to consecutive granules, so a warp's LDGSTS lands in four 128-byte lines and asks L2 for every sector once.  (With
+// thread-major destinations, 528 bytes apart, every thread's 16 bytes became a request of their own: 2x the sectors from
+// L2 and ~28 shared-memory wavefronts per instruction -- ncu, profiles/ncu_stream_kernel_r02.md.)  The neighbours' halo
+// values of a level-0 row sit one granule to the left / right; granules 0 and NT + 1 of every row are pads.
+//
+// THREAD-major chunks for what the threads write themselves (levels >= 1, u_y): every thread owns one chunk of
+// StreamLay<T>::CHUNK floats that holds its 4 columns (one 16-byte granule) of every ring row, so that each access is
+// `chunk base + compile-time offset` -- the neighbours' halo values sit at +-CHUNK.  CHUNK is an odd number of granules,
+// which keeps the 16-byte accesses of consecutive threads on distinct banks.  One pad chunk on each side of the CTA
+// absorbs the halo reads of its first and last thread (garbage that only reaches columns which are never stored).
 //
 // Ring slots are functions of the CTA-local iteration index i alone, so that the steady-state loop, unrolled by 4
 // with the phase i & 3 as a template parameter, addresses every slot with a compile-time offset:
 //   U(0)     8 slots: level-0 row rin0 + i (the newest input of stage 0 at iteration i) sits in slot i & 7; it is
-//            fetched at iteration i - FK_PF.  The two halves of this ring are passed as tA (holding slot i & 7) and tB.
+//            fetched at iteration i - FK_PF.
 //   U(s>=1)  4 slots: the level-s row stage s receives at iteration i goes to slot i & 3 -- the slot of the row it read
 //            as its window's oldest row (rho) a moment before; only row rho + 1 is ever read by the neighbours.
 //   V/W(0)   4 slots: level-0 v, w of the row stage 0 emits at iteration i: slot i & 3, fetched at iteration i - FK_PF.
@@ -163,15 +172,23 @@ enum { FK_PF = 3 };      // level-0 rows are fetched this many iterations ahead
 template <int T>
 struct StreamLay {
     enum {
-        U0 = 0,
-        U1 = 32,                     // U(s) = U1 + 16 (s - 1) for s >= 1
-        GY = U1 + 16 * (T - 1),      // GY(s) = GY + 8 s
-        V = GY + 8 * T,              // V(s) = V + 16 s
-        W = V + 16 * T,              // W(s) = W + 16 s
-        CHUNK = W + 16 * T + 4       // + one pad granule: (5 + 14 T) granules, odd
+        ROWS = 16, ROW_U = 0, ROW_V = 8, ROW_W = 12,   // the row-major region
+        U1 = 0,                          // U(s) = U1 + 16 (s - 1) for s >= 1
+        GY = 16 * (T - 1),               // GY(s) = GY + 8 s
+        V = GY + 8 * T - 16,             // V(s) = V + 16 s for s >= 1
+        W = V + 16 * (T - 1),            // W(s) = W + 16 s for s >= 1
+        CHUNK = W + 16 * T + 4           // + one pad granule: (14 T - 11) granules, odd
     };
-    static FK_HD int U(int s) { return s == 0 ? (int)U0 : (int)U1 + 16 * (s - 1); }
+    static FK_HD int U(int s) { return (int)U1 + 16 * (s - 1); }   // s >= 1
 };
+
+// a thread's view of the CTA's shared memory
+struct StreamMem {
+    float* tb;    // its thread-major chunk
+    float* rb;    // its granule of row 0 of the row-major region
+    int pitch;    // floats per row of that region: 4 (NT + 2)
+};
+FK_HD float* row_at(const StreamMem& M, int row) { return M.rb + row * M.pitch; }
 
 // Largest CTA of the streaming kernel and the resident CTAs per SM its register budget is compiled for: 2 x 192
 // threads at T = 2 (168 registers; shared memory allows no more than 13 warps anyway), 2 x 256 at T = 1.
@@ -270,7 +287,16 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
 
 // this thread's chunk of the CTA's shared memory, and its registers at the start of a CTA
 template <int T>
-FK_HD float* stream_chunk(float* smem, int tid) { return smem + (long long)(tid + 1) * StreamLay<T>::CHUNK; }
+FK_HD StreamMem stream_mem(float* smem, int tid, int NT) {
+    StreamMem M;
+    M.pitch = 4 * (NT + 2);
+    M.rb = smem + 4 * (tid + 1);
+    M.tb = smem + (long long)StreamLay<T>::ROWS * M.pitch + (long long)(tid + 1) * StreamLay<T>::CHUNK;
+    return M;
+}
+// the split barrier of the steady-state loop lives in the pad granule of the CTA's first (pad) chunk
+template <int T>
+FK_HD float* stream_bar(float* smem, int NT) { return smem + (long long)StreamLay<T>::ROWS * 4 * (NT + 2) + StreamLay<T>::CHUNK - 4; }
 
 template <int T>
 FK_HD void stream_state_init(const TileArgs& A, const StreamCta& C, int tid, StreamState<T>& R) {
@@ -302,11 +328,11 @@ FK_HD void stream_prefetch_to(const TileArgs& A, const StreamCta& C, float* udst
     async_commit();
 }
 
-// the same with the slots computed from i (pipeline prologue); tb: the thread's chunk
+// the same with the slots computed from i (pipeline prologue)
 template <int T>
-FK_HD void stream_prefetch(const TileArgs& A, const StreamCta& C, float* tb, int i, int tid, bool act) {
+FK_HD void stream_prefetch(const TileArgs& A, const StreamCta& C, const StreamMem& M, int i, int tid, bool act) {
     typedef StreamLay<T> L;
-    stream_prefetch_to<T>(A, C, tb + L::U0 + 4 * (i & 7), tb + L::V + 4 * (i & 3), tb + L::W + 4 * (i & 3), i,
+    stream_prefetch_to<T>(A, C, row_at(M, L::ROW_U + (i & 7)), row_at(M, L::ROW_V + (i & 3)), row_at(M, L::ROW_W + (i & 3)), i,
                           C.boff + (long long)(C.rin0 + i) * A.W + C.cs + 4 * tid, act);
 }
 
@@ -361,13 +387,13 @@ FK_HD int stream_nbody(const StreamCta& C) {
     return n > 0 ? n / stream_unroll(T) : 0;
 }
 
-// u_y (solve.py:50) of one row at the thread's 4 columns: u1 = the row's own values, r1p = its granule in the thread's
-// chunk (the neighbours' values sit one chunk to the left / right); gypad: u_y of the pad column at a tissue edge
+// u_y (solve.py:50) of one row at the thread's 4 columns: u1 = the row's own values, r1p = its granule (the neighbours'
+// values sit hs floats to the left / right: one chunk in the thread-major rings, one granule in a level-0 row); gypad:
+// u_y of the pad column at a tissue edge
 template <bool EXACT, int T>
-FK_HD void stream_make_gy(const Consts& K, const float* r1p, const float* u1, bool edgeL, bool edgeR, float* gy,
+FK_HD void stream_make_gy(const Consts& K, const float* r1p, int hs, const float* u1, bool edgeL, bool edgeR, float* gy,
                           float& gypad) {
-    constexpr int CH = StreamLay<T>::CHUNK;
-    const F2 Lh = ld2(r1p - CH + 2), Rh = ld2(r1p + CH);
+    const F2 Lh = ld2(r1p - hs + 2), Rh = ld2(r1p + hs);
     // edge-pad (solve.py:31): the column outside the tissue repeats the edge column
     const float e[8] = {Lh.x, edgeL ? u1[0] : Lh.y, u1[0], u1[1], u1[2], u1[3], edgeR ? u1[3] : Rh.x, Rh.y};
     dcen_span4<EXACT>(K, e, gy);
@@ -392,25 +418,26 @@ template <int T>
 FK_HD bool stream_use_warm(const StreamCta& C) { return !C.top && !(C.bot && C.niter - 4 * T - 1 < FK_WARM); }
 
 template <int T>
-FK_HD void stream_warm_load(const TileArgs& A, const StreamCta& C, float* tb, int tid) {
+FK_HD void stream_warm_load(const TileArgs& A, const StreamCta& C, const StreamMem& M, int tid) {
     const int c = C.cs + 4 * tid;
     if (c < C.c_end) {
         const long long g = C.boff + (long long)C.rin0 * A.W + c;
 #pragma unroll
-        for (int m = 0; m < FK_WARM; ++m) async_copy16(tb + StreamLay<T>::U0 + 4 * m, A.u_in + g + (long long)m * A.W);
+        for (int m = 0; m < FK_WARM; ++m) async_copy16(row_at(M, StreamLay<T>::ROW_U + m), A.u_in + g + (long long)m * A.W);
     }
     async_commit();
 }
 
 template <bool EXACT, int T>
-FK_HD void stream_warm_start(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int tid) {
+FK_HD void stream_warm_start(const TileArgs& A, const StreamCta& C, StreamState<T>& R, const StreamMem& M, int tid) {
     typedef StreamLay<T> L;
+    float* const tb = M.tb;
     const int c = C.cs + 4 * tid;
     const bool act = c < C.c_end;
     if (act) {
         float u[FK_WARM][4];
 #pragma unroll
-        for (int m = 0; m < FK_WARM; ++m) unpack4(ld4(tb + L::U0 + 4 * m), u[m]);
+        for (int m = 0; m < FK_WARM; ++m) unpack4(ld4(row_at(M, L::ROW_U + m)), u[m]);
         // u_x of rows rin0 + 2 .. rin0 + 5: the window (rho-2 .. rho+1) of iteration 8, rho = rin0 + 4
 #pragma unroll
         for (int m = 0; m < 4; ++m)
@@ -418,11 +445,11 @@ FK_HD void stream_warm_start(const TileArgs& A, const StreamCta& C, StreamState<
             for (int k = 0; k < 4; ++k) R.GX[0][m][k] = dcen<EXACT>(A.K, u[m][k], u[m + 1][k], u[m + 3][k], u[m + 4][k]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) R.prev[0][k] = u[7][k];
-        stream_make_gy<EXACT, T>(A.K, tb + L::U0 + 4 * 4, u[4], tid == C.edgeL, tid == C.edgeR, R.gy[0], R.gypad[0]);
+        stream_make_gy<EXACT, T>(A.K, row_at(M, L::ROW_U + 4), 4, u[4], tid == C.edgeL, tid == C.edgeR, R.gy[0], R.gypad[0]);
         st4(tb + L::GY + 4 * 1, R.gy[0]);
     }
     // rows 0 .. FK_PF-1 of the ring are free again: fetch what iterations 8 .. 8 + FK_PF - 1 consume
-    for (int m = 0; m < FK_PF; ++m) stream_prefetch<T>(A, C, tb, FK_WARM + m, tid, act);
+    for (int m = 0; m < FK_PF; ++m) stream_prefetch<T>(A, C, M, FK_WARM + m, tid, act);
     R.g0 = opaque(R.g0 + (long long)FK_WARM * A.W);
     R.gd = opaque(R.gd + (long long)FK_WARM * A.W);
 }
@@ -491,22 +518,25 @@ FK_HD void stream_emit(const Consts& K, const float* u0, const float* v, const f
 struct StreamPtrs {
     float* bj;     // chunk base shifted to slot j = i & 3 of the 4-slot rings
     float* bj1;    // ... to slot (j + 1) & 3
-    float* bpf;    // ... to slot (j + FK_PF) & 3
-    float *u0new, *u0r1, *u0r0, *u0pf;   // stage-0 ring granules of iterations i, i-3, i-4, i+FK_PF
+    float *u0new, *u0r1, *u0r0, *u0pf;   // stage-0 ring granules (row-major region) of iterations i, i-3, i-4, i+FK_PF
+    float *v0, *w0, *v0pf, *w0pf;        // level-0 v, w: slot j and slot (j + FK_PF) & 3
 };
 
 // general body: everything computed from i
 template <int T>
-FK_HD StreamPtrs stream_ptrs_any(float* tb, int i) {
+FK_HD StreamPtrs stream_ptrs_any(const StreamMem& M, int i) {
     typedef StreamLay<T> L;
     StreamPtrs P;
-    P.bj = tb + 4 * (i & 3);
-    P.bj1 = tb + 4 * ((i + 1) & 3);
-    P.bpf = tb + 4 * ((i + FK_PF) & 3);
-    P.u0new = tb + L::U0 + 4 * (i & 7);
-    P.u0r1 = tb + L::U0 + 4 * ((i + 5) & 7);
-    P.u0r0 = tb + L::U0 + 4 * ((i + 4) & 7);
-    P.u0pf = tb + L::U0 + 4 * ((i + FK_PF) & 7);
+    P.bj = M.tb + 4 * (i & 3);
+    P.bj1 = M.tb + 4 * ((i + 1) & 3);
+    P.u0new = row_at(M, L::ROW_U + (i & 7));
+    P.u0r1 = row_at(M, L::ROW_U + ((i + 5) & 7));
+    P.u0r0 = row_at(M, L::ROW_U + ((i + 4) & 7));
+    P.u0pf = row_at(M, L::ROW_U + ((i + FK_PF) & 7));
+    P.v0 = row_at(M, L::ROW_V + (i & 3));
+    P.w0 = row_at(M, L::ROW_W + (i & 3));
+    P.v0pf = row_at(M, L::ROW_V + ((i + FK_PF) & 3));
+    P.w0pf = row_at(M, L::ROW_W + ((i + FK_PF) & 3));
     return P;
 }
 
@@ -514,25 +544,32 @@ FK_HD StreamPtrs stream_ptrs_any(float* tb, int i) {
 template <int T>
 struct StreamBody {
     float* tb;
-    float *tA, *tB;         // U = 4: halves of the stage-0 ring, slot i & 7 in tA
+    float* rb;
+    int ou[8];              // row-major region: offset of U(0) slot (i + k) & 7, k = 0..7 (i = the body's first iteration)
+    int ov[4], ow[4];       // ... of V(0) / W(0) slot (i + k) & 3
     float *tH, *tO;         // U = 2: chunk base shifted to the pair of 4-ring slots holding slot i & 3 / the other pair
-    float *Q0, *Q1, *Q2, *Q3;   // U = 2: stage-0 ring shifted to slot pairs q, q+1, q+2, q+3 (q = (i >> 1) & 3)
 };
 
 template <int T>
-FK_HD StreamBody<T> stream_body_at(float* tb, int i) {   // i: first iteration of the body
-    typedef StreamLay<T> L;
+FK_HD StreamBody<T> stream_body_at(const StreamMem& M, int i) {   // i: first iteration of the body
     StreamBody<T> Y;
-    Y.tb = tb;
-    Y.tA = tb + L::U0 + ((i & 4) ? 16 : 0);
-    Y.tB = tb + L::U0 + ((i & 4) ? 0 : 16);
-    const int qo = (i & 6) * 4;   // floats: 8 per slot pair
-    Y.tH = tb + (qo & 8);
-    Y.tO = tb + (8 - (qo & 8));
-    Y.Q0 = tb + L::U0 + qo;
-    Y.Q1 = tb + L::U0 + ((qo + 8) & 24);
-    Y.Q2 = tb + L::U0 + ((qo + 16) & 24);
-    Y.Q3 = tb + L::U0 + ((qo + 24) & 24);
+    Y.tb = M.tb;
+    Y.rb = M.rb;
+    typedef StreamLay<T> L;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; ++k) Y.ou[k] = (L::ROW_U + ((i + k) & 7)) * M.pitch;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+        Y.ov[k] = (L::ROW_V + ((i + k) & 3)) * M.pitch;
+        Y.ow[k] = (L::ROW_W + ((i + k) & 3)) * M.pitch;
+    }
+    const int qo = (i & 2) * 4;   // floats: 8 per slot pair
+    Y.tH = M.tb + qo;
+    Y.tO = M.tb + (8 - qo);
     return Y;
 }
 
@@ -543,23 +580,21 @@ FK_HD StreamPtrs stream_ptrs_phase(const StreamBody<T>& Y) {
     if (U == 4) {
         P.bj = Y.tb + 4 * PH;
         P.bj1 = Y.tb + 4 * ((PH + 1) & 3);
-        P.bpf = Y.tb + 4 * ((PH + FK_PF) & 3);
-        P.u0new = Y.tA + 4 * PH;
-        P.u0r0 = Y.tB + 4 * PH;
-        P.u0r1 = PH == 3 ? Y.tA : Y.tB + 4 * (PH + 1);
-        P.u0pf = PH + FK_PF < 4 ? Y.tA + 4 * (PH + FK_PF) : Y.tB + 4 * (PH + FK_PF - 4);
-    } else {   // U == 2, FK_PF == 3: slot j = 2 h + PH, stage-0 slot = 2 q + PH
+    } else {   // U == 2: slot j = 2 h + PH
         P.bj = Y.tH + 4 * PH;
         P.bj1 = PH == 0 ? Y.tH + 4 : Y.tO;
-        P.bpf = PH == 0 ? Y.tO + 4 : Y.tH;
-        P.u0new = Y.Q0 + 4 * PH;
-        P.u0r0 = Y.Q2 + 4 * PH;                    // i + 4
-        P.u0r1 = PH == 0 ? Y.Q2 + 4 : Y.Q3;        // i + 5
-        P.u0pf = PH == 0 ? Y.Q1 + 4 : Y.Q2;        // i + 3
     }
+    // the rows of the row-major region: uniform offsets (functions of the body's first iteration alone)
+    P.u0new = Y.rb + Y.ou[PH];
+    P.u0r0 = Y.rb + Y.ou[(PH + 4) & 7];
+    P.u0r1 = Y.rb + Y.ou[(PH + 5) & 7];
+    P.u0pf = Y.rb + Y.ou[(PH + FK_PF) & 7];
+    P.v0 = Y.rb + Y.ov[PH];
+    P.w0 = Y.rb + Y.ow[PH];
+    P.v0pf = Y.rb + Y.ov[(PH + FK_PF) & 3];
+    P.w0pf = Y.rb + Y.ow[(PH + FK_PF) & 3];
     return P;
 }
-static_assert(FK_PF == 3, "stream_ptrs_phase<U = 2> spells the prefetch slots out for FK_PF == 3");
 
 // one row iteration of one thread.  `tid` in [0, NT), its 4 columns start at C.cs + 4 tid, its chunk is tb.
 //   PH < 0   general body: every per-stage condition evaluated, ring slots computed from i, u_x window slid by moves;
@@ -576,9 +611,10 @@ static_assert(FK_PF == 3, "stream_ptrs_phase<U = 2> spells the prefetch slots ou
 //            neighbouring GPU's memory as well) -- separate kernel instantiations on the device, run-time flags on the CPU
 enum { FK_STORE_PLAIN = 0, FK_STORE_HEUN = 1, FK_STORE_MIRROR = 2 };
 template <bool EXACT, int T, int PH, bool UNI, bool EDGE, int U = 4, int MODE = 0>
-FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid,
+FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R, const StreamMem& M, int i, int tid,
                        const StreamPtrs& P, float* bar) {
     typedef StreamLay<T> L;
+    float* const tb = M.tb;
     constexpr bool ST = PH >= 0;
     // fast Heun's closing pass in the last level's store (TileArgs::hy_*): its own kernel instantiation on the device --
     // even a uniform run-time branch here cost the plain Euler kernel 7 % -- a run-time flag in the CPU emulation
@@ -604,7 +640,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
     if (!UNI) R.gd = opaque(gd + A.W);
     // rows fetched FK_PF iterations ago have landed (this thread's own columns; the neighbours'
     // columns of a row are only read three barriers later)
-    stream_prefetch_to<T>(A, C, P.u0pf, P.bpf + L::V, P.bpf + L::W, i + FK_PF, g0 + (long long)FK_PF * A.W, act);
+    stream_prefetch_to<T>(A, C, P.u0pf, P.v0pf, P.w0pf, i + FK_PF, g0 + (long long)FK_PF * A.W, act);
     async_wait<FK_PF>();
     // Threads beyond the strip's last needed column: the general body skips them.  The steady-state body lets them
     // compute on whatever their chunk holds (nothing of theirs is stored, nobody reads their columns): an early exit
@@ -622,8 +658,8 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
     bool have_in = ST || n0 < C.rin_end;
 #pragma unroll
     for (int s = 0; s < T; ++s) {
-        unpack4(ld4(P.bj + L::V + 16 * s), vv[s]);
-        unpack4(ld4(P.bj + L::W + 16 * s), ww[s]);
+        unpack4(ld4(s == 0 ? P.v0 : P.bj + L::V + 16 * s), vv[s]);
+        unpack4(ld4(s == 0 ? P.w0 : P.bj + L::W + 16 * s), ww[s]);
         // input rows rho, rho+1 of the stage (row rho+3 is still in registers, row rho+4 arrives below)
         if (s == 0) {
             r0p[s] = P.u0r0; r1p[s] = P.u0r1;
@@ -713,7 +749,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         if (!ST && (C.top || C.bot)) {
             float rm2[4] = {0.f, 0.f, 0.f, 0.f};   // row m-2: the only window row the ordinary formulas never read
             if ((C.top && m == 3) || (C.bot && m == A.H - 1))
-                unpack4(ld4(s == 0 ? tb + L::U0 + 4 * ((i + 6) & 7) : tb + L::U(s) + 4 * ((i + 2) & 3)), rm2);
+                unpack4(ld4(s == 0 ? row_at(M, L::ROW_U + ((i + 6) & 7)) : tb + L::U(s) + 4 * ((i + 2) & 3)), rm2);
             if (C.top && m == 3) {
                 top_init = true;
 #pragma unroll
@@ -879,7 +915,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         }
         // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
         if (ST || (rho + 1 >= lo && rho + 1 < hi)) {
-            stream_make_gy<EXACT, T>(A.K, r1p[s], u1[s], edgeL, edgeR, R.gy[s], R.gypad[s]);
+            stream_make_gy<EXACT, T>(A.K, r1p[s], s == 0 ? 4 : CH, u1[s], edgeL, edgeR, R.gy[s], R.gypad[s]);
             st4(tb + L::GY + 8 * s + 4 * (ST ? PH & 1 : i & 1), R.gy[s]);
         }
         // the u_x window takes the new row
@@ -911,27 +947,27 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
 // launch with an active stimulus; phase (i - nfill) & 3 of the unrolled body in between.  (The CUDA kernel spells the
 // same schedule out as three loops; the CPU emulation calls this.)
 template <bool EXACT, int T, bool UNI, int U, int PH>
-FK_HD void stream_iter_phase(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid,
+FK_HD void stream_iter_phase(const TileArgs& A, const StreamCta& C, StreamState<T>& R, const StreamMem& M, int i, int tid,
                              const StreamBody<T>& Y, bool edge, float* bar) {
-    if (edge) stream_iter<EXACT, T, PH, UNI, true, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, PH>(Y), bar);
-    else stream_iter<EXACT, T, PH, UNI, false, U>(A, C, R, tb, i, tid, stream_ptrs_phase<T, U, PH>(Y), bar);
+    if (edge) stream_iter<EXACT, T, PH, UNI, true, U>(A, C, R, M, i, tid, stream_ptrs_phase<T, U, PH>(Y), bar);
+    else stream_iter<EXACT, T, PH, UNI, false, U>(A, C, R, M, i, tid, stream_ptrs_phase<T, U, PH>(Y), bar);
 }
 
 template <bool EXACT, int T, bool UNI>
-FK_HD void stream_iter_any(const TileArgs& A, const StreamCta& C, StreamState<T>& R, float* tb, int i, int tid) {
+FK_HD void stream_iter_any(const TileArgs& A, const StreamCta& C, StreamState<T>& R, const StreamMem& M, int i, int tid) {
     constexpr int U = stream_unroll(T);
     const int nfill = stream_nfill<T>(C), nbody = stream_nbody<T>(C);
     if (i < nfill || i >= nfill + U * nbody) {
-        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, tb, i, tid, stream_ptrs_any<T>(tb, i), nullptr);
+        stream_iter<EXACT, T, -1, UNI, true>(A, C, R, M, i, tid, stream_ptrs_any<T>(M, i), nullptr);
         return;
     }
     const int ph = (i - nfill) % U;   // nfill is a multiple of U
-    const StreamBody<T> Y = stream_body_at<T>(tb, i - ph);
+    const StreamBody<T> Y = stream_body_at<T>(M, i - ph);
     const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
-    if (ph == 0) stream_iter_phase<EXACT, T, UNI, U, 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
-    else if (ph == 1) stream_iter_phase<EXACT, T, UNI, U, 1>(A, C, R, tb, i, tid, Y, edge, nullptr);
-    else if (ph == 2) stream_iter_phase<EXACT, T, UNI, U == 4 ? 4 : 4, U == 4 ? 2 : 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
-    else stream_iter_phase<EXACT, T, UNI, U == 4 ? 4 : 4, U == 4 ? 3 : 0>(A, C, R, tb, i, tid, Y, edge, nullptr);
+    if (ph == 0) stream_iter_phase<EXACT, T, UNI, U, 0>(A, C, R, M, i, tid, Y, edge, nullptr);
+    else if (ph == 1) stream_iter_phase<EXACT, T, UNI, U, 1>(A, C, R, M, i, tid, Y, edge, nullptr);
+    else if (ph == 2) stream_iter_phase<EXACT, T, UNI, U == 4 ? 4 : 4, U == 4 ? 2 : 0>(A, C, R, M, i, tid, Y, edge, nullptr);
+    else stream_iter_phase<EXACT, T, UNI, U == 4 ? 4 : 4, U == 4 ? 3 : 0>(A, C, R, M, i, tid, Y, edge, nullptr);
 }
 
 // ---------------------------------------------------------------- host-side planning (no CUDA calls)
@@ -1041,21 +1077,21 @@ inline void emu_stream_cta(const TileArgs& A, const StreamGeom& G, int strip, in
     std::vector<StreamState<T>> R((size_t)G.NT);
     for (int tid = 0; tid < G.NT; ++tid) {
         stream_state_init<T>(A, C, tid, R[tid]);
-        float* tb = stream_chunk<T>(smem.data(), tid);
-        if (!stream_use_warm<T>(C)) for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, C, tb, j, tid, C.cs + 4 * tid < C.c_end);
-        else stream_warm_load<T>(A, C, tb, tid);
+        const StreamMem M = stream_mem<T>(smem.data(), tid, G.NT);
+        if (!stream_use_warm<T>(C)) for (int j = 0; j < FK_PF; ++j) stream_prefetch<T>(A, C, M, j, tid, C.cs + 4 * tid < C.c_end);
+        else stream_warm_load<T>(A, C, M, tid);
     }
     if (stream_use_warm<T>(C))
         for (int q = 0; q < G.NT; ++q) {   // after the first block barrier
             const int tid = reverse ? G.NT - 1 - q : q;
-            stream_warm_start<EXACT, T>(A, C, R[tid], stream_chunk<T>(smem.data(), tid), tid);
+            stream_warm_start<EXACT, T>(A, C, R[tid], stream_mem<T>(smem.data(), tid, G.NT), tid);
         }
     for (int i = stream_use_warm<T>(C) ? (int)FK_WARM : 0; i < C.niter; ++i)
         for (int q = 0; q < G.NT; ++q) {
             const int tid = reverse ? G.NT - 1 - q : q;
-            float* tb = stream_chunk<T>(smem.data(), tid);
-            if (G.uniformD) stream_iter_any<EXACT, T, true>(A, C, R[tid], tb, i, tid);
-            else stream_iter_any<EXACT, T, false>(A, C, R[tid], tb, i, tid);
+            const StreamMem M = stream_mem<T>(smem.data(), tid, G.NT);
+            if (G.uniformD) stream_iter_any<EXACT, T, true>(A, C, R[tid], M, i, tid);
+            else stream_iter_any<EXACT, T, false>(A, C, R[tid], M, i, tid);
         }
 }
 
