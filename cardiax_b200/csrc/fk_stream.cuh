@@ -55,9 +55,9 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     if (i < i_end) {
         sb_arrive(bar);   // phase 0: the fill loop's last block barrier stands for "iteration -1"
         const bool edge = C.edgeL >= 0 || C.edgeR >= 0;
+        StreamBody<T> Y = stream_body_at<T>(M, i);
 #define FK_STEADY_LOOP(EDGE)                                                                                           \
     for (; i < i_end; i += U) {                                                                                        \
-        const StreamBody<T> Y = stream_body_at<T>(M, i);                                                               \
         stream_iter<EXACT, T, 0, UNI, EDGE, U, MODE>(A, C, R, M, i, tid, stream_ptrs_phase<T, U, 0>(Y), bar);               \
         stream_iter<EXACT, T, 1, UNI, EDGE, U, MODE>(A, C, R, M, i + 1, tid, stream_ptrs_phase<T, U, 1>(Y), bar);           \
         if (U == 4) {                                                                                                  \
@@ -66,6 +66,7 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
             stream_iter<EXACT, T, U == 4 ? 3 : 1, UNI, EDGE, U, MODE>(A, C, R, M, i + 3, tid,                               \
                                                                 stream_ptrs_phase<T, U, U == 4 ? 3 : 1>(Y), bar);      \
         }                                                                                                              \
+        stream_body_next<T, U>(Y);                                                                                     \
     }
         if (edge) { FK_STEADY_LOOP(true) } else { FK_STEADY_LOOP(false) }
 #undef FK_STEADY_LOOP

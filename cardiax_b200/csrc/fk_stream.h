@@ -89,6 +89,12 @@ FK_HD long long opaque(long long x) {
 #endif
     return x;
 }
+FK_HD int opaque_i(int x) {   // the same for a 32-bit value (stops the compiler from rebuilding it from threadIdx inside the loop)
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(x));
+#endif
+    return x;
+}
 FK_HD void async_commit() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -146,12 +152,14 @@ enum { FK_PF = 3 };      // level-0 rows are fetched this many iterations ahead
 
 // Shared memory has two regions.
 //
-// ROW-major rows for what cp.async brings in from global memory (level 0): 16 rows of (NT + 2) 16-byte granules, granule
-// tid + 1 of a row being thread tid's 4 columns -- rows 0..7 the U(0) ring, 8..11 V(0), 12..15 W(0).  Consecutive threads
-// copy to consecutive granules, so a warp's LDGSTS lands in four 128-byte lines and asks L2 for every sector once.  (With
-// thread-major destinations, 528 bytes apart, every thread's 16 bytes became a request of their own: 2x the sectors from
-// L2 and ~28 shared-memory wavefronts per instruction -- ncu, profiles/ncu_stream_kernel_r02.md.)  The neighbours' halo
-// values of a level-0 row sit one granule to the left / right; granules 0 and NT + 1 of every row are pads.
+// LINE-major blocks for what cp.async brings in from global memory (level 0): every group of 8 consecutive threads owns a
+// block of 16 rows x 128 bytes -- rows 0..7 the U(0) ring, 8..11 V(0), 12..15 W(0) -- in which lane l of the group holds
+// its 4 columns at byte 16 l of every row.  A warp's LDGSTS therefore lands in four whole 128-byte lines and asks L2 for
+// every sector once.  (With thread-major destinations, 528 bytes apart, every thread's 16 bytes became a request of their
+// own: 2x the sectors from L2 and ~28 shared-memory wavefronts per instruction -- ncu source page of round 2.)  Rows are a
+// compile-time 128 bytes apart whatever the CTA's size.  The neighbours' halo values of a level-0 row sit one granule to
+// the left / right, in the adjacent block for the first / last lane of a group (StreamMem::hl, hr); the CTA's first and
+// last thread read their own granule instead (garbage that only reaches columns which are never stored).
 //
 // THREAD-major chunks for what the threads write themselves (levels >= 1, u_y): every thread owns one chunk of
 // StreamLay<T>::CHUNK floats that holds its 4 columns (one 16-byte granule) of every ring row, so that each access is
@@ -172,7 +180,7 @@ enum { FK_PF = 3 };      // level-0 rows are fetched this many iterations ahead
 template <int T>
 struct StreamLay {
     enum {
-        ROWS = 16, ROW_U = 0, ROW_V = 8, ROW_W = 12,   // the row-major region
+        ROWS = 16, ROW_U = 0, ROW_V = 8, ROW_W = 12, PITCH = 32, BLOCK = 16 * 32,   // the line-major region (floats)
         U1 = 0,                          // U(s) = U1 + 16 (s - 1) for s >= 1
         GY = 16 * (T - 1),               // GY(s) = GY + 8 s
         V = GY + 8 * T - 16,             // V(s) = V + 16 s for s >= 1
@@ -185,10 +193,11 @@ struct StreamLay {
 // a thread's view of the CTA's shared memory
 struct StreamMem {
     float* tb;    // its thread-major chunk
-    float* rb;    // its granule of row 0 of the row-major region
-    int pitch;    // floats per row of that region: 4 (NT + 2)
+    float* rb;    // its granule of row 0 of its group's line-major block
+    int hl, hr;   // where the left / right neighbour's granule of a level-0 row sits, relative to its own (floats)
 };
-FK_HD float* row_at(const StreamMem& M, int row) { return M.rb + row * M.pitch; }
+FK_HD float* row_at(const StreamMem& M, int row) { return M.rb + row * 32; }
+FK_HD long long stream_line_floats(int NT) { return (long long)((NT + 7) / 8) * 512; }
 
 // Largest CTA of the streaming kernel and the resident CTAs per SM its register budget is compiled for: 2 x 192
 // threads at T = 2 (168 registers; shared memory allows no more than 13 warps anyway), 2 x 256 at T = 1.
@@ -207,7 +216,7 @@ struct StreamGeom {  // per launch
     int row0, row1;  // output rows of this launch (every one needs 4T rows of input above and below)
 };
 
-FK_HD long long stream_smem_floats(int T, int NT) { return (long long)(NT + 2) * (20 + 56 * T); }
+FK_HD long long stream_smem_floats(int T, int NT) { return stream_line_floats(NT) + (long long)(NT + 2) * (56 * T - 44); }
 
 template <int T>
 struct StreamState {     // registers of one thread
@@ -288,15 +297,17 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
 // this thread's chunk of the CTA's shared memory, and its registers at the start of a CTA
 template <int T>
 FK_HD StreamMem stream_mem(float* smem, int tid, int NT) {
+    typedef StreamLay<T> L;
     StreamMem M;
-    M.pitch = 4 * (NT + 2);
-    M.rb = smem + 4 * (tid + 1);
-    M.tb = smem + (long long)StreamLay<T>::ROWS * M.pitch + (long long)(tid + 1) * StreamLay<T>::CHUNK;
+    M.rb = smem + opaque_i((tid >> 3) * (int)L::BLOCK + (tid & 7) * 4);
+    M.hl = tid == 0 ? 0 : ((tid & 7) == 0 ? -((int)L::BLOCK - 28) : -4);
+    M.hr = tid == NT - 1 ? 0 : ((tid & 7) == 7 ? (int)L::BLOCK - 28 : 4);
+    M.tb = smem + stream_line_floats(NT) + (long long)(tid + 1) * L::CHUNK;
     return M;
 }
 // the split barrier of the steady-state loop lives in the pad granule of the CTA's first (pad) chunk
 template <int T>
-FK_HD float* stream_bar(float* smem, int NT) { return smem + (long long)StreamLay<T>::ROWS * 4 * (NT + 2) + StreamLay<T>::CHUNK - 4; }
+FK_HD float* stream_bar(float* smem, int NT) { return smem + stream_line_floats(NT) + StreamLay<T>::CHUNK - 4; }
 
 template <int T>
 FK_HD void stream_state_init(const TileArgs& A, const StreamCta& C, int tid, StreamState<T>& R) {
@@ -388,12 +399,12 @@ FK_HD int stream_nbody(const StreamCta& C) {
 }
 
 // u_y (solve.py:50) of one row at the thread's 4 columns: u1 = the row's own values, r1p = its granule (the neighbours'
-// values sit hs floats to the left / right: one chunk in the thread-major rings, one granule in a level-0 row); gypad:
+// granules sit at r1p + hl / r1p + hr: one chunk away in the thread-major rings, StreamMem::hl, hr in a level-0 row); gypad:
 // u_y of the pad column at a tissue edge
 template <bool EXACT, int T>
-FK_HD void stream_make_gy(const Consts& K, const float* r1p, int hs, const float* u1, bool edgeL, bool edgeR, float* gy,
+FK_HD void stream_make_gy(const Consts& K, const float* r1p, int hl, int hr, const float* u1, bool edgeL, bool edgeR, float* gy,
                           float& gypad) {
-    const F2 Lh = ld2(r1p - hs + 2), Rh = ld2(r1p + hs);
+    const F2 Lh = ld2(r1p + hl + 2), Rh = ld2(r1p + hr);
     // edge-pad (solve.py:31): the column outside the tissue repeats the edge column
     const float e[8] = {Lh.x, edgeL ? u1[0] : Lh.y, u1[0], u1[1], u1[2], u1[3], edgeR ? u1[3] : Rh.x, Rh.y};
     dcen_span4<EXACT>(K, e, gy);
@@ -445,7 +456,7 @@ FK_HD void stream_warm_start(const TileArgs& A, const StreamCta& C, StreamState<
             for (int k = 0; k < 4; ++k) R.GX[0][m][k] = dcen<EXACT>(A.K, u[m][k], u[m + 1][k], u[m + 3][k], u[m + 4][k]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) R.prev[0][k] = u[7][k];
-        stream_make_gy<EXACT, T>(A.K, row_at(M, L::ROW_U + 4), 4, u[4], tid == C.edgeL, tid == C.edgeR, R.gy[0], R.gypad[0]);
+        stream_make_gy<EXACT, T>(A.K, row_at(M, L::ROW_U + 4), M.hl, M.hr, u[4], tid == C.edgeL, tid == C.edgeR, R.gy[0], R.gypad[0]);
         st4(tb + L::GY + 4 * 1, R.gy[0]);
     }
     // rows 0 .. FK_PF-1 of the ring are free again: fetch what iterations 8 .. 8 + FK_PF - 1 consume
@@ -540,37 +551,52 @@ FK_HD StreamPtrs stream_ptrs_any(const StreamMem& M, int i) {
     return P;
 }
 
-// the per-body bases of the unrolled loop (body = U consecutive iterations starting at a multiple of U)
+// the per-body bases of the unrolled loop (body = U consecutive iterations starting at a multiple of U).  They are CARRIED
+// from body to body (stream_body_next: a rotation of four offsets, two swaps) rather than rebuilt from the iteration index,
+// which cost ~40 integer instructions per body.
 template <int T>
 struct StreamBody {
     float* tb;
     float* rb;
-    int ou[8];              // row-major region: offset of U(0) slot (i + k) & 7, k = 0..7 (i = the body's first iteration)
-    int ov[4], ow[4];       // ... of V(0) / W(0) slot (i + k) & 3
+    // line-major region, offsets in BYTES from rb (so that they fold into `register + uniform register + immediate`).  U = 2 (i even): U(0) slots i & 7, (i + 2) & 7, (i + 4) & 7, (i + 6) & 7
+    // (the odd slots follow their even ones: + one row); V(0) slots i & 3 and (i + 2) & 3 (W(0): + 4 rows).  U = 4 (i a
+    // multiple of 4): ua, ub = the halves of the U(0) ring holding slot i & 7 / the other one, ve = V(0) slot 0.
+    int ua, uc, ub, ud, ve, vf;
     float *tH, *tO;         // U = 2: chunk base shifted to the pair of 4-ring slots holding slot i & 3 / the other pair
 };
 
 template <int T>
 FK_HD StreamBody<T> stream_body_at(const StreamMem& M, int i) {   // i: first iteration of the body
+    typedef StreamLay<T> L;
     StreamBody<T> Y;
     Y.tb = M.tb;
     Y.rb = M.rb;
-    typedef StreamLay<T> L;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = 0; k < 8; ++k) Y.ou[k] = (L::ROW_U + ((i + k) & 7)) * M.pitch;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = 0; k < 4; ++k) {
-        Y.ov[k] = (L::ROW_V + ((i + k) & 3)) * M.pitch;
-        Y.ow[k] = (L::ROW_W + ((i + k) & 3)) * M.pitch;
-    }
+    Y.ua = (L::ROW_U + (i & 7)) * (int)L::PITCH * 4;
+    Y.uc = (L::ROW_U + ((i + 2) & 7)) * (int)L::PITCH * 4;
+    Y.ub = (L::ROW_U + ((i + 4) & 7)) * (int)L::PITCH * 4;
+    Y.ud = (L::ROW_U + ((i + 6) & 7)) * (int)L::PITCH * 4;
+    Y.ve = (L::ROW_V + (i & 3)) * (int)L::PITCH * 4;
+    Y.vf = (L::ROW_V + ((i + 2) & 3)) * (int)L::PITCH * 4;
     const int qo = (i & 2) * 4;   // floats: 8 per slot pair
     Y.tH = M.tb + qo;
     Y.tO = M.tb + (8 - qo);
     return Y;
+}
+
+// ... of the next body (U iterations later)
+template <int T, int U>
+FK_HD void stream_body_next(StreamBody<T>& Y) {
+    if (U == 2) {
+        const int a = Y.ua;
+        Y.ua = Y.uc; Y.uc = Y.ub; Y.ub = Y.ud; Y.ud = a;
+        const int e = Y.ve;
+        Y.ve = Y.vf; Y.vf = e;
+        float* h = Y.tH;
+        Y.tH = Y.tO; Y.tO = h;
+    } else {
+        const int a = Y.ua;
+        Y.ua = Y.ub; Y.ub = a;
+    }
 }
 
 // slots of phase PH of a body, every offset a compile-time constant
@@ -585,14 +611,23 @@ FK_HD StreamPtrs stream_ptrs_phase(const StreamBody<T>& Y) {
         P.bj1 = PH == 0 ? Y.tH + 4 : Y.tO;
     }
     // the rows of the row-major region: uniform offsets (functions of the body's first iteration alone)
-    P.u0new = Y.rb + Y.ou[PH];
-    P.u0r0 = Y.rb + Y.ou[(PH + 4) & 7];
-    P.u0r1 = Y.rb + Y.ou[(PH + 5) & 7];
-    P.u0pf = Y.rb + Y.ou[(PH + FK_PF) & 7];
-    P.v0 = Y.rb + Y.ov[PH];
-    P.w0 = Y.rb + Y.ow[PH];
-    P.v0pf = Y.rb + Y.ov[(PH + FK_PF) & 3];
-    P.w0pf = Y.rb + Y.ow[(PH + FK_PF) & 3];
+    // U(0) slot (i + k) & 7 and V(0) slot (i + k) & 3 of the body that starts at iteration i: a carried base + a constant
+    constexpr int PT = (int)StreamLay<T>::PITCH * 4, WV = ((int)StreamLay<T>::ROW_W - (int)StreamLay<T>::ROW_V) * PT;
+#define FK_OU(k) (U == 4 ? ((k) < 4 ? Y.ua + PT * (k) : Y.ub + PT * ((k) - 4))                                               \
+                         : (((k) >> 1) == 0 ? Y.ua : ((k) >> 1) == 1 ? Y.uc : ((k) >> 1) == 2 ? Y.ub : Y.ud) + PT * ((k) & 1))
+#define FK_AT(off) reinterpret_cast<float*>(reinterpret_cast<char*>(Y.rb) + (off))
+#define FK_OV(k) (U == 4 ? Y.ve + PT * (k) : ((k) < 2 ? Y.ve : Y.vf) + PT * ((k) & 1))
+    P.u0new = FK_AT(FK_OU(PH));
+    P.u0r0 = FK_AT(FK_OU((PH + 4) & 7));
+    P.u0r1 = FK_AT(FK_OU((PH + 5) & 7));
+    P.u0pf = FK_AT(FK_OU((PH + FK_PF) & 7));
+    P.v0 = FK_AT(FK_OV(PH));
+    P.w0 = FK_AT(FK_OV(PH) + WV);
+    P.v0pf = FK_AT(FK_OV((PH + FK_PF) & 3));
+    P.w0pf = FK_AT(FK_OV((PH + FK_PF) & 3) + WV);
+#undef FK_OU
+#undef FK_OV
+#undef FK_AT
     return P;
 }
 
@@ -915,7 +950,7 @@ FK_HD void stream_iter(const TileArgs& A, const StreamCta& C, StreamState<T>& R,
         }
         // u_y of row rho+1 (solve.py:50) for the next iteration, published for the neighbours
         if (ST || (rho + 1 >= lo && rho + 1 < hi)) {
-            stream_make_gy<EXACT, T>(A.K, r1p[s], s == 0 ? 4 : CH, u1[s], edgeL, edgeR, R.gy[s], R.gypad[s]);
+            stream_make_gy<EXACT, T>(A.K, r1p[s], s == 0 ? M.hl : -CH, s == 0 ? M.hr : CH, u1[s], edgeL, edgeR, R.gy[s], R.gypad[s]);
             st4(tb + L::GY + 8 * s + 4 * (ST ? PH & 1 : i & 1), R.gy[s]);
         }
         // the u_x window takes the new row
