@@ -15,11 +15,46 @@ inline int cur_device() {
     return d;
 }
 
+// Which (strip, chunk) a block works on.  The CTAs of the tissue's first and last strip carry the one-sided column formulas
+// (+20 % time, tools/probe_stream_timing.py) and a launch is one wave, so they come FIRST in block order: the hardware hands
+// blocks out round-robin, which puts at most one of them on an SM as long as there are no more of them than SMs (4096^2: 98
+// on 148), and a block that is resident first is also the one the warp schedulers favour.  In (strip, chunk) order every
+// ninth SM held two of them and the launch ended 8 % after the average SM.  The other strips' last and first row chunks
+// follow (their general-body iterations at the physical bottom / top edge made them the last blocks to finish).
+__device__ __forceinline__ void stream_block_work(const StreamGeom& G, int b, int& strip, int& chunk) {
+    if (G.nstrips < 3 || G.nchunks < 3) { strip = b % G.nstrips; chunk = b / G.nstrips; return; }
+    const int ne = 2 * G.nchunks, ni = G.nstrips - 2;
+    if (b < ne) { strip = (b & 1) ? G.nstrips - 1 : 0; chunk = b >> 1; return; }
+    b -= ne;
+    if (b < ni) { strip = 1 + b; chunk = G.nchunks - 1; return; }
+    b -= ni;
+    if (b < ni) { strip = 1 + b; chunk = 0; return; }
+    b -= ni;
+    strip = 1 + b % ni;
+    chunk = 1 + b / ni;
+}
+
+// development (-DFK_STREAM_TIMING, tools/probe_stream_timing.py): every CTA records when it started and ended (globaltimer,
+// ns) and on which SM it ran -- where a launch's time goes when its CTAs do not finish together
+#ifdef FK_STREAM_TIMING
+enum { FK_STREAM_TIMING_CTAS = 8192 };
+__device__ unsigned long long fk_stream_timing_buf[3 * FK_STREAM_TIMING_CTAS];
+__device__ __forceinline__ unsigned long long fk_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <bool EXACT, int T, bool UNI, int MODE = FK_STORE_PLAIN>
 __global__ void __launch_bounds__(T == 2 ? 192 : 256, T <= 2 ? 2 : 1)
 fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ StreamGeom G) {
     extern __shared__ __align__(16) float fk_stream_smem[];
-    const int strip = blockIdx.x % G.nstrips, chunk = blockIdx.x / G.nstrips;
+#ifdef FK_STREAM_TIMING
+    const unsigned long long t_start = fk_globaltimer();
+#endif
+    int strip, chunk;
+    stream_block_work(G, (int)blockIdx.x, strip, chunk);
     StreamCta C;
     stream_cta_setup<T>(A, G, strip, chunk, blockIdx.y, C);
     const int tid = threadIdx.x;
@@ -86,6 +121,17 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     // halo mirror: this thread's stores into the neighbouring GPUs' memory are performed, system wide, before the kernel
     // ends -- the flag the neighbour waits for is written by a later operation of the same stream
     if (MODE == FK_STORE_MIRROR) __threadfence_system();
+#ifdef FK_STREAM_TIMING
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.y == 0 && gridDim.x <= FK_STREAM_TIMING_CTAS) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        const int rec = chunk * G.nstrips + strip;   // (records in (chunk, strip) order whatever the block order)
+        fk_stream_timing_buf[3 * rec] = t_start;
+        fk_stream_timing_buf[3 * rec + 1] = fk_globaltimer();
+        fk_stream_timing_buf[3 * rec + 2] = smid;
+    }
+#endif
 }
 
 template <bool EXACT, int T, bool UNI>

@@ -21,3 +21,11 @@ int FK_NAME(stream_occupancy_T, FK_TU_T, _E, FK_TU_EXACT)(int uni, int NT, long 
 }
 
 }  // namespace fk
+
+#ifdef FK_STREAM_TIMING
+// development: the per-CTA records of this translation unit's last launch (start ns, end ns, SM) -- 3 values per CTA
+extern "C" int FK_NAME(fk_stream_timing_T, FK_TU_T, _E, FK_TU_EXACT)(unsigned long long* out, int nctas) {
+    if (nctas > fk::FK_STREAM_TIMING_CTAS) nctas = fk::FK_STREAM_TIMING_CTAS;
+    return (int)cudaMemcpyFromSymbol(out, fk::fk_stream_timing_buf, sizeof(unsigned long long) * 3 * (size_t)nctas);
+}
+#endif
