@@ -2,6 +2,7 @@
 // the kernels run.  fk_api.cu instantiates it with the CUDA backend; tests/emu with the CPU
 // emulation, so the ping-pong / frame / tail logic is unit-tested without a GPU.
 #pragma once
+#include <cstdlib>
 #include "fk_stream.h"
 #include "fk_tile.h"
 #include "fk_wide.h"
@@ -178,7 +179,8 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             rows(T, R0, R1, ok);
             return ok && R1 > R0 && plan_stream(R0, R1, W, batch, T, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
                                           opt.uniform_diffusivity, stream_max_threads(T),
-                                          [&](int NT, long long smem) { return be.occupancy(T, opt.exact, opt.uniform_diffusivity, NT, smem); }, P);
+                                          [&](int NT, long long smem) { return be.occupancy(T, opt.exact, opt.uniform_diffusivity, NT, smem); }, P,
+                                          getenv("FK_FIRST_DISCOUNT") ? atoi(getenv("FK_FIRST_DISCOUNT")) : 0);
         };
         use_stream = try_plan(Tmax, plan);
         if (opt.steps_per_launch == 0 && !slab && opt.row1 <= 0 && nsteps > 1 && (long long)H * W * batch < (1LL << 21)) {

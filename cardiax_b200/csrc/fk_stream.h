@@ -1022,8 +1022,7 @@ struct StreamPlan {
 // rounds * iterations-per-CTA * resident warps / issue-efficiency(resident warps).
 template <class OccFn>
 inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_threads, int rows_per_cta, int num_sms,
-                        int uniformD, int max_threads, OccFn occ, StreamPlan& P, int first_chunk_discount = 0,
-                        int last_chunk_discount = 0) {
+                        int uniformD, int max_threads, OccFn occ, StreamPlan& P, int first_chunk_rows_off = 0) {
     if (T < 1 || T > 4) return false;
     if (W % 4 != 0) return false;                       // float4 rows
     if (row1 - row0 < 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
@@ -1053,10 +1052,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             if (RH <= 0) {
                 long long nch = waves * slots / units;
                 if (nch < 1) nch = 1;
-                // (discounts: rows a first / last chunk could be made shorter by.  Measured on 4096^2: the chunks at the
-                // physical top / bottom edge, which run 4T + 2 / 4T + 1 iterations in the general body, are NOT the
-                // last to finish, and any discount only lengthens the others -- so the driver passes 0)
-                RH = (int)((Hint + first_chunk_discount + last_chunk_discount + nch - 1) / nch);
+                RH = (int)((Hint + nch - 1) / nch);
                 RH = (RH + 3) / 4 * 4;   // whole bodies of the 4-way unrolled steady-state loop
             }
             // every chunk but the first / last must stay clear of the one-sided rows at a physical edge at every level:
@@ -1064,12 +1060,18 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             if (RH < 8) RH = 8;
             if (RH < 4 * T) RH = 4 * T;
             if (RH > Hint) RH = Hint;
-            int RH0 = RH - first_chunk_discount;
-            if (RH0 < 8) RH0 = 8;
-            if (RH0 < 4 * T) RH0 = 4 * T;
-            if (RH0 > Hint) RH0 = Hint;
+            int RH0 = RH;
             int nchunks = 1 + (Hint - RH0 + RH - 1) / RH;
             if (nchunks > 1 && Hint - RH0 - (nchunks - 2) * RH < 4 * T) --nchunks;
+            // first_chunk_rows_off: rows the first chunk hands to the last one when that one has the room (rounding RH up
+            // leaves it short) -- the chunk at the physical top edge runs its first 4T + 2 iterations in the general body,
+            // which made the tissue's two top corners the last CTAs of a launch (tools/probe_stream_timing.py)
+            if (rows_per_cta <= 0 && nchunks >= 3 && first_chunk_rows_off > 0) {
+                const int last = Hint - RH0 - (nchunks - 2) * RH;
+                int d = RH - last < first_chunk_rows_off ? RH - last : first_chunk_rows_off;
+                d = d / 4 * 4;
+                if (d > 0 && RH0 - d >= 8 && RH0 - d >= 4 * T) RH0 -= d;
+            }
             const long long ncta = units * nchunks;
             const double rounds = (double)((ncta + slots - 1) / slots);
             // CTAs actually resident on an SM (a small tissue does not fill the machine), their active warps, and
