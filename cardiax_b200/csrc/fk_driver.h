@@ -180,7 +180,8 @@ int drive_euler(Backend& be, const DriveBuffers& B, int d_batched, int H, int W,
             return ok && R1 > R0 && plan_stream(R0, R1, W, batch, T, opt.cta_threads, opt.rows_per_cta, be.num_sms(),
                                           opt.uniform_diffusivity, stream_max_threads(T),
                                           [&](int NT, long long smem) { return be.occupancy(T, opt.exact, opt.uniform_diffusivity, NT, smem); }, P,
-                                          getenv("FK_FIRST_DISCOUNT") ? atoi(getenv("FK_FIRST_DISCOUNT")) : 0);
+                                          (opt.phys_top && R0 == 0) ? stream_top_off(T) : 0,
+                                          (opt.phys_bottom && R1 == H) ? stream_bot_off(T) : 0);
         };
         use_stream = try_plan(Tmax, plan);
         if (opt.steps_per_launch == 0 && !slab && opt.row1 <= 0 && nsteps > 1 && (long long)H * W * batch < (1LL << 21)) {

@@ -20,6 +20,7 @@
 // Written as FK_HD code over an explicit per-thread state so tests/emu can run it on the CPU
 // (threads of a block executed one after the other inside each iteration).
 #pragma once
+#include <cstdlib>
 #include "fk_core.h"
 #include "fk_tile.h"
 
@@ -208,6 +209,8 @@ struct StreamGeom {  // per launch
     int NT;          // threads per CTA
     int CW;          // 4 * NT, columns a CTA reads
     int RH;          // output rows per CTA
+    int ntall;       // the first ntall chunks after the first one have RH rows, the following ones RH - 4 (plan_stream
+                     // balances the launch: the chunks at a physical top / bottom edge get fewer rows than the others)
     int RH0;         // ... of the first row chunk (shorter when it starts at the physical top edge); the last chunk
                      // takes what is left
     int nstrips, nchunks;
@@ -215,6 +218,14 @@ struct StreamGeom {  // per launch
     int uniformD;    // diffusivity (and so D_x, D_y) is one constant over the interior
     int row0, row1;  // output rows of this launch (every one needs 4T rows of input above and below)
 };
+
+// first output row of row chunk c; chunk c covers [stream_chunk_row(c), stream_chunk_row(c + 1))
+FK_HD int stream_chunk_row(const StreamGeom& G, int c) {
+    if (c <= 0) return G.row0;
+    if (c >= G.nchunks) return G.row1;
+    const int k = c - 1;   // whole chunks between the first one and chunk c
+    return G.row0 + G.RH0 + k * G.RH - 4 * (k > G.ntall ? k - G.ntall : 0);
+}
 
 FK_HD long long stream_smem_floats(int T, int NT) { return stream_line_floats(NT) + (long long)(NT + 2) * (56 * T - 44); }
 
@@ -253,8 +264,8 @@ FK_HD void stream_cta_setup(const TileArgs& A, const StreamGeom& G, int strip, i
     // strip j owns output columns [j stride, (j+1) stride); it reads 4T more on each side unless that side is the
     // tissue's physical left/right edge, which the edge thread handles with the reference's one-sided formulas
     C.cs = strip * G.cstride - 4 * T < 0 ? 0 : strip * G.cstride - 4 * T;
-    C.r0 = G.row0 + (chunk == 0 ? 0 : G.RH0 + (chunk - 1) * G.RH);
-    C.r1 = chunk == G.nchunks - 1 ? G.row1 : C.r0 + (chunk == 0 ? G.RH0 : G.RH);   // the last chunk takes the remainder (>= 4T rows)
+    C.r0 = stream_chunk_row(G, chunk);
+    C.r1 = stream_chunk_row(G, chunk + 1);   // (the last chunk takes the remainder, >= 4T rows)
     // A chunk at a physical edge has no rows beyond it: its stages start at row 0 / run dry after row H-1 and use the
     // reference's one-sided formulas there.  Every other chunk reads 4T apron rows on that side.
     C.top = A.phys_top && C.r0 == 0;
@@ -1020,9 +1031,16 @@ struct StreamPlan {
 // Strips are balanced (equal widths, multiple of 4 columns) and the row chunks are sized so that the
 // grid is a whole number of waves of num_sms * occ CTAs; candidates are ranked by a simple model:
 // rounds * iterations-per-CTA * resident warps / issue-efficiency(resident warps).
+// rows fewer than the others that the chunk at the physical top / bottom edge gets (plan_stream: top_off, bot_off).
+// FK_TOP_OFF / FK_BOT_OFF in the environment: development sweeps.
+// (measured on 4096^2, T = 2: 350.5 Gcell-steps/s without, 357 .. 359 for (12, 20), (16, 28), (20, 36); the 128 x 256^2
+// ensemble, whose SMs hold six small CTAs each, is indifferent up to (12, 20) and loses beyond)
+inline int stream_top_off(int T) { const char* e = getenv("FK_TOP_OFF"); return e ? atoi(e) : 6 * T; }
+inline int stream_bot_off(int T) { const char* e = getenv("FK_BOT_OFF"); return e ? atoi(e) : 10 * T; }
+
 template <class OccFn>
 inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_threads, int rows_per_cta, int num_sms,
-                        int uniformD, int max_threads, OccFn occ, StreamPlan& P, int first_chunk_rows_off = 0) {
+                        int uniformD, int max_threads, OccFn occ, StreamPlan& P, int top_off = 0, int bot_off = 0) {
     if (T < 1 || T > 4) return false;
     if (W % 4 != 0) return false;                       // float4 rows
     if (row1 - row0 < 8 || W < 8 * T + 32) return false;  // too small: the general tile kernel does it all
@@ -1063,14 +1081,22 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             int RH0 = RH;
             int nchunks = 1 + (Hint - RH0 + RH - 1) / RH;
             if (nchunks > 1 && Hint - RH0 - (nchunks - 2) * RH < 4 * T) --nchunks;
-            // first_chunk_rows_off: rows the first chunk hands to the last one when that one has the room (rounding RH up
-            // leaves it short) -- the chunk at the physical top edge runs its first 4T + 2 iterations in the general body,
-            // which made the tissue's two top corners the last CTAs of a launch (tools/probe_stream_timing.py)
-            if (rows_per_cta <= 0 && nchunks >= 3 && first_chunk_rows_off > 0) {
-                const int last = Hint - RH0 - (nchunks - 2) * RH;
-                int d = RH - last < first_chunk_rows_off ? RH - last : first_chunk_rows_off;
-                d = d / 4 * 4;
-                if (d > 0 && RH0 - d >= 8 && RH0 - d >= 4 * T) RH0 -= d;
+            int ntall = nchunks;
+            // top_off / bot_off: how many rows FEWER than the others the first / last chunk should get.  A chunk at the
+            // physical top edge runs its first 4T + 2 iterations in the general body, one at the bottom edge its last
+            // 4T + 1: per-CTA timelines (tools/probe_stream_timing.py) put them 18 and 30 steady-state iterations behind
+            // a chunk of the same height at T = 2, and a launch is one wave -- it ends with its slowest CTA.  The same
+            // number of chunks is kept; the rows taken off go to the others, 4 at a time.
+            if (rows_per_cta <= 0 && nchunks >= 4 && (top_off > 0 || bot_off > 0)) {
+                const int n = nchunks, lo = 4 * T > 8 ? 4 * T : 8;
+                int RHi = (Hint + top_off + bot_off + n - 1) / n;
+                RHi = (RHi + 3) / 4 * 4;
+                const int surplus = n * RHi - top_off - bot_off - Hint;            // rows to take off again
+                int nshort = surplus / 4 < n - 2 ? surplus / 4 : n - 2;             // ... 4 from each of that many chunks
+                const int last = RHi - bot_off - (surplus - 4 * nshort);            // ... and the rest from the last one
+                if (RHi - top_off >= lo && RHi - 4 >= lo && last >= 4 * T) {
+                    RH = RHi; RH0 = RHi - top_off; ntall = n - 2 - nshort;
+                }
             }
             const long long ncta = units * nchunks;
             const double rounds = (double)((ncta + slots - 1) / slots);
@@ -1086,7 +1112,7 @@ inline bool plan_stream(int row0, int row1, int W, int batch, int T, int cta_thr
             const double cost = rounds * (RH + 8.0 * T) * T * (warps + 8.0) / 4.0 * (1.0 + 0.02 * (wpc > 4 ? wpc - 4 : 0));
             if (best < 0 || cost < best) {
                 best = cost;
-                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RH = RH; P.G.RH0 = RH0;
+                P.G.NT = NT; P.G.CW = 4 * NT; P.G.RH = RH; P.G.RH0 = RH0; P.G.ntall = ntall;
                 P.G.nstrips = nstrips; P.G.nchunks = nchunks; P.G.cstride = stride; P.G.uniformD = uniformD;
                 P.G.row0 = row0; P.G.row1 = row1;
                 P.T = T;

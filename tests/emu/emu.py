@@ -127,6 +127,14 @@ def plan_resident(H, W, batch=1, tiles=(0, 0), threads=0, nc=0, edge_tile=(0, 0)
                      "edge_colgroups", "single_phase", "maps_in_l2", "two_pass"), list(out)))
 
 
+def plan_rows(H, W, batch=1, T=2, regs=168, top_off=0, bot_off=0):
+    """Row-chunk boundaries of the streaming kernel's plan for a whole tissue: list of first rows, ending with H (or None)."""
+    out = (ctypes.c_int * 4096)()
+    if not lib().fk_emu_plan_rows(H, W, batch, T, regs, top_off, bot_off, out, 4096):
+        return None
+    return list(out[1:out[0] + 2])
+
+
 def _pack_stims(stimuli):
     keep, arr = [], (_Stim * max(1, len(stimuli)))()
     for i, s in enumerate(stimuli):

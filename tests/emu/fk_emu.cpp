@@ -177,6 +177,22 @@ extern "C" int fk_emu_plan(int H, int W, int batch, int T, int cta_threads, int 
     return 1;
 }
 
+// the whole-tissue plan with balanced row chunks (the chunks at the physical top / bottom edge top_off / bot_off rows shorter):
+// out = {nchunks, first row of every chunk ..., H}
+extern "C" int fk_emu_plan_rows(int H, int W, int batch, int T, int regs, int top_off, int bot_off, int* out, int cap) {
+    fk::StreamPlan P;
+    const bool ok = fk::plan_stream(0, H, W, batch, T, 0, 0, 148, 0, 256,
+                                    [&](int NT, long long smem) {
+                                        const int a = 65536 / (((regs + 7) / 8 * 8) * NT);
+                                        const int b = (int)((228 * 1024) / (smem + 1024));
+                                        return a < b ? a : b;
+                                    }, P, top_off, bot_off);
+    if (!ok || P.G.nchunks + 2 > cap) return 0;
+    out[0] = P.G.nchunks;
+    for (int c = 0; c <= P.G.nchunks; ++c) out[1 + c] = fk::stream_chunk_row(P.G, c);
+    return 1;
+}
+
 // resident planner probe (tests): {ntr, ntc, th_max, tw_max, threads, smem bytes, cells per thread, mailbox bytes}
 extern "C" int fk_emu_plan_resident(int H, int W, int batch, int* out, const int* force6) {   // force6[6] = maps_global
     fk::ResPlan P;

@@ -1,5 +1,7 @@
 """CPU emulation of the CUDA kernel bodies (tests/emu) against the oracle: index, boundary, ring and launch logic of
 the product's kernels, checked without a GPU.  EXACT mode must be bit-identical; fast mode within tolerance."""
+import os
+
 import numpy as np
 import pytest
 
@@ -441,3 +443,24 @@ def test_quiet_launches_are_never_wrongly_declared():
                     assert not (quiet and active), (proto, t0, nsteps, typed_int)
                     said_quiet += quiet
     assert said_quiet > 300     # ... and it does recognise the sleeping launches
+
+
+def test_balanced_row_chunks():
+    """The chunks at the physical top / bottom edge get fewer rows than the others (their special iterations run in the
+    general body), the number of chunks stays, every row is covered once; a run on such a plan is bit-exact."""
+    base = emu.plan_rows(4096, 4096, T=2)
+    bal = emu.plan_rows(4096, 4096, T=2, top_off=16, bot_off=28)
+    assert base and bal and len(base) == len(bal) and bal[0] == 0 and bal[-1] == 4096
+    rows = [b - a for a, b in zip(bal, bal[1:])]
+    inner = rows[1:-1]
+    assert max(inner) - min(inner) <= 4 and all(r % 4 == 0 for r in rows[:-1])
+    assert rows[0] == max(inner) - 16 and max(inner) - 28 - 4 < rows[-1] <= max(inner) - 28
+    assert sorted(inner, reverse=True) == inner                      # the taller chunks first
+    assert emu.plan_rows(256, 256, batch=128, T=2, top_off=16, bot_off=28) is not None
+    for sh, T in (((200, 64), 2), ((333, 96), 3), ((200, 64), 1)):   # small chunks: offsets of 4 rows exercise the same code
+        os.environ["FK_TOP_OFF"], os.environ["FK_BOT_OFF"] = "4", "4"
+        try:
+            info = _exact(sh, T, nsteps=2 * T, kernel=2)
+        finally:
+            del os.environ["FK_TOP_OFF"], os.environ["FK_BOT_OFF"]
+        assert info[1] > 0
