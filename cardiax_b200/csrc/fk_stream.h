@@ -35,7 +35,7 @@ FK_HD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
 #define FK_MAP_PF 3
 #endif
 #ifndef FK_MAP_LATE
-#define FK_MAP_LATE 2
+#define FK_MAP_LATE 1
 #endif
 // which stages load their maps at the point of use: 0 none (all up front), 1 all, 2 all but the first, 3 the first only
 #define FK_MAP_IS_LATE(s) (FK_MAP_LATE == 1 || (FK_MAP_LATE == 2 && (s) > 0) || (FK_MAP_LATE == 3 && (s) == 0))
