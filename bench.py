@@ -56,14 +56,27 @@ def peaks():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread of this process (a handful of driver
+    queries every 50 ms).  An `nvidia-smi -lms` child did the same job until its queries were seen to cost the unprofiled
+    4096^2 pass 5 % (tools/probe_step_jitter.py) and its start-up to stall launches; it remains the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nvml, self.run = [], None, index, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.run = pynvml, True
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -72,17 +85,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        N = self.nvml
+        names = (("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap))
+        while self.run:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+                mx = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append([str(self.index), str(sm), str(mx), ""] + ["Active" if r & bit else "Not Active" for _, bit in names])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            time.sleep(0.06)
+            self.run = False
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in list(self.rows):
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -91,7 +122,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "via": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ workloads (host side, NumPy)
@@ -389,34 +420,47 @@ def main():
 
     # ---- device-resident measurement
     st, t = state0, 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # (before the warm-up: NVML's / nvidia-smi's start-up takes driver locks that can stall launches)
+        time.sleep(0.2)
     for _ in range(args.warmup):
         st = step_fn(st, t); t += seg
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.rows.clear()   # only the samples taken during the timed region count
+    # The timed region of `value`: exactly K steps as the product runs them (no per-launch events: the pair the library
+    # records around every launch when profiling is on costs ~6 % of a 4096^2 step -- 357 vs 378 Gcell-steps/s --
+    # so the per-launch figures of `roofline` come from a second pass of the same K steps right after, with its own clock)
+    def timed_pass(st, t, profile):
+        L.fk_profile_enable(1 if profile else 0)
+        L.fk_profile_collect(None, None, None, None, None)
+        L.fk_profile_dropped()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            if flush is not None:
+                flush.fill_(1.0)
+            st = step_fn(st, t); t += seg
+            marks[k].record()   # (one event per 500-step segment: how evenly the steps of the region ran)
+        e1.record()
+        barrier()
+        per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        return st, t, e0.elapsed_time(e1), per_step
+
     launches0 = L.fk_launch_count()
-    L.fk_profile_enable(0 if os.environ.get("FK_BENCH_NOPROF") else 1)
-    L.fk_profile_collect(None, None, None, None, None)
-    L.fk_profile_dropped()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        if flush is not None:
-            flush.fill_(1.0)
-        st = step_fn(st, t); t += seg
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    st, t, ms, step_ms = timed_pass(st, t, False)
+    launches = L.fk_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    st, t, ms_prof, _ = timed_pass(st, t, not os.environ.get("FK_BENCH_NOPROF"))
     sm_ms, sm_n, tl_ms, tl_n, sm_cs = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     L.fk_profile_collect(ctypes.byref(sm_ms), ctypes.byref(sm_n), ctypes.byref(tl_ms), ctypes.byref(tl_n), ctypes.byref(sm_cs))
     prof_dropped = int(L.fk_profile_dropped())
     plan = _lib.last_plan()
     main_kernel_name = _lib.last_kernel()
     L.fk_profile_enable(0)
-    launches = L.fk_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     if flush is not None:  # take the flush writes out: time them alone
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); f0.record()
@@ -424,6 +468,7 @@ def main():
             flush.fill_(1.0)
         f1.record(); torch.cuda.synchronize()
         ms -= f0.elapsed_time(f1)
+        ms_prof -= f0.elapsed_time(f1)
     assert all(bool(torch.isfinite(x).all()) for x in st)
     ms = max_over_ranks(ms)
     total_cells = cells * world
@@ -731,8 +776,11 @@ def main():
                 "traffic": traffic, "peak_kind": peak_kind, "kernel": main_kernel,
                 "dram_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "alg_bytes_per_launch": ALG_BYTES * cs_per_launch, "avg_launch_ms": avg_ms,
-                "kernel_share_of_step": sm_ms.value / ms, "tile_kernel_share_of_step": tl_ms.value / ms,
+                "kernel_share_of_step": sm_ms.value / ms_prof, "tile_kernel_share_of_step": tl_ms.value / ms_prof,
                 "launches_timed": int(sm_n.value), "launches_not_timed": prof_dropped,
+                "timed_in": "a second pass of the same %d steps with a CUDA event pair around every launch (%.3f ms per step "
+                            "against %.3f in the pass `value` is timed in, which records none)" % (
+                                args.steps, ms_prof / args.steps, ms / args.steps),
                 "note": ("the streaming kernel covers the whole tissue, physical edges included; the rest of the step is "
                          "fk_dgrad_kernel (once per call) and launch gaps; dram_frac = the ncu-measured DRAM bytes of one "
                          "launch / its event-timed duration / peak") if main_kernel == "fk_stream_kernel" else
@@ -744,7 +792,7 @@ def main():
         achieved = ALG_BYTES * cells * seg * args.steps / (tl_ms.value * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_kind": peak_kind, "kernel": "fk_tile_kernel",
-                "kernel_share_of_step": tl_ms.value / ms}
+                "kernel_share_of_step": tl_ms.value / ms_prof}
     cpu = None
     if not args.no_cpu and world == 1:
         n_e = max(1, int(1.5e9 // cells)) if workload in ("fk4096",) else max(1, int(1.5e9 // (work["u"].shape[-1] * work["u"].shape[-2])))
@@ -757,6 +805,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "Gcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_link_gbs": link, "numa_node": numa},
+        "step_ms": [round(x, 3) for x in step_ms],
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "other_configs": other,
         "hbm_roofline_frac_whole_step": ALG_BYTES * value / world / peak,
     }

@@ -288,6 +288,27 @@ struct ProfScope {
     }
 };
 
+// ---- launch-queue throttle.  A long run enqueues a launch per T steps far faster than the GPU retires them (4096^2: 62 us
+// of host time per 94 us launch once the queue is full), and a hardware queue that has filled up makes the driver wait for
+// room on a slow path: 500-step segments of 4096^2 then took anything between 22.5 and 48 ms (gpurun_out/r02zs).  So the
+// host never runs more than 2 x FK_THROTTLE_EVERY streaming launches ahead: it records an event every FK_THROTTLE_EVERY
+// launches and first waits for the one recorded two periods earlier -- at most 768 launches (~70 ms of 4096^2 work) queued, never a full queue (~1000).
+enum { FK_THROTTLE_EVERY = 384 };
+struct Throttle {
+    std::mutex mu;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    long long n = 0;
+    void tick(cudaStream_t st) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (++n % FK_THROTTLE_EVERY) return;
+        const int k = (int)((n / FK_THROTTLE_EVERY) & 1);
+        if (!ev[k] && cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { ev[k] = nullptr; cudaGetLastError(); return; }
+        if (used[k]) cudaEventSynchronize(ev[k]);
+        used[k] = cudaEventRecord(ev[k], st) == cudaSuccess;
+    }
+} g_throttle;
+
 struct CudaBackend {
     cudaStream_t st;
     int num_sms() { return ::num_sms(); }
@@ -362,6 +383,7 @@ struct CudaBackend {
         g_last_kernel = "fk_stream_kernel";
         if (ps.active) g_prof.stream_cs += (double)(P.G.row1 - P.G.row0) * A.W * P.T * batch;
         ++g_launches;
+        g_throttle.tick(st);
         const int rc = fk::launch_stream(P, A, exact, batch, st);
         if (rc > 0) return cuda_fail((cudaError_t)rc, "streaming kernel launch");
         if (rc < 0) return fail(rc, "streaming kernel: unsupported steps_per_launch%s");
