@@ -123,10 +123,10 @@ fk_stream_kernel(const __grid_constant__ TileArgs A, const __grid_constant__ Str
     if (MODE == FK_STORE_MIRROR) __threadfence_system();
 #ifdef FK_STREAM_TIMING
     __syncthreads();
-    if (threadIdx.x == 0 && blockIdx.y == 0 && gridDim.x <= FK_STREAM_TIMING_CTAS) {
+    if (threadIdx.x == 0 && gridDim.x * gridDim.y <= FK_STREAM_TIMING_CTAS) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        const int rec = chunk * G.nstrips + strip;   // (records in (chunk, strip) order whatever the block order)
+        const int rec = (int)blockIdx.y * (int)gridDim.x + chunk * G.nstrips + strip;   // (records in (tissue, chunk, strip) order)
         fk_stream_timing_buf[3 * rec] = t_start;
         fk_stream_timing_buf[3 * rec + 1] = fk_globaltimer();
         fk_stream_timing_buf[3 * rec + 2] = smid;

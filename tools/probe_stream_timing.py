@@ -10,18 +10,28 @@ import bench
 from cardiax_b200 import _lib, options, solve, params as P
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-wk = bench.make_fk4096()
+ens = len(sys.argv) > 2 and sys.argv[2] == "ens256"
 dev = torch.device("cuda:0")
-st = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
-D = torch.as_tensor(wk["D"]).to(dev)
 options.verbose = False
 options.steps_per_launch = T
-for _ in range(3):
-    st = solve._forward_euler(st, 0, 40, P.PARAMSET_5, D, [], 0.01, 0.01)
+if ens:   # (only tissue 0's CTAs are recorded: blockIdx.y == 0)
+    from cardiax_b200 import stimulus
+    wk = bench.make_ens256(stimulus, 128)
+    st = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
+    D = torch.as_tensor(wk["D"]).to(dev)
+    for _ in range(3):
+        st = solve._forward_euler(st, 100, 140, P.PARAMSET_3, D, [], 0.01, 0.01)
+else:
+    wk = bench.make_fk4096()
+    st = solve.State(*[torch.as_tensor(wk[k]).to(dev) for k in "vwu"])
+    D = torch.as_tensor(wk["D"]).to(dev)
+    for _ in range(3):
+        st = solve._forward_euler(st, 0, 40, P.PARAMSET_5, D, [], 0.01, 0.01)
 torch.cuda.synchronize()
 plan = _lib.last_plan()
 print(_lib.last_kernel(), plan)
-n = plan["strips"] * plan["row_chunks"]
+nb = 128 if ens else 1
+n = plan["strips"] * plan["row_chunks"] * nb
 buf = (ctypes.c_ulonglong * (3 * n))()
 fn = getattr(_lib.lib(), "fk_stream_timing_T%d_E0" % T)
 fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -31,7 +41,7 @@ t0 = a[:, 0].min()
 start, end, sm = (a[:, 0] - t0) / 1e3, (a[:, 1] - t0) / 1e3, a[:, 2]
 dur = end - start
 ns = plan["strips"]
-strip, chunk = np.arange(n) % ns, np.arange(n) // ns
+strip, chunk = np.arange(n) % ns, (np.arange(n) // ns) % plan["row_chunks"]
 print("launch span %.1f us; CTA duration min/median/max %.1f / %.1f / %.1f us; start max %.1f us" % (end.max(), dur.min(), np.median(dur), dur.max(), start.max()))
 print("by strip: " + "  ".join("%d: %.1f" % (s, dur[strip == s].mean()) for s in range(ns)))
 for c in (0, 1, plan["row_chunks"] // 2, plan["row_chunks"] - 2, plan["row_chunks"] - 1):
