@@ -439,6 +439,46 @@ def test_large_field_properties_4096():
         assert np.array_equal(x[:sub, :sub].cpu().numpy(), r[:sub, :sub])
 
 
+@pytest.mark.parametrize("uniform", [True, False])
+def test_large_field_four_corners_4096_exact(uniform):
+    """BASELINE config 3 size at the launch geometry of the bench (one wave of 9 strips x 49 balanced row chunks: the
+    chunks at the physical top / bottom edge are shorter, the edge strips' CTAs come first in block order): the crops at
+    all four corners evolve exactly like the oracle's runs of tissues that contain their dependency cones -- the first /
+    last strip, the first / last chunk (general body at the top, tail at the bottom) and their intersections."""
+    from cardiax_b200 import _lib, options, solve
+    H = W = 4096
+    n, sub = 8, 96
+    m = sub + 4 * n
+    rng = np.random.default_rng(7)
+    u = torch.zeros(H, W, device="cuda")
+    v = torch.ones(H, W, device="cuda")
+    w = torch.ones(H, W, device="cuda")
+    D = torch.full((H, W), 1e-3, device="cuda")
+    for r0, c0 in ((0, 0), (0, W - m), (H - m, 0), (H - m, W - m)):   # something to diffuse in every corner
+        u[r0:r0 + m, c0:c0 + m] = torch.as_tensor(rng.random((m, m), dtype=np.float32)).cuda()
+        v[r0:r0 + m, c0:c0 + m] = torch.as_tensor(rng.random((m, m), dtype=np.float32)).cuda()
+        w[r0:r0 + m, c0:c0 + m] = torch.as_tensor(rng.random((m, m), dtype=np.float32)).cuda()
+        if not uniform:
+            D[r0:r0 + m, c0:c0 + m] = torch.as_tensor((rng.random((m, m), dtype=np.float32) * 9e-4 + 1e-4).astype(np.float32)).cuda()
+    st = solve.State(v, w, u)
+    P5 = O.PARAMSETS["5"]
+    options.numerics, options.kernel, options.steps_per_launch = "exact", 2, 2
+    try:
+        e = solve._forward_euler(st, 0, n, P5, D, [], 0.01, 0.01)
+        plan = _lib.last_plan()
+    finally:
+        options.numerics, options.kernel, options.steps_per_launch = "fast", 0, 0
+    assert _lib.last_kernel() == "fk_stream_kernel" and plan["strips"] >= 3 and plan["row_chunks"] >= 4
+    for r0, c0, rs, cs in ((0, 0, slice(0, sub), slice(0, sub)), (0, W - m, slice(0, sub), slice(m - sub, m)),
+                           (H - m, 0, slice(m - sub, m), slice(0, sub)), (H - m, W - m, slice(m - sub, m), slice(m - sub, m))):
+        crop = O.State(*[x[r0:r0 + m, c0:c0 + m].cpu().numpy() for x in st])
+        Dc = D[r0:r0 + m, c0:c0 + m].cpu().numpy()
+        ref = C.forward_euler(crop, 0, n, P5, Dc, [], 0.01, 0.01)
+        for name, x, r in zip("vwu", e, ref):
+            got = x[r0:r0 + m, c0:c0 + m].cpu().numpy()
+            assert np.array_equal(got[rs, cs], r[rs, cs]), (name, r0, c0, float(np.abs(got[rs, cs] - r[rs, cs]).max()))
+
+
 # --------------------------------------------------------------------------- vectors frozen from the reference's own source
 def _ref_fixture(name):
     import os
