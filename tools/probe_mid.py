@@ -20,7 +20,7 @@ def run(n, kernel=0, T=0, steps=400, uniform=False, mg=0, tiles=(0, 0), edge=(0,
     if uniform:
         D = np.full((n, n), 1e-3, np.float32)
     st = solve.State(torch.ones((n, n), device="cuda"), torch.ones((n, n), device="cuda"),
-                     torch.as_tensor(bench.make_fk4096(n, n)["u"]).cuda())
+                     torch.as_tensor(bench.make_fk4096(None, n, n)["u"]).cuda())
     D = torch.as_tensor(D).cuda()
     P = O.PARAMSETS["3"]
     try:
