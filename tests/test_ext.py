@@ -64,6 +64,27 @@ def test_dopri_restatement_is_a_fifth_order_integrator():
             assert np.median(d) < 2e-6 and d.max() < 5e-3, (i, j, float(np.median(d)), float(d.max()))
 
 
+def test_dopri_tableau_equals_an_independent_statement_of_dormand_prince():
+    """Known-answer check of the restated Butcher tableau: nodes, stage weights and the 5th-order solution weights of
+    jax.experimental.ode (alpha, beta, c_sol) are Dormand-Prince's, as SciPy states them independently (RK45.C / A / B).
+    (The error weights differ by construction: jax / TensorFlow use Shampine's embedded 4th-order solution, SciPy the
+    original one -- so c_error and c_mid stay anchored on the integrator-level check above only.)"""
+    from scipy.integrate._ivp.rk import RK45
+    from oracle import fk_oracle_ext as X
+    f32 = np.float32
+    assert [f32(c) for c in RK45.C[1:]] == X._ALPHA[:5] and X._ALPHA[5] == f32(1.0)
+    for s_, row in enumerate(RK45.A[1:]):                      # stages 2 .. 6
+        assert [f32(a) for a in row[:s_ + 1]] == X._BETA[s_][:s_ + 1], s_
+        assert all(b == 0 for b in X._BETA[s_][s_ + 1:])
+    assert [f32(b) for b in RK45.B] == X._C_SOL[:6] and X._C_SOL[6] == 0
+    assert X._BETA[5] == X._C_SOL                              # first-same-as-last: the 7th stage is the next step's first
+    # the embedded solution has order 4: its weights sum to 1 and satisfy the first three order conditions as well
+    c4 = np.array(X._C_SOL, np.float64) - np.array(X._C_ERR, np.float64)
+    nodes = np.array([0.0] + [float(a) for a in X._ALPHA[:6]])
+    assert abs(c4.sum() - 1) < 1e-6 and abs(c4 @ nodes - 0.5) < 1e-6 and abs(c4 @ nodes ** 2 - 1 / 3) < 1e-6 \
+        and abs(c4 @ nodes ** 3 - 0.25) < 1e-6
+
+
 def test_dopri_controller_scalars():
     """optimal_step_size of jax.experimental.ode: grow by at most 10x, shrink by at most 5x, safety 0.9."""
     f = X._optimal_step_size
