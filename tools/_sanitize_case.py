@@ -35,4 +35,7 @@ run((130, 516), 4, 2, 4, 0, 0, nt=64, rh=17)
 run((64, 256), 4, 2, 2, 2, 0, batch=3, numerics="fast")
 run((40, 64), 3, 3, 0, 2, 0)
 run((37, 53), 3, 1, 2, 2, 0)
+run((640, 1664), 4, 2, 2, 0, 1, numerics="fast")   # the planner's own geometry: >= 3 strips, balanced row chunks, block order
+run((640, 1664), 4, 2, 2, 2, 0)
+run((512, 256), 4, 2, 2, 0, 0, batch=4, numerics="fast")   # one strip per tissue (the ensemble shape)
 print("all ok")
