@@ -425,6 +425,8 @@ def main():
         sampler.start()   # (before the warm-up: NVML's / nvidia-smi's start-up takes driver locks that can stall launches)
         time.sleep(0.2)
     for _ in range(args.warmup):
+        if flush is not None:
+            flush.fill_(1.0)   # (the fill kernel's first use loads its module: ~10 ms that do not belong in the timed region)
         st = step_fn(st, t); t += seg
     barrier()
     if rank == 0:
