@@ -557,7 +557,8 @@ def main():
     link["all_ranks_both_directions_gbs_each_way"] = h2d / (both_ms * 1e-3) / 1e9
     for b in range(NB):
         ev_free[b].record(s_run); ev_out[b].record(s_out)
-    e2e_step(0, 0)
+    for i in range(NB):      # every host / device buffer used once before the clock starts: the first DMA into freshly pinned
+        e2e_step(i, 0)       # pages took 200-300 ms (first_attempt_step_ms of profiles/bench_r03j_default.json)
     barrier()
     def e2e_pass():
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -59,6 +59,23 @@ def build(force=False, verbose=False):
     fk_stream_tu.cu per (temporal-blocking depth, numerics), in parallel, then one link."""
     if not force and not needs_build():
         return SO_PATH
+    # One builder at a time: under torchrun every rank may find the library stale at once (a source file touched after the
+    # last build), and eight concurrent links into the same file left a truncated libfk.so behind.  The ranks queue on a
+    # lock file; whoever gets it second finds the library fresh and returns.  The link goes to a temporary name and is
+    # renamed into place, so a reader never sees a half-written file.
+    import fcntl
+    os.makedirs(os.path.dirname(SO_PATH), exist_ok=True)
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return SO_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
     env = dict(os.environ)
@@ -101,10 +118,14 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
         logs = list(pool.map(run, jobs))
-    out = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + [j[0] for j in jobs],
+    tmp = SO_PATH + ".tmp.%d" % os.getpid()
+    out = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + [j[0] for j in jobs],
                          capture_output=True, text=True, env=env)
     if out.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc link failed:\n" + out.stdout + out.stderr)
+    os.replace(tmp, SO_PATH)
     if verbose:
         print("\n".join(logs))
     return SO_PATH
