@@ -46,9 +46,37 @@ class FkPeerMirror(ctypes.Structure):
                 ("row0", ctypes.c_int * 2), ("row1", ctypes.c_int * 2), ("dst_row0", ctypes.c_int * 2)]
 
 
+def _source_digest():
+    """SHA-256 over the sources the library is built from (and the flags): what `libfk.so.sha` records at build time."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = [os.path.join(CSRC, s) for s in _SOURCES] + [os.path.join(_HERE, "..", "include", "fk.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        if os.path.exists(d):
+            with open(d, "rb") as f:
+                h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("FK_EXTRA_NVCC", "").encode())
+    h.update(os.environ.get("FK_DEPTHS", "").encode())
+    return h.hexdigest()
+
+
 def needs_build():
+    """Is the library missing or older than its sources?  Decided on the sources' CONTENT when the build left its digest
+    next to the library (a checkout or a copy of the tree changes modification times, not what would be compiled);
+    on modification times otherwise."""
     if not os.path.exists(SO_PATH):
         return True
+    if os.environ.get("FK_SO"):   # a development A/B library, built with its own flags: never rebuilt behind the user's back
+        return False
+    sha = SO_PATH + ".sha"
+    if os.path.exists(sha):
+        try:
+            with open(sha) as f:
+                return f.read().strip() != _source_digest()
+        except OSError:
+            pass
     t = os.path.getmtime(SO_PATH)
     deps = [os.path.join(CSRC, s) for s in _SOURCES] + [os.path.join(_HERE, "..", "include", "fk.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
@@ -125,7 +153,10 @@ def _build_locked(force, verbose):
         if os.path.exists(tmp):
             os.remove(tmp)
         raise RuntimeError("nvcc link failed:\n" + out.stdout + out.stderr)
+    digest = _source_digest()
     os.replace(tmp, SO_PATH)
+    with open(SO_PATH + ".sha", "w") as f:
+        f.write(digest + "\n")
     if verbose:
         print("\n".join(logs))
     return SO_PATH
