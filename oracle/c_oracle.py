@@ -13,9 +13,18 @@ _lib = None
 def build(force=False):
     """Compile oracle/fk_oracle.c with gcc (no GPU, no reference files needed)."""
     srcs = [os.path.join(_HERE, f) for f in ("fk_oracle.c", "fk_oracle_impl.h")]
-    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+    def fresh():
+        return os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)
+    if not force and fresh():
         return _SO
-    subprocess.check_call(["make", "-C", _HERE, "-B", "libfk_oracle.so"], stdout=subprocess.DEVNULL)
+    import fcntl   # (one builder at a time: several test / bench processes may find the library stale at once)
+    with open(_SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or not fresh():
+                subprocess.check_call(["make", "-C", _HERE, "-B", "libfk_oracle.so"], stdout=subprocess.DEVNULL)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

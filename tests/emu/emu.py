@@ -23,10 +23,21 @@ def _is_int(x):
 def build(force=False):
     deps = [os.path.join(_HERE, "fk_emu.cpp")] + [os.path.join(_CSRC, f) for f in
                                                     ("fk_core.h", "fk_tile.h", "fk_stream.h", "fk_driver.h", "fk_wide.h", "fk_resident.h", "fk_aux.h", "fk_ode.h")]
-    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+    def fresh():
+        return os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps)
+    if not force and fresh():
         return _SO
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
-                           "-Wno-unknown-pragmas", "-o", _SO, deps[0]])
+    import fcntl   # (the two processes of a gloo test may both find the library stale: one builds, the link is renamed into place)
+    with open(_SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or not fresh():
+                tmp = _SO + ".tmp.%d" % os.getpid()
+                subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                                       "-Wno-unknown-pragmas", "-o", tmp, deps[0]])
+                os.replace(tmp, _SO)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 
